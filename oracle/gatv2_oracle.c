@@ -1,0 +1,714 @@
+/*
+ * gatv2_oracle.c -- TEST INFRASTRUCTURE ONLY.  NOT part of the product path.
+ *
+ * Serial CPU restatement of the full-batch GATv2 training epoch computed by the
+ * reference's edge-centric variant (EB = /root/reference/GATv2_edge_based.cu).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library, and only as the checker or as the
+ * reported CPU baseline.  The product (graph-attention-network-gatv2-_b200/csrc)
+ * never links, loads or calls it and fails loudly when its CUDA library is
+ * missing.
+ *
+ * Parity pin: the reference ships NO tests, golden vectors or fixtures
+ * (SURVEY.md section 4).  This oracle is pinned by
+ *   (1) tests/golden/ref_edge_*.npz -- buffers dumped by the reference's own
+ *       edge-based binary (built from /root/reference by oracle/Makefile, run on
+ *       a B200 with injected weights; see oracle/gen_golden.py),
+ *   (2) a hand-computed known-answer graph (tests/test_oracle.py),
+ *   (3) central finite differences of its own loss for every gradient,
+ *   (4) agreement of its two arithmetic modes: "literal" (fp32, EB's exact loop
+ *       structure: per-edge mat-vec recompute, O(deg^2) softmax backward) and
+ *       "factored" (fp32 storage, fp64 accumulation, projection computed once per
+ *       node) which is the golden every CUDA parity test compares against.
+ *
+ * Conventions (all from EB): CSR is destination-major (row = dst, col_idx = src,
+ * EB:67-84); W is [H][D][2I] with columns 0..I-1 applied to the SOURCE features
+ * and I..2I-1 to the DESTINATION features (EB:304-316); a is [H][D]; W_o is
+ * [C][D_L]; LeakyReLU slope 0.01 everywhere (EB:1143, EB:1428); gradients are of
+ * the SUMMED loss (EB:572) while the printed loss is the mean (EB:544).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_SLOPE 0.01f
+
+static inline float lrelu_f(float x) { return x > 0.0f ? x : ORC_SLOPE * x; }
+static inline double lrelu_d(double x) { return x > 0.0 ? x : (double)ORC_SLOPE * x; }
+
+/* ------------------------------------------------------------------ graph prep */
+
+/* EB:67-84 csr_to_coo_kernel: src[e] = col_idx[e], dst[e] = row owning e. */
+void orc_csr_to_coo(int N, const int* row_ptr, const int* col_idx, int* src, int* dst) {
+  for (int i = 0; i < N; ++i)
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+      src[e] = col_idx[e];
+      dst[e] = i;
+    }
+}
+
+/* EB:89-99 compute_max_degree. */
+int orc_max_degree(const int* row_ptr, int N) {
+  int best = 0;
+  for (int i = 0; i < N; ++i) {
+    int d = row_ptr[i + 1] - row_ptr[i];
+    if (d > best) best = d;
+  }
+  return best;
+}
+
+/* EB:1106-1107: C = max(label) + 1. */
+int orc_num_classes(const int* labels, int N) {
+  int best = labels[0];
+  for (int i = 1; i < N; ++i)
+    if (labels[i] > best) best = labels[i];
+  return best + 1;
+}
+
+/* In-degree per destination row (row length), EB:93. */
+void orc_in_degree(int N, const int* row_ptr, int* deg) {
+  for (int i = 0; i < N; ++i) deg[i] = row_ptr[i + 1] - row_ptr[i];
+}
+
+/* Transposed graph (source-major) used by the deterministic backward scatter.
+ * For every source j the out-edges are listed in ascending CSR edge id (stable
+ * counting sort), csc_eid[q] is the CSR position of the edge and csc_dst[q] its
+ * destination.  New work (no reference counterpart); bit-exact target for the
+ * device graph-prep kernels. */
+void orc_csc_build(int N, int64_t E, const int* row_ptr, const int* col_idx, int* csc_ptr,
+                   int* csc_dst, int* csc_eid) {
+  memset(csc_ptr, 0, sizeof(int) * (size_t)(N + 1));
+  for (int64_t e = 0; e < E; ++e) csc_ptr[col_idx[e] + 1]++;
+  for (int i = 0; i < N; ++i) csc_ptr[i + 1] += csc_ptr[i];
+  int* cursor = (int*)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1));
+  memcpy(cursor, csc_ptr, sizeof(int) * (size_t)N);
+  for (int i = 0; i < N; ++i)
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+      int q = cursor[col_idx[e]]++;
+      csc_dst[q] = i;
+      csc_eid[q] = e;
+    }
+  free(cursor);
+}
+
+/* Destination-row partition for R ranks, balanced on EDGE counts: rank r owns rows
+ * [bounds[r], bounds[r+1]); bounds[r] = first row i with row_ptr[i] >= floor(r*E/R).
+ * New work; bit-exact target for gatx_partition_rows. */
+void orc_partition_rows(int N, const int* row_ptr, int R, int* bounds) {
+  int64_t E = row_ptr[N];
+  bounds[0] = 0;
+  int i = 0;
+  for (int r = 1; r < R; ++r) {
+    int64_t target = (E * (int64_t)r) / (int64_t)R;
+    while (i < N && (int64_t)row_ptr[i] < target) ++i;
+    bounds[r] = i;
+  }
+  bounds[R] = N;
+}
+
+/* ------------------------------------------------------------- factored forward */
+
+/* P_l[n][r] = sum_i W[r][i] X[n][i];  P_r[n][r] = sum_i W[r][I+i] X[n][i], r = h*D+k.
+ * Same contraction as the inner loops of EB:303-316, evaluated once per node. */
+void orc_project(int N, int I, int F, const float* X, const float* W, float* Pl, float* Pr) {
+#pragma omp parallel for schedule(static)
+  for (int n = 0; n < N; ++n) {
+    const float* x = X + (size_t)n * I;
+    for (int r = 0; r < F; ++r) {
+      const float* wl = W + (size_t)r * 2 * I;
+      const float* wr = wl + I;
+      double sl = 0.0, sr = 0.0;
+      for (int i = 0; i < I; ++i) {
+        sl += (double)wl[i] * (double)x[i];
+        sr += (double)wr[i] * (double)x[i];
+      }
+      Pl[(size_t)n * F + r] = (float)sl;
+      Pr[(size_t)n * F + r] = (float)sr;
+    }
+  }
+}
+
+/* One GATv2 layer forward on projected features.
+ *   score  EB:279-324   e[h][e] = sum_k a[h][k] LReLU(P_l[src] + P_r[dst])
+ *   max/sum EB:326-359  m initialised to -1e9f, s = sum exp(e - m)
+ *   alpha  EB:362-384   exp(e - m) / (s + 1e-8f)
+ *   aggregate EB:386-424  h[dst][h][k] = sum_e alpha P_l[src][h][k]   (0 for empty rows)
+ *   activation EB:426-459 hidden: LReLU(h) concat; last: mean_h LReLU(h_h)
+ * Outputs score/alpha are head-major [H][E] like the reference; mx/sm are [H][N];
+ * hpre is [N][H][D]; Hout is [N][H*D] (hidden) or [N][D] (last). */
+void orc_layer_forward(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
+                       const float* Pr, const float* a, int is_last, float* score, float* alpha,
+                       float* mx, float* sm, float* hpre, float* Hout) {
+  const int F = H * D;
+  const int64_t E = row_ptr[N];
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int i = 0; i < N; ++i) {
+    const int beg = row_ptr[i], end = row_ptr[i + 1];
+    for (int h = 0; h < H; ++h) {
+      const float* ah = a + (size_t)h * D;
+      const float* pr = Pr + (size_t)i * F + (size_t)h * D;
+      float m = -1e9f;
+      for (int e = beg; e < end; ++e) {
+        const float* pl = Pl + (size_t)col_idx[e] * F + (size_t)h * D;
+        double acc = 0.0;
+        for (int k = 0; k < D; ++k) acc += (double)ah[k] * lrelu_d((double)pl[k] + (double)pr[k]);
+        float sc = (float)acc;
+        score[(size_t)h * E + e] = sc;
+        if (sc > m) m = sc;
+      }
+      double s = 0.0;
+      for (int e = beg; e < end; ++e) s += exp((double)score[(size_t)h * E + e] - (double)m);
+      float sf = (float)s;
+      mx[(size_t)h * N + i] = m;
+      sm[(size_t)h * N + i] = sf;
+      for (int e = beg; e < end; ++e) {
+        double ex = exp((double)score[(size_t)h * E + e] - (double)m);
+        alpha[(size_t)h * E + e] = (float)(ex / ((double)sf + (double)1e-8f));
+      }
+      for (int k = 0; k < D; ++k) {
+        double acc = 0.0;
+        for (int e = beg; e < end; ++e)
+          acc += (double)alpha[(size_t)h * E + e] *
+                 (double)Pl[(size_t)col_idx[e] * F + (size_t)h * D + k];
+        hpre[((size_t)i * H + h) * D + k] = (float)acc;
+      }
+    }
+    if (is_last) {
+      for (int k = 0; k < D; ++k) {
+        double acc = 0.0;
+        for (int h = 0; h < H; ++h) acc += lrelu_d((double)hpre[((size_t)i * H + h) * D + k]);
+        Hout[(size_t)i * D + k] = (float)(acc / (double)H);
+      }
+    } else {
+      for (int r = 0; r < F; ++r) Hout[(size_t)i * F + r] = lrelu_f(hpre[(size_t)i * F + r]);
+    }
+  }
+}
+
+/* Classifier + softmax, EB:463-511 with the softmax of EB:132-141
+ * (max-subtracted expf, denominator sum + 1e-8 evaluated in double). */
+void orc_head_forward(int N, int C, int DL, const float* Wo, const float* HL, float* z, float* y) {
+#pragma omp parallel for schedule(static)
+  for (int n = 0; n < N; ++n) {
+    const float* x = HL + (size_t)n * DL;
+    float* zn = z + (size_t)n * C;
+    float* yn = y + (size_t)n * C;
+    for (int c = 0; c < C; ++c) {
+      double acc = 0.0;
+      for (int j = 0; j < DL; ++j) acc += (double)Wo[(size_t)c * DL + j] * (double)x[j];
+      zn[c] = (float)acc;
+    }
+    float m = zn[0];
+    for (int c = 1; c < C; ++c)
+      if (zn[c] > m) m = zn[c];
+    double s = 0.0;
+    for (int c = 0; c < C; ++c) s += exp((double)zn[c] - (double)m);
+    float sf = (float)s;
+    for (int c = 0; c < C; ++c) yn[c] = (float)(exp((double)zn[c] - (double)m) / ((double)sf + 1e-8));
+  }
+}
+
+/* Per-node CE loss, first-max argmax (EB:514-537) and their reductions (EB:539-550).
+ * Returns the summed loss; avg_loss = sum/N, accuracy = correct/N. */
+double orc_loss_acc(int N, int C, const float* y, const int* labels, float* losses, int* pred,
+                    int* correct, float* avg_loss, float* accuracy) {
+  double total = 0.0;
+  int64_t ok = 0;
+  for (int n = 0; n < N; ++n) {
+    const float* yn = y + (size_t)n * C;
+    float p = yn[labels[n]];
+    float loss = -logf(fmaxf(p, 1e-12f));
+    float best = yn[0];
+    int arg = 0;
+    for (int c = 1; c < C; ++c)
+      if (yn[c] > best) {
+        best = yn[c];
+        arg = c;
+      }
+    if (losses) losses[n] = loss;
+    if (pred) pred[n] = arg;
+    if (correct) correct[n] = (arg == labels[n]);
+    total += (double)loss;
+    ok += (arg == labels[n]);
+  }
+  if (avg_loss) *avg_loss = (float)(total / (double)N);
+  if (accuracy) *accuracy = (float)((double)ok / (double)N);
+  return total;
+}
+
+/* ------------------------------------------------------------ factored backward */
+
+/* EB:553-608 compute_output_gradients.  dz = y - onehot (sum loss, no 1/N);
+ * gWo[c][d] += dz[c] H_L[d]; g_h[n][h][d] = (Wo^T dz)[d] * LReLU'(h_pre[n][h][d]) / Hl.
+ * For Hl == 1 this is exactly the reference; for Hl > 1 the reference indexes the
+ * pre-activations with the wrong stride (EB:598) and the per-head
+ * derivative used here is the true gradient of EB's forward (extension). */
+void orc_output_grads(int N, int C, int DL, int Hl, const float* y, const int* labels,
+                      const float* hpre_last, const float* HL, const float* Wo, float* gWo,
+                      float* g_h) {
+  double* acc = (double*)calloc((size_t)C * DL, sizeof(double));
+  double* dz = (double*)malloc(sizeof(double) * (size_t)C);
+  for (int n = 0; n < N; ++n) {
+    for (int c = 0; c < C; ++c)
+      dz[c] = (double)(float)(y[(size_t)n * C + c] - (c == labels[n] ? 1.0f : 0.0f));
+    for (int c = 0; c < C; ++c)
+      for (int d = 0; d < DL; ++d) acc[(size_t)c * DL + d] += dz[c] * (double)HL[(size_t)n * DL + d];
+    for (int d = 0; d < DL; ++d) {
+      double s = 0.0;
+      for (int c = 0; c < C; ++c) s += (double)Wo[(size_t)c * DL + d] * dz[c];
+      for (int h = 0; h < Hl; ++h) {
+        float hv = hpre_last[((size_t)n * Hl + h) * DL + d];
+        double der = hv > 0.0f ? 1.0 : (double)ORC_SLOPE;
+        g_h[((size_t)n * Hl + h) * DL + d] = (float)(s * der / (double)Hl);
+      }
+    }
+  }
+  for (size_t i = 0; i < (size_t)C * DL; ++i) gWo[i] += (float)acc[i];
+  free(acc);
+  free(dz);
+}
+
+/* One GATv2 layer backward.
+ *   galpha EB:612-651   g_h[dst][h] . P_l[src][h]
+ *   ge     EB:654-696   sum_k galpha_k alpha_k (delta_ke - alpha_e) = alpha_e (galpha_e - sum_k alpha_k galpha_k)
+ *   ga, gW EB:698-798   ga += ge LReLU(s);  gW_l += (g_h alpha + ge a LReLU'(s)) x_src^T;
+ *                       gW_r += ge a LReLU'(s) x_dst^T
+ *   gX     EB:801-874   gX[src] += W_l^T (g_h alpha + ge a L'(s)); gX[dst] += W_r^T (ge a L'(s))
+ * evaluated in factored form: gP_l[src] / gP_r[dst] are accumulated per node (fp64)
+ * and contracted with X and W once.  gW/ga are accumulated (+=) like the reference's
+ * atomics; gX (may be NULL for layer 0, EB:1528) is overwritten. gPl/gPr/galpha/ge
+ * are optional outputs for per-kernel parity tests. */
+void orc_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, int D, int I,
+                        const float* X, const float* W, const float* a, const float* Pl,
+                        const float* Pr, const float* alpha, const float* g_h, float* gW, float* ga,
+                        float* gX, float* galpha_out, float* ge_out, float* gPl_out, float* gPr_out) {
+  const int F = H * D;
+  const int64_t E = row_ptr[N];
+  double* gPl = (double*)calloc((size_t)N * F, sizeof(double));
+  double* gPr = (double*)calloc((size_t)N * F, sizeof(double));
+  double* gad = (double*)calloc((size_t)F, sizeof(double));
+  for (int i = 0; i < N; ++i) {
+    const int beg = row_ptr[i], end = row_ptr[i + 1];
+    for (int h = 0; h < H; ++h) {
+      const float* gh = g_h + ((size_t)i * H + h) * D;
+      const float* pr = Pr + (size_t)i * F + (size_t)h * D;
+      const float* ah = a + (size_t)h * D;
+      double dotsum = 0.0;
+      for (int e = beg; e < end; ++e) {
+        const float* pl = Pl + (size_t)col_idx[e] * F + (size_t)h * D;
+        double g = 0.0;
+        for (int k = 0; k < D; ++k) g += (double)gh[k] * (double)pl[k];
+        float gf = (float)g;
+        if (galpha_out) galpha_out[(size_t)h * E + e] = gf;
+        dotsum += (double)alpha[(size_t)h * E + e] * (double)gf;
+      }
+      for (int e = beg; e < end; ++e) {
+        const int j = col_idx[e];
+        const float* pl = Pl + (size_t)j * F + (size_t)h * D;
+        double g = 0.0;
+        for (int k = 0; k < D; ++k) g += (double)gh[k] * (double)pl[k];
+        const double al = (double)alpha[(size_t)h * E + e];
+        const float gef = (float)(al * ((double)(float)g - dotsum));
+        if (ge_out) ge_out[(size_t)h * E + e] = gef;
+        const double gee = (double)gef;
+        for (int k = 0; k < D; ++k) {
+          double s = (double)pl[k] + (double)pr[k];
+          gad[(size_t)h * D + k] += gee * lrelu_d(s);
+          double mk = gee * (double)ah[k] * (s > 0.0 ? 1.0 : (double)ORC_SLOPE);
+          gPr[(size_t)i * F + (size_t)h * D + k] += mk;
+          gPl[(size_t)j * F + (size_t)h * D + k] += al * (double)gh[k] + mk;
+        }
+      }
+    }
+  }
+  for (int r = 0; r < F; ++r) ga[r] += (float)gad[r];
+  /* gW[r][0..I) = sum_n gP_l[n][r] X[n][:],  gW[r][I..2I) = sum_n gP_r[n][r] X[n][:] */
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < F; ++r) {
+    double* accl = (double*)calloc((size_t)2 * I, sizeof(double));
+    double* accr = accl + I;
+    for (int n = 0; n < N; ++n) {
+      const double gl = gPl[(size_t)n * F + r], gr = gPr[(size_t)n * F + r];
+      if (gl == 0.0 && gr == 0.0) continue;
+      const float* x = X + (size_t)n * I;
+      for (int i = 0; i < I; ++i) {
+        accl[i] += gl * (double)x[i];
+        accr[i] += gr * (double)x[i];
+      }
+    }
+    for (int i = 0; i < 2 * I; ++i) gW[(size_t)r * 2 * I + i] += (float)accl[i];
+    free(accl);
+  }
+  if (gX) {
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < N; ++n)
+      for (int i = 0; i < I; ++i) {
+        double acc = 0.0;
+        for (int r = 0; r < F; ++r)
+          acc += gPl[(size_t)n * F + r] * (double)W[(size_t)r * 2 * I + i] +
+                 gPr[(size_t)n * F + r] * (double)W[(size_t)r * 2 * I + I + i];
+        gX[(size_t)n * I + i] = (float)acc;
+      }
+  }
+  if (gPl_out)
+    for (size_t t = 0; t < (size_t)N * F; ++t) gPl_out[t] = (float)gPl[t];
+  if (gPr_out)
+    for (size_t t = 0; t < (size_t)N * F; ++t) gPr_out[t] = (float)gPr[t];
+  free(gPl);
+  free(gPr);
+  free(gad);
+}
+
+/* EB:879-893: g[n][d] *= LReLU'(h_pre_prev[n][d]). */
+void orc_preact_grad(int N, int I, const float* hpre_prev, float* g) {
+  for (size_t t = 0; t < (size_t)N * I; ++t) g[t] = g[t] * (hpre_prev[t] > 0.0f ? 1.0f : ORC_SLOPE);
+}
+
+/* ---------------------------------------------------------------------- update */
+
+/* EB:250-278 clip_grad_norm: norm = sqrt(sum g^2); if norm > thresh scale by
+ * thresh / (norm + 1e-9f).  Returns the norm. */
+float orc_clip_grad_norm(float* g, int64_t n, float thresh) {
+  double ss = 0.0;
+  for (int64_t i = 0; i < n; ++i) ss += (double)g[i] * (double)g[i];
+  float norm = (float)sqrt((double)(float)ss);
+  float scale = 1.0f;
+  if (norm > thresh) scale = thresh / (norm + 1e-9f);
+  if (scale < 1.0f)
+    for (int64_t i = 0; i < n; ++i) g[i] *= scale;
+  return norm;
+}
+
+/* EB:896-916 adam_update_kernel (t = epoch, eps = 1e-8f, bias correction via powf). */
+void orc_adam(float* p, const float* g, float* m, float* v, float lr, int64_t n, float b1, float b2,
+              float eps, int t) {
+  const float c1 = 1.0f - powf(b1, (float)t), c2 = 1.0f - powf(b2, (float)t);
+  for (int64_t i = 0; i < n; ++i) {
+    m[i] = b1 * m[i] + (1.0f - b1) * g[i];
+    v[i] = b2 * v[i] + (1.0f - b2) * (g[i] * g[i]);
+    float mh = m[i] / c1, vh = v[i] / c2;
+    p[i] -= lr * mh / (sqrtf(vh) + eps);
+  }
+}
+
+/* EB:919-923 sgd_update_kernel. */
+void orc_sgd(float* p, const float* g, float lr, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) p[i] -= lr * g[i];
+}
+
+/* --------------------------------------------------------------- literal (fp32) */
+
+/* EB's exact per-edge arithmetic in fp32, in EB's loop order, for tiny graphs only:
+ * the projections are recomputed for every edge (EB:303-316, EB:415-420) and the
+ * softmax backward is the O(deg^2) double loop (EB:682-691).  Accumulation into
+ * h / gW / ga / gX is serial in CSR edge order (one of the orders the reference's
+ * atomics may produce).  expf stands in for the device's __expf. */
+void orc_lit_layer_forward(int N, const int* row_ptr, const int* col_idx, int H, int D, int I,
+                           const float* X, const float* W, const float* a, int is_last,
+                           float* score, float* alpha, float* hpre, float* Hout) {
+  const int64_t E = row_ptr[N];
+  const int F = H * D;
+  memset(hpre, 0, sizeof(float) * (size_t)N * F);
+  for (int h = 0; h < H; ++h)
+    for (int i = 0; i < N; ++i)
+      for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+        const float* xs = X + (size_t)col_idx[e] * I;
+        const float* xd = X + (size_t)i * I;
+        float ev = 0.f;
+        for (int k = 0; k < D; ++k) {
+          const float* wk = W + ((size_t)h * D + k) * 2 * I;
+          float acc = 0.f;
+          for (int d = 0; d < I; ++d) acc += wk[d] * xs[d];
+          for (int d = 0; d < I; ++d) acc += wk[I + d] * xd[d];
+          ev += a[(size_t)h * D + k] * lrelu_f(acc);
+        }
+        score[(size_t)h * E + e] = ev;
+      }
+  for (int h = 0; h < H; ++h)
+    for (int i = 0; i < N; ++i) {
+      float m = -1e9f;
+      for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) m = fmaxf(m, score[(size_t)h * E + e]);
+      float s = 0.f;
+      for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) s += expf(score[(size_t)h * E + e] - m);
+      for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e)
+        alpha[(size_t)h * E + e] = expf(score[(size_t)h * E + e] - m) / (s + 1e-8f);
+    }
+  for (int h = 0; h < H; ++h)
+    for (int i = 0; i < N; ++i)
+      for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+        const float* xs = X + (size_t)col_idx[e] * I;
+        float al = alpha[(size_t)h * E + e];
+        for (int k = 0; k < D; ++k) {
+          const float* wk = W + ((size_t)h * D + k) * 2 * I;
+          float sum = 0.f;
+          for (int d = 0; d < I; ++d) sum += wk[d] * xs[d];
+          sum *= al;
+          hpre[((size_t)i * H + h) * D + k] += sum;
+        }
+      }
+  for (int i = 0; i < N; ++i) {
+    if (is_last) {
+      for (int k = 0; k < D; ++k) {
+        float sum = 0.f;
+        for (int h = 0; h < H; ++h) sum += lrelu_f(hpre[((size_t)i * H + h) * D + k]);
+        Hout[(size_t)i * D + k] = sum / (float)H;
+      }
+    } else {
+      for (int r = 0; r < F; ++r) Hout[(size_t)i * F + r] = lrelu_f(hpre[(size_t)i * F + r]);
+    }
+  }
+}
+
+void orc_lit_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, int D, int I,
+                            const float* X, const float* W, const float* a, const float* alpha,
+                            const float* g_h, float* gW, float* ga, float* gX, float* galpha,
+                            float* ge) {
+  const int64_t E = row_ptr[N];
+  /* EB:612-651 */
+  for (int i = 0; i < N; ++i)
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e)
+      for (int h = 0; h < H; ++h) {
+        const float* xs = X + (size_t)col_idx[e] * I;
+        float tmp = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float* wk = W + ((size_t)h * D + d) * 2 * I;
+          float wx = 0.f;
+          for (int k = 0; k < I; ++k) wx += wk[k] * xs[k];
+          tmp += g_h[((size_t)i * H + h) * D + d] * wx;
+        }
+        galpha[(size_t)h * E + e] = tmp;
+      }
+  /* EB:654-696 */
+  for (int h = 0; h < H; ++h)
+    for (int i = 0; i < N; ++i)
+      for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+        float aij = alpha[(size_t)h * E + e], sum = 0.f;
+        for (int q = row_ptr[i]; q < row_ptr[i + 1]; ++q) {
+          float delta = (q == e) ? 1.f : 0.f;
+          sum += galpha[(size_t)h * E + q] * alpha[(size_t)h * E + q] * (delta - aij);
+        }
+        ge[(size_t)h * E + e] = sum;
+      }
+  /* EB:698-798 and EB:801-874 */
+  if (gX) memset(gX, 0, sizeof(float) * (size_t)N * I);
+  for (int i = 0; i < N; ++i)
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+      const int j = col_idx[e];
+      const float* xs = X + (size_t)j * I;
+      const float* xd = X + (size_t)i * I;
+      for (int h = 0; h < H; ++h) {
+        float dl = ge[(size_t)h * E + e], al = alpha[(size_t)h * E + e];
+        for (int k = 0; k < D; ++k) {
+          const float* wk = W + ((size_t)h * D + k) * 2 * I;
+          float s = 0.f;
+          for (int q = 0; q < I; ++q) s += wk[q] * xs[q];
+          for (int q = 0; q < I; ++q) s += wk[I + q] * xd[q];
+          ga[(size_t)h * D + k] += dl * lrelu_f(s);
+          float der = s > 0.f ? 1.f : ORC_SLOPE;
+          float common = dl * a[(size_t)h * D + k] * der;
+          float gd = g_h[((size_t)i * H + h) * D + k];
+          float* gw = gW + ((size_t)h * D + k) * 2 * I;
+          for (int q = 0; q < I; ++q) gw[q] += gd * al * xs[q] + common * xs[q];
+          for (int q = 0; q < I; ++q) gw[I + q] += common * xd[q];
+          if (gX)
+            for (int q = 0; q < I; ++q) {
+              gX[(size_t)j * I + q] += gd * al * wk[q] + common * wk[q];
+              gX[(size_t)i * I + q] += common * wk[I + q];
+            }
+        }
+      }
+    }
+}
+
+/* ------------------------------------------------------------------ full model */
+
+typedef struct orc_model {
+  int L, N, I0, C;
+  int64_t E;
+  int *heads, *outdims, *indims;
+  const int *row_ptr, *col_idx, *labels; /* borrowed */
+  const float* X0;                       /* borrowed */
+  float **W, **a, *Wo;                   /* params per layer */
+  float **gW, **ga, *gWo;
+  float **mW, **vW, **ma, **va, *mWo, *vWo;
+  float **Pl, **Pr, **score, **alpha, **mx, **sm, **hpre, **Hout, **g_h;
+  float *z, *y;
+  int optimizer; /* 0 sgd, 1 adam */
+  int clip;
+  float lr, b1, b2;
+} orc_model;
+
+static float* falloc(size_t n) { return (float*)calloc(n > 0 ? n : 1, sizeof(float)); }
+
+orc_model* orc_model_create(int L, const int* heads, const int* outdims, int N, int64_t E, int I0,
+                            int C, const int* row_ptr, const int* col_idx, const float* X0,
+                            const int* labels, int optimizer, int clip, float lr, float b1,
+                            float b2) {
+  orc_model* m = (orc_model*)calloc(1, sizeof(orc_model));
+  m->L = L; m->N = N; m->E = E; m->I0 = I0; m->C = C;
+  m->row_ptr = row_ptr; m->col_idx = col_idx; m->X0 = X0; m->labels = labels;
+  m->optimizer = optimizer; m->clip = clip; m->lr = lr; m->b1 = b1; m->b2 = b2;
+  m->heads = (int*)malloc(sizeof(int) * L);
+  m->outdims = (int*)malloc(sizeof(int) * L);
+  m->indims = (int*)malloc(sizeof(int) * L);
+#define PP(field) m->field = (float**)calloc(L, sizeof(float*))
+  PP(W); PP(a); PP(gW); PP(ga); PP(mW); PP(vW); PP(ma); PP(va);
+  PP(Pl); PP(Pr); PP(score); PP(alpha); PP(mx); PP(sm); PP(hpre); PP(Hout); PP(g_h);
+#undef PP
+  for (int l = 0; l < L; ++l) {
+    m->heads[l] = heads[l];
+    m->outdims[l] = outdims[l];
+    m->indims[l] = l == 0 ? I0 : heads[l - 1] * outdims[l - 1]; /* EB:1115-1118 */
+    size_t F = (size_t)heads[l] * outdims[l], nw = F * 2 * m->indims[l];
+    m->W[l] = falloc(nw); m->gW[l] = falloc(nw); m->mW[l] = falloc(nw); m->vW[l] = falloc(nw);
+    m->a[l] = falloc(F); m->ga[l] = falloc(F); m->ma[l] = falloc(F); m->va[l] = falloc(F);
+    m->Pl[l] = falloc((size_t)N * F); m->Pr[l] = falloc((size_t)N * F);
+    m->score[l] = falloc((size_t)heads[l] * E); m->alpha[l] = falloc((size_t)heads[l] * E);
+    m->mx[l] = falloc((size_t)heads[l] * N); m->sm[l] = falloc((size_t)heads[l] * N);
+    m->hpre[l] = falloc((size_t)N * F);
+    m->Hout[l] = falloc((size_t)N * (l == L - 1 ? (size_t)outdims[l] : F));
+    m->g_h[l] = falloc((size_t)N * F);
+  }
+  size_t nwo = (size_t)C * outdims[L - 1];
+  m->Wo = falloc(nwo); m->gWo = falloc(nwo); m->mWo = falloc(nwo); m->vWo = falloc(nwo);
+  m->z = falloc((size_t)N * C); m->y = falloc((size_t)N * C);
+  return m;
+}
+
+void orc_model_destroy(orc_model* m) {
+  if (!m) return;
+  for (int l = 0; l < m->L; ++l) {
+    free(m->W[l]); free(m->gW[l]); free(m->mW[l]); free(m->vW[l]);
+    free(m->a[l]); free(m->ga[l]); free(m->ma[l]); free(m->va[l]);
+    free(m->Pl[l]); free(m->Pr[l]); free(m->score[l]); free(m->alpha[l]);
+    free(m->mx[l]); free(m->sm[l]); free(m->hpre[l]); free(m->Hout[l]); free(m->g_h[l]);
+  }
+  free(m->W); free(m->a); free(m->gW); free(m->ga); free(m->mW); free(m->vW); free(m->ma);
+  free(m->va); free(m->Pl); free(m->Pr); free(m->score); free(m->alpha); free(m->mx); free(m->sm);
+  free(m->hpre); free(m->Hout); free(m->g_h);
+  free(m->Wo); free(m->gWo); free(m->mWo); free(m->vWo); free(m->z); free(m->y);
+  free(m->heads); free(m->outdims); free(m->indims);
+  free(m);
+}
+
+int64_t orc_model_w_size(const orc_model* m, int l) {
+  return (int64_t)m->heads[l] * m->outdims[l] * 2 * m->indims[l];
+}
+
+void orc_model_set_params(orc_model* m, int l, const float* W, const float* a) {
+  memcpy(m->W[l], W, sizeof(float) * (size_t)orc_model_w_size(m, l));
+  memcpy(m->a[l], a, sizeof(float) * (size_t)m->heads[l] * m->outdims[l]);
+}
+void orc_model_set_wo(orc_model* m, const float* Wo) {
+  memcpy(m->Wo, Wo, sizeof(float) * (size_t)m->C * m->outdims[m->L - 1]);
+}
+
+/* tensor ids shared with include/gatx.h (GATX_T_*) */
+float* orc_model_tensor(orc_model* m, int which, int l) {
+  switch (which) {
+    case 0: return m->W[l];
+    case 1: return m->a[l];
+    case 2: return m->Wo;
+    case 3: return m->gW[l];
+    case 4: return m->ga[l];
+    case 5: return m->gWo;
+    case 6: return m->Pl[l];
+    case 7: return m->Pr[l];
+    case 8: return m->score[l];
+    case 9: return m->alpha[l];
+    case 10: return m->hpre[l];
+    case 11: return m->Hout[l];
+    case 12: return m->y;
+    case 13: return m->g_h[l];
+    case 14: return m->z;
+    default: return NULL;
+  }
+}
+
+/* Forward of all layers + classifier (EB:1375-1452). */
+void orc_model_forward(orc_model* m) {
+  const float* X = m->X0;
+  for (int l = 0; l < m->L; ++l) {
+    int H = m->heads[l], D = m->outdims[l], I = m->indims[l];
+    orc_project(m->N, I, H * D, X, m->W[l], m->Pl[l], m->Pr[l]);
+    orc_layer_forward(m->N, m->row_ptr, m->col_idx, H, D, m->Pl[l], m->Pr[l], m->a[l],
+                      l == m->L - 1, m->score[l], m->alpha[l], m->mx[l], m->sm[l], m->hpre[l],
+                      m->Hout[l]);
+    X = m->Hout[l];
+  }
+  orc_head_forward(m->N, m->C, m->outdims[m->L - 1], m->Wo, X, m->z, m->y);
+}
+
+double orc_model_loss(orc_model* m, float* avg_loss, float* accuracy, int* pred) {
+  return orc_loss_acc(m->N, m->C, m->y, m->labels, NULL, pred, NULL, avg_loss, accuracy);
+}
+
+/* Backward of all layers (EB:1463-1557); gradients accumulate into gW/ga/gWo. */
+void orc_model_backward(orc_model* m) {
+  int L = m->L;
+  orc_output_grads(m->N, m->C, m->outdims[L - 1], m->heads[L - 1], m->y, m->labels, m->hpre[L - 1],
+                   m->Hout[L - 1], m->Wo, m->gWo, m->g_h[L - 1]);
+  for (int l = L - 1; l >= 0; --l) {
+    int H = m->heads[l], D = m->outdims[l], I = m->indims[l];
+    const float* X = l > 0 ? m->Hout[l - 1] : m->X0;
+    float* gX = l > 0 ? m->g_h[l - 1] : NULL;
+    orc_layer_backward(m->N, m->row_ptr, m->col_idx, H, D, I, X, m->W[l], m->a[l], m->Pl[l],
+                       m->Pr[l], m->alpha[l], m->g_h[l], m->gW[l], m->ga[l], gX, NULL, NULL, NULL,
+                       NULL);
+    if (l > 0) orc_preact_grad(m->N, I, m->hpre[l - 1], gX);
+  }
+}
+
+/* Clip (three groups: all W, all a, W_o; EB:1561-1566), Adam/SGD (EB:1570-1625),
+ * zero the gradients (EB:1631-1637).  t is the 1-based epoch. */
+void orc_model_step(orc_model* m, int t) {
+  int L = m->L;
+  size_t nwo = (size_t)m->C * m->outdims[L - 1];
+  if (m->clip) {
+    double ssw = 0.0, ssa = 0.0;
+    for (int l = 0; l < L; ++l) {
+      int64_t nw = orc_model_w_size(m, l), na = (int64_t)m->heads[l] * m->outdims[l];
+      for (int64_t i = 0; i < nw; ++i) ssw += (double)m->gW[l][i] * (double)m->gW[l][i];
+      for (int64_t i = 0; i < na; ++i) ssa += (double)m->ga[l][i] * (double)m->ga[l][i];
+    }
+    float nw_ = (float)sqrt((double)(float)ssw), na_ = (float)sqrt((double)(float)ssa);
+    float sw = nw_ > 5.0f ? 5.0f / (nw_ + 1e-9f) : 1.0f, sa = na_ > 5.0f ? 5.0f / (na_ + 1e-9f) : 1.0f;
+    for (int l = 0; l < L; ++l) {
+      int64_t nw = orc_model_w_size(m, l), na = (int64_t)m->heads[l] * m->outdims[l];
+      if (sw < 1.0f) for (int64_t i = 0; i < nw; ++i) m->gW[l][i] *= sw;
+      if (sa < 1.0f) for (int64_t i = 0; i < na; ++i) m->ga[l][i] *= sa;
+    }
+    orc_clip_grad_norm(m->gWo, (int64_t)nwo, 5.0f);
+  }
+  for (int l = 0; l < L; ++l) {
+    int64_t nw = orc_model_w_size(m, l), na = (int64_t)m->heads[l] * m->outdims[l];
+    if (m->optimizer == 1) {
+      orc_adam(m->W[l], m->gW[l], m->mW[l], m->vW[l], m->lr, nw, m->b1, m->b2, 1e-8f, t);
+      orc_adam(m->a[l], m->ga[l], m->ma[l], m->va[l], m->lr, na, m->b1, m->b2, 1e-8f, t);
+    } else {
+      orc_sgd(m->W[l], m->gW[l], m->lr, nw);
+      orc_sgd(m->a[l], m->ga[l], m->lr, na);
+    }
+    memset(m->gW[l], 0, sizeof(float) * (size_t)nw);
+    memset(m->ga[l], 0, sizeof(float) * (size_t)na);
+  }
+  if (m->optimizer == 1) orc_adam(m->Wo, m->gWo, m->mWo, m->vWo, m->lr, (int64_t)nwo, m->b1, m->b2, 1e-8f, t);
+  else orc_sgd(m->Wo, m->gWo, m->lr, (int64_t)nwo);
+  memset(m->gWo, 0, sizeof(float) * nwo);
+}
+
+/* One whole epoch exactly as timed by the reference (EB:1371 -> EB:1639). */
+void orc_model_epoch(orc_model* m, int t, float* avg_loss, float* accuracy) {
+  orc_model_forward(m);
+  orc_model_loss(m, avg_loss, accuracy, NULL);
+  orc_model_backward(m);
+  orc_model_step(m, t);
+}
+
+#ifdef _OPENMP
+#include <omp.h>
+int orc_num_threads(void) { return omp_get_max_threads(); }
+#else
+int orc_num_threads(void) { return 1; }
+#endif

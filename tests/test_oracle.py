@@ -1,0 +1,237 @@
+"""Pins for the CPU oracle (oracle/gatv2_oracle.c).  All CPU, no GPU.
+
+The reference ships no tests or golden vectors, so the oracle is pinned by
+a hand-computed known answer, an independent PyTorch float64 autograd restatement, agreement of
+its literal-fp32 (EB loop order) and factored-fp64 modes, and -- in test_golden_ref.py -- buffers
+dumped by the reference's own edge-based binary.
+"""
+import numpy as np
+import pytest
+
+import datasets
+import torch_ref
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def small_problem(seed=0, N=40, E=200, I=12, C=5, heads=(3, 1), outdims=(4, 6)):
+    row_ptr, col_idx = datasets.make_graph(N, E, "uniform", seed)
+    X = datasets.make_features(N, I, "uniform", seed)
+    y = datasets.make_labels(N, C, seed)
+    Ws, As, Wo = datasets.init_params(heads, outdims, I, C, seed)
+    # larger weights than Xavier so that attention is far from uniform
+    Ws = [w * 3 for w in Ws]
+    As = [a * 3 for a in As]
+    return row_ptr, col_idx, X, y, Ws, As, Wo
+
+
+# ------------------------------------------------------------------ integer work, bit-exact
+def test_csr_to_coo_and_degree(orc):
+    row_ptr = np.array([0, 2, 2, 5, 6], np.int32)
+    col_idx = np.array([1, 3, 0, 2, 3, 1], np.int32)
+    src, dst = orc.csr_to_coo(row_ptr, col_idx)
+    assert src.tolist() == [1, 3, 0, 2, 3, 1]
+    assert dst.tolist() == [0, 0, 2, 2, 2, 3]
+    assert orc.max_degree(row_ptr) == 3
+    assert orc.num_classes(np.array([0, 4, 2], np.int32)) == 5
+
+
+def test_csc_is_stable_transpose(orc):
+    row_ptr, col_idx = datasets.make_graph(200, 1500, "rmat", 3)
+    ptr, cdst, eid = orc.csc_build(row_ptr, col_idx)
+    src, dst = orc.csr_to_coo(row_ptr, col_idx)
+    assert ptr[0] == 0 and ptr[-1] == len(col_idx)
+    assert np.array_equal(np.diff(ptr), np.bincount(col_idx, minlength=200))
+    assert np.array_equal(np.sort(eid), np.arange(len(col_idx)))
+    assert np.array_equal(dst[eid], cdst)
+    seg = np.repeat(np.arange(200), np.diff(ptr))
+    assert np.array_equal(src[eid], seg)
+    # ascending edge id inside every source segment (stable)
+    same = seg[1:] == seg[:-1]
+    assert np.all(eid[1:][same] > eid[:-1][same])
+    # numpy's stable argsort is the same permutation
+    assert np.array_equal(eid, np.argsort(col_idx, kind="stable"))
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 8])
+def test_partition_rows(orc, R):
+    row_ptr, _ = datasets.make_graph(500, 6000, "rmat", 5)
+    b = orc.partition_rows(row_ptr, R)
+    assert b[0] == 0 and b[-1] == 500 and np.all(np.diff(b) >= 0)
+    E = int(row_ptr[-1])
+    for r in range(1, R):
+        t = (E * r) // R
+        assert row_ptr[b[r]] >= t and (b[r] == 0 or row_ptr[b[r] - 1] < t)
+    cnt = row_ptr[b[1:]] - row_ptr[b[:-1]]
+    assert cnt.sum() == E and cnt.max() - E / R <= orc.max_degree(row_ptr)
+
+
+# ------------------------------------------------------------------ hand-computed known answer
+def test_hand_known_answer(orc):
+    # nodes {0,1}; row 0 <- {0,1}, row 1 <- {1}; I = D = H = 1
+    row_ptr = np.array([0, 2, 3], np.int32)
+    col_idx = np.array([0, 1, 1], np.int32)
+    X = np.array([[1.0], [2.0]], np.float32)
+    W = np.array([[0.5, -1.0]], np.float32)  # W_l = 0.5 (source), W_r = -1 (destination)
+    a = np.array([2.0], np.float32)
+    Pl, Pr = orc.project(X, W, 1)
+    assert Pl.ravel().tolist() == [0.5, 1.0] and Pr.ravel().tolist() == [-1.0, -2.0]
+    out = orc.layer_forward(row_ptr, col_idx, 1, 1, Pl, Pr, a, False)
+    # e(0<-0) = 2*LReLU(0.5-1) = 2*(-0.005) = -0.01 ; e(0<-1) = 2*LReLU(1-1) = 0 ; e(1<-1) = 2*LReLU(1-2) = -0.02
+    np.testing.assert_allclose(out["score"].ravel(), [-0.01, 0.0, -0.02], rtol=1e-6, atol=1e-9)
+    e = np.exp(-0.01)
+    a00, a01 = e / (1 + e), 1 / (1 + e)
+    np.testing.assert_allclose(out["alpha"].ravel(), [a00, a01, 1.0], rtol=1e-6)
+    np.testing.assert_allclose(out["hpre"].ravel(), [a00 * 0.5 + a01 * 1.0, 1.0], rtol=1e-6)
+    np.testing.assert_allclose(out["mx"].ravel(), [0.0, -0.02], atol=1e-9)
+    # backward with g_h = [1, 0]: only row 0 contributes
+    g_h = np.array([[1.0], [0.0]], np.float32)
+    bw = orc.layer_backward(row_ptr, col_idx, 1, 1, X, W, a, Pl, Pr, out["alpha"], g_h)
+    galpha = np.array([0.5, 1.0, 0.0])
+    dot = a00 * 0.5 + a01 * 1.0
+    ge = np.array([a00 * (0.5 - dot), a01 * (1.0 - dot), 0.0])
+    np.testing.assert_allclose(bw["galpha"].ravel(), galpha, rtol=1e-6)
+    np.testing.assert_allclose(bw["ge"].ravel(), ge, rtol=1e-5)
+    # s = [-0.5, 0.0]: LReLU(s) = [-0.005, 0], LReLU'(s) = [0.01, 0.01]  (s > 0 is false at 0)
+    ga = ge[0] * -0.005 + ge[1] * 0.0
+    np.testing.assert_allclose(bw["ga"], [ga], rtol=1e-5)
+    m0, m1 = ge[0] * 2 * 0.01, ge[1] * 2 * 0.01
+    np.testing.assert_allclose(bw["gPr"].ravel(), [m0 + m1, 0.0], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(bw["gPl"].ravel(), [a00 * 1.0 + m0, a01 * 1.0 + m1], rtol=1e-5)
+    gwl = (a00 + m0) * 1.0 + (a01 + m1) * 2.0
+    gwr = (m0 + m1) * 1.0
+    np.testing.assert_allclose(bw["gW"].ravel(), [gwl, gwr], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(bw["gX"].ravel(),
+                               [(a00 + m0) * 0.5 + (m0 + m1) * -1.0, (a01 + m1) * 0.5], rtol=1e-5)
+
+
+# ------------------------------------------------------------------ against PyTorch float64
+@pytest.mark.parametrize("heads,outdims", [((3, 1), (4, 6)), ((2, 2, 1), (4, 3, 5)), ((2, 3), (4, 4))])
+def test_forward_backward_vs_torch_autograd(orc, heads, outdims):
+    row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(1, heads=heads, outdims=outdims)
+    m = orc.Model(heads, outdims, row_ptr, col_idx, X, y)
+    for l in range(len(heads)):
+        m.set_params(l, Ws[l], As[l])
+    m.set_wo(Wo)
+    m.forward()
+    loss = m.loss()
+    m.backward()
+    vals, grads = torch_ref.forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, y)
+    for l in range(len(heads)):
+        for name, tid in (("Pl", orc.T_PL), ("Pr", orc.T_PR), ("score", orc.T_SCORE),
+                          ("alpha", orc.T_ALPHA), ("hpre", orc.T_HPRE), ("Hout", orc.T_HOUT)):
+            assert rel_err(m.tensor(tid, l), vals[name][l]) < 2e-6, (name, l)
+    assert rel_err(m.tensor(orc.T_Y), vals["y"]) < 2e-6
+    assert abs(loss["total"] - vals["loss_sum"]) / vals["loss_sum"] < 1e-6
+    assert np.array_equal(loss["pred"], vals["pred"])
+    for l in range(len(heads)):
+        assert rel_err(m.tensor(orc.T_GW, l), grads["gW"][l]) < 2e-5, l
+        assert rel_err(m.tensor(orc.T_GA, l), grads["ga"][l]) < 2e-5, l
+    assert rel_err(m.tensor(orc.T_GWO), grads["gWo"]) < 2e-5
+
+
+def test_literal_fp32_matches_factored(orc):
+    row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(2)
+    H, D = 3, 4
+    lit = orc.lit_layer_forward(row_ptr, col_idx, H, D, X, Ws[0], As[0], False)
+    Pl, Pr = orc.project(X, Ws[0], H * D)
+    fac = orc.layer_forward(row_ptr, col_idx, H, D, Pl, Pr, As[0], False)
+    for k in ("score", "alpha", "hpre", "Hout"):
+        assert rel_err(lit[k], fac[k]) < 5e-6, k
+    g_h = np.random.default_rng(0).standard_normal((len(row_ptr) - 1, H * D)).astype(np.float32)
+    lb = orc.lit_layer_backward(row_ptr, col_idx, H, D, X, Ws[0], As[0], fac["alpha"], g_h)
+    fb = orc.layer_backward(row_ptr, col_idx, H, D, X, Ws[0], As[0], Pl, Pr, fac["alpha"], g_h)
+    for k in ("galpha", "ge", "gW", "ga", "gX"):
+        assert rel_err(lb[k], fb[k]) < 5e-5, k
+
+
+def test_finite_difference_of_oracle_loss(orc):
+    row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(4, N=20, E=80, I=6)
+    heads, outdims = (3, 1), (4, 6)
+
+    def loss_of(Ws_, As_, Wo_):
+        m = orc.Model(heads, outdims, row_ptr, col_idx, X, y)
+        for l in range(2):
+            m.set_params(l, Ws_[l], As_[l])
+        m.set_wo(Wo_)
+        m.forward()
+        return m.loss()["total"], m
+
+    _, m = loss_of(Ws, As, Wo)
+    m.backward()
+    rng = np.random.default_rng(0)
+    eps = 2e-3
+    for l, tid, arr in ((0, orc.T_GW, Ws), (1, orc.T_GW, Ws), (0, orc.T_GA, As), (1, orc.T_GA, As)):
+        g = m.tensor(tid, l).ravel()
+        for idx in rng.choice(arr[l].size, 6, replace=False):
+            hi = [w.copy() for w in arr]
+            lo = [w.copy() for w in arr]
+            hi[l].ravel()[idx] += eps
+            lo[l].ravel()[idx] -= eps
+            if arr is Ws:
+                fd = (loss_of(hi, As, Wo)[0] - loss_of(lo, As, Wo)[0]) / (2 * eps)
+            else:
+                fd = (loss_of(Ws, hi, Wo)[0] - loss_of(Ws, lo, Wo)[0]) / (2 * eps)
+            assert abs(fd - g[idx]) <= 3e-2 * max(abs(fd), abs(g[idx])) + 2e-3, (l, tid, idx, fd, g[idx])
+
+
+# ------------------------------------------------------------------ update rules
+def test_clip_adam_sgd(orc):
+    rng = np.random.default_rng(0)
+    g = rng.standard_normal(1000).astype(np.float32)
+    g2 = g.copy()
+    norm = orc.lib().orc_clip_grad_norm(orc.fp(g2), 1000, orc.C.c_float(5.0))
+    ref_norm = np.sqrt((g.astype(np.float64) ** 2).sum())
+    assert abs(norm - ref_norm) / ref_norm < 1e-6
+    np.testing.assert_allclose(g2, g * np.float32(5.0 / (np.float32(ref_norm) + 1e-9)), rtol=1e-6)
+    p = rng.standard_normal(1000).astype(np.float32)
+    p0, m, v = p.copy(), np.zeros(1000, np.float32), np.zeros(1000, np.float32)
+    for t in (1, 2, 3):
+        orc.lib().orc_adam(orc.fp(p), orc.fp(g), orc.fp(m), orc.fp(v), orc.C.c_float(0.01),
+                           orc.C.c_int64(1000), orc.C.c_float(0.9), orc.C.c_float(0.999),
+                           orc.C.c_float(1e-8), t)
+    # constant gradient: m_hat = g, v_hat = g^2 -> every step moves by lr * sign(g)
+    np.testing.assert_allclose(p, p0 - 3 * 0.01 * g / (np.abs(g) + 1e-8), rtol=1e-4, atol=1e-6)
+    q = p0.copy()
+    orc.lib().orc_sgd(orc.fp(q), orc.fp(g), orc.C.c_float(0.5), orc.C.c_int64(1000))
+    np.testing.assert_allclose(q, p0 - np.float32(0.5) * g, rtol=1e-6, atol=1e-7)
+
+
+def test_training_reduces_loss_on_sample(orc):
+    ds = datasets.make_dataset("sample")
+    cfg = ds["cfg"]
+    assert (cfg["N"], cfg["E"]) == (64, 512)
+    Ws, As, Wo = datasets.init_params(cfg["heads"], cfg["outdims"], cfg["I"], cfg["C"], 1)
+    m = orc.Model(cfg["heads"], cfg["outdims"], ds["row_ptr"], ds["col_idx"], ds["X"], ds["labels"],
+                  optimizer="adam", lr=0.01)
+    for l in range(2):
+        m.set_params(l, Ws[l], As[l])
+    m.set_wo(Wo)
+    losses = [m.epoch(t)[0] for t in range(1, 31)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] * 0.9
+    assert abs(losses[0] - np.log(cfg["C"])) < 0.3
+
+
+# ------------------------------------------------------------------ datasets / file format
+@pytest.mark.parametrize("name", ["sample", "cora", "pubmed"])
+def test_dataset_shapes(name, orc):
+    ds = datasets.make_dataset(name)
+    cfg = datasets.CONFIGS[name]
+    rp, ci = ds["row_ptr"], ds["col_idx"]
+    assert len(rp) == cfg["N"] + 1 and len(ci) == cfg["E"] == rp[-1]
+    assert ds["X"].shape == (cfg["N"], cfg["I"]) and orc.num_classes(ds["labels"]) == cfg["C"]
+    src, dst = orc.csr_to_coo(rp, ci)
+    key = dst.astype(np.int64) * cfg["N"] + src
+    assert np.all(np.diff(key) > 0)  # dst-major, sorted, no duplicates
+    assert np.all(np.diff(rp) >= 1) and np.isin(np.arange(cfg["N"]) * (cfg["N"] + 1), key).all()
+
+
+def test_txt_roundtrip(tmp_path):
+    ds = datasets.make_dataset("sample")
+    datasets.write_txt(str(tmp_path / "sample"), ds)
+    back = datasets.read_txt(str(tmp_path / "sample"))
+    for k in ("row_ptr", "col_idx", "labels", "X"):
+        assert np.array_equal(back[k], ds[k]), k
