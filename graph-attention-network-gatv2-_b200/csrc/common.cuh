@@ -1,0 +1,100 @@
+// Shared device helpers and launcher declarations of libgatx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gatx {
+
+constexpr float kSlope = 0.01f;  // LeakyReLU slope of the reference (EB:1143, EB:1428)
+constexpr int kNumSMs = 148;     // B200
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : kSlope * x; }
+__device__ __forceinline__ float lrelu_grad(float x) { return x > 0.f ? 1.f : kSlope; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming 128-bit load that does not allocate in L1 (gathered rows are used once per warp)
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---- launchers (each returns the number of kernels it launched) --------------------------
+
+// graph_prep.cu
+int launch_csr_to_coo(const int* row_ptr, const int* col_idx, int* src, int* dst, int* deg, int n_rows,
+                      cudaStream_t st);
+// builds the source-major transpose of a (local) CSR: csc_ptr[n_src+1], csc_dst[E], csc_eid[E];
+// stable (ascending CSR position inside every source segment).  Returns launches, <0 on error.
+int build_csc(const int* col_idx, const int* coo_dst, int64_t E, int n_src, int* csc_ptr, int* csc_dst,
+              int* csc_eid, cudaStream_t st);
+int launch_philox_uniform(float* out, int64_t n, float limit, uint64_t seed, uint64_t stream_id,
+                          cudaStream_t st);
+
+// gemm_simt.cu : C[m][n] (ldc) (+)= sum_k A(m,k) B(n,k), A(m,k) = A[m*sAm + k*sAk], same for B.
+int launch_gemm_simt(const float* A, int64_t sAm, int64_t sAk, const float* B, int64_t sBn, int64_t sBk,
+                     float* C, int64_t ldc, int M, int N, int64_t K, bool accumulate, float* splitk_ws,
+                     size_t splitk_ws_bytes, cudaStream_t st);
+// packs EB-layout W [F][2I] into Wcat [2F][ldk] (rows 0..F-1 = W_l, F..2F-1 = W_r, zero padded)
+// and WcatT [I][2F]
+int launch_pack_weights(const float* W, int F, int I, float* Wcat, int ldk, float* WcatT, cudaStream_t st);
+
+// edge_kernels.cu
+struct EdgeGraph {
+  int n_rows;            // local destination rows
+  const int* row_ptr;    // [n_rows+1] local CSR (positions are local edge ids)
+  const int* col_idx;    // [E] global source ids
+  int n_src;             // number of source rows (global N)
+  const int* csc_ptr;    // [n_src+1]
+  const int* csc_dst;    // [E] local destination row
+  const int* csc_eid;    // [E] local edge id
+  const int* heavy_rows; int n_heavy_rows;   // destination rows with degree > kHeavyDeg
+  const int* heavy_srcs; int n_heavy_srcs;   // sources with out-degree > kHeavyDeg
+  int64_t E;
+};
+constexpr int kHeavyDeg = 1024;
+bool edge_shape_supported(int H, int D);
+int edge_rec_words(int H, int D);  // 32-bit words per edge of the backward record
+int launch_edge_forward(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
+                        float* Hout, float* hpre /*nullable*/, float* score, float* mx, float* sinv,
+                        cudaStream_t st);
+// pass 1 (destination-major): gH (post-activation grad, [n_rows][F]) is overwritten in place with the
+// pre-activation grad; writes gPr, the per-edge record and per-block partial sums of ga.
+int launch_edge_backward_dst(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr,
+                             const float* a, const float* Hout, float* gH, const float* score,
+                             const float* mx, const float* sinv, float* gPr, uint32_t* rec,
+                             float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st);
+// pass 2 (source-major): gPl[n_src][F]
+int launch_edge_backward_src(const EdgeGraph& g, int H, int D, const float* a, const float* gH,
+                             const uint32_t* rec, float* gPl, cudaStream_t st);
+constexpr int kEdgeBwdBlocks = kNumSMs * 4;
+// out[i] (+)= sum_b partials[b][i], fixed order
+int launch_reduce_partials(const float* partials, int n_partials, int n, float* out, bool accumulate,
+                           cudaStream_t st);
+int launch_unpack_rec(const uint32_t* rec, int64_t E, int H, int D, float* alpha, float* ge, cudaStream_t st);
+int launch_alpha_from_score(const float* score, const int* coo_dst, const float* mx, const float* sinv, int64_t E,
+                            int H, float* alpha, cudaStream_t st);
+int launch_head_mean(const float* Hfull, int N, int H, int D, float* Hout, cudaStream_t st);
+int launch_head_bcast_grad(const float* gHout, int N, int H, int D, float* gHfull, cudaStream_t st);
+
+// head_loss.cu : classifier + softmax + CE + argmax + output gradients (EB:463-608)
+constexpr int kHeadBlocks = kNumSMs * 2;
+int launch_head(const float* HL, const float* Wo, const int* labels, int N, int C, int DL, float* y, float* dz,
+                float* z_dbg, int* pred, float* gH, double* loss_partials, int* correct_partials, int* n_partials,
+                cudaStream_t st);
+int launch_loss_finalize(const double* loss_partials, const int* correct_partials, int n_partials,
+                         double* loss_sum, long long* correct, cudaStream_t st);
+
+// optim.cu
+struct OptimGroups {
+  int64_t begin[3], end[3];  // {all W}, {all a}, {W_o} ranges of the flat parameter buffer
+};
+constexpr int kOptimBlocks = 256;
+int launch_optimizer(float* params, float* grads, float* m, float* v, int64_t n, OptimGroups grp, bool clip,
+                     int optimizer, float lr, float b1, float b2, int t, float* norm_partials,
+                     cudaStream_t st);
+
+}  // namespace gatx

@@ -1,0 +1,931 @@
+// C ABI (include/gatx.h) and epoch orchestration of the B200-native GATv2 engine.
+// Replaces the host side of the reference's main(): allocation EB:1115-1357 and the epoch loop
+// EB:1370-1642 (one stream, no per-kernel cudaDeviceSynchronize, no host round trips except the
+// two loss/accuracy scalars).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gatx.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+using namespace gatx;
+
+namespace {
+
+// ---- NCCL through dlopen: single-GPU use needs no NCCL at all ------------------------------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) return false;
+#define L(sym) *(void**)(&sym) = dlsym(h, "nccl" #sym)
+    L(GetUniqueId); L(CommInitRank); L(CommDestroy); L(AllReduce); L(Broadcast); L(Reduce);
+    L(GroupStart); L(GroupEnd); L(GetErrorString);
+#undef L
+    return GetUniqueId && CommInitRank && AllReduce && Broadcast && Reduce && GroupStart && GroupEnd;
+  }
+};
+NcclApi g_nccl;
+
+enum Phase { PH_GEMM_FWD = 0, PH_EDGE_FWD, PH_HEAD, PH_EDGE_BWD, PH_GEMM_BWD, PH_OPT, PH_COMM, PH_EPOCH, PH_COUNT };
+
+struct Layer {
+  int H = 0, D = 0, F = 0, I = 0, Fout = 0, ldx = 0, ldk = 0, recw = 0;
+  int64_t w_off = 0, a_off = 0;
+  float *Wcat = nullptr, *WcatT = nullptr;
+  float *Pl = nullptr, *Pr = nullptr, *Hfull = nullptr, *Hout = nullptr, *hpre = nullptr;
+  float *score = nullptr, *mx = nullptr, *sinv = nullptr, *gH = nullptr, *gHout = nullptr;
+  float *galpha_dbg = nullptr, *gPl_dbg = nullptr, *gPr_dbg = nullptr, *alpha_dbg = nullptr, *ge_dbg = nullptr;
+};
+
+}  // namespace
+
+struct gatx_ctx {
+  // config
+  int L = 0, optimizer = 0, clip = 0, device = 0, gemm_mode = 0, keep_debug = 0, rank = 0, world = 1;
+  float lr = 1e-4f, b1 = 0.9f, b2 = 0.999f;
+  std::vector<int> heads, outdims;
+  std::string err;
+  cudaStream_t st = nullptr;
+  int64_t launches = 0;
+  // graph
+  int N = 0;          // global nodes
+  int64_t Eg = 0;     // global edges
+  int r0 = 0, r1 = 0; // owned destination rows
+  int n_rows = 0;
+  int64_t E = 0;      // local edges
+  int max_degree = 0;
+  std::vector<int> bounds;
+  int *row_ptr = nullptr, *col_idx = nullptr, *coo_src = nullptr, *coo_dst = nullptr, *in_deg = nullptr;
+  int *csc_ptr = nullptr, *csc_dst = nullptr, *csc_eid = nullptr, *heavy_rows = nullptr, *heavy_srcs = nullptr;
+  int n_heavy_rows = 0, n_heavy_srcs = 0;
+  bool have_graph = false, have_feat = false, have_labels = false, have_bufs = false, have_params = false;
+  // data
+  int I0 = 0, ld0 = 0, C = 0;
+  float* X0 = nullptr;
+  int* labels = nullptr;
+  // params: flat [W_0..W_{L-1} | a_0..a_{L-1} | W_o]
+  int64_t n_params = 0, wo_off = 0;
+  OptimGroups grp{};
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  std::vector<Layer> layers;
+  // scratch
+  float *gPl = nullptr, *gPr = nullptr, *ga_partials = nullptr, *splitk_ws = nullptr, *norm_partials = nullptr;
+  uint32_t* rec = nullptr;
+  size_t splitk_ws_bytes = 0;
+  float *y = nullptr, *dz = nullptr, *z_dbg = nullptr;
+  int* pred = nullptr;
+  double *loss_partials = nullptr, *loss_sum = nullptr;  // loss_sum[0] = sum loss, [1] = correct (as double)
+  int* correct_partials = nullptr;
+  long long* correct = nullptr;
+  double* red2 = nullptr;  // [2] all-reduce staging
+  // comm
+  ncclComm_t comm = nullptr;
+  // timing
+  cudaEvent_t sw_a = nullptr, sw_b = nullptr;
+  bool timing = false;
+  struct Span { int phase; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t spans_used = 0;
+  float phase_ms[PH_COUNT] = {0};
+};
+
+namespace {
+
+int fail(gatx_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? GATX_ERR_OOM : GATX_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess)                                                                         \
+      return fail(ctx, GATX_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+  } while (0)
+#define LAUNCHED(expr)                                                                             \
+  do {                                                                                             \
+    int n_ = (expr);                                                                               \
+    if (n_ < 0) return fail(ctx, GATX_ERR_UNSUPPORTED, "%s failed", #expr);                        \
+    ctx->launches += n_;                                                                           \
+  } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+  if (*p) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  return cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
+}
+template <typename T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+struct PhaseTimer {
+  gatx_ctx* c;
+  size_t idx = (size_t)-1;
+  PhaseTimer(gatx_ctx* ctx, int phase) : c(ctx) {
+    if (!c->timing) return;
+    if (c->spans_used == c->spans.size()) {
+      gatx_ctx::Span s{phase, nullptr, nullptr};
+      cudaEventCreate(&s.a);
+      cudaEventCreate(&s.b);
+      c->spans.push_back(s);
+    }
+    idx = c->spans_used++;
+    c->spans[idx].phase = phase;
+    cudaEventRecord(c->spans[idx].a, c->st);
+  }
+  ~PhaseTimer() {
+    if (idx != (size_t)-1) cudaEventRecord(c->spans[idx].b, c->st);
+  }
+};
+
+void free_graph(gatx_ctx* c) {
+  dfree(c->row_ptr); dfree(c->col_idx); dfree(c->coo_src); dfree(c->coo_dst); dfree(c->in_deg);
+  dfree(c->csc_ptr); dfree(c->csc_dst); dfree(c->csc_eid); dfree(c->heavy_rows); dfree(c->heavy_srcs);
+  c->have_graph = false;
+}
+void free_bufs(gatx_ctx* c) {
+  for (auto& l : c->layers) {
+    dfree(l.Wcat); dfree(l.WcatT); dfree(l.Pl); dfree(l.Pr);
+    if (l.Hout != l.Hfull) dfree(l.Hout);
+    l.Hout = nullptr;
+    dfree(l.Hfull); dfree(l.hpre); dfree(l.score); dfree(l.mx); dfree(l.sinv); dfree(l.gH); dfree(l.gHout);
+    dfree(l.galpha_dbg); dfree(l.gPl_dbg); dfree(l.gPr_dbg); dfree(l.alpha_dbg); dfree(l.ge_dbg);
+  }
+  dfree(c->params); dfree(c->grads); dfree(c->adam_m); dfree(c->adam_v);
+  dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials);
+  dfree(c->rec); dfree(c->y); dfree(c->dz); dfree(c->z_dbg); dfree(c->pred);
+  dfree(c->loss_partials); dfree(c->loss_sum); dfree(c->correct_partials); dfree(c->correct); dfree(c->red2);
+  c->have_bufs = false;
+  c->have_params = false;
+}
+
+// All device state that depends on (graph, in_dim, classes): EB:1196-1357.
+int ensure_buffers(gatx_ctx* ctx) {
+  if (ctx->have_bufs) return GATX_OK;
+  if (!ctx->have_graph || !ctx->have_feat || !ctx->have_labels)
+    return fail(ctx, GATX_ERR_INVALID, "graph, features and labels must be set first");
+  const int L = ctx->L, N = ctx->N, nr = ctx->n_rows;
+  const int64_t E = ctx->E;
+  int64_t off = 0, Fmax = 0, recmax = 0;
+  for (int l = 0; l < L; ++l) {
+    Layer& ly = ctx->layers[l];
+    ly.H = ctx->heads[l];
+    ly.D = ctx->outdims[l];
+    ly.F = ly.H * ly.D;
+    ly.I = l == 0 ? ctx->I0 : ctx->layers[l - 1].Fout;  // EB:1115-1118
+    ly.ldx = l == 0 ? ctx->ld0 : ctx->layers[l - 1].Fout;
+    // EB semantics: hidden layers concatenate heads; the last layer averages them (EB:440-459)
+    ly.Fout = (l == L - 1) ? ly.D : ly.F;
+    ly.ldk = (ly.I + 3) / 4 * 4;
+    ly.recw = edge_rec_words(ly.H, ly.D);
+    if (!edge_shape_supported(ly.H, ly.D))
+      return fail(ctx, GATX_ERR_UNSUPPORTED,
+                  "layer %d: heads=%d outdim=%d not covered by the edge kernels (need outdim in {4,8,..,128}, "
+                  "heads*outdim/4 a power of two below 32 or a multiple of 32 up to 256)", l, ly.H, ly.D);
+    ly.w_off = off;
+    off += (int64_t)ly.F * 2 * ly.I;
+    if (ly.F > Fmax) Fmax = ly.F;
+    if (ly.recw > recmax) recmax = ly.recw;
+  }
+  ctx->grp.begin[0] = 0;
+  ctx->grp.end[0] = off;
+  ctx->grp.begin[1] = off;
+  for (int l = 0; l < L; ++l) {
+    ctx->layers[l].a_off = off;
+    off += ctx->layers[l].F;
+  }
+  ctx->grp.end[1] = off;
+  ctx->grp.begin[2] = off;
+  ctx->wo_off = off;
+  const int DL = ctx->outdims[L - 1];
+  off += (int64_t)ctx->C * DL;
+  ctx->grp.end[2] = off;
+  ctx->n_params = off;
+  CK(dalloc(&ctx->params, off));
+  CK(dalloc(&ctx->grads, off));
+  CK(dalloc(&ctx->adam_m, off));
+  CK(dalloc(&ctx->adam_v, off));
+  CK(cudaMemsetAsync(ctx->params, 0, sizeof(float) * off, ctx->st));
+  CK(cudaMemsetAsync(ctx->grads, 0, sizeof(float) * off, ctx->st));   // EB:1262-1266
+  CK(cudaMemsetAsync(ctx->adam_m, 0, sizeof(float) * off, ctx->st));  // EB:1275-1295
+  CK(cudaMemsetAsync(ctx->adam_v, 0, sizeof(float) * off, ctx->st));
+  for (int l = 0; l < L; ++l) {
+    Layer& ly = ctx->layers[l];
+    CK(dalloc(&ly.Wcat, (size_t)2 * ly.F * ly.ldk));
+    CK(dalloc(&ly.WcatT, (size_t)ly.I * 2 * ly.F));
+    CK(dalloc(&ly.Pl, (size_t)N * ly.F));
+    CK(dalloc(&ly.Pr, (size_t)nr * ly.F));
+    CK(dalloc(&ly.Hfull, (size_t)nr * ly.F));
+    if (ly.Fout != ly.F) CK(dalloc(&ly.Hout, (size_t)nr * ly.Fout));
+    else ly.Hout = ly.Hfull;
+    CK(dalloc(&ly.score, (size_t)E * ly.H));
+    CK(dalloc(&ly.mx, (size_t)nr * ly.H));
+    CK(dalloc(&ly.sinv, (size_t)nr * ly.H));
+    CK(dalloc(&ly.gH, (size_t)nr * ly.F));
+    if (ly.Fout != ly.F) CK(dalloc(&ly.gHout, (size_t)nr * ly.Fout));
+    if (ctx->keep_debug) {
+      CK(dalloc(&ly.hpre, (size_t)nr * ly.F));
+      CK(dalloc(&ly.galpha_dbg, (size_t)E * ly.H));
+      CK(dalloc(&ly.alpha_dbg, (size_t)E * ly.H));
+      CK(dalloc(&ly.ge_dbg, (size_t)E * ly.H));
+      CK(dalloc(&ly.gPl_dbg, (size_t)N * ly.F));
+      CK(dalloc(&ly.gPr_dbg, (size_t)nr * ly.F));
+    }
+  }
+  CK(dalloc(&ctx->gPl, (size_t)N * Fmax));
+  CK(dalloc(&ctx->gPr, (size_t)nr * Fmax));
+  CK(dalloc(&ctx->rec, (size_t)E * recmax));
+  CK(dalloc(&ctx->ga_partials, (size_t)(kNumSMs * 8 + ctx->n_heavy_rows + 1) * Fmax));
+  ctx->splitk_ws_bytes = (size_t)256 << 20;
+  CK(dalloc(&ctx->splitk_ws, ctx->splitk_ws_bytes / sizeof(float)));
+  CK(dalloc(&ctx->norm_partials, (size_t)3 * kOptimBlocks));
+  CK(dalloc(&ctx->y, (size_t)nr * ctx->C));
+  CK(dalloc(&ctx->dz, (size_t)nr * ctx->C));
+  if (ctx->keep_debug) CK(dalloc(&ctx->z_dbg, (size_t)nr * ctx->C));
+  CK(dalloc(&ctx->pred, (size_t)nr));
+  CK(dalloc(&ctx->loss_partials, (size_t)kHeadBlocks));
+  CK(dalloc(&ctx->correct_partials, (size_t)kHeadBlocks));
+  CK(dalloc(&ctx->loss_sum, 1));
+  CK(dalloc(&ctx->correct, 1));
+  CK(dalloc(&ctx->red2, 2));
+  ctx->have_bufs = true;
+  return GATX_OK;
+}
+
+EdgeGraph edge_graph(const gatx_ctx* c) {
+  EdgeGraph g{};
+  g.n_rows = c->n_rows; g.row_ptr = c->row_ptr; g.col_idx = c->col_idx; g.n_src = c->N;
+  g.csc_ptr = c->csc_ptr; g.csc_dst = c->csc_dst; g.csc_eid = c->csc_eid;
+  g.heavy_rows = c->heavy_rows; g.n_heavy_rows = c->n_heavy_rows;
+  g.heavy_srcs = c->heavy_srcs; g.n_heavy_srcs = c->n_heavy_srcs;
+  g.E = c->E;
+  return g;
+}
+
+// C[M][N] (ldc) (+)= A B^T with K-major operands (both row-major with K contiguous).
+int gemm_tn(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
+            int N, int K, bool accumulate) {
+  if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
+    int n = launch_gemm_tc_tn(A, lda, B, ldb, C, ldc, M, N, K, accumulate, ctx->st);
+    if (n >= 0) {
+      ctx->launches += n;
+      return GATX_OK;
+    }
+  }
+  LAUNCHED(launch_gemm_simt(A, lda, 1, B, ldb, 1, C, ldc, M, N, K, accumulate, nullptr, 0, ctx->st));
+  return GATX_OK;
+}
+// C[M][N] (ldc) += A^T B with A [K][>=M] (lda), B [K][>=N] (ldb): contraction over the node dimension.
+int gemm_nt_reduce(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int M, int N, int64_t K) {
+  if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
+    int n = launch_gemm_tc_atb(A, lda, B, ldb, C, ldc, M, N, K, ctx->splitk_ws, ctx->splitk_ws_bytes, ctx->st);
+    if (n >= 0) {
+      ctx->launches += n;
+      return GATX_OK;
+    }
+  }
+  LAUNCHED(launch_gemm_simt(A, 1, lda, B, 1, ldb, C, ldc, M, N, K, true, ctx->splitk_ws, ctx->splitk_ws_bytes,
+                            ctx->st));
+  return GATX_OK;
+}
+
+int comm_allgather_rows(gatx_ctx* ctx, float* full, int F) {
+  if (ctx->world == 1) return GATX_OK;
+  if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
+  PhaseTimer t(ctx, PH_COMM);
+  NK(g_nccl.GroupStart());
+  for (int r = 0; r < ctx->world; ++r) {
+    float* p = full + (int64_t)ctx->bounds[r] * F;
+    const size_t cnt = (size_t)(ctx->bounds[r + 1] - ctx->bounds[r]) * F;
+    if (cnt) NK(g_nccl.Broadcast(p, p, cnt, ncclFloat, r, ctx->comm, ctx->st));
+  }
+  NK(g_nccl.GroupEnd());
+  return GATX_OK;
+}
+int comm_reduce_rows(gatx_ctx* ctx, float* full, int F) {
+  if (ctx->world == 1) return GATX_OK;
+  if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
+  PhaseTimer t(ctx, PH_COMM);
+  NK(g_nccl.GroupStart());
+  for (int r = 0; r < ctx->world; ++r) {
+    float* p = full + (int64_t)ctx->bounds[r] * F;
+    const size_t cnt = (size_t)(ctx->bounds[r + 1] - ctx->bounds[r]) * F;
+    if (cnt) NK(g_nccl.Reduce(p, p, cnt, ncclFloat, ncclSum, r, ctx->comm, ctx->st));
+  }
+  NK(g_nccl.GroupEnd());
+  return GATX_OK;
+}
+
+int do_forward(gatx_ctx* ctx) {
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  if (!ctx->have_params) return fail(ctx, GATX_ERR_INVALID, "parameters not initialised");
+  const EdgeGraph g = edge_graph(ctx);
+  const float* X = ctx->X0;
+  for (int l = 0; l < ctx->L; ++l) {
+    Layer& ly = ctx->layers[l];
+    {
+      PhaseTimer t(ctx, PH_GEMM_FWD);
+      LAUNCHED(launch_pack_weights(ctx->params + ly.w_off, ly.F, ly.I, ly.Wcat, ly.ldk, ly.WcatT, ctx->st));
+      // P_l = X W_l^T, P_r = X W_r^T : the only dense contraction of the forward (EB:303-316)
+      rc = gemm_tn(ctx, X, ly.ldx, ly.Wcat, ly.ldk, ly.Pl + (int64_t)ctx->r0 * ly.F, ly.F, ctx->n_rows, ly.F, ly.I,
+                   false);
+      if (rc) return rc;
+      rc = gemm_tn(ctx, X, ly.ldx, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, ly.Pr, ly.F, ctx->n_rows, ly.F, ly.I,
+                   false);
+      if (rc) return rc;
+    }
+    rc = comm_allgather_rows(ctx, ly.Pl, ly.F);
+    if (rc) return rc;
+    {
+      PhaseTimer t(ctx, PH_EDGE_FWD);
+      LAUNCHED(launch_edge_forward(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre, ly.score,
+                                   ly.mx, ly.sinv, ctx->st));
+      if (ly.Hout != ly.Hfull) LAUNCHED(launch_head_mean(ly.Hfull, ctx->n_rows, ly.H, ly.D, ly.Hout, ctx->st));
+    }
+    X = ly.Hout;
+  }
+  {
+    PhaseTimer t(ctx, PH_HEAD);
+    Layer& last = ctx->layers[ctx->L - 1];
+    float* gH_out = last.gHout ? last.gHout : last.gH;
+    int n_part = 0;
+    LAUNCHED(launch_head(last.Hout, ctx->params + ctx->wo_off, ctx->labels, ctx->n_rows, ctx->C, last.D, ctx->y,
+                         ctx->dz, ctx->z_dbg, ctx->pred, gH_out, ctx->loss_partials, ctx->correct_partials, &n_part,
+                         ctx->st));
+    LAUNCHED(launch_loss_finalize(ctx->loss_partials, ctx->correct_partials, n_part, ctx->loss_sum, ctx->correct,
+                                  ctx->st));
+    if (last.gHout) LAUNCHED(launch_head_bcast_grad(last.gHout, ctx->n_rows, last.H, last.D, last.gH, ctx->st));
+  }
+  return GATX_OK;
+}
+
+int do_backward(gatx_ctx* ctx) {
+  if (!ctx->have_bufs) return fail(ctx, GATX_ERR_INVALID, "forward must run before backward");
+  const EdgeGraph g = edge_graph(ctx);
+  int rc;
+  {
+    // gW_o += dz^T H_L  (EB:576-581)
+    PhaseTimer t(ctx, PH_GEMM_BWD);
+    Layer& last = ctx->layers[ctx->L - 1];
+    LAUNCHED(launch_gemm_simt(ctx->dz, 1, ctx->C, last.Hout, 1, last.D, ctx->grads + ctx->wo_off, last.D, ctx->C,
+                              last.D, ctx->n_rows, true, ctx->splitk_ws, ctx->splitk_ws_bytes, ctx->st));
+  }
+  for (int l = ctx->L - 1; l >= 0; --l) {
+    Layer& ly = ctx->layers[l];
+    const float* X = l == 0 ? ctx->X0 : ctx->layers[l - 1].Hout;
+    {
+      PhaseTimer t(ctx, PH_EDGE_BWD);
+      int n_part = 0;
+      LAUNCHED(launch_edge_backward_dst(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
+                                        ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->rec, ctx->ga_partials, &n_part,
+                                        ly.galpha_dbg, ctx->st));
+      LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
+      LAUNCHED(launch_edge_backward_src(g, ly.H, ly.D, ctx->params + ly.a_off, ly.gH, ctx->rec, ctx->gPl, ctx->st));
+      if (ctx->keep_debug) {
+        LAUNCHED(launch_unpack_rec(ctx->rec, ctx->E, ly.H, ly.D, ly.alpha_dbg, ly.ge_dbg, ctx->st));
+        CK(cudaMemcpyAsync(ly.gPl_dbg, ctx->gPl, sizeof(float) * (size_t)ctx->N * ly.F, cudaMemcpyDeviceToDevice,
+                           ctx->st));
+        CK(cudaMemcpyAsync(ly.gPr_dbg, ctx->gPr, sizeof(float) * (size_t)ctx->n_rows * ly.F,
+                           cudaMemcpyDeviceToDevice, ctx->st));
+      }
+    }
+    rc = comm_reduce_rows(ctx, ctx->gPl, ly.F);
+    if (rc) return rc;
+    {
+      PhaseTimer t(ctx, PH_GEMM_BWD);
+      const float* gPl_own = ctx->gPl + (int64_t)ctx->r0 * ly.F;
+      float* gW = ctx->grads + ly.w_off;
+      // gW_l = gP_l^T X, gW_r = gP_r^T X  (EB:771-782), W row stride 2I, W_r at column offset I
+      rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+      if (rc) return rc;
+      rc = gemm_nt_reduce(ctx, ctx->gPr, ly.F, X, ly.ldx, gW + ly.I, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+      if (rc) return rc;
+      if (l > 0) {
+        // dL/dHout[l-1] = gP_l W_l + gP_r W_r  (EB:859-869); the LReLU derivative of EB:879-893 is
+        // applied by the next edge backward when it loads this gradient.
+        Layer& prev = ctx->layers[l - 1];
+        rc = gemm_tn(ctx, gPl_own, ly.F, ly.WcatT, 2 * ly.F, prev.gH, prev.F, ctx->n_rows, ly.I, ly.F, false);
+        if (rc) return rc;
+        rc = gemm_tn(ctx, ctx->gPr, ly.F, ly.WcatT + ly.F, 2 * ly.F, prev.gH, prev.F, ctx->n_rows, ly.I, ly.F, true);
+        if (rc) return rc;
+      }
+    }
+  }
+  return GATX_OK;
+}
+
+int do_step(gatx_ctx* ctx, int t) {
+  if (!ctx->have_bufs) return fail(ctx, GATX_ERR_INVALID, "nothing to update");
+  if (ctx->world > 1) {
+    if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
+    PhaseTimer tm(ctx, PH_COMM);
+    NK(g_nccl.AllReduce(ctx->grads, ctx->grads, (size_t)ctx->n_params, ncclFloat, ncclSum, ctx->comm, ctx->st));
+  }
+  PhaseTimer tm(ctx, PH_OPT);
+  LAUNCHED(launch_optimizer(ctx->params, ctx->grads, ctx->adam_m, ctx->adam_v, ctx->n_params, ctx->grp, ctx->clip != 0,
+                            ctx->optimizer, ctx->lr, ctx->b1, ctx->b2, t, ctx->norm_partials, ctx->st));
+  return GATX_OK;
+}
+
+__global__ void pack_loss_kernel(const double* loss_sum, const long long* correct, double* out2) {
+  out2[0] = *loss_sum;
+  out2[1] = (double)*correct;
+}
+
+int read_loss(gatx_ctx* ctx, float* avg_loss, float* accuracy) {
+  pack_loss_kernel<<<1, 1, 0, ctx->st>>>(ctx->loss_sum, ctx->correct, ctx->red2);
+  ctx->launches += 1;
+  if (ctx->world > 1) {
+    if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
+    NK(g_nccl.AllReduce(ctx->red2, ctx->red2, 2, ncclDouble, ncclSum, ctx->comm, ctx->st));
+  }
+  double h[2];
+  CK(cudaMemcpyAsync(h, ctx->red2, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  if (avg_loss) *avg_loss = (float)(h[0] / (double)ctx->N);  // EB:544
+  if (accuracy) *accuracy = (float)(h[1] / (double)ctx->N);  // EB:546
+  return GATX_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* gatx_version(void) { return "gatx 0.1 (sm_100a)"; }
+
+int gatx_create(gatx_ctx** out, const gatx_config* cfg) {
+  if (!out || !cfg || cfg->num_layers <= 0 || !cfg->heads || !cfg->outdims) return GATX_ERR_INVALID;
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return GATX_ERR_INVALID;
+  if (cfg->optimizer == GATX_OPT_ADAM &&
+      !(cfg->beta1 > 0.f && cfg->beta1 < 1.f && cfg->beta2 > 0.f && cfg->beta2 < 1.f))
+    return GATX_ERR_INVALID;  // EB:1011-1015
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return GATX_ERR_CUDA;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return GATX_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10) return GATX_ERR_CUDA;
+  gatx_ctx* c = new gatx_ctx();
+  c->L = cfg->num_layers;
+  c->heads.assign(cfg->heads, cfg->heads + c->L);
+  c->outdims.assign(cfg->outdims, cfg->outdims + c->L);
+  c->optimizer = cfg->optimizer; c->clip = cfg->clip; c->device = cfg->device;
+  c->gemm_mode = cfg->gemm_mode; c->keep_debug = cfg->keep_debug; c->rank = cfg->rank; c->world = cfg->world;
+  c->lr = cfg->lr; c->b1 = cfg->beta1; c->b2 = cfg->beta2;
+  c->layers.resize(c->L);
+  for (int l = 0; l < c->L; ++l)
+    if (c->heads[l] <= 0 || c->outdims[l] <= 0) {
+      delete c;
+      return GATX_ERR_INVALID;
+    }
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return GATX_ERR_CUDA;
+  }
+  *out = c;
+  return GATX_OK;
+}
+
+void gatx_destroy(gatx_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->st);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  free_bufs(ctx);
+  free_graph(ctx);
+  dfree(ctx->X0);
+  dfree(ctx->labels);
+  for (auto& s : ctx->spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  if (ctx->sw_a) {
+    cudaEventDestroy(ctx->sw_a);
+    cudaEventDestroy(ctx->sw_b);
+  }
+  cudaStreamDestroy(ctx->st);
+  delete ctx;
+}
+
+const char* gatx_last_error(const gatx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gatx_partition_rows(int32_t num_nodes, const int32_t* row_ptr, int32_t world, int32_t* bounds) {
+  if (num_nodes < 0 || !row_ptr || world < 1 || !bounds) return GATX_ERR_INVALID;
+  // rank r owns rows [bounds[r], bounds[r+1]); bounds[r] = first row with row_ptr >= floor(r*E/world)
+  const int64_t E = row_ptr[num_nodes];
+  bounds[0] = 0;
+  int i = 0;
+  for (int r = 1; r < world; ++r) {
+    const int64_t target = E * (int64_t)r / (int64_t)world;
+    while (i < num_nodes && (int64_t)row_ptr[i] < target) ++i;
+    bounds[r] = i;
+  }
+  bounds[world] = num_nodes;
+  return GATX_OK;
+}
+
+int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_ptr, const int32_t* col_idx) {
+  if (!ctx || N <= 0 || E < 0 || !row_ptr || (E > 0 && !col_idx)) return fail(ctx, GATX_ERR_INVALID, "bad graph");
+  if (row_ptr[0] != 0 || (int64_t)row_ptr[N] != E) return fail(ctx, GATX_ERR_INVALID, "row_ptr[N] != num_edges");
+  CK(cudaSetDevice(ctx->device));
+  free_bufs(ctx);  // every buffer is sized by the graph
+  free_graph(ctx);
+  dfree(ctx->X0);
+  dfree(ctx->labels);
+  ctx->have_feat = ctx->have_labels = false;
+  ctx->N = N;
+  ctx->Eg = E;
+  ctx->bounds.resize(ctx->world + 1);
+  gatx_partition_rows(N, row_ptr, ctx->world, ctx->bounds.data());
+  ctx->r0 = ctx->bounds[ctx->rank];
+  ctx->r1 = ctx->bounds[ctx->rank + 1];
+  ctx->n_rows = ctx->r1 - ctx->r0;
+  const int64_t e0 = row_ptr[ctx->r0], e1 = row_ptr[ctx->r1];
+  ctx->E = e1 - e0;
+  int maxdeg = 0;
+  std::vector<int> local_ptr(ctx->n_rows + 1), heavy;
+  for (int i = 0; i < N; ++i) {
+    if (row_ptr[i + 1] < row_ptr[i]) return fail(ctx, GATX_ERR_INVALID, "row_ptr not monotone at %d", i);
+    const int d = row_ptr[i + 1] - row_ptr[i];
+    if (d > maxdeg) maxdeg = d;  // EB:89-99
+  }
+  ctx->max_degree = maxdeg;
+  for (int i = 0; i <= ctx->n_rows; ++i) local_ptr[i] = (int)(row_ptr[ctx->r0 + i] - e0);
+  for (int i = 0; i < ctx->n_rows; ++i)
+    if (local_ptr[i + 1] - local_ptr[i] > kHeavyDeg) heavy.push_back(i);
+  for (int64_t e = e0; e < e1; ++e)
+    if (col_idx[e] < 0 || col_idx[e] >= N) return fail(ctx, GATX_ERR_INVALID, "col_idx[%lld] out of range", (long long)e);
+  CK(dalloc(&ctx->row_ptr, (size_t)ctx->n_rows + 1));
+  CK(dalloc(&ctx->col_idx, (size_t)ctx->E));
+  CK(dalloc(&ctx->coo_src, (size_t)ctx->E));
+  CK(dalloc(&ctx->coo_dst, (size_t)ctx->E));
+  CK(dalloc(&ctx->in_deg, (size_t)ctx->n_rows));
+  CK(dalloc(&ctx->csc_ptr, (size_t)N + 1));
+  CK(dalloc(&ctx->csc_dst, (size_t)ctx->E));
+  CK(dalloc(&ctx->csc_eid, (size_t)ctx->E));
+  CK(cudaMemcpyAsync(ctx->row_ptr, local_ptr.data(), sizeof(int) * local_ptr.size(), cudaMemcpyHostToDevice, ctx->st));
+  if (ctx->E)
+    CK(cudaMemcpyAsync(ctx->col_idx, col_idx + e0, sizeof(int) * (size_t)ctx->E, cudaMemcpyHostToDevice, ctx->st));
+  ctx->n_heavy_rows = (int)heavy.size();
+  CK(dalloc(&ctx->heavy_rows, heavy.size()));
+  if (!heavy.empty())
+    CK(cudaMemcpyAsync(ctx->heavy_rows, heavy.data(), sizeof(int) * heavy.size(), cudaMemcpyHostToDevice, ctx->st));
+  LAUNCHED(launch_csr_to_coo(ctx->row_ptr, ctx->col_idx, ctx->coo_src, ctx->coo_dst, ctx->in_deg, ctx->n_rows, ctx->st));
+  int n = build_csc(ctx->col_idx, ctx->coo_dst, ctx->E, N, ctx->csc_ptr, ctx->csc_dst, ctx->csc_eid, ctx->st);
+  if (n < 0) return fail(ctx, GATX_ERR_CUDA, "build_csc: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches += n;
+  // sources with a heavy out-degree (CTA-per-row in the source-major backward pass)
+  std::vector<int> cptr((size_t)N + 1), heavy_s;
+  CK(cudaMemcpyAsync(cptr.data(), ctx->csc_ptr, sizeof(int) * cptr.size(), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  for (int j = 0; j < N; ++j)
+    if (cptr[j + 1] - cptr[j] > kHeavyDeg) heavy_s.push_back(j);
+  ctx->n_heavy_srcs = (int)heavy_s.size();
+  CK(dalloc(&ctx->heavy_srcs, heavy_s.size()));
+  if (!heavy_s.empty())
+    CK(cudaMemcpyAsync(ctx->heavy_srcs, heavy_s.data(), sizeof(int) * heavy_s.size(), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->have_graph = true;
+  return GATX_OK;
+}
+
+int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim) {
+  if (!ctx || !X || in_dim <= 0) return fail(ctx, GATX_ERR_INVALID, "bad features");
+  if (!ctx->have_graph) return fail(ctx, GATX_ERR_INVALID, "set the graph before the features");
+  CK(cudaSetDevice(ctx->device));
+  const int ld = (in_dim + 3) / 4 * 4;  // 16-byte row pitch for TMA / 128-bit loads, zero padded
+  if (!ctx->X0 || ctx->I0 != in_dim) {
+    if (ctx->have_bufs) free_bufs(ctx);
+    CK(dalloc(&ctx->X0, (size_t)ctx->n_rows * ld));
+    CK(cudaMemsetAsync(ctx->X0, 0, sizeof(float) * (size_t)ctx->n_rows * ld, ctx->st));
+    ctx->I0 = in_dim;
+    ctx->ld0 = ld;
+  }
+  if (ctx->n_rows)
+    CK(cudaMemcpy2DAsync(ctx->X0, sizeof(float) * ld, X + (int64_t)ctx->r0 * in_dim, sizeof(float) * in_dim,
+                         sizeof(float) * in_dim, ctx->n_rows, cudaMemcpyHostToDevice, ctx->st));
+  ctx->have_feat = true;
+  return GATX_OK;
+}
+
+int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes) {
+  if (!ctx || !labels) return fail(ctx, GATX_ERR_INVALID, "bad labels");
+  if (!ctx->have_graph) return fail(ctx, GATX_ERR_INVALID, "set the graph before the labels");
+  CK(cudaSetDevice(ctx->device));
+  int C = num_classes;
+  if (C <= 0) {
+    int mx = labels[0];
+    for (int i = 1; i < ctx->N; ++i) mx = labels[i] > mx ? labels[i] : mx;  // EB:1106-1107
+    C = mx + 1;
+  }
+  if (ctx->have_bufs && C != ctx->C) free_bufs(ctx);
+  ctx->C = C;
+  if (!ctx->labels) CK(dalloc(&ctx->labels, (size_t)ctx->n_rows));
+  if (ctx->n_rows)
+    CK(cudaMemcpyAsync(ctx->labels, labels + ctx->r0, sizeof(int) * (size_t)ctx->n_rows, cudaMemcpyHostToDevice,
+                       ctx->st));
+  ctx->have_labels = true;
+  return GATX_OK;
+}
+
+int gatx_graph_info(gatx_ctx* ctx, int32_t* max_degree, int32_t* num_classes, int32_t* row_begin, int32_t* row_end) {
+  if (!ctx || !ctx->have_graph) return fail(ctx, GATX_ERR_INVALID, "no graph");
+  if (max_degree) *max_degree = ctx->max_degree;
+  if (num_classes) *num_classes = ctx->C;
+  if (row_begin) *row_begin = ctx->r0;
+  if (row_end) *row_end = ctx->r1;
+  return GATX_OK;
+}
+
+int gatx_init_params(gatx_ctx* ctx, uint64_t seed) {
+  if (!ctx) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  for (int l = 0; l < ctx->L; ++l) {
+    Layer& ly = ctx->layers[l];
+    const float limit = sqrtf(6.0f / (float)(2 * ly.I + ly.D));  // EB:208
+    LAUNCHED(launch_philox_uniform(ctx->params + ly.w_off, (int64_t)ly.F * 2 * ly.I, limit, seed, 2 * l, ctx->st));
+    LAUNCHED(launch_philox_uniform(ctx->params + ly.a_off, ly.F, limit, seed, 2 * l + 1, ctx->st));
+  }
+  const int DL = ctx->outdims[ctx->L - 1];
+  const float limit = sqrtf(6.0f / (float)(ctx->C + DL));  // EB:236
+  LAUNCHED(launch_philox_uniform(ctx->params + ctx->wo_off, (int64_t)ctx->C * DL, limit, seed, 1000, ctx->st));
+  ctx->have_params = true;
+  return GATX_OK;
+}
+
+int gatx_set_params(gatx_ctx* ctx, int32_t layer, const float* W, const float* a) {
+  if (!ctx || layer < 0 || layer >= ctx->L || !W || !a) return fail(ctx, GATX_ERR_INVALID, "bad set_params");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  Layer& ly = ctx->layers[layer];
+  CK(cudaMemcpyAsync(ctx->params + ly.w_off, W, sizeof(float) * (size_t)ly.F * 2 * ly.I, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->params + ly.a_off, a, sizeof(float) * (size_t)ly.F, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->have_params = true;
+  return GATX_OK;
+}
+
+int gatx_set_wo(gatx_ctx* ctx, const float* Wo) {
+  if (!ctx || !Wo) return fail(ctx, GATX_ERR_INVALID, "bad set_wo");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->params + ctx->wo_off, Wo, sizeof(float) * (size_t)ctx->C * ctx->outdims[ctx->L - 1],
+                     cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->have_params = true;
+  return GATX_OK;
+}
+
+int gatx_forward(gatx_ctx* ctx) {
+  if (!ctx) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  ctx->spans_used = 0;
+  int rc = do_forward(ctx);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return GATX_OK;
+}
+
+int gatx_loss_acc(gatx_ctx* ctx, float* avg_loss, float* accuracy) {
+  if (!ctx || !ctx->have_bufs) return fail(ctx, GATX_ERR_INVALID, "forward must run first");
+  CK(cudaSetDevice(ctx->device));
+  return read_loss(ctx, avg_loss, accuracy);
+}
+
+int gatx_backward(gatx_ctx* ctx) {
+  if (!ctx) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = do_backward(ctx);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return GATX_OK;
+}
+
+int gatx_step(gatx_ctx* ctx, int32_t t) {
+  if (!ctx || t < 1) return fail(ctx, GATX_ERR_INVALID, "step index is the 1-based epoch");
+  CK(cudaSetDevice(ctx->device));
+  int rc = do_step(ctx, t);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return GATX_OK;
+}
+
+int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy) {
+  if (!ctx || t < 1) return fail(ctx, GATX_ERR_INVALID, "epoch index is 1-based");
+  CK(cudaSetDevice(ctx->device));
+  ctx->spans_used = 0;
+  int rc;
+  {
+    PhaseTimer whole(ctx, PH_EPOCH);
+    if ((rc = do_forward(ctx))) return rc;
+    if ((rc = do_backward(ctx))) return rc;
+    if ((rc = do_step(ctx, t))) return rc;
+  }
+  CK(cudaGetLastError());
+  if (avg_loss || accuracy) return read_loss(ctx, avg_loss, accuracy);
+  return GATX_OK;
+}
+
+int gatx_sync(gatx_ctx* ctx) {
+  if (!ctx) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->st));
+  return GATX_OK;
+}
+
+int gatx_enable_timing(gatx_ctx* ctx, int32_t on) {
+  if (!ctx) return GATX_ERR_INVALID;
+  ctx->timing = on != 0;
+  ctx->spans_used = 0;
+  return GATX_OK;
+}
+
+int gatx_get_timing(gatx_ctx* ctx, float* out_ms, int32_t n) {
+  if (!ctx || !out_ms) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->st));
+  for (int p = 0; p < PH_COUNT; ++p) ctx->phase_ms[p] = 0.f;
+  for (size_t i = 0; i < ctx->spans_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b) == cudaSuccess) ctx->phase_ms[ctx->spans[i].phase] += ms;
+  }
+  for (int p = 0; p < n && p < PH_COUNT; ++p) out_ms[p] = ctx->phase_ms[p];
+  return GATX_OK;
+}
+
+int gatx_timer_start(gatx_ctx* ctx) {
+  if (!ctx) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->sw_a) {
+    CK(cudaEventCreate(&ctx->sw_a));
+    CK(cudaEventCreate(&ctx->sw_b));
+  }
+  CK(cudaEventRecord(ctx->sw_a, ctx->st));
+  return GATX_OK;
+}
+
+int gatx_timer_stop(gatx_ctx* ctx, float* elapsed_ms) {
+  if (!ctx || !elapsed_ms || !ctx->sw_a) return fail(ctx, GATX_ERR_INVALID, "timer not started");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->sw_b, ctx->st));
+  CK(cudaEventSynchronize(ctx->sw_b));
+  CK(cudaEventElapsedTime(elapsed_ms, ctx->sw_a, ctx->sw_b));
+  return GATX_OK;
+}
+
+int64_t gatx_launch_count(const gatx_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int gatx_edge_bytes(gatx_ctx* ctx, int32_t layer, double* fwd_bytes, double* bwd_bytes) {
+  if (!ctx || !ctx->have_bufs || layer < 0 || layer >= ctx->L) return fail(ctx, GATX_ERR_INVALID, "bad layer");
+  const Layer& ly = ctx->layers[layer];
+  const double N = ctx->n_rows, E = (double)ctx->E, F = ly.F, H = ly.H, b = 4.0;
+  // algorithmic bytes of the fused passes with b-byte projected features
+  if (fwd_bytes) *fwd_bytes = 4.0 * (N + 1) + E * (4.0 + b * F) + N * F * (b + 4.0) + 4.0 * H * E;
+  if (bwd_bytes) *bwd_bytes = 8.0 * (N + 1) + E * (12.0 + (b + 4.0) * F) + N * F * (b + 12.0) + 16.0 * H * E;
+  return GATX_OK;
+}
+
+int64_t gatx_tensor_size(gatx_ctx* ctx, int32_t which, int32_t layer) {
+  if (!ctx) return -1;
+  const bool per_layer = !(which == GATX_T_WO || which == GATX_T_GWO || which == GATX_T_Y || which == GATX_T_Z ||
+                           which == GATX_T_PRED || (which >= GATX_T_COO_SRC && which <= GATX_T_CSC_EID));
+  if (per_layer && (layer < 0 || layer >= ctx->L)) return -1;
+  if (which >= GATX_T_COO_SRC && which <= GATX_T_CSC_EID) {
+    if (!ctx->have_graph) return -1;
+    switch (which) {
+      case GATX_T_IN_DEGREE: return ctx->n_rows;
+      case GATX_T_CSC_PTR: return (int64_t)ctx->N + 1;
+      default: return ctx->E;
+    }
+  }
+  if (!ctx->have_bufs) return -1;
+  const Layer* ly = per_layer ? &ctx->layers[layer] : nullptr;
+  const int DL = ctx->outdims[ctx->L - 1];
+  switch (which) {
+    case GATX_T_W: case GATX_T_GW: return (int64_t)ly->F * 2 * ly->I;
+    case GATX_T_A: case GATX_T_GA: return ly->F;
+    case GATX_T_WO: case GATX_T_GWO: return (int64_t)ctx->C * DL;
+    case GATX_T_PL: case GATX_T_GPL: return (int64_t)ctx->N * ly->F;
+    case GATX_T_PR: case GATX_T_GPR: case GATX_T_HPRE: case GATX_T_GH: return (int64_t)ctx->n_rows * ly->F;
+    case GATX_T_SCORE: case GATX_T_ALPHA: return ctx->E * ly->H;
+    case GATX_T_HOUT: return (int64_t)ctx->n_rows * ly->Fout;
+    case GATX_T_Y: case GATX_T_Z: return (int64_t)ctx->n_rows * ctx->C;
+    case GATX_T_PRED: return ctx->n_rows;
+    default: return -1;
+  }
+}
+
+int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size_t bytes) {
+  if (!ctx || !dst) return fail(ctx, GATX_ERR_INVALID, "bad get_tensor");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t n = gatx_tensor_size(ctx, which, layer);
+  if (n < 0) return fail(ctx, GATX_ERR_INVALID, "tensor %d/%d not available", which, layer);
+  if (bytes != (size_t)n * 4) return fail(ctx, GATX_ERR_INVALID, "tensor %d needs %lld bytes, got %zu", which, (long long)n * 4, bytes);
+  const void* src = nullptr;
+  Layer* ly = (layer >= 0 && layer < ctx->L) ? &ctx->layers[layer] : nullptr;
+  float* tmp = nullptr;
+  switch (which) {
+    case GATX_T_W: src = ctx->params + ly->w_off; break;
+    case GATX_T_A: src = ctx->params + ly->a_off; break;
+    case GATX_T_WO: src = ctx->params + ctx->wo_off; break;
+    case GATX_T_GW: src = ctx->grads + ly->w_off; break;
+    case GATX_T_GA: src = ctx->grads + ly->a_off; break;
+    case GATX_T_GWO: src = ctx->grads + ctx->wo_off; break;
+    case GATX_T_PL: src = ly->Pl; break;
+    case GATX_T_PR: src = ly->Pr; break;
+    case GATX_T_SCORE: src = ly->score; break;
+    case GATX_T_ALPHA:
+      CK(cudaMalloc(&tmp, (size_t)n * 4 + 4));
+      LAUNCHED(launch_alpha_from_score(ly->score, ctx->coo_dst, ly->mx, ly->sinv, ctx->E, ly->H, tmp, ctx->st));
+      src = tmp;
+      break;
+    case GATX_T_HPRE: src = ly->hpre; break;
+    case GATX_T_HOUT: src = ly->Hout; break;
+    case GATX_T_Y: src = ctx->y; break;
+    case GATX_T_Z: src = ctx->z_dbg; break;
+    case GATX_T_GH: src = ly->gH; break;
+    case GATX_T_PRED: src = ctx->pred; break;
+    case GATX_T_COO_SRC: src = ctx->coo_src; break;
+    case GATX_T_COO_DST: src = ctx->coo_dst; break;
+    case GATX_T_IN_DEGREE: src = ctx->in_deg; break;
+    case GATX_T_CSC_PTR: src = ctx->csc_ptr; break;
+    case GATX_T_CSC_DST: src = ctx->csc_dst; break;
+    case GATX_T_CSC_EID: src = ctx->csc_eid; break;
+    case GATX_T_GPL: src = ly->gPl_dbg; break;
+    case GATX_T_GPR: src = ly->gPr_dbg; break;
+    default: break;
+  }
+  if (!src) return fail(ctx, GATX_ERR_INVALID, "tensor %d needs keep_debug=1", which);
+  cudaError_t e = n ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->st) : cudaSuccess;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+  if (tmp) cudaFree(tmp);
+  if (e != cudaSuccess) return fail(ctx, GATX_ERR_CUDA, "get_tensor copy: %s", cudaGetErrorString(e));
+  return GATX_OK;
+}
+
+int gatx_comm_unique_id(void* out128) {
+  if (!out128 || !g_nccl.load()) return GATX_ERR_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return GATX_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id is 128 bytes");
+  memcpy(out128, &id, 128);
+  return GATX_OK;
+}
+
+int gatx_comm_init(gatx_ctx* ctx, const void* id128) {
+  if (!ctx || !id128) return GATX_ERR_INVALID;
+  if (!g_nccl.load()) return fail(ctx, GATX_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror());
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NK(g_nccl.CommInitRank(&ctx->comm, ctx->world, id, ctx->rank));
+  return GATX_OK;
+}
+
+}  // extern "C"

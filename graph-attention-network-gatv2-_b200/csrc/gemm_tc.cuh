@@ -1,0 +1,15 @@
+// tcgen05 / TMEM / TMA tensor-core GEMMs (TF32 inputs, fp32 accumulate) for sm_100a.
+// Each launcher returns the number of kernels launched, or -1 when the shape is outside what the
+// kernel covers (the caller then uses the fp32 CUDA-core path of gemm_simt.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gatx {
+// C[M][N] (ldc) (+)= A[M][K] (lda) * B[N][K]^T (ldb); all row-major with K contiguous.
+int launch_gemm_tc_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                      int K, bool accumulate, cudaStream_t st);
+// C[M][N] (ldc) += A[K][M]^T (lda) * B[K][N] (ldb): contraction over the (huge) node dimension K.
+int launch_gemm_tc_atb(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                       int64_t K, float* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace gatx

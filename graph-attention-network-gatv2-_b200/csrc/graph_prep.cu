@@ -1,0 +1,126 @@
+// Graph preparation (one-off, integer, bit-exact against the oracle) and parameter init.
+//   csr -> coo + in-degree      replaces csr_to_coo_kernel (EB:67-84) and the degree loop (EB:89-99)
+//   stable source-major transpose (csc_ptr / csc_dst / csc_eid): new, feeds the deterministic
+//     backward scatter that replaces the reference's global float atomics (EB:786, EB:868-869)
+//   Philox Xavier-uniform init   replaces setup_states_kernel / xavier_init_kernel_curand (EB:181-248)
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace gatx {
+
+__global__ void csr_to_coo_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                  int* __restrict__ src, int* __restrict__ dst, int* __restrict__ deg,
+                                  int n_rows) {
+  // one warp per row: coalesced over the row's edges (the reference walks a row per thread)
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_rows) return;
+  const int beg = row_ptr[warp], end = row_ptr[warp + 1];
+  if (lane == 0 && deg) deg[warp] = end - beg;
+  for (int e = beg + lane; e < end; e += 32) {
+    src[e] = col_idx[e];
+    dst[e] = warp;
+  }
+}
+
+int launch_csr_to_coo(const int* row_ptr, const int* col_idx, int* src, int* dst, int* deg, int n_rows,
+                      cudaStream_t st) {
+  if (n_rows <= 0) return 0;
+  const int threads = 256, rows_per_block = threads / 32;
+  csr_to_coo_kernel<<<(n_rows + rows_per_block - 1) / rows_per_block, threads, 0, st>>>(row_ptr, col_idx, src,
+                                                                                      dst, deg, n_rows);
+  return 1;
+}
+
+__global__ void iota_kernel(int* p, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = (int)i;
+}
+__global__ void count_sources_kernel(const int* __restrict__ col_idx, int64_t E, int* __restrict__ counts) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&counts[col_idx[i]], 1);  // integer: order-independent, bit-exact
+}
+__global__ void gather_int_kernel(const int* __restrict__ table, const int* __restrict__ idx, int64_t n,
+                                  int* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = table[idx[i]];
+}
+
+int build_csc(const int* col_idx, const int* coo_dst, int64_t E, int n_src, int* csc_ptr, int* csc_dst,
+              int* csc_eid, cudaStream_t st) {
+  int launches = 0;
+  if (cudaMemsetAsync(csc_ptr, 0, sizeof(int) * (size_t)(n_src + 1), st) != cudaSuccess) return -1;
+  if (E == 0) return 0;
+  int *keys_out = nullptr, *iota = nullptr, *counts = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0, scan_bytes = 0;
+  int end_bit = 1;
+  while ((1ll << end_bit) < (long long)n_src) ++end_bit;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, col_idx, keys_out, iota, csc_eid, (int)E, 0, end_bit, st);
+  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, counts, csc_ptr + 1, n_src, st);
+  if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
+  bool ok = cudaMalloc(&keys_out, sizeof(int) * (size_t)E) == cudaSuccess &&
+            cudaMalloc(&iota, sizeof(int) * (size_t)E) == cudaSuccess &&
+            cudaMalloc(&counts, sizeof(int) * (size_t)n_src) == cudaSuccess &&
+            cudaMalloc(&tmp, tmp_bytes) == cudaSuccess;
+  if (ok) {
+    const int threads = 256;
+    const int blocks = (int)((E + threads - 1) / threads < 148 * 16 ? (E + threads - 1) / threads : 148 * 16);
+    iota_kernel<<<blocks, threads, 0, st>>>(iota, E);
+    cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)n_src, st);
+    count_sources_kernel<<<blocks, threads, 0, st>>>(col_idx, E, counts);
+    // LSD radix sort is stable: equal sources keep ascending CSR position
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, col_idx, keys_out, iota, csc_eid, (int)E, 0, end_bit, st);
+    cub::DeviceScan::InclusiveSum(tmp, scan_bytes, counts, csc_ptr + 1, n_src, st);
+    gather_int_kernel<<<blocks, threads, 0, st>>>(coo_dst, csc_eid, E, csc_dst);
+    launches = 6;
+    ok = cudaStreamSynchronize(st) == cudaSuccess;
+  }
+  cudaFree(keys_out);
+  cudaFree(iota);
+  cudaFree(counts);
+  cudaFree(tmp);
+  return ok ? launches : -1;
+}
+
+// ---- Philox4x32-10 counter-based generator -------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__global__ void philox_uniform_kernel(float* __restrict__ out, int64_t n, float limit, uint64_t seed,
+                                      uint64_t stream_id) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q * 4 < n; q += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int64_t i = q * 4 + t;
+      if (i < n) {
+        // (0,1] like curand_uniform, then the reference's affine map rnd*2*limit - limit (EB:217-219)
+        const float u = ((float)(c[t] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+        out[i] = u * 2.0f * limit - limit;
+      }
+    }
+  }
+}
+int launch_philox_uniform(float* out, int64_t n, float limit, uint64_t seed, uint64_t stream_id,
+                          cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int threads = 256;
+  int64_t blocks = (n / 4 + threads) / threads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  philox_uniform_kernel<<<(int)blocks, threads, 0, st>>>(out, n, limit, seed, stream_id);
+  return 1;
+}
+
+}  // namespace gatx

@@ -1,0 +1,238 @@
+"""ctypes binding of libgatx.so (include/gatx.h) -- the call surface tests and bench.py use.
+
+There is deliberately no fallback: if the CUDA library is missing, cannot be built, or no
+sm_100 device is present, every entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgatx.so")
+
+(T_W, T_A, T_WO, T_GW, T_GA, T_GWO, T_PL, T_PR, T_SCORE, T_ALPHA, T_HPRE, T_HOUT, T_Y, T_GH, T_Z, T_PRED,
+ T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR) = range(24)
+_INT_TENSORS = {T_PRED, T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID}
+GEMM_TF32_TC, GEMM_FP32_SIMT = 0, 1
+PHASES = ("gemm_fwd", "edge_fwd", "head", "edge_bwd", "gemm_bwd", "optimizer", "comm", "epoch")
+
+EXPORTS = [
+    "gatx_create", "gatx_destroy", "gatx_last_error", "gatx_version", "gatx_set_graph_csr",
+    "gatx_set_features", "gatx_set_labels", "gatx_graph_info", "gatx_partition_rows", "gatx_init_params",
+    "gatx_set_params", "gatx_set_wo", "gatx_forward", "gatx_loss_acc", "gatx_backward", "gatx_step",
+    "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
+    "gatx_get_timing", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_comm_unique_id", "gatx_comm_init",
+]
+
+
+class GatxConfig(C.Structure):
+    _fields_ = [("num_layers", C.c_int32), ("heads", C.POINTER(C.c_int32)), ("outdims", C.POINTER(C.c_int32)),
+                ("optimizer", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("clip", C.c_int32), ("device", C.c_int32), ("gemm_mode", C.c_int32), ("keep_debug", C.c_int32),
+                ("rank", C.c_int32), ("world", C.c_int32)]
+
+
+class GatxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(build_if_missing=False):
+    """Loads libgatx.so; raises if it is not there (no CPU path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise GatxError("libgatx.so is not built: run `python graph-attention-network-gatv2-_b200/build.py` "
+                            "(there is no CPU fallback)")
+        import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    lib.gatx_last_error.restype = C.c_char_p
+    lib.gatx_version.restype = C.c_char_p
+    lib.gatx_tensor_size.restype = C.c_int64
+    lib.gatx_launch_count.restype = C.c_int64
+    lib.gatx_destroy.restype = None
+    lib.gatx_set_graph_csr.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.gatx_set_features.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.gatx_set_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.gatx_init_params.argtypes = [C.c_void_p, C.c_uint64]
+    lib.gatx_set_params.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gatx_set_wo.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gatx_get_tensor.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]
+    lib.gatx_tensor_size.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.gatx_train_epoch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gatx_loss_acc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gatx_step.argtypes = [C.c_void_p, C.c_int32]
+    lib.gatx_timer_stop.argtypes = [C.c_void_p, C.c_void_p]
+    for fn in ("gatx_forward", "gatx_backward", "gatx_sync", "gatx_destroy", "gatx_last_error", "gatx_launch_count",
+               "gatx_timer_start"):
+        getattr(lib, fn).argtypes = [C.c_void_p]
+    lib.gatx_enable_timing.argtypes = [C.c_void_p, C.c_int32]
+    lib.gatx_get_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.gatx_edge_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gatx_graph_info.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    lib.gatx_partition_rows.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.gatx_comm_unique_id.argtypes = [C.c_void_p]
+    lib.gatx_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def partition_rows(row_ptr, world):
+    row_ptr = np.ascontiguousarray(row_ptr, np.int32)
+    b = np.empty(world + 1, np.int32)
+    rc = load().gatx_partition_rows(len(row_ptr) - 1, row_ptr.ctypes.data, world, b.ctypes.data)
+    if rc:
+        raise GatxError("gatx_partition_rows failed: %d" % rc)
+    return b
+
+
+def comm_unique_id():
+    buf = (C.c_char * 128)()
+    rc = load().gatx_comm_unique_id(buf)
+    if rc:
+        raise GatxError("gatx_comm_unique_id failed: %d" % rc)
+    return bytes(buf)
+
+
+class Engine:
+    """One context (one GPU / rank).  Mirrors the reference's epoch: forward, loss_acc, backward, step."""
+
+    def __init__(self, heads, outdims, optimizer="sgd", lr=1e-4, beta1=0.9, beta2=0.999, clip=False, device=0,
+                 gemm_mode=GEMM_TF32_TC, keep_debug=False, rank=0, world=1):
+        self.lib = load()
+        self.heads, self.outdims = list(heads), list(outdims)
+        self.L = len(self.heads)
+        self._h = (C.c_int32 * self.L)(*self.heads)
+        self._d = (C.c_int32 * self.L)(*self.outdims)
+        cfg = GatxConfig(self.L, self._h, self._d, 1 if optimizer == "adam" else 0, lr, beta1, beta2, int(clip),
+                         device, gemm_mode, int(keep_debug), rank, world)
+        self.ctx = C.c_void_p()
+        rc = self.lib.gatx_create(C.byref(self.ctx), C.byref(cfg))
+        if rc:
+            self.ctx = None
+            raise GatxError("gatx_create failed with %d (no usable sm_100 CUDA device?)" % rc)
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.gatx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc:
+            raise GatxError("%s failed (%d): %s" % (what, rc, self.lib.gatx_last_error(self.ctx).decode()))
+
+    # ---- data
+    def set_graph(self, row_ptr, col_idx):
+        self._row_ptr = np.ascontiguousarray(row_ptr, np.int32)
+        self._col_idx = np.ascontiguousarray(col_idx, np.int32)
+        self.N, self.E = len(self._row_ptr) - 1, len(self._col_idx)
+        self._ck(self.lib.gatx_set_graph_csr(self.ctx, self.N, self.E, self._row_ptr.ctypes.data,
+                                             self._col_idx.ctypes.data), "gatx_set_graph_csr")
+
+    def set_features(self, X):
+        X = np.ascontiguousarray(X, np.float32)
+        self.I0 = X.shape[1]
+        self._ck(self.lib.gatx_set_features(self.ctx, X.ctypes.data, X.shape[1]), "gatx_set_features")
+
+    def set_features_ptr(self, ptr, in_dim):
+        self._ck(self.lib.gatx_set_features(self.ctx, ptr, in_dim), "gatx_set_features")
+
+    def set_labels(self, labels, num_classes=0):
+        labels = np.ascontiguousarray(labels, np.int32)
+        self._ck(self.lib.gatx_set_labels(self.ctx, labels.ctypes.data, num_classes), "gatx_set_labels")
+
+    def set_labels_ptr(self, ptr, num_classes):
+        self._ck(self.lib.gatx_set_labels(self.ctx, ptr, num_classes), "gatx_set_labels")
+
+    def graph_info(self):
+        v = [C.c_int32() for _ in range(4)]
+        self._ck(self.lib.gatx_graph_info(self.ctx, *[C.byref(x) for x in v]), "gatx_graph_info")
+        return dict(max_degree=v[0].value, num_classes=v[1].value, row_begin=v[2].value, row_end=v[3].value)
+
+    # ---- parameters
+    def init_params(self, seed=0):
+        self._ck(self.lib.gatx_init_params(self.ctx, seed), "gatx_init_params")
+
+    def set_params(self, layer, W, a):
+        W, a = np.ascontiguousarray(W, np.float32), np.ascontiguousarray(a, np.float32)
+        self._ck(self.lib.gatx_set_params(self.ctx, layer, W.ctypes.data, a.ctypes.data), "gatx_set_params")
+
+    def set_wo(self, Wo):
+        Wo = np.ascontiguousarray(Wo, np.float32)
+        self._ck(self.lib.gatx_set_wo(self.ctx, Wo.ctypes.data), "gatx_set_wo")
+
+    # ---- epoch
+    def forward(self):
+        self._ck(self.lib.gatx_forward(self.ctx), "gatx_forward")
+
+    def loss_acc(self):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.lib.gatx_loss_acc(self.ctx, C.byref(a), C.byref(b)), "gatx_loss_acc")
+        return a.value, b.value
+
+    def backward(self):
+        self._ck(self.lib.gatx_backward(self.ctx), "gatx_backward")
+
+    def step(self, t):
+        self._ck(self.lib.gatx_step(self.ctx, t), "gatx_step")
+
+    def train_epoch(self, t, want_loss=True):
+        if not want_loss:
+            self._ck(self.lib.gatx_train_epoch(self.ctx, t, None, None), "gatx_train_epoch")
+            return None
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.lib.gatx_train_epoch(self.ctx, t, C.byref(a), C.byref(b)), "gatx_train_epoch")
+        return a.value, b.value
+
+    def sync(self):
+        self._ck(self.lib.gatx_sync(self.ctx), "gatx_sync")
+
+    # ---- introspection
+    def tensor(self, which, layer=0):
+        n = self.lib.gatx_tensor_size(self.ctx, which, layer)
+        if n < 0:
+            raise GatxError("tensor %d/%d not available" % (which, layer))
+        out = np.empty(n, np.int32 if which in _INT_TENSORS else np.float32)
+        self._ck(self.lib.gatx_get_tensor(self.ctx, which, layer, out.ctypes.data, out.nbytes), "gatx_get_tensor")
+        return out
+
+    def enable_timing(self, on=True):
+        self._ck(self.lib.gatx_enable_timing(self.ctx, int(on)), "gatx_enable_timing")
+
+    def timing(self):
+        buf = (C.c_float * 8)()
+        self._ck(self.lib.gatx_get_timing(self.ctx, buf, 8), "gatx_get_timing")
+        return dict(zip(PHASES, list(buf)))
+
+    def timer_start(self):
+        self._ck(self.lib.gatx_timer_start(self.ctx), "gatx_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.gatx_timer_stop(self.ctx, C.byref(ms)), "gatx_timer_stop")
+        return ms.value
+
+    def launch_count(self):
+        return self.lib.gatx_launch_count(self.ctx)
+
+    def edge_bytes(self, layer):
+        f, b = C.c_double(), C.c_double()
+        self._ck(self.lib.gatx_edge_bytes(self.ctx, layer, C.byref(f), C.byref(b)), "gatx_edge_bytes")
+        return f.value, b.value
+
+    def comm_init(self, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.gatx_comm_init(self.ctx, buf), "gatx_comm_init")

@@ -1,0 +1,166 @@
+/*
+ * gatx.h -- C ABI of the B200-native GATv2 full-batch training engine.
+ *
+ * The reference (saurabh260918/Graph-Attention-Network-GATv2-) has no operator / plugin / FFI
+ * boundary: `main` launches its kernels directly (GATv2_edge_based.cu:927-1646, "EB").  This
+ * header IS the boundary for the one hot path -- one full-batch training epoch
+ * (EB:1370-1642) -- and every entry point names the reference code it replaces.  The library
+ * behind it (libgatx.so) is plain CUDA C++ for sm_100a: no PyTorch, no Triton, no CPU
+ * fallback.  If no CUDA device is usable, gatx_create fails with GATX_ERR_CUDA.
+ *
+ * Conventions: every call returns 0 on success or a negative gatx_status; the text of the last
+ * error of a context is gatx_last_error(ctx).  Nothing throws, nothing exits.  The caller owns
+ * all host buffers (copied on set_*, filled on get_*); the context owns device memory and its
+ * streams.  A context is not thread-safe; distinct contexts (one per device / rank) may be
+ * driven from distinct host threads or processes.
+ *
+ * Layouts are the reference's: CSR is destination-major (row = destination, col_idx = source,
+ * EB:67-84); W of a layer is [H][D][2*I] row-major with columns 0..I-1 applied to the SOURCE
+ * node and I..2I-1 to the DESTINATION node (EB:304-316); a is [H][D]; W_o is [C][D_last]
+ * (EB:1243-1258).  Per-edge tensors are returned edge-major [E][H] (the reference stores
+ * [H][E], EB:297); callers transpose if they need the reference order.
+ */
+#ifndef GATX_H_
+#define GATX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gatx_ctx gatx_ctx;
+
+typedef enum gatx_status {
+  GATX_OK = 0,
+  GATX_ERR_INVALID = -1,     /* bad argument / call order */
+  GATX_ERR_CUDA = -2,        /* CUDA runtime error (text in gatx_last_error) */
+  GATX_ERR_UNSUPPORTED = -3, /* shape outside the implemented kernels */
+  GATX_ERR_NCCL = -4,
+  GATX_ERR_OOM = -5
+} gatx_status;
+
+enum { GATX_OPT_SGD = 0, GATX_OPT_ADAM = 1 };
+/* Projection / gradient GEMM arithmetic. */
+enum {
+  GATX_GEMM_TF32_TC = 0, /* tcgen05 tensor cores, TF32 inputs, fp32 accumulate (default) */
+  GATX_GEMM_FP32_SIMT = 1 /* fp32 FMA on CUDA cores (tight-tolerance parity runs) */
+};
+
+/* Replaces the CLI-derived locals of EB:934-1040 (L, head[], out_dim[], optimizer, lr, betas,
+ * clip).  Gradient clipping threshold is the reference's fixed 5.0 (EB:1563). */
+typedef struct gatx_config {
+  int32_t num_layers;
+  const int32_t* heads;   /* [num_layers] */
+  const int32_t* outdims; /* [num_layers] per-head output dim */
+  int32_t optimizer;      /* GATX_OPT_* */
+  float lr, beta1, beta2;
+  int32_t clip;        /* 0/1 */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t gemm_mode;   /* GATX_GEMM_* */
+  int32_t keep_debug;  /* 1: also keep pre-activation h, galpha for gatx_get_tensor */
+  int32_t rank, world; /* destination-row partition; world = 1 for single GPU */
+} gatx_config;
+
+/* Tensor ids for gatx_get_tensor / gatx_tensor_size (same ids as the oracle's). */
+enum {
+  GATX_T_W = 0,      /* [H][D][2I]  layer parameter (EB d_w + w_offset[l]) */
+  GATX_T_A = 1,      /* [H][D]      (EB d_a + a_offset[l]) */
+  GATX_T_WO = 2,     /* [C][D_last] (EB d_wo) */
+  GATX_T_GW = 3,     /* grad of W   (EB grad_d_w) -- valid after gatx_backward, before gatx_step */
+  GATX_T_GA = 4,     /* grad of a   (EB grad_d_a) */
+  GATX_T_GWO = 5,    /* grad of W_o (EB grad_wo) */
+  GATX_T_PL = 6,     /* [N][F] projected source features  W_l x */
+  GATX_T_PR = 7,     /* [N_local][F] projected destination features W_r x */
+  GATX_T_SCORE = 8,  /* [E][H] attention logits (EB attn_score, transposed) */
+  GATX_T_ALPHA = 9,  /* [E][H] attention coefficients (EB attn_coeff, transposed) */
+  GATX_T_HPRE = 10,  /* [N][F] pre-activation aggregate (EB d_h) -- needs keep_debug */
+  GATX_T_HOUT = 11,  /* [N][F] or [N][D_last] layer output (EB d_layer_outputs) */
+  GATX_T_Y = 12,     /* [N][C] class probabilities (EB d_y) */
+  GATX_T_GH = 13,    /* [N][F] grad wrt pre-activation aggregate (EB input_gradients[l]) */
+  GATX_T_Z = 14,     /* [N][C] logits before softmax -- needs keep_debug */
+  GATX_T_PRED = 15,  /* int32 [N] predicted labels (EB:530-535 first-max argmax) */
+  GATX_T_COO_SRC = 16, /* int32 [E] (EB d_src, EB:67-84) */
+  GATX_T_COO_DST = 17, /* int32 [E] (EB d_dst) */
+  GATX_T_IN_DEGREE = 18, /* int32 [N] row lengths (EB:93) */
+  GATX_T_CSC_PTR = 19,   /* int32 [N+1] transposed graph used by the deterministic backward */
+  GATX_T_CSC_DST = 20,   /* int32 [E] */
+  GATX_T_CSC_EID = 21,   /* int32 [E] CSR position of each transposed edge */
+  GATX_T_GPL = 22,   /* [N][F] grad wrt projected source features */
+  GATX_T_GPR = 23    /* [N][F] grad wrt projected destination features */
+};
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+/* Replaces EB:934-1040 + all cudaMalloc/cudaMemset of EB:1115-1357 (done lazily once graph,
+ * features and labels are known). */
+int gatx_create(gatx_ctx** out, const gatx_config* cfg);
+void gatx_destroy(gatx_ctx* ctx);
+const char* gatx_last_error(const gatx_ctx* ctx);
+const char* gatx_version(void);
+
+/* ---- data ------------------------------------------------------------------------------- */
+/* Replaces EB:1158-1192 (H2D of CSR + csr_to_coo_kernel) and adds the transposed graph and
+ * the destination-row partition.  row_ptr [N+1], col_idx [E] describe the GLOBAL graph on every
+ * rank; a rank keeps rows [bounds[rank], bounds[rank+1]). */
+int gatx_set_graph_csr(gatx_ctx* ctx, int32_t num_nodes, int64_t num_edges,
+                       const int32_t* row_ptr, const int32_t* col_idx);
+/* Replaces EB:1151-1155.  X is the GLOBAL row-major [N][in_dim] matrix. */
+int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim);
+/* Replaces EB:1169-1172 + EB:1106-1107 (num_classes <= 0: derived as max(label)+1). */
+int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes);
+/* max row length (EB:89-99) and number of classes (EB:1106-1107) as the reference prints them */
+int gatx_graph_info(gatx_ctx* ctx, int32_t* max_degree, int32_t* num_classes,
+                    int32_t* row_begin, int32_t* row_end);
+/* Destination-row partition bounds [world+1] for a global row_ptr (host-side helper). */
+int gatx_partition_rows(int32_t num_nodes, const int32_t* row_ptr, int32_t world,
+                        int32_t* bounds);
+
+/* ---- parameters ------------------------------------------------------------------------- */
+/* Replaces setup_states_kernel + xavier_init_kernel_curand (EB:181-248, launch EB:1300-1323):
+ * same distributions (limits EB:208, EB:236), counter-based and reproducible from `seed`. */
+int gatx_init_params(gatx_ctx* ctx, uint64_t seed);
+int gatx_set_params(gatx_ctx* ctx, int32_t layer, const float* W, const float* a);
+int gatx_set_wo(gatx_ctx* ctx, const float* Wo);
+
+/* ---- the epoch (EB:1370-1642) ----------------------------------------------------------- */
+/* EB:1375-1452: per layer projection + score + segmented softmax + aggregation + activation,
+ * then classifier + softmax. */
+int gatx_forward(gatx_ctx* ctx);
+/* EB:1455-1460 (compute_loss_accuracy_kernel + the two thrust reductions); synchronises. */
+int gatx_loss_acc(gatx_ctx* ctx, float* avg_loss, float* accuracy);
+/* EB:1463-1557. */
+int gatx_backward(gatx_ctx* ctx);
+/* EB:1560-1637: optional clip (3 groups), Adam (t = 1-based epoch) or SGD, zero gradients. */
+int gatx_step(gatx_ctx* ctx, int32_t t);
+/* forward + loss/accuracy + backward + step in one call, asynchronous until the scalars are
+ * read; avg_loss/accuracy may be NULL (then no host sync at all). */
+int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy);
+int gatx_sync(gatx_ctx* ctx);
+
+/* ---- introspection (parity tests, checkpoints) ------------------------------------------- */
+int64_t gatx_tensor_size(gatx_ctx* ctx, int32_t which, int32_t layer); /* elements, <0 on error */
+int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size_t bytes);
+/* Device milliseconds of the phases of the last gatx_train_epoch / forward / backward call:
+ * out[0]=projection GEMMs, [1]=edge forward, [2]=classifier+loss, [3]=edge backward,
+ * [4]=gradient GEMMs, [5]=optimizer, [6]=collectives, [7]=whole epoch.  Needs
+ * gatx_enable_timing(ctx, 1) (adds event records, no host syncs). */
+int gatx_enable_timing(gatx_ctx* ctx, int32_t on);
+int gatx_get_timing(gatx_ctx* ctx, float* out_ms, int32_t n);
+/* CUDA-event stopwatch on the context's launching stream (bench.py times its K steps with it). */
+int gatx_timer_start(gatx_ctx* ctx);
+int gatx_timer_stop(gatx_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */
+/* Kernels launched by this context since creation (the bench's gpu_launches claim). */
+int64_t gatx_launch_count(const gatx_ctx* ctx);
+/* Algorithmic bytes of the fused edge forward / backward of one layer (SURVEY 8d formulas). */
+int gatx_edge_bytes(gatx_ctx* ctx, int32_t layer, double* fwd_bytes, double* bwd_bytes);
+
+/* ---- multi-GPU (one context per rank, NCCL over NVLink) --------------------------------- */
+/* 128-byte NCCL unique id made on rank 0, distributed by the caller (torchrun store, MPI, file) */
+int gatx_comm_unique_id(void* out128);
+int gatx_comm_init(gatx_ctx* ctx, const void* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GATX_H_ */
