@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ref_edge_*.npz from the reference's own edge-based program.
+
+Run ON A GPU BOX (the reference has no CPU path):  python oracle/gen_golden.py <out_dir>
+For each case it writes the dataset in the reference's text format, injects fixed weights into
+oracle/_ref/edge_patched (see patch_ref.py), runs it and stores inputs, the buffers dumped after
+the first forward+backward, the parameters after the first update and the printed loss curve.
+Cases are tiny so the fixtures stay small; they cover Adam, SGD+clip, 2 and 3 layers.
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "graph-attention-network-gatv2-_b200"))
+import datasets  # noqa: E402
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "edge_patched")
+
+CASES = {
+    # name: N, E, I, C, heads, outdims, optimizer, lr, clip, graph kind, epochs
+    "sample_adam": (64, 512, 16, 4, [8, 1], [8, 8], "adam", 0.01, False, "uniform", 12),
+    "small_sgd_clip": (96, 600, 10, 3, [4, 1], [16, 8], "sgd", 0.001, True, "rmat", 12),
+    "three_layer_adam": (80, 480, 12, 5, [4, 4, 1], [8, 8, 16], "adam", 0.005, True, "rmat", 8),
+}
+
+
+def run_case(name, spec, out_dir):
+    N, E, I, C, heads, outdims, opt, lr, clip, kind, epochs = spec
+    seed = 4000 + len(name)
+    row_ptr, col_idx = datasets.make_graph(N, E, kind, seed)
+    X = datasets.make_features(N, I, "uniform", seed)
+    y = datasets.make_labels(N, C, seed)
+    Ws, As, Wo = datasets.init_params(heads, outdims, I, C, seed)
+    Ws = [w * 2 for w in Ws]
+    As = [a * 2 for a in As]
+    tmp = tempfile.mkdtemp(prefix="gatx_golden_")
+    ds = dict(row_ptr=row_ptr, col_idx=col_idx, X=X, labels=y)
+    datasets.write_txt(os.path.join(tmp, "data", name), ds)
+    wdir, ddir = os.path.join(tmp, "w"), os.path.join(tmp, "dump")
+    os.makedirs(wdir)
+    os.makedirs(ddir)
+    np.concatenate([w.ravel() for w in Ws]).astype(np.float32).tofile(os.path.join(wdir, "W.bin"))
+    np.concatenate([a.ravel() for a in As]).astype(np.float32).tofile(os.path.join(wdir, "a.bin"))
+    Wo.astype(np.float32).tofile(os.path.join(wdir, "Wo.bin"))
+    cmd = [BIN, "--num-layers", str(len(heads)), "--heads", ",".join(map(str, heads)), "--outdims",
+           ",".join(map(str, outdims)), "--epochs", str(epochs), "--optimizer", opt, "--lr", str(lr), "--dataset", name,
+           "--data-root", os.path.join(tmp, "data")] + (["--clip"] if clip else [])
+    env = dict(os.environ, GATX_REF_WEIGHTS=wdir, GATX_REF_DUMP=ddir, GATX_REF_DUMP_EPOCH="1", GATX_REF_ZERO_H="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    if out.returncode != 0:
+        raise RuntimeError("reference failed: %s\n%s" % (out.returncode, out.stderr[-2000:]))
+    curve = [(float(a), float(b)) for a, b in re.findall(r"Avg Loss: ([0-9.eE+-]+), Accuracy: ([0-9.]+)%", out.stdout)]
+    assert len(curve) == epochs, (len(curve), out.stdout[-1000:])
+    # the same run WITHOUT clearing d_h: documents reference defect D1 (loss curve after epoch 1)
+    env2 = dict(env)
+    del env2["GATX_REF_ZERO_H"], env2["GATX_REF_DUMP"]
+    out2 = subprocess.run(cmd, capture_output=True, text=True, env=env2, timeout=600)
+    curve_d1 = [(float(a), float(b)) for a, b in re.findall(r"Avg Loss: ([0-9.eE+-]+), Accuracy: ([0-9.]+)%", out2.stdout)]
+    m = re.search(r"Max degree = (\d+)", out.stdout)
+    c = re.search(r"Number of classes = (\d+)", out.stdout)
+    rec = dict(row_ptr=row_ptr, col_idx=col_idx, X=X, labels=y, Wo=Wo, heads=np.array(heads), outdims=np.array(outdims),
+               optimizer=np.array(opt), lr=np.array(lr), clip=np.array(clip), loss_curve=np.array(curve),
+               loss_curve_unpatched_d1=np.array(curve_d1), max_degree=np.array(int(m.group(1))),
+               num_classes=np.array(int(c.group(1))))
+    for l in range(len(heads)):
+        rec["W_%d" % l] = Ws[l]
+        rec["a_%d" % l] = As[l]
+    for fn in sorted(os.listdir(ddir)):
+        dt = np.int32 if fn.startswith(("coo_", "correct")) else np.float32
+        rec["ref_" + fn[:-4]] = np.fromfile(os.path.join(ddir, fn), dtype=dt)
+    os.makedirs(out_dir, exist_ok=True)
+    np.savez_compressed(os.path.join(out_dir, "ref_edge_%s.npz" % name), **rec)
+    print(name, "ok: loss curve", curve[:3], "...", "D1-unpatched", curve_d1[:3])
+
+
+if __name__ == "__main__":
+    out_dir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    for name, spec in CASES.items():
+        run_case(name, spec, out_dir)

@@ -3,11 +3,12 @@ import numpy as np
 import datasets
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=1e-30):
+    """max |a-b| / max(max |b|, floor); `floor` keeps an exactly-zero reference comparable."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     if a.size == 0:
         return 0.0
-    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
 
 
 def make_problem(N, E, I, C, heads, outdims, kind="uniform", seed=0, wscale=2.0, hub=None):

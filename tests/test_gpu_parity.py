@@ -86,7 +86,8 @@ def test_forward_backward_parity(gatx, orc, shape, mode):
     for l in range(L):
         assert rel_err(eng.tensor(gatx.T_GH, l), ref.tensor(orc.T_GH, l).ravel()) < bt, ("g_h", l)
         assert rel_err(eng.tensor(gatx.T_GW, l), ref.tensor(orc.T_GW, l).ravel()) < bt, ("gW", l)
-        assert rel_err(eng.tensor(gatx.T_GA, l), ref.tensor(orc.T_GA, l).ravel()) < bt, ("ga", l)
+        # floor: with one in-edge per row the true ga is exactly 0 (alpha = 1)
+        assert rel_err(eng.tensor(gatx.T_GA, l), ref.tensor(orc.T_GA, l).ravel(), floor=1e-2) < bt, ("ga", l)
     assert rel_err(eng.tensor(gatx.T_GWO), ref.tensor(orc.T_GWO).ravel()) < bt
     eng.close()
 
