@@ -24,7 +24,11 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "edge_patched")
 CASES = {
     # name: N, E, I, C, heads, outdims, optimizer, lr, clip, graph kind, epochs
     "sample_adam": (64, 512, 16, 4, [8, 1], [8, 8], "adam", 0.01, False, "uniform", 12),
-    "small_sgd_clip": (96, 600, 10, 3, [4, 1], [16, 8], "sgd", 0.001, True, "rmat", 12),
+    "small_sgd_clip": (96, 640, 10, 3, [4, 1], [16, 8], "sgd", 0.001, True, "rmat", 12),
+    # E % 256 = 88 < 2*in_dim of layer 1: the reference's last CTA exits 168 threads before they zero
+    # their share of sh_grad_w (EB:722 + EB:747-749), so columns >= 88 of that layer's gW are garbage.
+    # Kept to document the defect ("D13"); only the unaffected quantities are compared.
+    "tail_block_defect": (96, 600, 10, 3, [4, 1], [16, 8], "sgd", 0.001, False, "rmat", 4),
     "three_layer_adam": (80, 480, 12, 5, [4, 4, 1], [8, 8, 16], "adam", 0.005, True, "rmat", 8),
 }
 
