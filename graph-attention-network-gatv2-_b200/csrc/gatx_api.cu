@@ -302,17 +302,37 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   return g;
 }
 
-// C[M][N] (ldc) (+)= A B^T with K-major operands (both row-major with K contiguous).
-int gemm_tn(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
-            int N, int K, bool accumulate) {
+// P_l | P_r = X [W_l ; W_r]^T in one pass over X (Wcat is [2F][ldk], rows 0..F-1 = W_l).
+int gemm_project(gatx_ctx* ctx, const float* X, int ldx, const Layer& ly) {
+  float* Pl_own = ly.Pl + (int64_t)ctx->r0 * ly.F;
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
-    int n = launch_gemm_tc_tn(A, lda, B, ldb, C, ldc, M, N, K, accumulate, ctx->st);
+    int n = launch_gemm_tc_tn2(X, ldx, ly.Wcat, ly.ldk, ly.I, nullptr, 0, nullptr, 0, 0, Pl_own, ly.Pr, ly.F, ly.F,
+                               ctx->n_rows, 2 * ly.F, false, ctx->st);
     if (n >= 0) {
       ctx->launches += n;
       return GATX_OK;
     }
   }
-  LAUNCHED(launch_gemm_simt(A, lda, 1, B, ldb, 1, C, ldc, M, N, K, accumulate, nullptr, 0, ctx->st));
+  LAUNCHED(launch_gemm_simt(X, ldx, 1, ly.Wcat, ly.ldk, 1, Pl_own, ly.F, ctx->n_rows, ly.F, ly.I, false, nullptr, 0,
+                            ctx->st));
+  LAUNCHED(launch_gemm_simt(X, ldx, 1, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, 1, ly.Pr, ly.F, ctx->n_rows, ly.F,
+                            ly.I, false, nullptr, 0, ctx->st));
+  return GATX_OK;
+}
+// gX[n][i] = sum_r gP_l[n][r] W_l[r][i] + gP_r[n][r] W_r[r][i]   (WcatT is [I][2F])
+int gemm_input_grad(gatx_ctx* ctx, const float* gPl_own, const float* gPr, const Layer& ly, float* gX, int ldg) {
+  if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
+    int n = launch_gemm_tc_tn2(gPl_own, ly.F, ly.WcatT, 2 * ly.F, ly.F, gPr, ly.F, ly.WcatT + ly.F, 2 * ly.F, ly.F, gX,
+                               gX, ly.I, ldg, ctx->n_rows, ly.I, false, ctx->st);
+    if (n >= 0) {
+      ctx->launches += n;
+      return GATX_OK;
+    }
+  }
+  LAUNCHED(launch_gemm_simt(gPl_own, ly.F, 1, ly.WcatT, 2 * ly.F, 1, gX, ldg, ctx->n_rows, ly.I, ly.F, false, nullptr,
+                            0, ctx->st));
+  LAUNCHED(launch_gemm_simt(gPr, ly.F, 1, ly.WcatT + ly.F, 2 * ly.F, 1, gX, ldg, ctx->n_rows, ly.I, ly.F, true, nullptr,
+                            0, ctx->st));
   return GATX_OK;
 }
 // C[M][N] (ldc) += A^T B with A [K][>=M] (lda), B [K][>=N] (ldb): contraction over the node dimension.
@@ -369,11 +389,7 @@ int do_forward(gatx_ctx* ctx) {
       PhaseTimer t(ctx, PH_GEMM_FWD);
       LAUNCHED(launch_pack_weights(ctx->params + ly.w_off, ly.F, ly.I, ly.Wcat, ly.ldk, ly.WcatT, ctx->st));
       // P_l = X W_l^T, P_r = X W_r^T : the only dense contraction of the forward (EB:303-316)
-      rc = gemm_tn(ctx, X, ly.ldx, ly.Wcat, ly.ldk, ly.Pl + (int64_t)ctx->r0 * ly.F, ly.F, ctx->n_rows, ly.F, ly.I,
-                   false);
-      if (rc) return rc;
-      rc = gemm_tn(ctx, X, ly.ldx, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, ly.Pr, ly.F, ctx->n_rows, ly.F, ly.I,
-                   false);
+      rc = gemm_project(ctx, X, ly.ldx, ly);
       if (rc) return rc;
     }
     rc = comm_allgather_rows(ctx, ly.Pl, ly.F);
@@ -446,9 +462,7 @@ int do_backward(gatx_ctx* ctx) {
         // dL/dHout[l-1] = gP_l W_l + gP_r W_r  (EB:859-869); the LReLU derivative of EB:879-893 is
         // applied by the next edge backward when it loads this gradient.
         Layer& prev = ctx->layers[l - 1];
-        rc = gemm_tn(ctx, gPl_own, ly.F, ly.WcatT, 2 * ly.F, prev.gH, prev.F, ctx->n_rows, ly.I, ly.F, false);
-        if (rc) return rc;
-        rc = gemm_tn(ctx, ctx->gPr, ly.F, ly.WcatT + ly.F, 2 * ly.F, prev.gH, prev.F, ctx->n_rows, ly.I, ly.F, true);
+        rc = gemm_input_grad(ctx, gPl_own, ctx->gPr, ly, prev.gH, prev.F);
         if (rc) return rc;
       }
     }
@@ -907,6 +921,39 @@ int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size
   if (tmp) cudaFree(tmp);
   if (e != cudaSuccess) return fail(ctx, GATX_ERR_CUDA, "get_tensor copy: %s", cudaGetErrorString(e));
   return GATX_OK;
+}
+
+int gatx_op_gemm(int32_t mode, int32_t form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                 int64_t ldc, int32_t M, int32_t N, int64_t K) {
+  // host-pointer GEMM used by the parity tests and ncu: form 0: C = A[M][K] B[N][K]^T; form 1: C = A[K][M]^T B[K][N]
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return GATX_ERR_INVALID;
+  const int64_t a_rows = form == 0 ? M : K, b_rows = form == 0 ? N : K;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *ws = nullptr;
+  const size_t ws_bytes = (size_t)64 << 20;
+  int rc = GATX_OK;
+  cudaStream_t st = nullptr;
+  if (cudaMalloc(&dA, sizeof(float) * a_rows * lda) != cudaSuccess || cudaMalloc(&dB, sizeof(float) * b_rows * ldb) != cudaSuccess ||
+      cudaMalloc(&dC, sizeof(float) * (size_t)M * ldc) != cudaSuccess || cudaMalloc(&ws, ws_bytes) != cudaSuccess ||
+      cudaStreamCreate(&st) != cudaSuccess)
+    rc = GATX_ERR_CUDA;
+  if (!rc) {
+    cudaMemcpyAsync(dA, A, sizeof(float) * a_rows * lda, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dB, B, sizeof(float) * b_rows * ldb, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(dC, 0, sizeof(float) * (size_t)M * ldc, st);
+    int n = -1;
+    if (form == 0)
+      n = mode == GATX_GEMM_TF32_TC ? launch_gemm_tc_tn(dA, lda, dB, ldb, dC, ldc, M, N, (int)K, false, st)
+                                    : launch_gemm_simt(dA, lda, 1, dB, ldb, 1, dC, ldc, M, N, K, false, nullptr, 0, st);
+    else
+      n = mode == GATX_GEMM_TF32_TC ? launch_gemm_tc_atb(dA, lda, dB, ldb, dC, ldc, M, N, K, ws, ws_bytes, st)
+                                    : launch_gemm_simt(dA, 1, lda, dB, 1, ldb, dC, ldc, M, N, K, true, ws, ws_bytes, st);
+    if (n < 0) rc = GATX_ERR_UNSUPPORTED;
+    if (!rc && cudaMemcpyAsync(C, dC, sizeof(float) * (size_t)M * ldc, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = GATX_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = rc ? rc : GATX_ERR_CUDA;
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(ws);
+  if (st) cudaStreamDestroy(st);
+  return rc;
 }
 
 int gatx_comm_unique_id(void* out128) {

@@ -1,12 +1,359 @@
+// tcgen05 tensor-core GEMMs for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma kind::tf32 with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+// These are the dense contractions the reference recomputes per edge with scalar FMAs:
+//   projection   P_l|P_r = X [W_l;W_r]^T                (EB:303-316, EB:415-420)      -> gemm_tn
+//   input grad   gX = gP_l W_l + gP_r W_r               (EB:859-869)                  -> gemm_tn (dual operand)
+//   weight grad  gW_l|gW_r = gP^T X                     (EB:771-782)                  -> gemm_atb (MN-major operands)
+// Inputs stay fp32 in HBM; kind::tf32 reads the fp32 words and uses their top 19 bits, accumulation is
+// fp32.  Stated tolerance (tests/test_gpu_parity.py): 5e-3 relative on forward tensors.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (each owns the TMEM lane quadrant warp_id % 4).  One CTA computes one 128 x BN
+// output tile; two CTAs fit per SM so one tile's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include <cstdio>
+
+#include "common.cuh"
 #include "gemm_tc.cuh"
 
 namespace gatx {
-int launch_gemm_tc_tn(const float*, int64_t, const float*, int64_t, float*, int64_t, int, int, int, bool,
-                      cudaStream_t) {
+namespace {
+
+constexpr int BM = 128;      // UMMA_M (cta_group::1)
+constexpr int BK = 32;       // fp32 elements per k-block = 128 bytes = one swizzle span
+constexpr int UMMA_K = 8;    // tf32
+constexpr int kThreads = 192;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], single-thread issue
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
+// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
+// layout type in [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6), a/b format TF32 = 2 at
+// [7,10) / [10,13), a_major at 15, b_major at 16 (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct TnSmem {
+  static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+  static constexpr int kABytes = BM * BK * 4, kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingFloats = 4 * 32 * 33;  // epilogue transpose buffers alias the drained pipeline stages
+  static_assert(kStages * kStageBytes >= kStagingFloats * 4, "staging must fit in the pipeline buffers");
+  static constexpr int kBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256;
+};
+
+// C[m][n] (+)= sum_k A0[m][k] B0[n][k] + sum_k A1[m][k] B1[n][k]   (second pair optional, K1 = 0)
+// columns n >= n_split go to C1 (column n - n_split); used to write P_l and P_r from one pass over X.
+template <int BN>
+__global__ void __launch_bounds__(kThreads)
+gemm_tf32_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, int K0,
+                    int K1, float* __restrict__ C0, float* __restrict__ C1, int n_split, int64_t ldc, int M, int N,
+                    int accumulate) {
+  using S = TnSmem<BN>;
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  float* staging = reinterpret_cast<float*>(smem);  // reused only after tmem_full_bar (all TMA + MMA done)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int kb0 = (K0 + BK - 1) / BK, kb1 = (K1 + BK - 1) / BK, num_kb = kb0 + kb1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (K1 > 0) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S::kStages;
+        const uint32_t ph = (kb / S::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = tiles + s * S::kStageBytes;
+        uint8_t* b_dst = a_dst + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        if (kb < kb0) {
+          tma_load_2d(&tmA0, &full_bar[s], a_dst, kb * BK, m0);
+          tma_load_2d(&tmB0, &full_bar[s], b_dst, kb * BK, n0);
+        } else {
+          tma_load_2d(&tmA1, &full_bar[s], a_dst, (kb - kb0) * BK, m0);
+          tma_load_2d(&tmB1, &full_bar[s], b_dst, (kb - kb0) * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN < 16 ? 16 : BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S::kStages;
+        const uint32_t ph = (kb / S::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major SWIZZLE_128B: rows are 128 B apart, 8-row groups 1024 B apart (SBO); a UMMA_K step of
+          // 8 tf32 = 32 B advances the start address inside the swizzle span
+          const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 4, 16, 1024);
+          const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 4, 16, 1024);
+          umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global stores =====
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    float* st = staging + (warp - 2) * 32 * 33;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int col = n0 + c0 + lane;
+      float* Cb = C0;
+      int ccol = col;
+      if (col >= n_split) {
+        Cb = C1;
+        ccol = col - n_split;
+      }
+      if (col < N) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int row = m0 + q * 32 + r;
+          if (row < M) {
+            float* p = Cb + (int64_t)row * ldc + ccol;
+            const float val = st[r * 33 + lane];
+            *p = accumulate ? *p + val : val;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---- host side: tensor maps -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows][cols] with row pitch ld (elements); box = box_cols x box_rows, 128B swizzle
+bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16 || rows <= 0 || cols <= 0) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+int launch_tn(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, int K0,
+              int K1, float* C0, float* C1, int n_split, int64_t ldc, int M, int N, bool accumulate, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tf32_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TnSmem<BN>::kBytes) != cudaSuccess)
+      return -1;
+    configured = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  gemm_tf32_tn_kernel<BN><<<grid, kThreads, TnSmem<BN>::kBytes, st>>>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M,
+                                                                      N, accumulate ? 1 : 0);
+  return 1;
+}
+
+int pick_bn(int N, int n_split) {
+  // widest tile (<= 128 so that two CTAs share an SM) that does not straddle the C0/C1 split
+  for (int bn : {128, 64, 32, 16}) {
+    if (n_split < N && n_split % bn) continue;
+    if (bn == 16 || N >= bn || N > bn / 2) return bn;
+  }
   return -1;
 }
+
+}  // namespace
+
+int launch_gemm_tc_tn2(const float* A0, int64_t lda0, const float* B0, int64_t ldb0, int K0, const float* A1,
+                       int64_t lda1, const float* B1, int64_t ldb1, int K1, float* C0, float* C1, int n_split,
+                       int64_t ldc, int M, int N, bool accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K0 <= 0) return -1;
+  if (n_split <= 0 || n_split > N) n_split = N;
+  const int bn = pick_bn(N, n_split);
+  if (bn < 0) return -1;
+  CUtensorMap a0, b0, a1, b1;
+  if (!make_map(&a0, A0, M, K0, lda0, BK, BM) || !make_map(&b0, B0, N, K0, ldb0, BK, bn)) return -1;
+  if (K1 > 0) {
+    if (!make_map(&a1, A1, M, K1, lda1, BK, BM) || !make_map(&b1, B1, N, K1, ldb1, BK, bn)) return -1;
+  } else {
+    a1 = a0;
+    b1 = b0;
+  }
+  switch (bn) {
+    case 128: return launch_tn<128>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    case 64: return launch_tn<64>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    case 32: return launch_tn<32>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    default: return launch_tn<16>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+  }
+}
+
+int launch_gemm_tc_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                      int K, bool accumulate, cudaStream_t st) {
+  return launch_gemm_tc_tn2(A, lda, B, ldb, K, nullptr, 0, nullptr, 0, 0, C, C, N, ldc, M, N, accumulate, st);
+}
+
 int launch_gemm_tc_atb(const float*, int64_t, const float*, int64_t, float*, int64_t, int, int, int64_t, float*,
                        size_t, cudaStream_t) {
-  return -1;
+  return -1;  // MN-major split-K kernel: see below (not enabled yet)
 }
+
 }  // namespace gatx

@@ -9,6 +9,11 @@ namespace gatx {
 // C[M][N] (ldc) (+)= A[M][K] (lda) * B[N][K]^T (ldb); all row-major with K contiguous.
 int launch_gemm_tc_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                       int K, bool accumulate, cudaStream_t st);
+// C[m][n] (+)= A0 B0^T + A1 B1^T (second pair optional: K1 = 0); columns n >= n_split are written to C1
+// (at column n - n_split), so P_l and P_r come out of one pass over X.
+int launch_gemm_tc_tn2(const float* A0, int64_t lda0, const float* B0, int64_t ldb0, int K0, const float* A1,
+                       int64_t lda1, const float* B1, int64_t ldb1, int K1, float* C0, float* C1, int n_split,
+                       int64_t ldc, int M, int N, bool accumulate, cudaStream_t st);
 // C[M][N] (ldc) += A[K][M]^T (lda) * B[K][N] (ldb): contraction over the (huge) node dimension K.
 int launch_gemm_tc_atb(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                        int64_t K, float* ws, size_t ws_bytes, cudaStream_t st);

@@ -22,7 +22,8 @@ EXPORTS = [
     "gatx_set_features", "gatx_set_labels", "gatx_graph_info", "gatx_partition_rows", "gatx_init_params",
     "gatx_set_params", "gatx_set_wo", "gatx_forward", "gatx_loss_acc", "gatx_backward", "gatx_step",
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
-    "gatx_get_timing", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_comm_unique_id", "gatx_comm_init",
+    "gatx_get_timing", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_op_gemm",
+    "gatx_comm_unique_id", "gatx_comm_init",
 ]
 
 
@@ -90,6 +91,23 @@ def partition_rows(row_ptr, world):
     if rc:
         raise GatxError("gatx_partition_rows failed: %d" % rc)
     return b
+
+
+def op_gemm(A, B, form=0, mode=GEMM_TF32_TC):
+    """form 0: A[M][K] @ B[N][K].T ; form 1: A[K][M].T @ B[K][N] -- through the engine's GEMM kernels."""
+    A, B = np.ascontiguousarray(A, np.float32), np.ascontiguousarray(B, np.float32)
+    if form == 0:
+        (M, K), N = A.shape, B.shape[0]
+    else:
+        (K, M), N = A.shape, B.shape[1]
+    Cm = np.zeros((M, N), np.float32)
+    lib = load()
+    lib.gatx_op_gemm.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_int64, C.c_int32, C.c_int32, C.c_int64]
+    rc = lib.gatx_op_gemm(mode, form, A.ctypes.data, A.shape[1], B.ctypes.data, B.shape[1], Cm.ctypes.data, N, M, N, K)
+    if rc:
+        raise GatxError("gatx_op_gemm failed: %d" % rc)
+    return Cm
 
 
 def comm_unique_id():

@@ -155,6 +155,13 @@ int64_t gatx_launch_count(const gatx_ctx* ctx);
 /* Algorithmic bytes of the fused edge forward / backward of one layer (SURVEY 8d formulas). */
 int gatx_edge_bytes(gatx_ctx* ctx, int32_t layer, double* fwd_bytes, double* bwd_bytes);
 
+/* ---- op-level entry point (per-kernel parity tests, ncu) ---------------------------------- */
+/* Dense contraction on host buffers with the engine's GEMM kernels (mode = GATX_GEMM_*):
+ *   form 0: C[M][N] = A[M][K] B[N][K]^T      (projection W x of EB:303-316, input gradient EB:859-869)
+ *   form 1: C[M][N] = A[K][M]^T B[K][N]      (weight gradient of EB:771-782, contraction over nodes) */
+int gatx_op_gemm(int32_t mode, int32_t form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                 int64_t ldc, int32_t M, int32_t N, int64_t K);
+
 /* ---- multi-GPU (one context per rank, NCCL over NVLink) --------------------------------- */
 /* 128-byte NCCL unique id made on rank 0, distributed by the caller (torchrun store, MPI, file) */
 int gatx_comm_unique_id(void* out128);
