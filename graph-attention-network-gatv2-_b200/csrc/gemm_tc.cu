@@ -108,14 +108,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
-// layout type in [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout type in [61,64) (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6), a/b format TF32 = 2 at
@@ -241,7 +242,7 @@ gemm_tf32_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         Cb = C1;
         ccol = col - n_split;
       }
-      if (col < N) {
+      if (col < N && c0 + lane < BN) {
 #pragma unroll 4
         for (int r = 0; r < 32; ++r) {
           const int row = m0 + q * 32 + r;
@@ -283,7 +284,8 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [rows][cols] with row pitch ld (elements); box = box_cols x box_rows, 128B swizzle
-bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16 || rows <= 0 || cols <= 0) return false;
@@ -292,7 +294,7 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -319,6 +321,189 @@ int pick_bn(int N, int n_split) {
     if (bn == 16 || N >= bn || N > bn / 2) return bn;
   }
   return -1;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// C[m][n] += sum_k A[k][m] B[k][n]: both operands are MN-major (the contraction index k -- the node id --
+// is the slow index in memory).  TMA boxes of 32 floats (one 128-byte swizzle span along m / n) x 32 rows
+// (k) are laid down slab by slab.  For 32-bit MN-major operands tcgen05 accepts only the SWIZZLE_128B_BASE32B
+// layout (32-byte chunks XOR-ed with the row index mod 4; TMA mode SWIZZLE_128B_ATOM_32B): k-groups of 4 rows are
+// 512 B apart (SBO), 32-float slabs are 32 rows * 128 B apart (LBO), and one UMMA (K = 8) spans two k-groups.  The node dimension is split across
+// CTAs (split-K); partial tiles go to a workspace and are added in a fixed order (deterministic).
+constexpr int BKN = 32;  // nodes per k-block
+
+template <int BN>
+struct AtbSmem {
+  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int kSlabBytes = BKN * 128;
+  static constexpr int kABytes = (BM / 32) * kSlabBytes, kBBytes = (BN / 32) * kSlabBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBytes = 1024 + kStages * kStageBytes + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads)
+gemm_tf32_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t K,
+                     int kb_per_split, float* __restrict__ out, int64_t ld_out, int64_t split_stride, int M, int N,
+                     int n_tiles_n, int accumulate) {
+  using S = AtbSmem<BN>;
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  float* staging = reinterpret_cast<float*>(smem);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x % n_tiles_n) * BN, m0 = (blockIdx.x / n_tiles_n) * BM;
+  const int total_kb = (int)((K + BKN - 1) / BKN);
+  const int kb_begin = blockIdx.y * kb_per_split;
+  int num_kb = total_kb - kb_begin;
+  if (num_kb > kb_per_split) num_kb = kb_per_split;
+  if (num_kb < 0) num_kb = 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S::kStages;
+        const uint32_t ph = (kb / S::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = tiles + s * S::kStageBytes;
+        uint8_t* b_dst = a_dst + S::kABytes;
+        const int krow = (kb_begin + kb) * BKN;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < BM / 32; ++j) tma_load_2d(&tmA, &full_bar[s], a_dst + j * S::kSlabBytes, m0 + 32 * j, krow);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, &full_bar[s], b_dst + j * S::kSlabBytes, n0 + 32 * j, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 1, 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S::kStages;
+        const uint32_t ph = (kb / S::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+        for (int kg = 0; kg < BKN / UMMA_K; ++kg) {
+          const uint64_t da = make_smem_desc(a_addr + kg * 1024, S::kSlabBytes, 512, 1);
+          const uint64_t db = make_smem_desc(b_addr + kg * 1024, S::kSlabBytes, 512, 1);
+          umma_tf32(tmem_base, da, db, idesc, (kb | kg) != 0);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    float* st = staging + (warp - 2) * 32 * 33;
+    float* dst = out + (int64_t)blockIdx.y * split_stride;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int col = n0 + c0 + lane;
+      if (col < N && c0 + lane < BN) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int row = m0 + q * 32 + r;
+          if (row < M) {
+            float* p = dst + (int64_t)row * ld_out + col;
+            const float val = st[r * 33 + lane];
+            *p = accumulate ? *p + val : val;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+__global__ void atb_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float* __restrict__ C,
+                                  int64_t ldc) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * total + i];  // fixed order
+    C[(i / N) * ldc + (i % N)] += s;
+  }
+}
+
+template <int BN>
+int launch_atb(const CUtensorMap& a, const CUtensorMap& b, int64_t K, float* C, int64_t ldc, int M, int N, float* ws,
+               size_t ws_bytes, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tf32_atb_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             AtbSmem<BN>::kBytes) != cudaSuccess)
+      return -1;
+    configured = true;
+  }
+  const int tn = (N + BN - 1) / BN, tm = (M + BM - 1) / BM, tiles = tn * tm;
+  const int total_kb = (int)((K + BKN - 1) / BKN);
+  int splits = (kNumSMs + tiles - 1) / tiles;
+  if (splits > total_kb) splits = total_kb;
+  const size_t per = sizeof(float) * (size_t)M * N;
+  if (splits > 1 && (!ws || per * splits > ws_bytes)) splits = ws ? (int)(ws_bytes / per) : 1;
+  if (splits < 1) splits = 1;
+  int kbps = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kbps - 1) / kbps;
+  dim3 grid(tiles, splits);
+  if (splits == 1) {
+    gemm_tf32_atb_kernel<BN><<<grid, kThreads, AtbSmem<BN>::kBytes, st>>>(a, b, K, kbps, C, ldc, 0, M, N, tn, 1);
+    return 1;
+  }
+  gemm_tf32_atb_kernel<BN><<<grid, kThreads, AtbSmem<BN>::kBytes, st>>>(a, b, K, kbps, ws, N, (int64_t)M * N, M, N, tn,
+                                                                        0);
+  const int64_t total = (int64_t)M * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  atb_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, M, N, C, ldc);
+  return 2;
 }
 
 }  // namespace
@@ -351,9 +536,19 @@ int launch_gemm_tc_tn(const float* A, int64_t lda, const float* B, int64_t ldb, 
   return launch_gemm_tc_tn2(A, lda, B, ldb, K, nullptr, 0, nullptr, 0, 0, C, C, N, ldc, M, N, accumulate, st);
 }
 
-int launch_gemm_tc_atb(const float*, int64_t, const float*, int64_t, float*, int64_t, int, int, int64_t, float*,
-                       size_t, cudaStream_t) {
-  return -1;  // MN-major split-K kernel: see below (not enabled yet)
+int launch_gemm_tc_atb(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                       int64_t K, float* ws, size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  CUtensorMap a, b;
+  if (!make_map(&a, A, K, M, lda, 32, BKN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&b, B, K, N, ldb, 32, BKN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    return -1;
+  switch (bn) {
+    case 256: return launch_atb<256>(a, b, K, C, ldc, M, N, ws, ws_bytes, st);
+    case 128: return launch_atb<128>(a, b, K, C, ldc, M, N, ws, ws_bytes, st);
+    default: return launch_atb<64>(a, b, K, C, ldc, M, N, ws, ws_bytes, st);
+  }
 }
 
 }  // namespace gatx
