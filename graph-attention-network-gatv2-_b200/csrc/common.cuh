@@ -54,6 +54,10 @@ struct EdgeGraph {
   const int* heavy_rows; int n_heavy_rows;   // destination rows with degree > kHeavyDeg
   const int* heavy_srcs; int n_heavy_srcs;   // sources with out-degree > kHeavyDeg
   int64_t E;
+  // edge-balanced chunks (edge_stream.cu): chunk c = edges [c*chunk_T, (c+1)*chunk_T)
+  int chunk_T, n_chunks;
+  const int* chunk_row;  // [n_chunks] destination row containing edge c*chunk_T
+  const int* chunk_src;  // [n_chunks] source row containing transposed position c*chunk_T
 };
 constexpr int kHeavyDeg = 1024;
 bool edge_shape_supported(int H, int D);
@@ -79,6 +83,19 @@ int launch_alpha_from_score(const float* score, const int* coo_dst, const float*
                             int H, float* alpha, cudaStream_t st);
 int launch_head_mean(const float* Hfull, int N, int H, int D, float* Hout, cudaStream_t st);
 int launch_head_bcast_grad(const float* gHout, int N, int H, int D, float* gHfull, cudaStream_t st);
+
+// edge_stream.cu : edge-balanced streaming kernels (bulk-async-copy ring) for rows of 128/256/512 floats
+bool edge_stream_supported(int H, int D);
+int64_t edge_stream_part_floats(int H, int D, int n_chunks);
+int launch_chunk_rows(const int* row_ptr, int n_rows, int64_t E, int T, int n_chunks, int* chunk_row, cudaStream_t st);
+int launch_edge_forward_stream(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
+                               float* Hout, float* hpre, float* score, float* mx, float* sinv, float* part,
+                               cudaStream_t st);
+// prep (g_h in place + cdot) + pass 1 (gPr, rec, ga partials) + pass 2 (gPl)
+int launch_edge_backward_stream(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
+                                const float* Hout, float* gH, float* cdot, const float* score, const float* mx,
+                                const float* sinv, float* gPr, float* gPl, uint32_t* rec, float* part,
+                                float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st);
 
 // head_loss.cu : classifier + softmax + CE + argmax + output gradients (EB:463-608)
 constexpr int kHeadBlocks = kNumSMs * 2;

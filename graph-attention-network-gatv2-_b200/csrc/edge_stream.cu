@@ -1,0 +1,846 @@
+// Edge-balanced streaming versions of the fused edge passes for feature rows of >= 128 floats.
+//
+// The CSR edge array is cut into chunks of T consecutive edges; one warp owns one chunk at a time
+// (grid-stride, static assignment -> deterministic) and streams it:
+//   * the gathered rows (P_l[src] forward / pass 1, g_h[dst] + the per-edge record in pass 2) are fetched
+//     with 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) into a per-warp shared-memory ring of R
+//     slots, completion tracked by one mbarrier per slot -- R rows are always in flight per warp without
+//     holding them in registers;
+//   * destination rows are segments of the chunk; a segment that covers its whole row is finalised in
+//     place, a segment of a row that straddles a chunk boundary writes its partial state to a side buffer
+//     and a fix-up kernel merges the pieces in chunk order.
+// Every warp processes the same number of edges regardless of the degree distribution, so power-law hubs
+// need no special casing, and there are no atomics anywhere.
+//
+// Same math and reference citations as edge_kernels.cu (which keeps the narrow-row shapes).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace gatx {
+namespace {
+
+constexpr int kSW = 4;  // warps per CTA
+
+struct Shape {
+  int H, D, F, lph, lg_lph;
+};
+
+struct StreamGraph {
+  int E, T, n_chunks, n_rows;
+  const int* row_ptr;    // [n_rows + 1]
+  const int* chunk_row;  // [n_chunks] row that contains edge c*T
+};
+
+__device__ __forceinline__ float head_reduce(float p, int lph) {
+  for (int off = lph >> 1; off > 0; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+  return p;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int NV>
+__device__ __forceinline__ void load_row(float4 (&x)[NV], const float* __restrict__ base, int row, int lane) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) x[j] = ldg4(base + (int64_t)row * (NV * 128) + 4 * (lane + 32 * j));
+}
+
+// Partial-state slots: [chunk][2][PF] floats.  Slot 0: the segment that starts at the first edge of the chunk,
+// slot 1: a segment that starts later and runs past the end of the chunk.
+template <int NV>
+struct FwdState {
+  float m[NV], s[NV];
+  float4 acc[NV];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      m[j] = -1e9f;  // EB:336
+      s[j] = 0.f;
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ __forceinline__ void merge(int j, float m2, float s2, float4 a2) {
+    const float mn = fmaxf(m[j], m2);
+    const float c1 = __expf(m[j] - mn), c2 = __expf(m2 - mn);
+    s[j] = s[j] * c1 + s2 * c2;
+    acc[j].x = acc[j].x * c1 + a2.x * c2;
+    acc[j].y = acc[j].y * c1 + a2.y * c2;
+    acc[j].z = acc[j].z * c1 + a2.z * c2;
+    acc[j].w = acc[j].w * c1 + a2.w * c2;
+    m[j] = mn;
+  }
+};
+template <int NV>
+constexpr int fwd_part_floats() { return NV * 128 + 2 * NV * 32; }
+
+template <int NV>
+__device__ __forceinline__ void fwd_store_partial(const FwdState<NV>& st, float* __restrict__ p, int lane) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    st4(p + 4 * (lane + 32 * j), st.acc[j]);
+    p[NV * 128 + j * 32 + lane] = st.m[j];
+    p[NV * 128 + NV * 32 + j * 32 + lane] = st.s[j];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, const Shape sh, float* __restrict__ Hout,
+                                             float* __restrict__ hpre, float* __restrict__ mx,
+                                             float* __restrict__ sinv, int lane) {
+  const bool head_lane = (lane & (sh.lph - 1)) == 0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float inv = 1.0f / (st.s[j] + 1e-8f);  // EB:379
+    const float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
+    const int64_t off = (int64_t)row * sh.F + 4 * (lane + 32 * j);
+    if (hpre) st4(hpre + off, h);
+    st4(Hout + off, make_float4(lrelu(h.x), lrelu(h.y), lrelu(h.z), lrelu(h.w)));  // EB:440-457
+    if (head_lane) {
+      const int hd = (lane + 32 * j) >> sh.lg_lph;
+      mx[(int64_t)row * sh.H + hd] = st.m[j];
+      sinv[(int64_t)row * sh.H + hd] = inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <int NV, int R>
+__global__ void __launch_bounds__(kSW * 32)
+edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const float* __restrict__ Pl,
+                       const float* __restrict__ Pr, const float* __restrict__ a, Shape sh, float* __restrict__ Hout,
+                       float* __restrict__ hpre, float* __restrict__ score, float* __restrict__ mx,
+                       float* __restrict__ sinv, float* __restrict__ part) {
+  constexpr int F = NV * 128;
+  constexpr uint32_t kRowBytes = F * 4;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * R * F;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kSW * R * F * 4) + warp * R;
+  if (lane == 0) {
+    for (int s = 0; s < R; ++s) mbar_init(&bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  float4 av[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) av[j] = ldg4(a + 4 * (lane + 32 * j));
+  const bool head_lane = (lane & (sh.lph - 1)) == 0;
+  const int total_warps = gridDim.x * kSW;
+  uint32_t it = 0;  // ring position: edges consumed by this warp so far
+  for (int chunk = blockIdx.x * kSW + warp; chunk < g.n_chunks; chunk += total_warps) {
+    const int e0 = chunk * g.T;
+    const int e1 = min(g.E, e0 + g.T);
+    const int n = e1 - e0;
+    int r = __ldg(g.chunk_row + chunk);
+    const bool started_before = __ldg(g.row_ptr + r) < e0;
+    int row_end = __ldg(g.row_ptr + r + 1);
+    int idx_cur = lane < n ? __ldg(col_idx + e0 + lane) : 0;
+    int idx_nxt = 32 + lane < n ? __ldg(col_idx + e0 + 32 + lane) : 0;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      const int src = __shfl_sync(0xffffffffu, idx_cur, s);
+      if (s < n && lane == 0) {
+        const uint32_t slot = (it + s) % R;
+        mbar_expect_tx(&bar[slot], kRowBytes);
+        bulk_g2s(ring + slot * F, Pl + (int64_t)src * F, kRowBytes, &bar[slot]);
+      }
+    }
+    float4 pr[NV], pr_n[NV];
+    load_row<NV>(pr, Pr, r, lane);
+    int next_end = 0x7fffffff;
+    if (r + 1 < g.n_rows) {
+      load_row<NV>(pr_n, Pr, r + 1, lane);
+      next_end = __ldg(g.row_ptr + r + 2);
+    }
+    FwdState<NV> st;
+    st.init();
+    bool first_row = true;
+    for (int i = 0; i < n; ++i) {
+      const int e = e0 + i;
+      while (e >= row_end) {  // warp-uniform: the current row ended inside this chunk
+        if (first_row && started_before)
+          fwd_store_partial<NV>(st, part + ((int64_t)chunk * 2 + 0) * fwd_part_floats<NV>(), lane);
+        else if (e > e0 || !first_row)
+          fwd_finalize<NV>(st, r, sh, Hout, hpre, mx, sinv, lane);
+        first_row = false;
+        ++r;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) pr[j] = pr_n[j];
+        row_end = next_end;
+        next_end = 0x7fffffff;
+        if (r + 1 < g.n_rows) {
+          load_row<NV>(pr_n, Pr, r + 1, lane);
+          next_end = __ldg(g.row_ptr + r + 2);
+        }
+        st.init();
+      }
+      if ((i & 31) == 0 && i > 0) {
+        idx_cur = idx_nxt;
+        const int p = i + 32 + lane;
+        idx_nxt = p < n ? __ldg(col_idx + e0 + p) : 0;
+      }
+      const uint32_t pos = it + i, slot = pos % R, ph = (pos / R) & 1;
+      mbar_wait(&bar[slot], ph);
+      float4 v[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + 4 * (lane + 32 * j));
+      __syncwarp();  // every lane has read the slot before it is refilled
+      {
+        const int ni = i + R;
+        const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
+        if (ni < n && lane == 0) {
+          mbar_expect_tx(&bar[slot], kRowBytes);
+          bulk_g2s(ring + slot * F, Pl + (int64_t)srcn * F, kRowBytes, &bar[slot]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float p = av[j].x * lrelu(v[j].x + pr[j].x) + av[j].y * lrelu(v[j].y + pr[j].y) +
+                  av[j].z * lrelu(v[j].z + pr[j].z) + av[j].w * lrelu(v[j].w + pr[j].w);  // EB:303-320
+        p = head_reduce(p, sh.lph);
+        if (head_lane) score[(int64_t)e * sh.H + ((lane + 32 * j) >> sh.lg_lph)] = p;
+        const float mn = fmaxf(st.m[j], p);
+        const float corr = __expf(st.m[j] - mn), w = __expf(p - mn);  // online form of EB:336-349
+        st.s[j] = st.s[j] * corr + w;
+        st.acc[j].x = st.acc[j].x * corr + w * v[j].x;  // EB:415-422 without atomics
+        st.acc[j].y = st.acc[j].y * corr + w * v[j].y;
+        st.acc[j].z = st.acc[j].z * corr + w * v[j].z;
+        st.acc[j].w = st.acc[j].w * corr + w * v[j].w;
+        st.m[j] = mn;
+      }
+    }
+    // the segment that reaches the end of the chunk
+    {
+      const bool ended = row_end == e1;
+      const bool from_start = first_row;  // segment began at e0
+      const bool complete = ended && !(first_row && started_before);
+      if (complete)
+        fwd_finalize<NV>(st, r, sh, Hout, hpre, mx, sinv, lane);
+      else
+        fwd_store_partial<NV>(st, part + ((int64_t)chunk * 2 + (from_start ? 0 : 1)) * fwd_part_floats<NV>(), lane);
+    }
+    it += n;
+  }
+}
+
+// One warp per chunk boundary: if a row straddles the boundary and this is the first boundary it crosses,
+// merge all its pieces (chunk order) and finalise it.
+template <int NV>
+__global__ void __launch_bounds__(kSW * 32)
+edge_fwd_fixup_kernel(StreamGraph g, Shape sh, const float* __restrict__ part, float* __restrict__ Hout,
+                      float* __restrict__ hpre, float* __restrict__ mx, float* __restrict__ sinv) {
+  const int c = blockIdx.x * kSW + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= g.n_chunks - 1) return;
+  const int b = (c + 1) * g.T;
+  const int rr = __ldg(g.chunk_row + c + 1);
+  const int rs = __ldg(g.row_ptr + rr);
+  if (rs >= b || rs < c * g.T) return;
+  const int c_last = (__ldg(g.row_ptr + rr + 1) - 1) / g.T;
+  constexpr int PF = fwd_part_floats<NV>();
+  FwdState<NV> st;
+  {
+    const float* p = part + ((int64_t)c * 2 + (rs == c * g.T ? 0 : 1)) * PF;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      st.acc[j] = lds4(p + 4 * (lane + 32 * j));
+      st.m[j] = p[NV * 128 + j * 32 + lane];
+      st.s[j] = p[NV * 128 + NV * 32 + j * 32 + lane];
+    }
+  }
+  for (int cc = c + 1; cc <= c_last; ++cc) {
+    const float* p = part + ((int64_t)cc * 2 + 0) * PF;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      st.merge(j, p[NV * 128 + j * 32 + lane], p[NV * 128 + NV * 32 + j * 32 + lane], lds4(p + 4 * (lane + 32 * j)));
+  }
+  fwd_finalize<NV>(st, rr, sh, Hout, hpre, mx, sinv, lane);
+}
+
+// rows without any edge: h = 0, m = -1e9, 1/(s+eps) = 1e8
+__global__ void fill_empty_fwd_kernel(const int* __restrict__ row_ptr, int n_rows, int F, int H,
+                                      float* __restrict__ Hout, float* __restrict__ hpre, float* __restrict__ mx,
+                                      float* __restrict__ sinv) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows || row_ptr[r + 1] != row_ptr[r]) return;
+  for (int k = 0; k < F; ++k) {
+    Hout[(int64_t)r * F + k] = 0.f;
+    if (hpre) hpre[(int64_t)r * F + k] = 0.f;
+  }
+  for (int h = 0; h < H; ++h) {
+    mx[(int64_t)r * H + h] = -1e9f;
+    sinv[(int64_t)r * H + h] = 1e8f;
+  }
+}
+__global__ void fill_empty_rows_kernel(const int* __restrict__ row_ptr, int n_rows, int F, float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows || row_ptr[r + 1] != row_ptr[r]) return;
+  for (int k = 0; k < F; ++k) out[(int64_t)r * F + k] = 0.f;
+}
+
+// ------------------------------------------------------------------------- backward, preparation
+// Node-wise: g_h = gH * LReLU'(h) in place (EB:879-893 / EB:599; LReLU'(h) has the sign of LReLU(h)) and
+// cdot[row][h] = gH . Hout = sum over the row's edges of alpha * galpha (the softmax-backward segment sum).
+template <int NV>
+__global__ void __launch_bounds__(256)
+edge_bwd_prep_kernel(int n_rows, Shape sh, const float* __restrict__ Hout, float* __restrict__ gH,
+                     float* __restrict__ cdot) {
+  const int lane = threadIdx.x & 31;
+  const bool head_lane = (lane & (sh.lph - 1)) == 0;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 8) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int64_t off = (int64_t)row * sh.F + 4 * (lane + 32 * j);
+      const float4 g = *reinterpret_cast<const float4*>(gH + off);
+      const float4 ho = ldg4(Hout + off);
+      const float c = head_reduce(dot4(g, ho), sh.lph);
+      st4(gH + off, make_float4(g.x * lrelu_grad(ho.x), g.y * lrelu_grad(ho.y), g.z * lrelu_grad(ho.z),
+                                g.w * lrelu_grad(ho.w)));
+      if (head_lane) cdot[(int64_t)row * sh.H + ((lane + 32 * j) >> sh.lg_lph)] = c;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- backward, pass 1
+__host__ __device__ inline int rec_words(int H, int NV) { return (4 * NV + 2 * H + 3) / 4 * 4; }
+
+template <int NV>
+struct RowScalars {
+  float c[NV], m[NV], inv[NV];
+};
+template <int NV>
+__device__ __forceinline__ void load_scalars(RowScalars<NV>& q, int row, const Shape sh, const float* __restrict__ cdot,
+                                             const float* __restrict__ mx, const float* __restrict__ sinv, int lane) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int64_t o = (int64_t)row * sh.H + ((lane + 32 * j) >> sh.lg_lph);
+    q.c[j] = __ldg(cdot + o);
+    q.m[j] = __ldg(mx + o);
+    q.inv[j] = __ldg(sinv + o);
+  }
+}
+
+// smem per warp: ring [R][F] | rowbuf [2][2F] (g_h row, P_r row) | score window [2][32*H] | barriers [R + 2]
+template <int NV, int R>
+__global__ void __launch_bounds__(kSW * 32)
+edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const float* __restrict__ Pl,
+                           const float* __restrict__ Pr, const float* __restrict__ a, Shape sh,
+                           const float* __restrict__ gh, const float* __restrict__ cdot,
+                           const float* __restrict__ score, const float* __restrict__ mx,
+                           const float* __restrict__ sinv, float* __restrict__ gPr, uint32_t* __restrict__ rec,
+                           float* __restrict__ part, float* __restrict__ ga_partials, float* __restrict__ galpha_dbg,
+                           int max_h) {
+  constexpr int F = NV * 128;
+  constexpr uint32_t kRowBytes = F * 4;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp_floats = R * F + 4 * F + 2 * 32 * max_h;
+  float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * per_warp_floats;
+  float* ring = wbase;
+  float* rowbuf = wbase + R * F;        // [2][2F]
+  float* scwin = rowbuf + 4 * F;        // [2][32*H]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kSW * per_warp_floats * 4) + warp * (R + 2);
+  uint64_t* rbar = bar + R;
+  if (lane == 0) {
+    for (int s = 0; s < R + 2; ++s) mbar_init(&bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  float4 av[NV], ga[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    av[j] = ldg4(a + 4 * (lane + 32 * j));
+    ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int RW = rec_words(sh.H, NV);
+  const bool head_lane = (lane & (sh.lph - 1)) == 0;
+  const int total_warps = gridDim.x * kSW;
+  const int H = sh.H;
+  uint32_t it = 0;   // ring position
+  uint32_t rk = 0;   // row-buffer position: row loads issued so far
+  for (int chunk = blockIdx.x * kSW + warp; chunk < g.n_chunks; chunk += total_warps) {
+    const int e0 = chunk * g.T;
+    const int e1 = min(g.E, e0 + g.T);
+    const int n = e1 - e0;
+    int r = __ldg(g.chunk_row + chunk);
+    const bool started_before = __ldg(g.row_ptr + r) < e0;
+    int row_end = __ldg(g.row_ptr + r + 1);
+    int idx_cur = lane < n ? __ldg(col_idx + e0 + lane) : 0;
+    int idx_nxt = 32 + lane < n ? __ldg(col_idx + e0 + 32 + lane) : 0;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      const int src = __shfl_sync(0xffffffffu, idx_cur, s);
+      if (s < n && lane == 0) {
+        const uint32_t slot = (it + s) % R;
+        mbar_expect_tx(&bar[slot], kRowBytes);
+        bulk_g2s(ring + slot * F, Pl + (int64_t)src * F, kRowBytes, &bar[slot]);
+      }
+    }
+    // row data of r (now) and r + 1 (prefetch) through the row buffers
+    if (lane == 0) {
+      const uint32_t b0 = rk & 1;
+      mbar_expect_tx(&rbar[b0], 2 * kRowBytes);
+      bulk_g2s(rowbuf + b0 * 2 * F, gh + (int64_t)r * F, kRowBytes, &rbar[b0]);
+      bulk_g2s(rowbuf + b0 * 2 * F + F, Pr + (int64_t)r * F, kRowBytes, &rbar[b0]);
+      if (r + 1 < g.n_rows) {
+        const uint32_t b1 = (rk + 1) & 1;
+        mbar_expect_tx(&rbar[b1], 2 * kRowBytes);
+        bulk_g2s(rowbuf + b1 * 2 * F, gh + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
+        bulk_g2s(rowbuf + b1 * 2 * F + F, Pr + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
+      }
+    }
+    // score window: the scores of 32 consecutive edges are contiguous ([E][H]); the next window is
+    // prefetched into registers while the current one is consumed from shared memory
+    float scp[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < H) {
+        const int t = lane + 32 * k;
+        scwin[t] = (t < n * H) ? __ldg(score + (int64_t)e0 * H + t) : 0.f;
+      }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = 32 * H + lane + 32 * k;
+      scp[k] = (k < H && t < n * H) ? __ldg(score + (int64_t)e0 * H + t) : 0.f;
+    }
+    RowScalars<NV> q, qn;
+    load_scalars<NV>(q, r, sh, cdot, mx, sinv, lane);
+    int next_end = 0x7fffffff;
+    if (r + 1 < g.n_rows) {
+      load_scalars<NV>(qn, r + 1, sh, cdot, mx, sinv, lane);
+      next_end = __ldg(g.row_ptr + r + 2);
+    }
+    float4 ghr[NV], pr[NV], gpr[NV];
+    mbar_wait(&rbar[rk & 1], (rk >> 1) & 1);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      ghr[j] = lds4(rowbuf + (rk & 1) * 2 * F + 4 * (lane + 32 * j));
+      pr[j] = lds4(rowbuf + (rk & 1) * 2 * F + F + 4 * (lane + 32 * j));
+      gpr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    bool first_row = true;
+    for (int i = 0; i < n; ++i) {
+      const int e = e0 + i;
+      while (e >= row_end) {
+        // finish row r: gP_r[r] (EB:781 summed over the row) complete or partial
+        float* dst = (first_row && started_before) ? part + ((int64_t)chunk * 2 + 0) * F : gPr + (int64_t)r * F;
+        if (e > e0 || !first_row) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) st4(dst + 4 * (lane + 32 * j), gpr[j]);
+        }
+        first_row = false;
+        ++r;
+        ++rk;
+        q = qn;
+        row_end = next_end;
+        next_end = 0x7fffffff;
+        // the prefetched row r is in buffer rk & 1; refill the other buffer with row r + 1
+        mbar_wait(&rbar[rk & 1], (rk >> 1) & 1);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          ghr[j] = lds4(rowbuf + (rk & 1) * 2 * F + 4 * (lane + 32 * j));
+          pr[j] = lds4(rowbuf + (rk & 1) * 2 * F + F + 4 * (lane + 32 * j));
+          gpr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (r + 1 < g.n_rows) {
+          if (lane == 0) {
+            const uint32_t b1 = (rk + 1) & 1;
+            mbar_expect_tx(&rbar[b1], 2 * kRowBytes);
+            bulk_g2s(rowbuf + b1 * 2 * F, gh + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
+            bulk_g2s(rowbuf + b1 * 2 * F + F, Pr + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
+          }
+          load_scalars<NV>(qn, r + 1, sh, cdot, mx, sinv, lane);
+          next_end = __ldg(g.row_ptr + r + 2);
+        }
+      }
+      if ((i & 31) == 0 && i > 0) {
+        idx_cur = idx_nxt;
+        const int p = i + 32 + lane;
+        idx_nxt = p < n ? __ldg(col_idx + e0 + p) : 0;
+        float* w = scwin + ((i >> 5) & 1) * 32 * H;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < H) w[lane + 32 * k] = scp[k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int t = (i + 32) * H + lane + 32 * k;
+          scp[k] = (k < H && t < n * H) ? __ldg(score + (int64_t)e0 * H + t) : 0.f;
+        }
+      }
+      const uint32_t pos = it + i, slot = pos % R, ph = (pos / R) & 1;
+      mbar_wait(&bar[slot], ph);
+      float4 v[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + 4 * (lane + 32 * j));
+      __syncwarp();
+      {
+        const int ni = i + R;
+        const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
+        if (ni < n && lane == 0) {
+          mbar_expect_tx(&bar[slot], kRowBytes);
+          bulk_g2s(ring + slot * F, Pl + (int64_t)srcn * F, kRowBytes, &bar[slot]);
+        }
+      }
+      const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
+      uint32_t* re = rec + (int64_t)e * RW;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int hd = (lane + 32 * j) >> sh.lg_lph;
+        const float galpha = head_reduce(dot4(ghr[j], v[j]), sh.lph);  // EB:636-646
+        const float alpha = __expf(sc[hd] - q.m[j]) * q.inv[j];        // EB:378-379
+        const float ge = alpha * (galpha - q.c[j]);                    // EB:689-690 in closed form
+        const float sx = v[j].x + pr[j].x, sy = v[j].y + pr[j].y, sz = v[j].z + pr[j].z, sw = v[j].w + pr[j].w;
+        ga[j].x += ge * lrelu(sx); ga[j].y += ge * lrelu(sy);  // EB:769
+        ga[j].z += ge * lrelu(sz); ga[j].w += ge * lrelu(sw);
+        gpr[j].x += ge * av[j].x * lrelu_grad(sx); gpr[j].y += ge * av[j].y * lrelu_grad(sy);  // EB:774-781
+        gpr[j].z += ge * av[j].z * lrelu_grad(sz); gpr[j].w += ge * av[j].w * lrelu_grad(sw);
+        const uint32_t bx = __ballot_sync(0xffffffffu, sx > 0.f), by = __ballot_sync(0xffffffffu, sy > 0.f),
+                       bz = __ballot_sync(0xffffffffu, sz > 0.f), bw = __ballot_sync(0xffffffffu, sw > 0.f);
+        if (lane == 0) *reinterpret_cast<uint4*>(re + 4 * j) = make_uint4(bx, by, bz, bw);
+        if (head_lane) {
+          re[4 * NV + hd] = __float_as_uint(alpha);
+          re[4 * NV + H + hd] = __float_as_uint(ge);
+          if (galpha_dbg) galpha_dbg[(int64_t)e * H + hd] = galpha;
+        }
+      }
+    }
+    {
+      const bool ended = row_end == e1;
+      const bool complete = ended && !(first_row && started_before);
+      float* dst = complete ? gPr + (int64_t)r * F : part + ((int64_t)chunk * 2 + (first_row ? 0 : 1)) * F;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) st4(dst + 4 * (lane + 32 * j), gpr[j]);
+    }
+    it += n;
+    // the row-buffer pipeline restarts at the next chunk: drain the outstanding prefetch of row r + 1
+    if (r + 1 < g.n_rows) {
+      mbar_wait(&rbar[(rk + 1) & 1], ((rk + 1) >> 1) & 1);
+      rk += 2;
+    } else {
+      rk += 1;
+    }
+    __syncwarp();
+  }
+  // deterministic block sum of the per-warp ga accumulators
+  __syncthreads();
+  float4* sm = reinterpret_cast<float4*>(smem_raw);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) sm[warp * (NV * 32) + lane + 32 * j] = ga[j];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float4 t = sm[lane + 32 * j];
+      for (int w = 1; w < kSW; ++w) {
+        const float4 o = sm[w * (NV * 32) + lane + 32 * j];
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      }
+      st4(ga_partials + (int64_t)blockIdx.x * F + 4 * (lane + 32 * j), t);
+    }
+  }
+}
+
+// sums the pieces of a row that straddles chunk boundaries (pass 1: gP_r, pass 2: gP_l)
+template <int NV>
+__global__ void __launch_bounds__(kSW * 32)
+edge_sum_fixup_kernel(StreamGraph g, const float* __restrict__ part, float* __restrict__ out) {
+  constexpr int F = NV * 128;
+  const int c = blockIdx.x * kSW + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= g.n_chunks - 1) return;
+  const int b = (c + 1) * g.T;
+  const int rr = __ldg(g.chunk_row + c + 1);
+  const int rs = __ldg(g.row_ptr + rr);
+  if (rs >= b || rs < c * g.T) return;
+  const int c_last = (__ldg(g.row_ptr + rr + 1) - 1) / g.T;
+  float4 acc[NV];
+  {
+    const float* p = part + ((int64_t)c * 2 + (rs == c * g.T ? 0 : 1)) * F;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = lds4(p + 4 * (lane + 32 * j));
+  }
+  for (int cc = c + 1; cc <= c_last; ++cc) {
+    const float* p = part + ((int64_t)cc * 2 + 0) * F;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 o = lds4(p + 4 * (lane + 32 * j));
+      acc[j].x += o.x; acc[j].y += o.y; acc[j].z += o.z; acc[j].w += o.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) st4(out + (int64_t)rr * F + 4 * (lane + 32 * j), acc[j]);
+}
+
+// ------------------------------------------------------------------------- backward, pass 2
+// ring slot: [F floats of g_h[dst]] [RW words of the edge record], padded to 32 floats
+template <int NV, int R>
+__global__ void __launch_bounds__(kSW * 32)
+edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const int* __restrict__ csc_eid,
+                           const float* __restrict__ a, Shape sh, const float* __restrict__ gh,
+                           const uint32_t* __restrict__ rec, float* __restrict__ gPl, float* __restrict__ part,
+                           int slot_floats) {
+  constexpr int F = NV * 128;
+  constexpr uint32_t kRowBytes = F * 4;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * R * slot_floats;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kSW * R * slot_floats * 4) + warp * R;
+  if (lane == 0) {
+    for (int s = 0; s < R; ++s) mbar_init(&bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  float4 av[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) av[j] = ldg4(a + 4 * (lane + 32 * j));
+  const int RW = rec_words(sh.H, NV);
+  const uint32_t kRecBytes = RW * 4;
+  const int total_warps = gridDim.x * kSW;
+  uint32_t it = 0;
+  for (int chunk = blockIdx.x * kSW + warp; chunk < g.n_chunks; chunk += total_warps) {
+    const int e0 = chunk * g.T;
+    const int e1 = min(g.E, e0 + g.T);
+    const int n = e1 - e0;
+    int r = __ldg(g.chunk_row + chunk);
+    const bool started_before = __ldg(g.row_ptr + r) < e0;
+    int row_end = __ldg(g.row_ptr + r + 1);
+    int next_end = r + 1 < g.n_rows ? __ldg(g.row_ptr + r + 2) : 0x7fffffff;
+    int dst_cur = lane < n ? __ldg(csc_dst + e0 + lane) : 0, eid_cur = lane < n ? __ldg(csc_eid + e0 + lane) : 0;
+    int dst_nxt = 32 + lane < n ? __ldg(csc_dst + e0 + 32 + lane) : 0;
+    int eid_nxt = 32 + lane < n ? __ldg(csc_eid + e0 + 32 + lane) : 0;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      const int d = __shfl_sync(0xffffffffu, dst_cur, s), ee = __shfl_sync(0xffffffffu, eid_cur, s);
+      if (s < n && lane == 0) {
+        const uint32_t slot = (it + s) % R;
+        mbar_expect_tx(&bar[slot], kRowBytes + kRecBytes);
+        bulk_g2s(ring + slot * slot_floats, gh + (int64_t)d * F, kRowBytes, &bar[slot]);
+        bulk_g2s(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot]);
+      }
+    }
+    float4 acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool first_row = true;
+    for (int i = 0; i < n; ++i) {
+      const int e = e0 + i;
+      while (e >= row_end) {
+        float* dstp = (first_row && started_before) ? part + ((int64_t)chunk * 2 + 0) * F : gPl + (int64_t)r * F;
+        if (e > e0 || !first_row) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) st4(dstp + 4 * (lane + 32 * j), acc[j]);
+        }
+        first_row = false;
+        ++r;
+        row_end = next_end;
+        next_end = r + 1 < g.n_rows ? __ldg(g.row_ptr + r + 2) : 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if ((i & 31) == 0 && i > 0) {
+        dst_cur = dst_nxt;
+        eid_cur = eid_nxt;
+        const int p = i + 32 + lane;
+        dst_nxt = p < n ? __ldg(csc_dst + e0 + p) : 0;
+        eid_nxt = p < n ? __ldg(csc_eid + e0 + p) : 0;
+      }
+      const uint32_t pos = it + i, slot = pos % R, ph = (pos / R) & 1;
+      mbar_wait(&bar[slot], ph);
+      const float* sl = ring + slot * slot_floats;
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(sl + F);
+      float4 gv[NV];
+      uint4 kk[NV];
+      float al[NV], ge[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int hd = (lane + 32 * j) >> sh.lg_lph;
+        gv[j] = lds4(sl + 4 * (lane + 32 * j));
+        kk[j] = *reinterpret_cast<const uint4*>(rw + 4 * j);
+        al[j] = __uint_as_float(rw[4 * NV + hd]);
+        ge[j] = __uint_as_float(rw[4 * NV + sh.H + hd]);
+      }
+      __syncwarp();
+      {
+        const int ni = i + R;
+        const bool same = (ni >> 5) == (i >> 5);
+        const int d = __shfl_sync(0xffffffffu, same ? dst_cur : dst_nxt, ni & 31);
+        const int ee = __shfl_sync(0xffffffffu, same ? eid_cur : eid_nxt, ni & 31);
+        if (ni < n && lane == 0) {
+          mbar_expect_tx(&bar[slot], kRowBytes + kRecBytes);
+          bulk_g2s(ring + slot * slot_floats, gh + (int64_t)d * F, kRowBytes, &bar[slot]);
+          bulk_g2s(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        // EB:865-866: g_h[dst] * alpha + ge * a * LReLU'(s), LReLU'(s) from the recorded sign bit
+        acc[j].x += al[j] * gv[j].x + ge[j] * av[j].x * (((kk[j].x >> lane) & 1u) ? 1.f : kSlope);
+        acc[j].y += al[j] * gv[j].y + ge[j] * av[j].y * (((kk[j].y >> lane) & 1u) ? 1.f : kSlope);
+        acc[j].z += al[j] * gv[j].z + ge[j] * av[j].z * (((kk[j].z >> lane) & 1u) ? 1.f : kSlope);
+        acc[j].w += al[j] * gv[j].w + ge[j] * av[j].w * (((kk[j].w >> lane) & 1u) ? 1.f : kSlope);
+      }
+    }
+    {
+      const bool ended = row_end == e1;
+      const bool complete = ended && !(first_row && started_before);
+      float* dstp = complete ? gPl + (int64_t)r * F : part + ((int64_t)chunk * 2 + (first_row ? 0 : 1)) * F;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) st4(dstp + 4 * (lane + 32 * j), acc[j]);
+    }
+    it += n;
+  }
+}
+
+bool make_stream_shape(int H, int D, Shape* sh, int* nv) {
+  if (H < 1 || D < 4 || D % 4 || D > 128 || H > 8) return false;
+  const int lph = D / 4;
+  if (lph & (lph - 1)) return false;
+  const int F = H * D;
+  if (F % 128) return false;
+  const int NV = F / 128;
+  if (NV != 1 && NV != 2 && NV != 4) return false;
+  int lg = 0;
+  while ((1 << lg) < lph) ++lg;
+  *sh = Shape{H, D, F, lph, lg};
+  *nv = NV;
+  return true;
+}
+
+int stream_grid(const void* kernel, size_t smem, int n_chunks) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSW * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  int blocks = kNumSMs * per_sm;
+  const int need = (n_chunks + kSW - 1) / kSW;
+  return blocks < need ? blocks : need;
+}
+
+template <int NV>
+constexpr int ring_depth() { return NV == 4 ? 8 : (NV == 2 ? 8 : 16); }
+
+#define STREAM_DISPATCH(nv, ...)                       \
+  do {                                                 \
+    if (nv == 4) { constexpr int NV = 4; __VA_ARGS__; } \
+    else if (nv == 2) { constexpr int NV = 2; __VA_ARGS__; } \
+    else { constexpr int NV = 1; __VA_ARGS__; }        \
+  } while (0)
+
+}  // namespace
+
+bool edge_stream_supported(int H, int D) {
+  Shape sh;
+  int nv;
+  return make_stream_shape(H, D, &sh, &nv);
+}
+int64_t edge_stream_part_floats(int H, int D, int n_chunks) {
+  Shape sh;
+  int nv;
+  if (!make_stream_shape(H, D, &sh, &nv)) return 0;
+  return (int64_t)n_chunks * 2 * (sh.F + 2 * nv * 32);
+}
+
+int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* Pl, const float* Pr, const float* a,
+                               float* Hout, float* hpre, float* score, float* mx, float* sinv, float* part,
+                               cudaStream_t st) {
+  Shape sh;
+  int nv, launches = 0;
+  if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
+  if (eg.n_rows <= 0) return 0;
+  fill_empty_fwd_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, sh.F, H, Hout, hpre, mx, sinv);
+  ++launches;
+  if (eg.E == 0) return launches;
+  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
+  STREAM_DISPATCH(nv, {
+    constexpr int R = ring_depth<NV>();
+    const size_t smem = (size_t)kSW * R * NV * 128 * 4 + (size_t)kSW * R * 8;
+    auto kern = edge_fwd_stream_kernel<NV, R>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
+    kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, sh, Hout, hpre, score, mx, sinv, part);
+    ++launches;
+    if (g.n_chunks > 1) {
+      edge_fwd_fixup_kernel<NV><<<(g.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(g, sh, part, Hout, hpre, mx, sinv);
+      ++launches;
+    }
+  });
+  return launches;
+}
+
+int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* Pl, const float* Pr, const float* a,
+                                const float* Hout, float* gH, float* cdot, const float* score, const float* mx,
+                                const float* sinv, float* gPr, float* gPl, uint32_t* rec, float* part,
+                                float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st) {
+  Shape sh;
+  int nv, launches = 0;
+  if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
+  *n_partials = 0;
+  if (eg.n_rows <= 0) return 0;
+  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
+  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src};
+  STREAM_DISPATCH(nv, {
+    constexpr int F = NV * 128;
+    {
+      int blocks = (eg.n_rows + 7) / 8;
+      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+      edge_bwd_prep_kernel<NV><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+      ++launches;
+    }
+    fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);
+    fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
+    launches += 2;
+    if (eg.E > 0) {
+      {
+        constexpr int R = NV == 4 ? 4 : 8;
+        const size_t per_warp = (size_t)(R * F + 4 * F + 2 * 32 * H) * 4;
+        const size_t smem = kSW * per_warp + (size_t)kSW * (R + 2) * 8;
+        auto kern = edge_bwd_dst_stream_kernel<NV, R>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);
+        kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, sh, gH, cdot, score, mx, sinv, gPr, rec, part,
+                                             ga_partials, galpha_dbg, H);
+        *n_partials = blocks;
+        ++launches;
+        if (gd.n_chunks > 1) {
+          edge_sum_fixup_kernel<NV><<<(gd.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gd, part, gPr);
+          ++launches;
+        }
+      }
+      {
+        constexpr int R = ring_depth<NV>();
+        const int slot_floats = F + (rec_words(H, NV) + 31) / 32 * 32;
+        const size_t smem = (size_t)kSW * R * slot_floats * 4 + (size_t)kSW * R * 8;
+        auto kern = edge_bwd_src_stream_kernel<NV, R>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks);
+        kern<<<blocks, kSW * 32, smem, st>>>(gs, eg.csc_dst, eg.csc_eid, a, sh, gH, rec, gPl, part, slot_floats);
+        ++launches;
+        if (gs.n_chunks > 1) {
+          edge_sum_fixup_kernel<NV><<<(gs.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gs, part, gPl);
+          ++launches;
+        }
+      }
+    }
+  });
+  return launches;
+}
+
+// chunk_row[c] = row that contains edge c*T (binary search on row_ptr)
+__global__ void chunk_rows_kernel(const int* __restrict__ row_ptr, int n_rows, int E, int T, int n_chunks,
+                                  int* __restrict__ chunk_row) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const int e = c * T;
+  int lo = 0, hi = n_rows;  // smallest r with row_ptr[r + 1] > e
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (row_ptr[mid + 1] > e) hi = mid; else lo = mid + 1;
+  }
+  chunk_row[c] = lo;
+}
+int launch_chunk_rows(const int* row_ptr, int n_rows, int64_t E, int T, int n_chunks, int* chunk_row, cudaStream_t st) {
+  if (n_chunks <= 0) return 0;
+  chunk_rows_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>(row_ptr, n_rows, (int)E, T, n_chunks, chunk_row);
+  return 1;
+}
+
+}  // namespace gatx

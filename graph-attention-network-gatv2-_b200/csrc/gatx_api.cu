@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -81,6 +82,9 @@ struct gatx_ctx {
   int *row_ptr = nullptr, *col_idx = nullptr, *coo_src = nullptr, *coo_dst = nullptr, *in_deg = nullptr;
   int *csc_ptr = nullptr, *csc_dst = nullptr, *csc_eid = nullptr, *heavy_rows = nullptr, *heavy_srcs = nullptr;
   int n_heavy_rows = 0, n_heavy_srcs = 0;
+  int chunk_T = 256, n_chunks = 0;
+  int *chunk_row = nullptr, *chunk_src = nullptr;
+  bool use_stream = true;
   bool have_graph = false, have_feat = false, have_labels = false, have_bufs = false, have_params = false;
   // data
   int I0 = 0, ld0 = 0, C = 0;
@@ -94,6 +98,7 @@ struct gatx_ctx {
   // scratch
   float *gPl = nullptr, *gPr = nullptr, *ga_partials = nullptr, *splitk_ws = nullptr, *norm_partials = nullptr;
   uint32_t* rec = nullptr;
+  float *part = nullptr, *cdot = nullptr;
   size_t splitk_ws_bytes = 0;
   float *y = nullptr, *dz = nullptr, *z_dbg = nullptr;
   int* pred = nullptr;
@@ -181,6 +186,7 @@ struct PhaseTimer {
 void free_graph(gatx_ctx* c) {
   dfree(c->row_ptr); dfree(c->col_idx); dfree(c->coo_src); dfree(c->coo_dst); dfree(c->in_deg);
   dfree(c->csc_ptr); dfree(c->csc_dst); dfree(c->csc_eid); dfree(c->heavy_rows); dfree(c->heavy_srcs);
+  dfree(c->chunk_row); dfree(c->chunk_src);
   c->have_graph = false;
 }
 void free_bufs(gatx_ctx* c) {
@@ -193,7 +199,7 @@ void free_bufs(gatx_ctx* c) {
   }
   dfree(c->params); dfree(c->grads); dfree(c->adam_m); dfree(c->adam_v);
   dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials);
-  dfree(c->rec); dfree(c->y); dfree(c->dz); dfree(c->z_dbg); dfree(c->pred);
+  dfree(c->rec); dfree(c->part); dfree(c->cdot); dfree(c->y); dfree(c->dz); dfree(c->z_dbg); dfree(c->pred);
   dfree(c->loss_partials); dfree(c->loss_sum); dfree(c->correct_partials); dfree(c->correct); dfree(c->red2);
   c->have_bufs = false;
   c->have_params = false;
@@ -275,6 +281,16 @@ int ensure_buffers(gatx_ctx* ctx) {
   CK(dalloc(&ctx->gPl, (size_t)N * Fmax));
   CK(dalloc(&ctx->gPr, (size_t)nr * Fmax));
   CK(dalloc(&ctx->rec, (size_t)E * recmax));
+  {
+    int64_t part_floats = 1, hmax = 1;
+    for (int l = 0; l < L; ++l) {
+      const int64_t pf = edge_stream_part_floats(ctx->layers[l].H, ctx->layers[l].D, ctx->n_chunks);
+      if (pf > part_floats) part_floats = pf;
+      if (ctx->layers[l].H > hmax) hmax = ctx->layers[l].H;
+    }
+    CK(dalloc(&ctx->part, (size_t)part_floats));
+    CK(dalloc(&ctx->cdot, (size_t)nr * hmax));
+  }
   CK(dalloc(&ctx->ga_partials, (size_t)(kNumSMs * 8 + ctx->n_heavy_rows + 1) * Fmax));
   ctx->splitk_ws_bytes = (size_t)256 << 20;
   CK(dalloc(&ctx->splitk_ws, ctx->splitk_ws_bytes / sizeof(float)));
@@ -299,6 +315,7 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   g.heavy_rows = c->heavy_rows; g.n_heavy_rows = c->n_heavy_rows;
   g.heavy_srcs = c->heavy_srcs; g.n_heavy_srcs = c->n_heavy_srcs;
   g.E = c->E;
+  g.chunk_T = c->chunk_T; g.n_chunks = c->n_chunks; g.chunk_row = c->chunk_row; g.chunk_src = c->chunk_src;
   return g;
 }
 
@@ -396,8 +413,12 @@ int do_forward(gatx_ctx* ctx) {
     if (rc) return rc;
     {
       PhaseTimer t(ctx, PH_EDGE_FWD);
-      LAUNCHED(launch_edge_forward(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre, ly.score,
-                                   ly.mx, ly.sinv, ctx->st));
+      if (ctx->use_stream && edge_stream_supported(ly.H, ly.D))
+        LAUNCHED(launch_edge_forward_stream(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
+                                            ly.score, ly.mx, ly.sinv, ctx->part, ctx->st));
+      else
+        LAUNCHED(launch_edge_forward(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre, ly.score,
+                                     ly.mx, ly.sinv, ctx->st));
       if (ly.Hout != ly.Hfull) LAUNCHED(launch_head_mean(ly.Hfull, ctx->n_rows, ly.H, ly.D, ly.Hout, ctx->st));
     }
     X = ly.Hout;
@@ -434,11 +455,18 @@ int do_backward(gatx_ctx* ctx) {
     {
       PhaseTimer t(ctx, PH_EDGE_BWD);
       int n_part = 0;
-      LAUNCHED(launch_edge_backward_dst(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
-                                        ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->rec, ctx->ga_partials, &n_part,
-                                        ly.galpha_dbg, ctx->st));
-      LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
-      LAUNCHED(launch_edge_backward_src(g, ly.H, ly.D, ctx->params + ly.a_off, ly.gH, ctx->rec, ctx->gPl, ctx->st));
+      if (ctx->use_stream && edge_stream_supported(ly.H, ly.D)) {
+        LAUNCHED(launch_edge_backward_stream(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
+                                             ctx->cdot, ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->gPl, ctx->rec,
+                                             ctx->part, ctx->ga_partials, &n_part, ly.galpha_dbg, ctx->st));
+        LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
+      } else {
+        LAUNCHED(launch_edge_backward_dst(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
+                                          ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->rec, ctx->ga_partials, &n_part,
+                                          ly.galpha_dbg, ctx->st));
+        LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
+        LAUNCHED(launch_edge_backward_src(g, ly.H, ly.D, ctx->params + ly.a_off, ly.gH, ctx->rec, ctx->gPl, ctx->st));
+      }
       if (ctx->keep_debug) {
         LAUNCHED(launch_unpack_rec(ctx->rec, ctx->E, ly.H, ly.D, ly.alpha_dbg, ly.ge_dbg, ctx->st));
         CK(cudaMemcpyAsync(ly.gPl_dbg, ctx->gPl, sizeof(float) * (size_t)ctx->N * ly.F, cudaMemcpyDeviceToDevice,
@@ -630,6 +658,17 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   int n = build_csc(ctx->col_idx, ctx->coo_dst, ctx->E, N, ctx->csc_ptr, ctx->csc_dst, ctx->csc_eid, ctx->st);
   if (n < 0) return fail(ctx, GATX_ERR_CUDA, "build_csc: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches += n;
+  // edge-balanced chunking for the streaming kernels
+  if (const char* ev = getenv("GATX_CHUNK")) {
+    const int t = atoi(ev);
+    if (t >= 32 && t <= (1 << 20)) ctx->chunk_T = t;
+  }
+  ctx->use_stream = getenv("GATX_NO_STREAM") == nullptr;
+  ctx->n_chunks = (int)((ctx->E + ctx->chunk_T - 1) / ctx->chunk_T);
+  CK(dalloc(&ctx->chunk_row, (size_t)ctx->n_chunks + 1));
+  CK(dalloc(&ctx->chunk_src, (size_t)ctx->n_chunks + 1));
+  LAUNCHED(launch_chunk_rows(ctx->row_ptr, ctx->n_rows, ctx->E, ctx->chunk_T, ctx->n_chunks, ctx->chunk_row, ctx->st));
+  LAUNCHED(launch_chunk_rows(ctx->csc_ptr, N, ctx->E, ctx->chunk_T, ctx->n_chunks, ctx->chunk_src, ctx->st));
   // sources with a heavy out-degree (CTA-per-row in the source-major backward pass)
   std::vector<int> cptr((size_t)N + 1), heavy_s;
   CK(cudaMemcpyAsync(cptr.data(), ctx->csc_ptr, sizeof(int) * cptr.size(), cudaMemcpyDeviceToHost, ctx->st));
