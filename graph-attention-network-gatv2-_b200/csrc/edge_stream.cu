@@ -37,6 +37,60 @@ __device__ __forceinline__ float head_reduce(float p, int lph) {
 }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// LeakyReLU with 0 < slope < 1 is max(x, slope*x): FMUL + FMNMX
+__device__ __forceinline__ float lrelu_fast(float x) { return fmaxf(x, kSlope * x); }
+__device__ __forceinline__ float shx(float v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+
+// Sums p[j] (j < NV, one partial per 128-float chunk row) over the LPH lanes of a head; afterwards every
+// lane holds all NV totals of its own lane group.  LPH is compile-time (0 = run-time sh.lph).  With several
+// values the reduction is transposed (reduce-scatter over the top xor offsets, butterfly over the rest,
+// all-gather back): 9 shuffles instead of 20 for NV = 4, LPH = 32.
+template <int NV, int LPH>
+__device__ __forceinline__ void reduce_heads(float (&p)[NV], int lane, int lph_rt) {
+  if constexpr (LPH == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) p[j] = head_reduce(p[j], lph_rt);
+  } else if constexpr (NV == 4 && LPH >= 4) {
+    constexpr int o1 = LPH / 2, o2 = LPH / 4;
+    const bool b1 = lane & o1, b2 = lane & o2;
+    float k0 = b1 ? p[2] : p[0], k1 = b1 ? p[3] : p[1];
+    const float s0 = b1 ? p[0] : p[2], s1 = b1 ? p[1] : p[3];
+    k0 += shx(s0, o1);
+    k1 += shx(s1, o1);
+    float k = b2 ? k1 : k0;
+    k += shx(b2 ? k0 : k1, o2);
+#pragma unroll
+    for (int off = o2 / 2; off > 0; off >>= 1) k += shx(k, off);
+    const float y = shx(k, o2);
+    const float lo = b2 ? y : k, hi = b2 ? k : y;
+    const float z0 = shx(lo, o1), z1 = shx(hi, o1);
+    p[0] = b1 ? z0 : lo; p[1] = b1 ? z1 : hi; p[2] = b1 ? lo : z0; p[3] = b1 ? hi : z1;
+  } else if constexpr (NV == 2 && LPH >= 2) {
+    constexpr int o1 = LPH / 2;
+    const bool b1 = lane & o1;
+    float k = b1 ? p[1] : p[0];
+    k += shx(b1 ? p[0] : p[1], o1);
+#pragma unroll
+    for (int off = o1 / 2; off > 0; off >>= 1) k += shx(k, off);
+    const float y = shx(k, o1);
+    p[0] = b1 ? y : k; p[1] = b1 ? k : y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int off = LPH / 2; off > 0; off >>= 1) p[j] += shx(p[j], off);
+  }
+}
+template <int LPH>
+__device__ __forceinline__ int head_of(int lane, int j, const Shape& sh) {
+  if constexpr (LPH == 0) return (lane + 32 * j) >> sh.lg_lph;
+  else return lane / LPH + j * (32 / LPH);
+}
+template <int LPH>
+__device__ __forceinline__ bool is_head_lane(int lane, const Shape& sh) {
+  if constexpr (LPH == 0) return (lane & (sh.lph - 1)) == 0;
+  else return (lane & (LPH - 1)) == 0;
+}
 
 template <int NV>
 __device__ __forceinline__ void load_row(float4 (&x)[NV], const float* __restrict__ base, int row, int lane) {
@@ -102,7 +156,7 @@ __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, co
 }
 
 // ------------------------------------------------------------------------------------ forward
-template <int NV, int R>
+template <int NV, int R, int LPH>
 __global__ void __launch_bounds__(kSW * 32)
 edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const float* __restrict__ Pl,
                        const float* __restrict__ Pr, const float* __restrict__ a, Shape sh, float* __restrict__ Hout,
@@ -122,7 +176,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
   float4 av[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) av[j] = ldg4(a + 4 * (lane + 32 * j));
-  const bool head_lane = (lane & (sh.lph - 1)) == 0;
+  const bool head_lane = is_head_lane<LPH>(lane, sh);
   const int total_warps = gridDim.x * kSW;
   uint32_t it = 0;  // ring position: edges consumed by this warp so far
   for (int chunk = blockIdx.x * kSW + warp; chunk < g.n_chunks; chunk += total_warps) {
@@ -191,14 +245,18 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
           bulk_g2s(ring + slot * F, Pl + (int64_t)srcn * F, kRowBytes, &bar[slot]);
         }
       }
+      float p[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j)  // EB:303-320
+        p[j] = av[j].x * lrelu_fast(v[j].x + pr[j].x) + av[j].y * lrelu_fast(v[j].y + pr[j].y) +
+               av[j].z * lrelu_fast(v[j].z + pr[j].z) + av[j].w * lrelu_fast(v[j].w + pr[j].w);
+      reduce_heads<NV, LPH>(p, lane, sh.lph);
+      float* sce = score + (int64_t)e * sh.H;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        float p = av[j].x * lrelu(v[j].x + pr[j].x) + av[j].y * lrelu(v[j].y + pr[j].y) +
-                  av[j].z * lrelu(v[j].z + pr[j].z) + av[j].w * lrelu(v[j].w + pr[j].w);  // EB:303-320
-        p = head_reduce(p, sh.lph);
-        if (head_lane) score[(int64_t)e * sh.H + ((lane + 32 * j) >> sh.lg_lph)] = p;
-        const float mn = fmaxf(st.m[j], p);
-        const float corr = __expf(st.m[j] - mn), w = __expf(p - mn);  // online form of EB:336-349
+        if (head_lane) sce[head_of<LPH>(lane, j, sh)] = p[j];
+        const float mn = fmaxf(st.m[j], p[j]);
+        const float corr = __expf(st.m[j] - mn), w = __expf(p[j] - mn);  // online form of EB:336-349
         st.s[j] = st.s[j] * corr + w;
         st.acc[j].x = st.acc[j].x * corr + w * v[j].x;  // EB:415-422 without atomics
         st.acc[j].y = st.acc[j].y * corr + w * v[j].y;
@@ -318,7 +376,7 @@ __device__ __forceinline__ void load_scalars(RowScalars<NV>& q, int row, const S
 }
 
 // smem per warp: ring [R][F] | rowbuf [2][2F] (g_h row, P_r row) | score window [2][32*H] | barriers [R + 2]
-template <int NV, int R>
+template <int NV, int R, int LPH>
 __global__ void __launch_bounds__(kSW * 32)
 edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const float* __restrict__ Pl,
                            const float* __restrict__ Pr, const float* __restrict__ a, Shape sh,
@@ -350,7 +408,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int RW = rec_words(sh.H, NV);
-  const bool head_lane = (lane & (sh.lph - 1)) == 0;
+  const bool head_lane = is_head_lane<LPH>(lane, sh);
   const int total_warps = gridDim.x * kSW;
   const int H = sh.H;
   uint32_t it = 0;   // ring position
@@ -425,7 +483,9 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         float* dst = (first_row && started_before) ? part + ((int64_t)chunk * 2 + 0) * F : gPr + (int64_t)r * F;
         if (e > e0 || !first_row) {
 #pragma unroll
-          for (int j = 0; j < NV; ++j) st4(dst + 4 * (lane + 32 * j), gpr[j]);
+          for (int j = 0; j < NV; ++j)
+            st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * av[j].x, gpr[j].y * av[j].y, gpr[j].z * av[j].z,
+                                                       gpr[j].w * av[j].w));
         }
         first_row = false;
         ++r;
@@ -484,24 +544,30 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       }
       const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
       uint32_t* re = rec + (int64_t)e * RW;
+      float galpha[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) galpha[j] = dot4(ghr[j], v[j]);  // EB:636-646
+      reduce_heads<NV, LPH>(galpha, lane, sh.lph);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const int hd = (lane + 32 * j) >> sh.lg_lph;
-        const float galpha = head_reduce(dot4(ghr[j], v[j]), sh.lph);  // EB:636-646
-        const float alpha = __expf(sc[hd] - q.m[j]) * q.inv[j];        // EB:378-379
-        const float ge = alpha * (galpha - q.c[j]);                    // EB:689-690 in closed form
+        const int hd = head_of<LPH>(lane, j, sh);
+        const float alpha = __expf(sc[hd] - q.m[j]) * q.inv[j];  // EB:378-379
+        const float ge = alpha * (galpha[j] - q.c[j]);           // EB:689-690 in closed form
+        const float ges = ge * kSlope;
         const float sx = v[j].x + pr[j].x, sy = v[j].y + pr[j].y, sz = v[j].z + pr[j].z, sw = v[j].w + pr[j].w;
-        ga[j].x += ge * lrelu(sx); ga[j].y += ge * lrelu(sy);  // EB:769
-        ga[j].z += ge * lrelu(sz); ga[j].w += ge * lrelu(sw);
-        gpr[j].x += ge * av[j].x * lrelu_grad(sx); gpr[j].y += ge * av[j].y * lrelu_grad(sy);  // EB:774-781
-        gpr[j].z += ge * av[j].z * lrelu_grad(sz); gpr[j].w += ge * av[j].w * lrelu_grad(sw);
-        const uint32_t bx = __ballot_sync(0xffffffffu, sx > 0.f), by = __ballot_sync(0xffffffffu, sy > 0.f),
-                       bz = __ballot_sync(0xffffffffu, sz > 0.f), bw = __ballot_sync(0xffffffffu, sw > 0.f);
+        const bool px = sx > 0.f, py = sy > 0.f, pz = sz > 0.f, pw = sw > 0.f;
+        // u = ge * LReLU'(s);  ga += u * s = ge * LReLU(s) (EB:769);  gP_r += a * u (EB:774-781, a applied per row)
+        const float ux = px ? ge : ges, uy = py ? ge : ges, uz = pz ? ge : ges, uw = pw ? ge : ges;
+        ga[j].x = fmaf(ux, sx, ga[j].x); ga[j].y = fmaf(uy, sy, ga[j].y);
+        ga[j].z = fmaf(uz, sz, ga[j].z); ga[j].w = fmaf(uw, sw, ga[j].w);
+        gpr[j].x += ux; gpr[j].y += uy; gpr[j].z += uz; gpr[j].w += uw;
+        const uint32_t bx = __ballot_sync(0xffffffffu, px), by = __ballot_sync(0xffffffffu, py),
+                       bz = __ballot_sync(0xffffffffu, pz), bw = __ballot_sync(0xffffffffu, pw);
         if (lane == 0) *reinterpret_cast<uint4*>(re + 4 * j) = make_uint4(bx, by, bz, bw);
         if (head_lane) {
           re[4 * NV + hd] = __float_as_uint(alpha);
           re[4 * NV + H + hd] = __float_as_uint(ge);
-          if (galpha_dbg) galpha_dbg[(int64_t)e * H + hd] = galpha;
+          if (galpha_dbg) galpha_dbg[(int64_t)e * H + hd] = galpha[j];
         }
       }
     }
@@ -510,7 +576,9 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       const bool complete = ended && !(first_row && started_before);
       float* dst = complete ? gPr + (int64_t)r * F : part + ((int64_t)chunk * 2 + (first_row ? 0 : 1)) * F;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) st4(dst + 4 * (lane + 32 * j), gpr[j]);
+      for (int j = 0; j < NV; ++j)
+        st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * av[j].x, gpr[j].y * av[j].y, gpr[j].z * av[j].z,
+                                                   gpr[j].w * av[j].w));
     }
     it += n;
     // the row-buffer pipeline restarts at the next chunk: drain the outstanding prefetch of row r + 1
@@ -718,11 +786,18 @@ int stream_grid(const void* kernel, size_t smem, int n_chunks) {
 template <int NV>
 constexpr int ring_depth() { return NV == 4 ? 8 : (NV == 2 ? 8 : 16); }
 
-#define STREAM_DISPATCH(nv, ...)                       \
-  do {                                                 \
-    if (nv == 4) { constexpr int NV = 4; __VA_ARGS__; } \
+#define STREAM_DISPATCH_NV(nv, ...)                          \
+  do {                                                       \
+    if (nv == 4) { constexpr int NV = 4; __VA_ARGS__; }      \
     else if (nv == 2) { constexpr int NV = 2; __VA_ARGS__; } \
-    else { constexpr int NV = 1; __VA_ARGS__; }        \
+    else { constexpr int NV = 1; __VA_ARGS__; }              \
+  } while (0)
+// lanes per head: 32 (D = 128) and 16 (D = 64) are compile-time fast paths, anything else is run-time
+#define STREAM_DISPATCH(nv, lph, ...)                                           \
+  do {                                                                          \
+    if (lph == 32) { constexpr int LPH = 32; STREAM_DISPATCH_NV(nv, __VA_ARGS__); }      \
+    else if (lph == 16) { constexpr int LPH = 16; STREAM_DISPATCH_NV(nv, __VA_ARGS__); } \
+    else { constexpr int LPH = 0; STREAM_DISPATCH_NV(nv, __VA_ARGS__); }                 \
   } while (0)
 
 }  // namespace
@@ -750,10 +825,10 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   ++launches;
   if (eg.E == 0) return launches;
   StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
-  STREAM_DISPATCH(nv, {
+  STREAM_DISPATCH(nv, sh.lph, {
     constexpr int R = ring_depth<NV>();
     const size_t smem = (size_t)kSW * R * NV * 128 * 4 + (size_t)kSW * R * 8;
-    auto kern = edge_fwd_stream_kernel<NV, R>;
+    auto kern = edge_fwd_stream_kernel<NV, R, LPH>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
     kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, sh, Hout, hpre, score, mx, sinv, part);
@@ -777,7 +852,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   if (eg.n_rows <= 0) return 0;
   StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
   StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src};
-  STREAM_DISPATCH(nv, {
+  STREAM_DISPATCH(nv, sh.lph, {
     constexpr int F = NV * 128;
     {
       int blocks = (eg.n_rows + 7) / 8;
@@ -793,7 +868,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         constexpr int R = NV == 4 ? 4 : 8;
         const size_t per_warp = (size_t)(R * F + 4 * F + 2 * 32 * H) * 4;
         const size_t smem = kSW * per_warp + (size_t)kSW * (R + 2) * 8;
-        auto kern = edge_bwd_dst_stream_kernel<NV, R>;
+        auto kern = edge_bwd_dst_stream_kernel<NV, R, LPH>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);
         kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, sh, gH, cdot, score, mx, sinv, gPr, rec, part,
