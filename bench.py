@@ -264,26 +264,52 @@ def run_gatx(args):
     h2d = rows * cfg["I"] * 4 + rows * 4
     d2h = 16
 
-    # roofline of the fused edge passes (HBM-bound): algorithmic bytes of SURVEY 8(d)
+    # Roofline (HBM-bound edge passes).  Algorithmic bytes per launch are SURVEY 8(d)'s formulas split by kernel
+    # (b = 4 bytes per stored projected element); durations are CUDA-event times of the individual launches in
+    # the last timed epoch.  The reported kernel is the one with the largest duration.
+    Nl, El = rows, None
+    kernels = []
     fb = bb = 0.0
     for l in range(len(cfg["heads"])):
         f, b = eng.edge_bytes(l)
         fb += f
         bb += b
+        H, D = cfg["heads"][l], cfg["outdims"][l]
+        F = H * D
+        El = (f - 4.0 * (Nl + 1) - Nl * F * 8.0) / (4.0 + 4.0 * F + 4.0 * H)  # local edges from the fwd formula
+        p1 = 4.0 * (Nl + 1) + El * (4.0 + 4.0 * F) + 8.0 * H * El + 12.0 * Nl * F
+        p2 = b - p1
+        ms3 = eng.edge_kernel_ms(l)
+        for name, key, by in (("edge_fwd_stream_kernel", "fwd", f), ("edge_bwd_dst_stream_kernel", "bwd_dst", p1),
+                              ("edge_bwd_src_stream_kernel", "bwd_src", p2)):
+            if ms3[key] > 0:
+                kernels.append({"kernel": name, "layer": l, "F": F, "ms": ms3[key], "algorithmic_gb": by / 1e9,
+                                "gbs": by / 1e9 / (ms3[key] * 1e-3)})
     edge_ms = (phase_acc.get("edge_fwd", 0.0) + phase_acc.get("edge_bwd", 0.0)) / args.steps
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = (fb + bb) / 1e9 / (edge_ms * 1e-3) if edge_ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": "fused edge forward+backward, all layers (edge_fwd_kernel, edge_bwd_dst_kernel, "
-                                      "edge_bwd_src_kernel)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-            "traffic": None, "algorithmic_gb_per_epoch": (fb + bb) / 1e9, "edge_ms_per_epoch": edge_ms,
-            "fwd_gbs": fb / 1e9 / (phase_acc.get("edge_fwd", 0.0) / args.steps * 1e-3) if phase_acc.get("edge_fwd") else None,
-            "bwd_gbs": bb / 1e9 / (phase_acc.get("edge_bwd", 0.0) / args.steps * 1e-3) if phase_acc.get("edge_bwd") else None}
+    agg = (fb + bb) / 1e9 / (edge_ms * 1e-3) if edge_ms > 0 else 0.0
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    if kernels:
+        dom = max(kernels, key=lambda k: k["ms"])
+        if os.path.exists(tj) and world == 1:
+            t = json.load(open(tj)).get("%s:%s:F%d" % (args.workload, dom["kernel"], dom["F"]))
+            traffic = t["dram_bytes_per_launch"] / 1e9 if t and abs(t["scale"] - args.scale) < 1e-9 else None
+    else:
+        dom = {"kernel": "edge kernels (narrow-row path, phase timing only)", "layer": -1, "F": 0, "ms": edge_ms,
+               "algorithmic_gb": (fb + bb) / 1e9, "gbs": agg}
+    roof = {"bound": "hbm", "kernel": "%s (layer %d, %d-float rows)" % (dom["kernel"], dom["layer"], dom["F"]),
+            "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
+            "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+            "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/)",
+            "algorithmic_gb_per_launch": dom["algorithmic_gb"], "ms_per_launch": dom["ms"],
+            "all_edge_kernels": kernels,
+            "edge_passes_aggregate": {"algorithmic_gb_per_epoch": (fb + bb) / 1e9, "ms_per_epoch": edge_ms,
+                                      "gbs": agg, "frac": agg / peak}}
     if rank == 0:
         line = {
             "metric": "train_edges_per_s", "value": E / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,

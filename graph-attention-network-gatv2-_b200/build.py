@@ -49,5 +49,16 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_cli():
+    """train_gatx: the reference-compatible command line (host C++ above the C ABI)."""
+    src = os.path.join(CSRC, "train_main.cpp")
+    out = os.path.join(HERE, "train_gatx")
+    if _stale(out, [src, OUT, os.path.join(HERE, "..", "include", "gatx.h")]):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", src, "-o", out, "-L" + HERE, "-lgatx",
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + "/usr/local/cuda/lib64", "-lpthread"])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cli())

@@ -58,6 +58,9 @@ struct EdgeGraph {
   int chunk_T, n_chunks;
   const int* chunk_row;  // [n_chunks] destination row containing edge c*chunk_T
   const int* chunk_src;  // [n_chunks] source row containing transposed position c*chunk_T
+  // optional CUDA-event pairs around the three main streaming kernels of the layer being launched
+  // (fwd, bwd pass 1, bwd pass 2); null = no timing
+  cudaEvent_t* kernel_events;  // [6] = {fwd_a, fwd_b, dst_a, dst_b, src_a, src_b}
 };
 constexpr int kHeavyDeg = 1024;
 bool edge_shape_supported(int H, int D);

@@ -831,7 +831,9 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
     auto kern = edge_fwd_stream_kernel<NV, R, LPH>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
+    if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
     kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, sh, Hout, hpre, score, mx, sinv, part);
+    if (eg.kernel_events) cudaEventRecord(eg.kernel_events[1], st);
     ++launches;
     if (g.n_chunks > 1) {
       edge_fwd_fixup_kernel<NV><<<(g.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(g, sh, part, Hout, hpre, mx, sinv);
@@ -871,8 +873,10 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         auto kern = edge_bwd_dst_stream_kernel<NV, R, LPH>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
         kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, sh, gH, cdot, score, mx, sinv, gPr, rec, part,
                                              ga_partials, galpha_dbg, H);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[3], st);
         *n_partials = blocks;
         ++launches;
         if (gd.n_chunks > 1) {
@@ -887,7 +891,9 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         auto kern = edge_bwd_src_stream_kernel<NV, R>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[4], st);
         kern<<<blocks, kSW * 32, smem, st>>>(gs, eg.csc_dst, eg.csc_eid, a, sh, gH, rec, gPl, part, slot_floats);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[5], st);
         ++launches;
         if (gs.n_chunks > 1) {
           edge_sum_fixup_kernel<NV><<<(gs.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gs, part, gPl);

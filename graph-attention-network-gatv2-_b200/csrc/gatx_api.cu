@@ -59,6 +59,8 @@ struct Layer {
   float *Pl = nullptr, *Pr = nullptr, *Hfull = nullptr, *Hout = nullptr, *hpre = nullptr;
   float *score = nullptr, *mx = nullptr, *sinv = nullptr, *gH = nullptr, *gHout = nullptr;
   float *galpha_dbg = nullptr, *gPl_dbg = nullptr, *gPr_dbg = nullptr, *alpha_dbg = nullptr, *ge_dbg = nullptr;
+  cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool kev_fwd = false, kev_bwd = false;  // recorded since timing was enabled
 };
 
 }  // namespace
@@ -196,6 +198,11 @@ void free_bufs(gatx_ctx* c) {
     l.Hout = nullptr;
     dfree(l.Hfull); dfree(l.hpre); dfree(l.score); dfree(l.mx); dfree(l.sinv); dfree(l.gH); dfree(l.gHout);
     dfree(l.galpha_dbg); dfree(l.gPl_dbg); dfree(l.gPr_dbg); dfree(l.alpha_dbg); dfree(l.ge_dbg);
+    for (auto& e : l.kev) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+    }
+    l.kev_fwd = l.kev_bwd = false;
   }
   dfree(c->params); dfree(c->grads); dfree(c->adam_m); dfree(c->adam_v);
   dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials);
@@ -316,6 +323,7 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   g.heavy_srcs = c->heavy_srcs; g.n_heavy_srcs = c->n_heavy_srcs;
   g.E = c->E;
   g.chunk_T = c->chunk_T; g.n_chunks = c->n_chunks; g.chunk_row = c->chunk_row; g.chunk_src = c->chunk_src;
+  g.kernel_events = nullptr;
   return g;
 }
 
@@ -413,8 +421,15 @@ int do_forward(gatx_ctx* ctx) {
     if (rc) return rc;
     {
       PhaseTimer t(ctx, PH_EDGE_FWD);
+      EdgeGraph gl = g;
+      if (ctx->timing) {
+        for (auto& e : ly.kev)
+          if (!e) cudaEventCreate(&e);
+        gl.kernel_events = ly.kev;
+        ly.kev_fwd = true;
+      }
       if (ctx->use_stream && edge_stream_supported(ly.H, ly.D))
-        LAUNCHED(launch_edge_forward_stream(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
+        LAUNCHED(launch_edge_forward_stream(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
                                             ly.score, ly.mx, ly.sinv, ctx->part, ctx->st));
       else
         LAUNCHED(launch_edge_forward(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre, ly.score,
@@ -455,8 +470,15 @@ int do_backward(gatx_ctx* ctx) {
     {
       PhaseTimer t(ctx, PH_EDGE_BWD);
       int n_part = 0;
+      EdgeGraph gl = g;
+      if (ctx->timing) {
+        for (auto& e : ly.kev)
+          if (!e) cudaEventCreate(&e);
+        gl.kernel_events = ly.kev;
+        ly.kev_bwd = true;
+      }
       if (ctx->use_stream && edge_stream_supported(ly.H, ly.D)) {
-        LAUNCHED(launch_edge_backward_stream(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
+        LAUNCHED(launch_edge_backward_stream(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
                                              ctx->cdot, ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->gPl, ctx->rec,
                                              ctx->part, ctx->ga_partials, &n_part, ly.galpha_dbg, ctx->st));
         LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
@@ -836,6 +858,7 @@ int gatx_enable_timing(gatx_ctx* ctx, int32_t on) {
   if (!ctx) return GATX_ERR_INVALID;
   ctx->timing = on != 0;
   ctx->spans_used = 0;
+  for (auto& l : ctx->layers) l.kev_fwd = l.kev_bwd = false;
   return GATX_OK;
 }
 
@@ -869,6 +892,23 @@ int gatx_timer_stop(gatx_ctx* ctx, float* elapsed_ms) {
   CK(cudaEventRecord(ctx->sw_b, ctx->st));
   CK(cudaEventSynchronize(ctx->sw_b));
   CK(cudaEventElapsedTime(elapsed_ms, ctx->sw_a, ctx->sw_b));
+  return GATX_OK;
+}
+
+int gatx_get_edge_kernel_ms(gatx_ctx* ctx, int32_t layer, float* out3) {
+  if (!ctx || !out3 || layer < 0 || layer >= ctx->L) return fail(ctx, GATX_ERR_INVALID, "bad layer");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->st));
+  Layer& ly = ctx->layers[layer];
+  out3[0] = out3[1] = out3[2] = 0.f;
+  const bool stream = ctx->use_stream && edge_stream_supported(ly.H, ly.D);
+  if (!stream) return GATX_OK;  // only the streaming kernels are individually timed
+  if (ly.kev_fwd) cudaEventElapsedTime(&out3[0], ly.kev[0], ly.kev[1]);
+  if (ly.kev_bwd) {
+    cudaEventElapsedTime(&out3[1], ly.kev[2], ly.kev[3]);
+    cudaEventElapsedTime(&out3[2], ly.kev[4], ly.kev[5]);
+  }
+  cudaGetLastError();
   return GATX_OK;
 }
 

@@ -1,0 +1,350 @@
+// train_gatx -- drop-in command line for the reference's train_edge / train_node binaries.
+//
+// Same dataset files, same flags, same stdout lines as GATv2_edge_based.cu:main (EB:927-1646); the epoch
+// itself runs in libgatx through the C ABI (include/gatx.h).  Host C++ only: no CUDA calls here.
+//   files  : <data-root>/<dataset>/{features,row_ptr,col_idx,labels}.txt          (EB:24-64, EB:1050-1100)
+//   flags  : --num-layers --heads --outdims --epochs --optimizer --beta1 --beta2 --lr --clip --dataset
+//            --data-root, env DATA_ROOT; unknown flags are ignored like the reference (EB:942-1077)
+//   stdout : configuration block (EB:1024-1040), dataset lines (EB:1076-1111), per epoch
+//            "\nEpoch %d\n", "\nAvg Loss: %f, Accuracy: %.2f%%\n", " total time: <ms> ms" (EB:1372, 547, 1641)
+// Additions that do not change the defaults: --seed S, --gemm tf32|fp32, --gpus N (destination-row partition,
+// one host thread + one context per GPU), --load-weights DIR / --dump-weights DIR (W.bin a.bin Wo.bin, raw fp32
+// in the reference's layouts), --quiet-epochs (print only every k-th epoch).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gatx.h"
+
+namespace {
+
+struct Mapped {
+  const char* p = nullptr;
+  size_t n = 0;
+  bool open(const std::string& path) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); return false; }
+    n = (size_t)st.st_size;
+    if (n) {
+      void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) { ::close(fd); return false; }
+      p = (const char*)m;
+    }
+    ::close(fd);
+    return true;
+  }
+  ~Mapped() { if (p) munmap((void*)p, n); }
+};
+
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// Line-oriented like the reference's load_features (EB:24-51): N = number of lines, I = tokens of the first
+// line, every line must have the same count ("Inconsistent input_dim on line k", exit 1).
+bool load_features(const std::string& path, std::vector<float>& out, int& n_nodes, int& in_dim) {
+  Mapped f;
+  n_nodes = 0;
+  in_dim = 0;
+  if (!f.open(path)) return true;  // the reference silently reads nothing from a missing file
+  const char *p = f.p, *end = f.p + f.n;
+  std::string tok;
+  while (p < end) {
+    const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+    if (!eol) eol = end;
+    int count = 0;
+    const char* q = p;
+    while (q < eol) {
+      while (q < eol && is_space(*q)) ++q;
+      if (q >= eol) break;
+      const char* t = q;
+      while (q < eol && !is_space(*q)) ++q;
+      tok.assign(t, (size_t)(q - t));
+      char* e2 = nullptr;
+      const float v = strtof(tok.c_str(), &e2);
+      if (e2 == tok.c_str()) break;  // like `iss >> val` failing: stop reading this line
+      out.push_back(v);
+      ++count;
+    }
+    if (in_dim == 0) in_dim = count;
+    else if (count != in_dim) {
+      std::cerr << "Inconsistent input_dim on line " << n_nodes << std::endl;
+      exit(1);
+    }
+    ++n_nodes;
+    p = eol < end ? eol + 1 : end;
+  }
+  return true;
+}
+
+// Whitespace-separated integers (EB:53-64).
+void load_int_array(const std::string& path, std::vector<int>& out) {
+  Mapped f;
+  if (!f.open(path)) return;
+  const char *p = f.p, *end = f.p + f.n;
+  while (p < end) {
+    while (p < end && is_space(*p)) ++p;
+    if (p >= end) break;
+    bool neg = false;
+    if (*p == '-' || *p == '+') { neg = *p == '-'; ++p; }
+    if (p >= end || *p < '0' || *p > '9') break;  // `file >> int` stops at the first non-integer
+    long long v = 0;
+    while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; }
+    out.push_back((int)(neg ? -v : v));
+  }
+}
+
+bool read_bin(const std::string& path, std::vector<float>& out, size_t n) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  out.resize(n);
+  const size_t got = fread(out.data(), sizeof(float), n, f);
+  fclose(f);
+  return got == n;
+}
+bool write_bin(const std::string& path, const std::vector<float>& v) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const size_t put = fwrite(v.data(), sizeof(float), v.size(), f);
+  fclose(f);
+  return put == v.size();
+}
+
+struct Args {
+  int epochs = 200, L = 2, gpus = 1, gemm = GATX_GEMM_TF32_TC, every = 1;
+  bool clip = false;
+  std::string optimizer = "sgd", dataset = "pubmed", data_root = "./data", load_w, dump_w;
+  float lr = 0.0001f, beta1 = 0.9f, beta2 = 0.999f;
+  unsigned long long seed = 0;
+  bool seed_given = false;
+  std::vector<int> heads, outdims;
+};
+
+int fail_ctx(gatx_ctx* c, const char* what, int rc) {
+  std::cerr << "Error: " << what << " failed (" << rc << "): " << gatx_last_error(c) << std::endl;
+  return 1;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Args a;
+  bool beta1_specified = false, beta2_specified = false;
+  // the reference pre-scans --num-layers so that the lists can be sized (EB:942-953)
+  for (int i = 1; i < argc; i++) {
+    std::string arg = argv[i];
+    if (arg == "--num-layers" && i + 1 < argc) {
+      a.L = std::atoi(argv[++i]);
+      if (a.L <= 0) {
+        std::cerr << "Error: Number of layers must be > 0\n";
+        return 1;
+      }
+      break;
+    }
+  }
+  bool have_heads = false, have_outdims = false;
+  for (int i = 1; i < argc; i++) {
+    std::string arg = argv[i];
+    auto parse_list = [&](const char* flagname, std::vector<int>& dst) -> bool {
+      std::stringstream ss(argv[++i]);
+      std::string item;
+      dst.assign(a.L, 0);
+      for (int l = 0; l < a.L; ++l) {
+        if (!std::getline(ss, item, ',')) {
+          std::cerr << "Error: " << flagname << " must have " << a.L << " values.\n";
+          return false;
+        }
+        dst[l] = std::atoi(item.c_str());
+      }
+      return true;
+    };
+    if (arg == "--epochs" && i + 1 < argc) a.epochs = std::atoi(argv[++i]);
+    else if (arg == "--heads" && i + 1 < argc) { if (!parse_list("--heads", a.heads)) return 1; have_heads = true; }
+    else if (arg == "--outdims" && i + 1 < argc) { if (!parse_list("--ooutdims", a.outdims)) return 1; have_outdims = true; }
+    else if (arg == "--clip") a.clip = true;
+    else if (arg == "--optimizer" && i + 1 < argc) {
+      a.optimizer = argv[++i];
+      if (a.optimizer != "sgd" && a.optimizer != "adam") {
+        std::cerr << "Invalid optimizer choice. Use 'sgd' or 'adam'\n";
+        return 1;
+      }
+    }
+    else if (arg == "--beta1" && i + 1 < argc) { a.beta1 = std::strtof(argv[++i], nullptr); beta1_specified = true; }
+    else if (arg == "--beta2" && i + 1 < argc) { a.beta2 = std::strtof(argv[++i], nullptr); beta2_specified = true; }
+    else if (arg == "--lr" && i + 1 < argc) a.lr = std::strtof(argv[++i], nullptr);
+    else if (arg == "--dataset" && i + 1 < argc) a.dataset = argv[++i];
+    else if (arg == "--data-root" && i + 1 < argc) a.data_root = argv[++i];
+    else if (arg == "--seed" && i + 1 < argc) { a.seed = std::strtoull(argv[++i], nullptr, 10); a.seed_given = true; }
+    else if (arg == "--gpus" && i + 1 < argc) a.gpus = std::max(1, std::atoi(argv[++i]));
+    else if (arg == "--gemm" && i + 1 < argc) a.gemm = std::string(argv[++i]) == "fp32" ? GATX_GEMM_FP32_SIMT : GATX_GEMM_TF32_TC;
+    else if (arg == "--load-weights" && i + 1 < argc) a.load_w = argv[++i];
+    else if (arg == "--dump-weights" && i + 1 < argc) a.dump_w = argv[++i];
+    else if (arg == "--quiet-epochs" && i + 1 < argc) a.every = std::max(1, std::atoi(argv[++i]));
+    // anything else is ignored, like the reference
+  }
+  if (!have_heads || !have_outdims) {
+    // the reference reads uninitialised memory here; refuse instead
+    std::cerr << "Error: --heads and --outdims must be given (" << a.L << " comma-separated values each).\n";
+    return 1;
+  }
+  if (a.optimizer == "adam") {
+    if (a.beta1 <= 0.0f || a.beta1 >= 1.0f || a.beta2 <= 0.0f || a.beta2 >= 1.0f) {
+      std::cerr << "Error: For Adam optimizer, beta1 and beta2 must be in (0,1).\n";
+      return 1;
+    }
+  } else if (beta1_specified || beta2_specified) {
+    std::cerr << "Warning: beta1/beta2 specified but ignored for SGD optimizer.\n";
+  }
+
+  std::cout << "Configuration:\n"
+            << "  Number of layers: " << a.L << "\n"
+            << "  Epochs: " << a.epochs << "\n"
+            << "  Attention heads: [";
+  for (int l = 0; l < a.L; ++l) std::cout << a.heads[l] << (l < a.L - 1 ? ", " : "");
+  std::cout << "]\n  Output dimensions: [";
+  for (int l = 0; l < a.L; ++l) std::cout << a.outdims[l] << (l < a.L - 1 ? ", " : "");
+  std::cout << "]\n"
+            << "  Gradient clipping: " << (a.clip ? "true" : "false") << "\n"
+            << "  Optimizer: " << a.optimizer << "\n"
+            << "  Learning rate: " << a.lr << "\n\n";
+
+  const char* env_root = std::getenv("DATA_ROOT");
+  if (env_root && a.data_root == "./data") a.data_root = env_root;  // EB:1064-1067
+  if (!a.data_root.empty() && a.data_root.back() != '/' && a.data_root.back() != '\\') a.data_root += '/';
+  const std::string path = a.data_root + a.dataset + "/";
+  std::cout << "Using dataset: " << a.dataset << std::endl;
+  std::cout << "Dataset path: " << path << std::endl;
+
+  std::vector<float> X;
+  std::vector<int> row_ptr, col_idx, labels;
+  int N = 0, I = 0;
+  load_features(path + "features.txt", X, N, I);
+  load_int_array(path + "row_ptr.txt", row_ptr);
+  if ((int)row_ptr.size() != N + 1) {
+    std::cerr << "Invalid row_ptr length\n";
+    return 1;
+  }
+  load_int_array(path + "col_idx.txt", col_idx);
+  load_int_array(path + "labels.txt", labels);
+  if ((int)labels.size() != N) {
+    std::cerr << "Invalid labels length\n";
+    return 1;
+  }
+  if (N == 0 || (long long)row_ptr[N] != (long long)col_idx.size()) {
+    std::cerr << "Invalid col_idx length\n";
+    return 1;
+  }
+  int max_degree = 0;
+  for (int i = 0; i < N; ++i) max_degree = std::max(max_degree, row_ptr[i + 1] - row_ptr[i]);
+  const int C = *std::max_element(labels.begin(), labels.end()) + 1;
+  std::cout << "Max degree = " << max_degree << std::endl;
+  std::cout << "Number of classes = " << C << std::endl;
+  std::cout << "Graph loaded: " << N << " nodes, " << col_idx.size() << " edges, "
+            << "input_feature_vector_dim = " << I << std::endl;
+
+  const int world = a.gpus;
+  std::vector<gatx_ctx*> ctx(world, nullptr);
+  unsigned char nccl_id[128];
+  if (world > 1 && gatx_comm_unique_id(nccl_id) != GATX_OK) {
+    std::cerr << "Error: NCCL is not available for --gpus " << world << "\n";
+    return 1;
+  }
+  std::atomic<int> failed{0};
+  auto setup = [&](int r) {
+    gatx_config cfg{};
+    cfg.num_layers = a.L;
+    cfg.heads = a.heads.data();
+    cfg.outdims = a.outdims.data();
+    cfg.optimizer = a.optimizer == "adam" ? GATX_OPT_ADAM : GATX_OPT_SGD;
+    cfg.lr = a.lr; cfg.beta1 = a.beta1; cfg.beta2 = a.beta2;
+    cfg.clip = a.clip ? 1 : 0;
+    cfg.device = r; cfg.gemm_mode = a.gemm; cfg.keep_debug = 0; cfg.rank = r; cfg.world = world;
+    int rc = gatx_create(&ctx[r], &cfg);
+    if (rc) { std::cerr << "Error: gatx_create failed (" << rc << ") on device " << r << " -- no usable sm_100 GPU?\n"; failed = 1; return; }
+    if (world > 1 && (rc = gatx_comm_init(ctx[r], nccl_id))) { failed = fail_ctx(ctx[r], "gatx_comm_init", rc); return; }
+    if ((rc = gatx_set_graph_csr(ctx[r], N, (int64_t)col_idx.size(), row_ptr.data(), col_idx.data()))) { failed = fail_ctx(ctx[r], "gatx_set_graph_csr", rc); return; }
+    if ((rc = gatx_set_features(ctx[r], X.data(), I))) { failed = fail_ctx(ctx[r], "gatx_set_features", rc); return; }
+    if ((rc = gatx_set_labels(ctx[r], labels.data(), C))) { failed = fail_ctx(ctx[r], "gatx_set_labels", rc); return; }
+    // the reference seeds with time(NULL) (EB:1305); --seed makes runs reproducible
+    const unsigned long long seed = a.seed_given ? a.seed : (unsigned long long)time(nullptr);
+    if ((rc = gatx_init_params(ctx[r], seed))) { failed = fail_ctx(ctx[r], "gatx_init_params", rc); return; }
+    if (!a.load_w.empty()) {
+      std::vector<float> W, av, Wo;
+      size_t wo = 0, ao = 0, tw = 0, ta = 0;
+      int in = I;
+      for (int l = 0; l < a.L; ++l) { tw += (size_t)a.heads[l] * a.outdims[l] * 2 * in; ta += (size_t)a.heads[l] * a.outdims[l]; in = a.heads[l] * a.outdims[l]; }
+      if (!read_bin(a.load_w + "/W.bin", W, tw) || !read_bin(a.load_w + "/a.bin", av, ta) ||
+          !read_bin(a.load_w + "/Wo.bin", Wo, (size_t)C * a.outdims[a.L - 1])) {
+        std::cerr << "Error: cannot read W.bin / a.bin / Wo.bin from " << a.load_w << "\n";
+        failed = 1;
+        return;
+      }
+      in = I;
+      for (int l = 0; l < a.L; ++l) {
+        if ((rc = gatx_set_params(ctx[r], l, W.data() + wo, av.data() + ao))) { failed = fail_ctx(ctx[r], "gatx_set_params", rc); return; }
+        wo += (size_t)a.heads[l] * a.outdims[l] * 2 * in;
+        ao += (size_t)a.heads[l] * a.outdims[l];
+        in = a.heads[l] * a.outdims[l];
+      }
+      if ((rc = gatx_set_wo(ctx[r], Wo.data()))) { failed = fail_ctx(ctx[r], "gatx_set_wo", rc); return; }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; ++r) th.emplace_back(setup, r);
+    for (auto& t : th) t.join();
+  }
+  if (failed) return 1;
+
+  auto dump_weights = [&](const std::string& dir) {
+    std::vector<float> W, av, Wo;
+    for (int l = 0; l < a.L; ++l) {
+      const int64_t nw = gatx_tensor_size(ctx[0], GATX_T_W, l), na = gatx_tensor_size(ctx[0], GATX_T_A, l);
+      std::vector<float> w((size_t)nw), v((size_t)na);
+      gatx_get_tensor(ctx[0], GATX_T_W, l, w.data(), w.size() * 4);
+      gatx_get_tensor(ctx[0], GATX_T_A, l, v.data(), v.size() * 4);
+      W.insert(W.end(), w.begin(), w.end());
+      av.insert(av.end(), v.begin(), v.end());
+    }
+    Wo.resize((size_t)gatx_tensor_size(ctx[0], GATX_T_WO, 0));
+    gatx_get_tensor(ctx[0], GATX_T_WO, 0, Wo.data(), Wo.size() * 4);
+    return write_bin(dir + "/W.bin", W) && write_bin(dir + "/a.bin", av) && write_bin(dir + "/Wo.bin", Wo);
+  };
+
+  for (int epoch = 1; epoch <= a.epochs; ++epoch) {
+    auto start = std::chrono::high_resolution_clock::now();
+    const bool show = (epoch % a.every) == 0 || epoch == 1 || epoch == a.epochs;
+    if (show) printf("\nEpoch %d\n", epoch);
+    std::vector<float> loss(world, 0.f), acc(world, 0.f);
+    std::vector<int> rcs(world, 0);
+    auto run = [&](int r) { rcs[r] = gatx_train_epoch(ctx[r], epoch, &loss[r], &acc[r]); };
+    if (world == 1) run(0);
+    else {
+      std::vector<std::thread> th;
+      for (int r = 0; r < world; ++r) th.emplace_back(run, r);
+      for (auto& t : th) t.join();
+    }
+    for (int r = 0; r < world; ++r)
+      if (rcs[r]) return fail_ctx(ctx[r], "gatx_train_epoch", rcs[r]);
+    if (show) printf("\nAvg Loss: %f, Accuracy: %.2f%%\n", loss[0], 100.0f * acc[0]);
+    auto stop = std::chrono::high_resolution_clock::now();
+    std::chrono::duration<double, std::milli> elapsed = stop - start;
+    if (show) std::cout << " total time: " << elapsed.count() << " ms" << std::endl;
+  }
+  if (!a.dump_w.empty() && !dump_weights(a.dump_w)) std::cerr << "Warning: could not write weights to " << a.dump_w << "\n";
+  for (auto c : ctx) gatx_destroy(c);
+  return 0;
+}

@@ -22,7 +22,7 @@ EXPORTS = [
     "gatx_set_features", "gatx_set_labels", "gatx_graph_info", "gatx_partition_rows", "gatx_init_params",
     "gatx_set_params", "gatx_set_wo", "gatx_forward", "gatx_loss_acc", "gatx_backward", "gatx_step",
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
-    "gatx_get_timing", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_op_gemm",
+    "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init",
 ]
 
@@ -234,6 +234,12 @@ class Engine:
         buf = (C.c_float * 8)()
         self._ck(self.lib.gatx_get_timing(self.ctx, buf, 8), "gatx_get_timing")
         return dict(zip(PHASES, list(buf)))
+
+    def edge_kernel_ms(self, layer):
+        buf = (C.c_float * 3)()
+        self.lib.gatx_get_edge_kernel_ms.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        self._ck(self.lib.gatx_get_edge_kernel_ms(self.ctx, layer, buf), "gatx_get_edge_kernel_ms")
+        return dict(fwd=buf[0], bwd_dst=buf[1], bwd_src=buf[2])
 
     def timer_start(self):
         self._ck(self.lib.gatx_timer_start(self.ctx), "gatx_timer_start")

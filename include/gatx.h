@@ -147,6 +147,10 @@ int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size
  * gatx_enable_timing(ctx, 1) (adds event records, no host syncs). */
 int gatx_enable_timing(gatx_ctx* ctx, int32_t on);
 int gatx_get_timing(gatx_ctx* ctx, float* out_ms, int32_t n);
+/* Device milliseconds of the three main streaming edge kernels of `layer` in the last epoch (timing enabled):
+ * out3[0] = fused edge forward, [1] = backward pass 1 (destination-major), [2] = backward pass 2 (source-major);
+ * zeros when the layer uses the narrow-row kernels. */
+int gatx_get_edge_kernel_ms(gatx_ctx* ctx, int32_t layer, float* out3);
 /* CUDA-event stopwatch on the context's launching stream (bench.py times its K steps with it). */
 int gatx_timer_start(gatx_ctx* ctx);
 int gatx_timer_stop(gatx_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */
