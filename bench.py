@@ -236,6 +236,7 @@ def run_gatx(args):
     if not args.phase_times:
         # per-phase device times of the last timed epoch (events were recorded inside the timed region)
         phase_acc = {k: v * args.steps for k, v in eng.timing().items()}
+    kernel_ms = [eng.edge_kernel_ms(l) for l in range(len(cfg["heads"]))]  # per-launch CUDA-event times, last epoch
     eng.enable_timing(False)
     loss, acc = eng.loss_acc()
     if dist is not None:
@@ -279,7 +280,7 @@ def run_gatx(args):
         El = (f - 4.0 * (Nl + 1) - Nl * F * 8.0) / (4.0 + 4.0 * F + 4.0 * H)  # local edges from the fwd formula
         p1 = 4.0 * (Nl + 1) + El * (4.0 + 4.0 * F) + 8.0 * H * El + 12.0 * Nl * F
         p2 = b - p1
-        ms3 = eng.edge_kernel_ms(l)
+        ms3 = kernel_ms[l]
         for name, key, by in (("edge_fwd_stream_kernel", "fwd", f), ("edge_bwd_dst_stream_kernel", "bwd_dst", p1),
                               ("edge_bwd_src_stream_kernel", "bwd_src", p2)):
             if ms3[key] > 0:
