@@ -102,7 +102,8 @@ struct gatx_ctx {
   uint32_t* rec = nullptr;
   float *part = nullptr, *cdot = nullptr;
   size_t splitk_ws_bytes = 0;
-  float *y = nullptr, *dz = nullptr, *z_dbg = nullptr;
+  float *y = nullptr, *dz = nullptr, *z_dbg = nullptr, *WoT = nullptr;
+  int ldc = 0;  // row pitch of y / dz / z: classes rounded up to 4 floats
   int* pred = nullptr;
   double *loss_partials = nullptr, *loss_sum = nullptr;  // loss_sum[0] = sum loss, [1] = correct (as double)
   int* correct_partials = nullptr;
@@ -206,7 +207,7 @@ void free_bufs(gatx_ctx* c) {
   }
   dfree(c->params); dfree(c->grads); dfree(c->adam_m); dfree(c->adam_v);
   dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials);
-  dfree(c->rec); dfree(c->part); dfree(c->cdot); dfree(c->y); dfree(c->dz); dfree(c->z_dbg); dfree(c->pred);
+  dfree(c->rec); dfree(c->part); dfree(c->cdot); dfree(c->y); dfree(c->dz); dfree(c->z_dbg); dfree(c->WoT); dfree(c->pred);
   dfree(c->loss_partials); dfree(c->loss_sum); dfree(c->correct_partials); dfree(c->correct); dfree(c->red2);
   c->have_bufs = false;
   c->have_params = false;
@@ -302,9 +303,11 @@ int ensure_buffers(gatx_ctx* ctx) {
   ctx->splitk_ws_bytes = (size_t)256 << 20;
   CK(dalloc(&ctx->splitk_ws, ctx->splitk_ws_bytes / sizeof(float)));
   CK(dalloc(&ctx->norm_partials, (size_t)3 * kOptimBlocks));
-  CK(dalloc(&ctx->y, (size_t)nr * ctx->C));
-  CK(dalloc(&ctx->dz, (size_t)nr * ctx->C));
-  if (ctx->keep_debug) CK(dalloc(&ctx->z_dbg, (size_t)nr * ctx->C));
+  ctx->ldc = (ctx->C + 3) / 4 * 4;
+  CK(dalloc(&ctx->y, (size_t)nr * ctx->ldc));
+  CK(dalloc(&ctx->dz, (size_t)nr * ctx->ldc));
+  CK(dalloc(&ctx->z_dbg, (size_t)nr * ctx->ldc));
+  CK(dalloc(&ctx->WoT, (size_t)DL * ctx->ldc));
   CK(dalloc(&ctx->pred, (size_t)nr));
   CK(dalloc(&ctx->loss_partials, (size_t)kHeadBlocks));
   CK(dalloc(&ctx->correct_partials, (size_t)kHeadBlocks));
@@ -443,9 +446,28 @@ int do_forward(gatx_ctx* ctx) {
     Layer& last = ctx->layers[ctx->L - 1];
     float* gH_out = last.gHout ? last.gHout : last.gH;
     int n_part = 0;
-    LAUNCHED(launch_head(last.Hout, ctx->params + ctx->wo_off, ctx->labels, ctx->n_rows, ctx->C, last.D, ctx->y,
-                         ctx->dz, ctx->z_dbg, ctx->pred, gH_out, ctx->loss_partials, ctx->correct_partials, &n_part,
-                         ctx->st));
+    const float* Wo = ctx->params + ctx->wo_off;
+    bool tc_done = false;
+    if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
+      // z = H_L W_o^T and dL/dH_L = dz W_o on the tensor cores, softmax / CE / argmax / dz in between
+      int n1 = launch_gemm_tc_tn(last.Hout, last.D, Wo, last.D, ctx->z_dbg, ctx->ldc, ctx->n_rows, ctx->C, last.D, false,
+                                 ctx->st);
+      if (n1 >= 0) {
+        ctx->launches += n1;
+        LAUNCHED(launch_softmax_ce(ctx->z_dbg, ctx->labels, ctx->n_rows, ctx->C, ctx->ldc, ctx->y, ctx->dz, ctx->pred,
+                                   ctx->loss_partials, ctx->correct_partials, &n_part, ctx->st));
+        LAUNCHED(launch_transpose_wo(Wo, ctx->C, last.D, ctx->ldc, ctx->WoT, ctx->st));
+        int n2 = launch_gemm_tc_tn(ctx->dz, ctx->ldc, ctx->WoT, ctx->ldc, gH_out, last.D, ctx->n_rows, last.D, ctx->C,
+                                   false, ctx->st);
+        if (n2 < 0) return fail(ctx, GATX_ERR_UNSUPPORTED, "tensor-core head gradient GEMM rejected its shape");
+        ctx->launches += n2;
+        tc_done = true;
+      }
+    }
+    if (!tc_done)
+      LAUNCHED(launch_head(last.Hout, Wo, ctx->labels, ctx->n_rows, ctx->C, last.D, ctx->ldc, ctx->y, ctx->dz,
+                           ctx->keep_debug ? ctx->z_dbg : nullptr, ctx->pred, gH_out, ctx->loss_partials,
+                           ctx->correct_partials, &n_part, ctx->st));
     LAUNCHED(launch_loss_finalize(ctx->loss_partials, ctx->correct_partials, n_part, ctx->loss_sum, ctx->correct,
                                   ctx->st));
     if (last.gHout) LAUNCHED(launch_head_bcast_grad(last.gHout, ctx->n_rows, last.H, last.D, last.gH, ctx->st));
@@ -461,8 +483,9 @@ int do_backward(gatx_ctx* ctx) {
     // gW_o += dz^T H_L  (EB:576-581)
     PhaseTimer t(ctx, PH_GEMM_BWD);
     Layer& last = ctx->layers[ctx->L - 1];
-    LAUNCHED(launch_gemm_simt(ctx->dz, 1, ctx->C, last.Hout, 1, last.D, ctx->grads + ctx->wo_off, last.D, ctx->C,
-                              last.D, ctx->n_rows, true, ctx->splitk_ws, ctx->splitk_ws_bytes, ctx->st));
+    rc = gemm_nt_reduce(ctx, ctx->dz, ctx->ldc, last.Hout, last.D, ctx->grads + ctx->wo_off, last.D, ctx->C, last.D,
+                        ctx->n_rows);
+    if (rc) return rc;
   }
   for (int l = ctx->L - 1; l >= 0; --l) {
     Layer& ly = ctx->layers[l];
@@ -718,7 +741,10 @@ int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim) {
     ctx->I0 = in_dim;
     ctx->ld0 = ld;
   }
-  if (ctx->n_rows)
+  if (ctx->n_rows && ld == in_dim)  // no padding: one contiguous DMA
+    CK(cudaMemcpyAsync(ctx->X0, X + (int64_t)ctx->r0 * in_dim, sizeof(float) * (size_t)ctx->n_rows * in_dim,
+                       cudaMemcpyHostToDevice, ctx->st));
+  else if (ctx->n_rows)
     CK(cudaMemcpy2DAsync(ctx->X0, sizeof(float) * ld, X + (int64_t)ctx->r0 * in_dim, sizeof(float) * in_dim,
                          sizeof(float) * in_dim, ctx->n_rows, cudaMemcpyHostToDevice, ctx->st));
   ctx->have_feat = true;
@@ -981,7 +1007,7 @@ int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size
     case GATX_T_HPRE: src = ly->hpre; break;
     case GATX_T_HOUT: src = ly->Hout; break;
     case GATX_T_Y: src = ctx->y; break;
-    case GATX_T_Z: src = ctx->z_dbg; break;
+    case GATX_T_Z: src = (ctx->keep_debug || ctx->gemm_mode == GATX_GEMM_TF32_TC) ? ctx->z_dbg : nullptr; break;
     case GATX_T_GH: src = ly->gH; break;
     case GATX_T_PRED: src = ctx->pred; break;
     case GATX_T_COO_SRC: src = ctx->coo_src; break;
@@ -995,7 +1021,12 @@ int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size
     default: break;
   }
   if (!src) return fail(ctx, GATX_ERR_INVALID, "tensor %d needs keep_debug=1", which);
-  cudaError_t e = n ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->st) : cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  if (n && (which == GATX_T_Y || which == GATX_T_Z) && ctx->ldc != ctx->C)
+    e = cudaMemcpy2DAsync(dst, sizeof(float) * ctx->C, src, sizeof(float) * ctx->ldc, sizeof(float) * ctx->C, ctx->n_rows,
+                          cudaMemcpyDeviceToHost, ctx->st);
+  else if (n)
+    e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
   if (tmp) cudaFree(tmp);
   if (e != cudaSuccess) return fail(ctx, GATX_ERR_CUDA, "get_tensor copy: %s", cudaGetErrorString(e));

@@ -11,7 +11,7 @@ constexpr int HT = 32;  // nodes per tile
 
 __global__ void __launch_bounds__(256)
 head_kernel(const float* __restrict__ HL, const float* __restrict__ Wo, const int* __restrict__ labels, int N,
-            int C, int DL, float* __restrict__ y, float* __restrict__ dz, float* __restrict__ z_dbg,
+            int C, int DL, int ldc, float* __restrict__ y, float* __restrict__ dz, float* __restrict__ z_dbg,
             int* __restrict__ pred, float* __restrict__ gH, double* __restrict__ loss_partials,
             int* __restrict__ correct_partials) {
   extern __shared__ __align__(16) float smem[];
@@ -40,7 +40,7 @@ head_kernel(const float* __restrict__ HL, const float* __restrict__ Wo, const in
       float acc = 0.f;
       for (int d = 0; d < DL; ++d) acc = fmaf(w[d], h[d], acc);
       ys[n * ldy + c] = acc;
-      if (z_dbg) z_dbg[(int64_t)(n0 + n) * C + c] = acc;
+      if (z_dbg) z_dbg[(int64_t)(n0 + n) * ldc + c] = acc;
     }
     __syncthreads();
     if (tid < nn) {
@@ -74,8 +74,8 @@ head_kernel(const float* __restrict__ HL, const float* __restrict__ Wo, const in
       const int n = p / C, c = p % C;
       const float prob = ys[n * ldy + c];
       const float d = prob - (c == lab[n] ? 1.0f : 0.0f);
-      y[(int64_t)n0 * C + p] = prob;
-      dz[(int64_t)n0 * C + p] = d;
+      y[(int64_t)(n0 + n) * ldc + c] = prob;
+      dz[(int64_t)(n0 + n) * ldc + c] = d;
       ys[n * ldy + c] = d;
     }
     __syncthreads();
@@ -120,7 +120,7 @@ static size_t head_smem_bytes(int C, int DL) {
   return sizeof(float) * ((size_t)C * (DL + 1) + (size_t)HT * (DL + 1) + (size_t)HT * (C + 1)) + sizeof(int) * HT;
 }
 
-int launch_head(const float* HL, const float* Wo, const int* labels, int N, int C, int DL, float* y, float* dz,
+int launch_head(const float* HL, const float* Wo, const int* labels, int N, int C, int DL, int ldc, float* y, float* dz,
                 float* z_dbg, int* pred, float* gH, double* loss_partials, int* correct_partials, int* n_partials,
                 cudaStream_t st) {
   const size_t smem = head_smem_bytes(C, DL);
@@ -129,9 +129,112 @@ int launch_head(const float* HL, const float* Wo, const int* labels, int N, int 
   int blocks = (N + HT - 1) / HT;
   if (blocks > kHeadBlocks) blocks = kHeadBlocks;
   if (blocks < 1) blocks = 1;
-  head_kernel<<<blocks, 256, smem, st>>>(HL, Wo, labels, N, C, DL, y, dz, z_dbg, pred, gH, loss_partials,
+  head_kernel<<<blocks, 256, smem, st>>>(HL, Wo, labels, N, C, DL, ldc, y, dz, z_dbg, pred, gH, loss_partials,
                                          correct_partials);
   *n_partials = blocks;
+  return 1;
+}
+
+// ---- tensor-core path: logits come from the tcgen05 GEMM, this kernel does softmax / CE / argmax / dz ----
+constexpr int ST = 128;  // nodes per tile, one thread per node
+
+__global__ void __launch_bounds__(ST)
+softmax_ce_kernel(const float* __restrict__ z, const int* __restrict__ labels, int N, int C, int ldc,
+                  float* __restrict__ y, float* __restrict__ dz, int* __restrict__ pred,
+                  double* __restrict__ loss_partials, int* __restrict__ correct_partials) {
+  extern __shared__ __align__(16) float smem[];
+  const int lds = ldc + 1;  // odd pitch: a thread walking its own row is bank-conflict free
+  float* zt = smem;             // [ST][ldc+1] logits -> probabilities
+  float* dt = smem + ST * lds;  // [ST][ldc+1] dz
+  __shared__ double red_l[ST / 32];
+  __shared__ int red_c[ST / 32];
+  const int tid = threadIdx.x;
+  double loss_acc = 0.0;
+  int correct_acc = 0;
+  const int n_tiles = (N + ST - 1) / ST;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n0 = tile * ST;
+    const int nn = N - n0 < ST ? N - n0 : ST;
+    __syncthreads();
+    for (int i = tid; i < nn * ldc; i += ST) zt[(i / ldc) * lds + (i % ldc)] = __ldg(z + (int64_t)n0 * ldc + i);
+    __syncthreads();
+    if (tid < nn) {
+      float* row = zt + tid * lds;
+      float* drow = dt + tid * lds;
+      float m = row[0];
+      for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) {
+        row[c] = expf(row[c] - m);  // EB:137
+        sum += row[c];
+      }
+      const double den = (double)sum + 1e-8;  // EB:140
+      const int l = __ldg(labels + n0 + tid);
+      float best = 0.f;
+      int arg = 0;
+      for (int c = 0; c < C; ++c) {
+        const float p = (float)((double)row[c] / den);
+        row[c] = p;
+        drow[c] = p - (c == l ? 1.0f : 0.0f);  // EB:572
+        if (c == 0 || p > best) {              // EB:530-535
+          best = p;
+          arg = c;
+        }
+      }
+      for (int c = C; c < ldc; ++c) row[c] = drow[c] = 0.f;
+      loss_acc += (double)(-logf(fmaxf(row[l], 1e-12f)));  // EB:527
+      correct_acc += (arg == l);
+      pred[n0 + tid] = arg;
+    }
+    __syncthreads();
+    for (int i = tid; i < nn * ldc; i += ST) {
+      y[(int64_t)n0 * ldc + i] = zt[(i / ldc) * lds + (i % ldc)];
+      dz[(int64_t)n0 * ldc + i] = dt[(i / ldc) * lds + (i % ldc)];
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
+    correct_acc += __shfl_down_sync(0xffffffffu, correct_acc, off);
+  }
+  if ((tid & 31) == 0) {
+    red_l[tid >> 5] = loss_acc;
+    red_c[tid >> 5] = correct_acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    int c = 0;
+    for (int w = 0; w < ST / 32; ++w) {
+      s += red_l[w];
+      c += red_c[w];
+    }
+    loss_partials[blockIdx.x] = s;
+    correct_partials[blockIdx.x] = c;
+  }
+}
+
+int launch_softmax_ce(const float* z, const int* labels, int N, int C, int ldc, float* y, float* dz, int* pred,
+                      double* loss_partials, int* correct_partials, int* n_partials, cudaStream_t st) {
+  const size_t smem = sizeof(float) * 2 * ST * (ldc + 1);
+  if (smem > 200 * 1024) return -1;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(softmax_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int blocks = (N + ST - 1) / ST;
+  if (blocks > kHeadBlocks) blocks = kHeadBlocks;
+  if (blocks < 1) blocks = 1;
+  softmax_ce_kernel<<<blocks, ST, smem, st>>>(z, labels, N, C, ldc, y, dz, pred, loss_partials, correct_partials);
+  *n_partials = blocks;
+  return 1;
+}
+
+// WoT[d][c] = Wo[c][d], row pitch ldc, zero padded (K-major B operand of gH = dz Wo)
+__global__ void transpose_wo_kernel(const float* __restrict__ Wo, int C, int DL, int ldc, float* __restrict__ WoT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= DL * ldc) return;
+  const int d = i / ldc, c = i % ldc;
+  WoT[i] = c < C ? Wo[c * DL + d] : 0.f;
+}
+int launch_transpose_wo(const float* Wo, int C, int DL, int ldc, float* WoT, cudaStream_t st) {
+  transpose_wo_kernel<<<(DL * ldc + 255) / 256, 256, 0, st>>>(Wo, C, DL, ldc, WoT);
   return 1;
 }
 
