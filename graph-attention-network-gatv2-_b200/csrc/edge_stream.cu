@@ -40,6 +40,27 @@ __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cas
 // LeakyReLU with 0 < slope < 1 is max(x, slope*x): FMUL + FMNMX
 __device__ __forceinline__ float lrelu_fast(float x) { return fmaxf(x, kSlope * x); }
 __device__ __forceinline__ float shx(float v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+// predicated global stores: one STG with a predicate instead of a divergent branch region per store
+__device__ __forceinline__ void st_pred_u32(uint32_t* p, uint32_t v, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %2, 0;\n"
+      "@q st.global.b32 [%0], %1;\n"
+      "}\n" ::"l"(p),
+      "r"(v), "r"((uint32_t)pred)
+      : "memory");
+}
+__device__ __forceinline__ void st_pred_v4(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n"
+      "}\n" ::"l"(p),
+      "r"(a), "r"(b), "r"(c), "r"(d), "r"((uint32_t)pred)
+      : "memory");
+}
 
 // Sums p[j] (j < NV, one partial per 128-float chunk row) over the LPH lanes of a head; afterwards every
 // lane holds all NV totals of its own lane group.  LPH is compile-time (0 = run-time sh.lph).  With several
@@ -254,7 +275,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       float* sce = score + (int64_t)e * sh.H;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        if (head_lane) sce[head_of<LPH>(lane, j, sh)] = p[j];
+        st_pred_u32(reinterpret_cast<uint32_t*>(sce + head_of<LPH>(lane, j, sh)), __float_as_uint(p[j]), head_lane);
         const float mn = fmaxf(st.m[j], p[j]);
         const float corr = __expf(st.m[j] - mn), w = __expf(p[j] - mn);  // online form of EB:336-349
         st.s[j] = st.s[j] * corr + w;
@@ -407,10 +428,10 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     av[j] = ldg4(a + 4 * (lane + 32 * j));
     ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const int RW = rec_words(sh.H, NV);
+  const int H = LPH > 0 ? NV * 32 / (LPH > 0 ? LPH : 1) : sh.H;  // compile-time when the head width is
+  const int RW = rec_words(H, NV);
   const bool head_lane = is_head_lane<LPH>(lane, sh);
   const int total_warps = gridDim.x * kSW;
-  const int H = sh.H;
   uint32_t it = 0;   // ring position
   uint32_t rk = 0;   // row-buffer position: row loads issued so far
   for (int chunk = blockIdx.x * kSW + warp; chunk < g.n_chunks; chunk += total_warps) {
@@ -563,12 +584,11 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         gpr[j].x += ux; gpr[j].y += uy; gpr[j].z += uz; gpr[j].w += uw;
         const uint32_t bx = __ballot_sync(0xffffffffu, px), by = __ballot_sync(0xffffffffu, py),
                        bz = __ballot_sync(0xffffffffu, pz), bw = __ballot_sync(0xffffffffu, pw);
-        if (lane == 0) *reinterpret_cast<uint4*>(re + 4 * j) = make_uint4(bx, by, bz, bw);
-        if (head_lane) {
-          re[4 * NV + hd] = __float_as_uint(alpha);
-          re[4 * NV + H + hd] = __float_as_uint(ge);
-          if (galpha_dbg) galpha_dbg[(int64_t)e * H + hd] = galpha[j];
-        }
+        // predicated stores (no divergence regions): lane 0 writes the sign words, head lanes write alpha / ge
+        st_pred_v4(re + 4 * j, bx, by, bz, bw, lane == 0);
+        st_pred_u32(re + 4 * NV + hd, __float_as_uint(alpha), head_lane);
+        st_pred_u32(re + 4 * NV + H + hd, __float_as_uint(ge), head_lane);
+        if (galpha_dbg && head_lane) galpha_dbg[(int64_t)e * H + hd] = galpha[j];
       }
     }
     {

@@ -972,7 +972,7 @@ int64_t gatx_tensor_size(gatx_ctx* ctx, int32_t which, int32_t layer) {
     case GATX_T_WO: case GATX_T_GWO: return (int64_t)ctx->C * DL;
     case GATX_T_PL: case GATX_T_GPL: return (int64_t)ctx->N * ly->F;
     case GATX_T_PR: case GATX_T_GPR: case GATX_T_HPRE: case GATX_T_GH: return (int64_t)ctx->n_rows * ly->F;
-    case GATX_T_SCORE: case GATX_T_ALPHA: return ctx->E * ly->H;
+    case GATX_T_SCORE: case GATX_T_ALPHA: case GATX_T_GALPHA: case GATX_T_GE: return ctx->E * ly->H;
     case GATX_T_HOUT: return (int64_t)ctx->n_rows * ly->Fout;
     case GATX_T_Y: case GATX_T_Z: return (int64_t)ctx->n_rows * ctx->C;
     case GATX_T_PRED: return ctx->n_rows;
@@ -1018,6 +1018,8 @@ int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size
     case GATX_T_CSC_EID: src = ctx->csc_eid; break;
     case GATX_T_GPL: src = ly->gPl_dbg; break;
     case GATX_T_GPR: src = ly->gPr_dbg; break;
+    case GATX_T_GALPHA: src = ly->galpha_dbg; break;
+    case GATX_T_GE: src = ly->ge_dbg; break;
     default: break;
   }
   if (!src) return fail(ctx, GATX_ERR_INVALID, "tensor %d needs keep_debug=1", which);

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgatx.so")
 
 (T_W, T_A, T_WO, T_GW, T_GA, T_GWO, T_PL, T_PR, T_SCORE, T_ALPHA, T_HPRE, T_HOUT, T_Y, T_GH, T_Z, T_PRED,
- T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR) = range(24)
+ T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR, T_GALPHA, T_GE) = range(26)
 _INT_TENSORS = {T_PRED, T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID}
 GEMM_TF32_TC, GEMM_FP32_SIMT = 0, 1
 PHASES = ("gemm_fwd", "edge_fwd", "head", "edge_bwd", "gemm_bwd", "optimizer", "comm", "epoch")

@@ -88,7 +88,9 @@ enum {
   GATX_T_CSC_DST = 20,   /* int32 [E] */
   GATX_T_CSC_EID = 21,   /* int32 [E] CSR position of each transposed edge */
   GATX_T_GPL = 22,   /* [N][F] grad wrt projected source features */
-  GATX_T_GPR = 23    /* [N][F] grad wrt projected destination features */
+  GATX_T_GPR = 23,   /* [N][F] grad wrt projected destination features */
+  GATX_T_GALPHA = 24, /* [E][H] grad wrt attention coefficients (EB grad_attn_coeff, transposed) -- keep_debug */
+  GATX_T_GE = 25     /* [E][H] grad wrt attention logits (EB grad_attn_score, transposed) -- keep_debug */
 };
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
