@@ -347,6 +347,19 @@ int gemm_project(gatx_ctx* ctx, const float* X, int ldx, const Layer& ly) {
                             ly.I, false, nullptr, 0, ctx->st));
   return GATX_OK;
 }
+// C[M][N] = A[M][K] B[N][K]^T with the configured arithmetic
+int gemm_tn_any(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
+                int N, int K) {
+  if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
+    int n = launch_gemm_tc_tn(A, lda, B, ldb, C, ldc, M, N, K, false, ctx->st);
+    if (n >= 0) {
+      ctx->launches += n;
+      return GATX_OK;
+    }
+  }
+  LAUNCHED(launch_gemm_simt(A, lda, 1, B, ldb, 1, C, ldc, M, N, K, false, nullptr, 0, ctx->st));
+  return GATX_OK;
+}
 // gX[n][i] = sum_r gP_l[n][r] W_l[r][i] + gP_r[n][r] W_r[r][i]   (WcatT is [I][2F])
 int gemm_input_grad(gatx_ctx* ctx, const float* gPl_own, const float* gPr, const Layer& ly, float* gX, int ldg) {
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
@@ -410,18 +423,26 @@ int do_forward(gatx_ctx* ctx) {
   if (rc) return rc;
   if (!ctx->have_params) return fail(ctx, GATX_ERR_INVALID, "parameters not initialised");
   const EdgeGraph g = edge_graph(ctx);
-  const float* X = ctx->X0;
+  const float* X = ctx->X0 + (int64_t)ctx->r0 * ctx->ld0;
   for (int l = 0; l < ctx->L; ++l) {
     Layer& ly = ctx->layers[l];
+    const bool replicated = l == 0 && ctx->world > 1;  // layer 0 with the input features on every rank
     {
       PhaseTimer t(ctx, PH_GEMM_FWD);
       LAUNCHED(launch_pack_weights(ctx->params + ly.w_off, ly.F, ly.I, ly.Wcat, ly.ldk, ly.WcatT, ctx->st));
       // P_l = X W_l^T, P_r = X W_r^T : the only dense contraction of the forward (EB:303-316)
-      rc = gemm_project(ctx, X, ly.ldx, ly);
+      if (replicated) {
+        rc = gemm_tn_any(ctx, ctx->X0, ly.ldx, ly.Wcat, ly.ldk, ly.Pl, ly.F, ctx->N, ly.F, ly.I);
+        if (!rc) rc = gemm_tn_any(ctx, X, ly.ldx, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, ly.Pr, ly.F, ctx->n_rows, ly.F, ly.I);
+      } else {
+        rc = gemm_project(ctx, X, ly.ldx, ly);
+      }
       if (rc) return rc;
     }
-    rc = comm_allgather_rows(ctx, ly.Pl, ly.F);
-    if (rc) return rc;
+    if (!replicated) {
+      rc = comm_allgather_rows(ctx, ly.Pl, ly.F);
+      if (rc) return rc;
+    }
     {
       PhaseTimer t(ctx, PH_EDGE_FWD);
       EdgeGraph gl = g;
@@ -489,7 +510,8 @@ int do_backward(gatx_ctx* ctx) {
   }
   for (int l = ctx->L - 1; l >= 0; --l) {
     Layer& ly = ctx->layers[l];
-    const float* X = l == 0 ? ctx->X0 : ctx->layers[l - 1].Hout;
+    const float* X = l == 0 ? ctx->X0 + (int64_t)ctx->r0 * ctx->ld0 : ctx->layers[l - 1].Hout;
+    const bool replicated = l == 0 && ctx->world > 1;
     {
       PhaseTimer t(ctx, PH_EDGE_BWD);
       int n_part = 0;
@@ -520,14 +542,21 @@ int do_backward(gatx_ctx* ctx) {
                            cudaMemcpyDeviceToDevice, ctx->st));
       }
     }
-    rc = comm_reduce_rows(ctx, ctx->gPl, ly.F);
-    if (rc) return rc;
+    if (!replicated) {
+      rc = comm_reduce_rows(ctx, ctx->gPl, ly.F);
+      if (rc) return rc;
+    }
     {
       PhaseTimer t(ctx, PH_GEMM_BWD);
       const float* gPl_own = ctx->gPl + (int64_t)ctx->r0 * ly.F;
       float* gW = ctx->grads + ly.w_off;
-      // gW_l = gP_l^T X, gW_r = gP_r^T X  (EB:771-782), W row stride 2I, W_r at column offset I
-      rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+      // gW_l = gP_l^T X, gW_r = gP_r^T X  (EB:771-782), W row stride 2I, W_r at column offset I.
+      // Replicated layer 0: this rank's PARTIAL gP_l over all sources is contracted with the full X; the
+      // all-reduce of the weight gradients completes the sum, so gP_l itself is never exchanged.
+      if (replicated)
+        rc = gemm_nt_reduce(ctx, ctx->gPl, ly.F, ctx->X0, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->N);
+      else
+        rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
       rc = gemm_nt_reduce(ctx, ctx->gPr, ly.F, X, ly.ldx, gW + ly.I, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
@@ -736,17 +765,18 @@ int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim) {
   const int ld = (in_dim + 3) / 4 * 4;  // 16-byte row pitch for TMA / 128-bit loads, zero padded
   if (!ctx->X0 || ctx->I0 != in_dim) {
     if (ctx->have_bufs) free_bufs(ctx);
-    CK(dalloc(&ctx->X0, (size_t)ctx->n_rows * ld));
-    CK(cudaMemsetAsync(ctx->X0, 0, sizeof(float) * (size_t)ctx->n_rows * ld, ctx->st));
+    // every rank keeps ALL rows of the (constant) input features: layer 0 can then project every source locally
+    // and contract its partial gP_l with the full X, so it needs no all-gather and no reduce (see do_forward)
+    CK(dalloc(&ctx->X0, (size_t)ctx->N * ld));
+    CK(cudaMemsetAsync(ctx->X0, 0, sizeof(float) * (size_t)ctx->N * ld, ctx->st));
     ctx->I0 = in_dim;
     ctx->ld0 = ld;
   }
-  if (ctx->n_rows && ld == in_dim)  // no padding: one contiguous DMA
-    CK(cudaMemcpyAsync(ctx->X0, X + (int64_t)ctx->r0 * in_dim, sizeof(float) * (size_t)ctx->n_rows * in_dim,
-                       cudaMemcpyHostToDevice, ctx->st));
-  else if (ctx->n_rows)
-    CK(cudaMemcpy2DAsync(ctx->X0, sizeof(float) * ld, X + (int64_t)ctx->r0 * in_dim, sizeof(float) * in_dim,
-                         sizeof(float) * in_dim, ctx->n_rows, cudaMemcpyHostToDevice, ctx->st));
+  if (ld == in_dim)  // no padding: one contiguous DMA
+    CK(cudaMemcpyAsync(ctx->X0, X, sizeof(float) * (size_t)ctx->N * in_dim, cudaMemcpyHostToDevice, ctx->st));
+  else
+    CK(cudaMemcpy2DAsync(ctx->X0, sizeof(float) * ld, X, sizeof(float) * in_dim, sizeof(float) * in_dim, ctx->N,
+                         cudaMemcpyHostToDevice, ctx->st));
   ctx->have_feat = true;
   return GATX_OK;
 }
