@@ -14,6 +14,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -315,8 +316,11 @@ int launch_tn(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a
 }
 
 int pick_bn(int N, int n_split) {
-  // widest tile (<= 128 so that two CTAs share an SM) that does not straddle the C0/C1 split
-  for (int bn : {128, 64, 32, 16}) {
+  // widest tile that does not straddle the C0/C1 split.  256 halves the re-reads of the A tile through L2
+  // (N/BN column tiles share it) and still lets two CTAs share an SM (2 x 96 KB smem, 2 x 256 TMEM columns).
+  static const bool wide = getenv("GATX_GEMM_BN128") == nullptr;
+  for (int bn : {256, 128, 64, 32, 16}) {
+    if (bn == 256 && (!wide || N < 256)) continue;
     if (n_split < N && n_split % bn) continue;
     if (bn == 16 || N >= bn || N > bn / 2) return bn;
   }
@@ -524,6 +528,7 @@ int launch_gemm_tc_tn2(const float* A0, int64_t lda0, const float* B0, int64_t l
     b1 = b0;
   }
   switch (bn) {
+    case 256: return launch_tn<256>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
     case 128: return launch_tn<128>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
     case 64: return launch_tn<64>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
     case 32: return launch_tn<32>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
