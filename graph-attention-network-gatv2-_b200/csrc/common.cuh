@@ -100,6 +100,18 @@ int launch_edge_backward_stream(const EdgeGraph& g, int H, int D, const float* P
                                 const float* sinv, float* gPr, float* gPl, uint32_t* rec, float* part,
                                 float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st);
 
+// edge_generic.cu : any heads <= 32, any per-head dim with heads*dim <= 1024 (scalar fallback)
+bool edge_generic_supported(int H, int D);
+int edge_generic_rec_words(int H);
+int edge_generic_partials();
+int launch_edge_forward_generic(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
+                                float* Hout, float* hpre, float* score, float* mx, float* sinv, cudaStream_t st);
+int launch_edge_backward_generic(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
+                                 const float* Hout, float* gH, const float* score, const float* mx, const float* sinv,
+                                 float* gPr, float* gPl, uint32_t* rec, float* ga_partials, int* n_partials,
+                                 float* galpha_dbg, cudaStream_t st);
+int launch_unpack_rec_generic(const uint32_t* rec, int64_t E, int H, float* alpha, float* ge, cudaStream_t st);
+
 // head_loss.cu : classifier + softmax + CE + argmax + output gradients (EB:463-608)
 constexpr int kHeadBlocks = kNumSMs * 2;
 int launch_head(const float* HL, const float* Wo, const int* labels, int N, int C, int DL, int ldc, float* y, float* dz,

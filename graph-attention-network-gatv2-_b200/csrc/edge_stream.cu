@@ -396,7 +396,7 @@ __device__ __forceinline__ void load_scalars(RowScalars<NV>& q, int row, const S
   }
 }
 
-// smem per warp: ring [R][F] | rowbuf [2][2F] (g_h row, P_r row) | score window [2][32*H] | barriers [R + 2]
+// smem per warp: ring [R][F] | rowbuf [2F] (g_h row, P_r row) | score window [2][32*H] | barriers [R + 1]
 template <int NV, int R, int LPH>
 __global__ void __launch_bounds__(kSW * 32)
 edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const float* __restrict__ Pl,
@@ -410,24 +410,21 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
   constexpr uint32_t kRowBytes = F * 4;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp_floats = R * F + 4 * F + 2 * 32 * max_h;
+  const int per_warp_floats = R * F + 2 * F + 2 * 32 * max_h;
   float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * per_warp_floats;
   float* ring = wbase;
-  float* rowbuf = wbase + R * F;        // [2][2F]
-  float* scwin = rowbuf + 4 * F;        // [2][32*H]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kSW * per_warp_floats * 4) + warp * (R + 2);
+  float* rowbuf = wbase + R * F;        // [2F]
+  float* scwin = rowbuf + 2 * F;        // [2][32*H]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kSW * per_warp_floats * 4) + warp * (R + 1);
   uint64_t* rbar = bar + R;
   if (lane == 0) {
-    for (int s = 0; s < R + 2; ++s) mbar_init(&bar[s], 1);
+    for (int s = 0; s < R + 1; ++s) mbar_init(&bar[s], 1);
     fence_mbar_init();
   }
   __syncwarp();
-  float4 av[NV], ga[NV];
+  float4 ga[NV];  // the attention vector a is only needed when a row segment is written: read it there (L1 hit)
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    av[j] = ldg4(a + 4 * (lane + 32 * j));
-    ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int j = 0; j < NV; ++j) ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int H = LPH > 0 ? NV * 32 / (LPH > 0 ? LPH : 1) : sh.H;  // compile-time when the head width is
   const int RW = rec_words(H, NV);
   const bool head_lane = is_head_lane<LPH>(lane, sh);
@@ -452,18 +449,12 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         bulk_g2s(ring + slot * F, Pl + (int64_t)src * F, kRowBytes, &bar[slot]);
       }
     }
-    // row data of r (now) and r + 1 (prefetch) through the row buffers
+    // row data (g_h row, P_r row) of r goes through the row buffer; once it sits in registers the buffer is free,
+    // so row r + 1 is prefetched into the same buffer while row r is being processed
     if (lane == 0) {
-      const uint32_t b0 = rk & 1;
-      mbar_expect_tx(&rbar[b0], 2 * kRowBytes);
-      bulk_g2s(rowbuf + b0 * 2 * F, gh + (int64_t)r * F, kRowBytes, &rbar[b0]);
-      bulk_g2s(rowbuf + b0 * 2 * F + F, Pr + (int64_t)r * F, kRowBytes, &rbar[b0]);
-      if (r + 1 < g.n_rows) {
-        const uint32_t b1 = (rk + 1) & 1;
-        mbar_expect_tx(&rbar[b1], 2 * kRowBytes);
-        bulk_g2s(rowbuf + b1 * 2 * F, gh + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
-        bulk_g2s(rowbuf + b1 * 2 * F + F, Pr + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
-      }
+      mbar_expect_tx(rbar, 2 * kRowBytes);
+      bulk_g2s(rowbuf, gh + (int64_t)r * F, kRowBytes, rbar);
+      bulk_g2s(rowbuf + F, Pr + (int64_t)r * F, kRowBytes, rbar);
     }
     // score window: the scores of 32 consecutive edges are contiguous ([E][H]); the next window is
     // prefetched into registers while the current one is consumed from shared memory
@@ -488,14 +479,20 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       next_end = __ldg(g.row_ptr + r + 2);
     }
     float4 ghr[NV], pr[NV], gpr[NV];
-    mbar_wait(&rbar[rk & 1], (rk >> 1) & 1);
+    mbar_wait(rbar, rk & 1);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      ghr[j] = lds4(rowbuf + (rk & 1) * 2 * F + 4 * (lane + 32 * j));
-      pr[j] = lds4(rowbuf + (rk & 1) * 2 * F + F + 4 * (lane + 32 * j));
+      ghr[j] = lds4(rowbuf + 4 * (lane + 32 * j));
+      pr[j] = lds4(rowbuf + F + 4 * (lane + 32 * j));
       gpr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
+    ++rk;
+    if (r + 1 < g.n_rows && lane == 0) {
+      mbar_expect_tx(rbar, 2 * kRowBytes);
+      bulk_g2s(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar);
+      bulk_g2s(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar);
+    }
     bool first_row = true;
     for (int i = 0; i < n; ++i) {
       const int e = e0 + i;
@@ -504,31 +501,32 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         float* dst = (first_row && started_before) ? part + ((int64_t)chunk * 2 + 0) * F : gPr + (int64_t)r * F;
         if (e > e0 || !first_row) {
 #pragma unroll
-          for (int j = 0; j < NV; ++j)
-            st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * av[j].x, gpr[j].y * av[j].y, gpr[j].z * av[j].z,
-                                                       gpr[j].w * av[j].w));
+          for (int j = 0; j < NV; ++j) {
+            const float4 avj = ldg4(a + 4 * (lane + 32 * j));
+            st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * avj.x, gpr[j].y * avj.y, gpr[j].z * avj.z,
+                                                       gpr[j].w * avj.w));
+          }
         }
         first_row = false;
         ++r;
-        ++rk;
         q = qn;
         row_end = next_end;
         next_end = 0x7fffffff;
-        // the prefetched row r is in buffer rk & 1; refill the other buffer with row r + 1
-        mbar_wait(&rbar[rk & 1], (rk >> 1) & 1);
+        // the prefetched row r has landed (or is landing) in the row buffer; take it and prefetch r + 1
+        mbar_wait(rbar, rk & 1);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          ghr[j] = lds4(rowbuf + (rk & 1) * 2 * F + 4 * (lane + 32 * j));
-          pr[j] = lds4(rowbuf + (rk & 1) * 2 * F + F + 4 * (lane + 32 * j));
+          ghr[j] = lds4(rowbuf + 4 * (lane + 32 * j));
+          pr[j] = lds4(rowbuf + F + 4 * (lane + 32 * j));
           gpr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
+        ++rk;
         if (r + 1 < g.n_rows) {
           if (lane == 0) {
-            const uint32_t b1 = (rk + 1) & 1;
-            mbar_expect_tx(&rbar[b1], 2 * kRowBytes);
-            bulk_g2s(rowbuf + b1 * 2 * F, gh + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
-            bulk_g2s(rowbuf + b1 * 2 * F + F, Pr + (int64_t)(r + 1) * F, kRowBytes, &rbar[b1]);
+            mbar_expect_tx(rbar, 2 * kRowBytes);
+            bulk_g2s(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar);
+            bulk_g2s(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar);
           }
           load_scalars<NV>(qn, r + 1, sh, cdot, mx, sinv, lane);
           next_end = __ldg(g.row_ptr + r + 2);
@@ -596,17 +594,17 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       const bool complete = ended && !(first_row && started_before);
       float* dst = complete ? gPr + (int64_t)r * F : part + ((int64_t)chunk * 2 + (first_row ? 0 : 1)) * F;
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * av[j].x, gpr[j].y * av[j].y, gpr[j].z * av[j].z,
-                                                   gpr[j].w * av[j].w));
+      for (int j = 0; j < NV; ++j) {
+        const float4 avj = ldg4(a + 4 * (lane + 32 * j));
+        st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * avj.x, gpr[j].y * avj.y, gpr[j].z * avj.z,
+                                                   gpr[j].w * avj.w));
+      }
     }
     it += n;
     // the row-buffer pipeline restarts at the next chunk: drain the outstanding prefetch of row r + 1
     if (r + 1 < g.n_rows) {
-      mbar_wait(&rbar[(rk + 1) & 1], ((rk + 1) >> 1) & 1);
-      rk += 2;
-    } else {
-      rk += 1;
+      mbar_wait(rbar, rk & 1);
+      ++rk;
     }
     __syncwarp();
   }
@@ -888,8 +886,8 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
     if (eg.E > 0) {
       {
         constexpr int R = NV == 4 ? 4 : 8;
-        const size_t per_warp = (size_t)(R * F + 4 * F + 2 * 32 * H) * 4;
-        const size_t smem = kSW * per_warp + (size_t)kSW * (R + 2) * 8;
+        const size_t per_warp = (size_t)(R * F + 2 * F + 2 * 32 * H) * 4;
+        const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
         auto kern = edge_bwd_dst_stream_kernel<NV, R, LPH>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);

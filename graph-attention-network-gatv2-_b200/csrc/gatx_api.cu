@@ -54,6 +54,7 @@ enum Phase { PH_GEMM_FWD = 0, PH_EDGE_FWD, PH_HEAD, PH_EDGE_BWD, PH_GEMM_BWD, PH
 
 struct Layer {
   int H = 0, D = 0, F = 0, I = 0, Fout = 0, ldx = 0, ldk = 0, recw = 0;
+  bool vec = true;
   int64_t w_off = 0, a_off = 0;
   float *Wcat = nullptr, *WcatT = nullptr;
   float *Pl = nullptr, *Pr = nullptr, *Hfull = nullptr, *Hout = nullptr, *hpre = nullptr;
@@ -231,11 +232,12 @@ int ensure_buffers(gatx_ctx* ctx) {
     // EB semantics: hidden layers concatenate heads; the last layer averages them (EB:440-459)
     ly.Fout = (l == L - 1) ? ly.D : ly.F;
     ly.ldk = (ly.I + 3) / 4 * 4;
-    ly.recw = edge_rec_words(ly.H, ly.D);
-    if (!edge_shape_supported(ly.H, ly.D))
+    ly.vec = edge_shape_supported(ly.H, ly.D);  // vectorised kernels; otherwise the generic scalar kernels
+    ly.recw = ly.vec ? edge_rec_words(ly.H, ly.D) : edge_generic_rec_words(ly.H);
+    if (!ly.vec && !edge_generic_supported(ly.H, ly.D))
       return fail(ctx, GATX_ERR_UNSUPPORTED,
-                  "layer %d: heads=%d outdim=%d not covered by the edge kernels (need outdim in {4,8,..,128}, "
-                  "heads*outdim/4 a power of two below 32 or a multiple of 32 up to 256)", l, ly.H, ly.D);
+                  "layer %d: heads=%d outdim=%d not covered by the edge kernels (need heads <= 32 and "
+                  "heads*outdim <= 1024)", l, ly.H, ly.D);
     ly.w_off = off;
     off += (int64_t)ly.F * 2 * ly.I;
     if (ly.F > Fmax) Fmax = ly.F;
@@ -452,7 +454,10 @@ int do_forward(gatx_ctx* ctx) {
         gl.kernel_events = ly.kev;
         ly.kev_fwd = true;
       }
-      if (ctx->use_stream && edge_stream_supported(ly.H, ly.D))
+      if (!ly.vec)
+        LAUNCHED(launch_edge_forward_generic(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
+                                             ly.score, ly.mx, ly.sinv, ctx->st));
+      else if (ctx->use_stream && edge_stream_supported(ly.H, ly.D))
         LAUNCHED(launch_edge_forward_stream(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
                                             ly.score, ly.mx, ly.sinv, ctx->part, ctx->st));
       else
@@ -522,7 +527,12 @@ int do_backward(gatx_ctx* ctx) {
         gl.kernel_events = ly.kev;
         ly.kev_bwd = true;
       }
-      if (ctx->use_stream && edge_stream_supported(ly.H, ly.D)) {
+      if (!ly.vec) {
+        LAUNCHED(launch_edge_backward_generic(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
+                                              ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->gPl, ctx->rec, ctx->ga_partials,
+                                              &n_part, ly.galpha_dbg, ctx->st));
+        LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
+      } else if (ctx->use_stream && edge_stream_supported(ly.H, ly.D)) {
         LAUNCHED(launch_edge_backward_stream(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
                                              ctx->cdot, ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->gPl, ctx->rec,
                                              ctx->part, ctx->ga_partials, &n_part, ly.galpha_dbg, ctx->st));
@@ -535,7 +545,8 @@ int do_backward(gatx_ctx* ctx) {
         LAUNCHED(launch_edge_backward_src(g, ly.H, ly.D, ctx->params + ly.a_off, ly.gH, ctx->rec, ctx->gPl, ctx->st));
       }
       if (ctx->keep_debug) {
-        LAUNCHED(launch_unpack_rec(ctx->rec, ctx->E, ly.H, ly.D, ly.alpha_dbg, ly.ge_dbg, ctx->st));
+        if (ly.vec) LAUNCHED(launch_unpack_rec(ctx->rec, ctx->E, ly.H, ly.D, ly.alpha_dbg, ly.ge_dbg, ctx->st));
+        else LAUNCHED(launch_unpack_rec_generic(ctx->rec, ctx->E, ly.H, ly.alpha_dbg, ly.ge_dbg, ctx->st));
         CK(cudaMemcpyAsync(ly.gPl_dbg, ctx->gPl, sizeof(float) * (size_t)ctx->N * ly.F, cudaMemcpyDeviceToDevice,
                            ctx->st));
         CK(cudaMemcpyAsync(ly.gPr_dbg, ctx->gPr, sizeof(float) * (size_t)ctx->n_rows * ly.F,
@@ -957,7 +968,7 @@ int gatx_get_edge_kernel_ms(gatx_ctx* ctx, int32_t layer, float* out3) {
   CK(cudaStreamSynchronize(ctx->st));
   Layer& ly = ctx->layers[layer];
   out3[0] = out3[1] = out3[2] = 0.f;
-  const bool stream = ctx->use_stream && edge_stream_supported(ly.H, ly.D);
+  const bool stream = ly.vec && ctx->use_stream && edge_stream_supported(ly.H, ly.D);
   if (!stream) return GATX_OK;  // only the streaming kernels are individually timed
   if (ly.kev_fwd) cudaEventElapsedTime(&out3[0], ly.kev[0], ly.kev[1]);
   if (ly.kev_bwd) {

@@ -29,6 +29,8 @@ SHAPES = [
     (150, 150, 7, 3, (1, 1), (4, 8), "uniform", None),          # self-loops only, tiny rows
     (2500, 9000, 12, 3, (4, 1), (32, 128), "uniform", 1500),    # streaming kernels: hub rows span several chunks
     (1200, 20000, 16, 4, (2, 4, 1), (64, 128, 128), "rmat", 700),  # streaming kernels, 128/512-float rows
+    (300, 2500, 11, 5, (3, 2, 1), (5, 12, 7), "rmat", None),    # generic scalar kernels: odd head dims
+    (200, 1500, 9, 3, (5, 1), (6, 200), "uniform", 150),        # generic kernels: D = 200 (> 128), F = 30
 ]
 
 
@@ -197,8 +199,8 @@ def test_init_params_distribution(gatx):
 
 
 def test_unsupported_shape_is_reported(gatx):
-    p = make_problem(50, 200, 8, 3, (3,), (5,), seed=2)
-    eng = gatx.Engine([3], [5])
+    p = make_problem(50, 200, 8, 3, (2,), (600,), seed=2)  # heads * outdim = 1200 > 1024
+    eng = gatx.Engine([2], [600])
     eng.set_graph(p["row_ptr"], p["col_idx"]); eng.set_features(p["X"]); eng.set_labels(p["labels"], 3)
     with pytest.raises(gatx.GatxError, match="not covered"):
         eng.init_params(0)
