@@ -348,10 +348,22 @@ __global__ void fill_empty_fwd_kernel(const int* __restrict__ row_ptr, int n_row
     sinv[(int64_t)r * H + h] = 1e8f;
   }
 }
+// warp-cooperative: each lane tests one row, the warp then zeroes every empty row with coalesced 128-bit stores
+// (on a multi-GPU shard many sources have no local out-edge, so this must run at memset speed)
 __global__ void fill_empty_rows_kernel(const int* __restrict__ row_ptr, int n_rows, int F, float* __restrict__ out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rows || row_ptr[r + 1] != row_ptr[r]) return;
-  for (int k = 0; k < F; ++k) out[(int64_t)r * F + k] = 0.f;
+  const int lane = threadIdx.x & 31;
+  const int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (base >= n_rows) return;
+  const int r = base + lane;
+  const bool empty = r < n_rows && __ldg(row_ptr + r + 1) == __ldg(row_ptr + r);
+  uint32_t mask = __ballot_sync(0xffffffffu, empty);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  while (mask) {
+    const int b = __ffs(mask) - 1;
+    mask &= mask - 1;
+    float* row = out + (int64_t)(base + b) * F;
+    for (int k = 4 * lane; k < F; k += 128) st4(row + k, z);
+  }
 }
 
 // ------------------------------------------------------------------------- backward, preparation
@@ -880,7 +892,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
       edge_bwd_prep_kernel<NV><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
       ++launches;
     }
-    fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);
+    fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);  // 8 warps x 32 rows
     fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
     launches += 2;
     if (eg.E > 0) {
