@@ -302,13 +302,10 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
 template <int BN>
 int launch_tn(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, int K0,
               int K1, float* C0, float* C1, int n_split, int64_t ldc, int M, int N, bool accumulate, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tf32_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TnSmem<BN>::kBytes) != cudaSuccess)
-      return -1;
-    configured = true;
-  }
+  // per launch: the attribute is per device, and one process may drive several devices (train_gatx --gpus N)
+  if (cudaFuncSetAttribute(gemm_tf32_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TnSmem<BN>::kBytes) !=
+      cudaSuccess)
+    return -1;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_tf32_tn_kernel<BN><<<grid, kThreads, TnSmem<BN>::kBytes, st>>>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M,
                                                                       N, accumulate ? 1 : 0);
@@ -480,13 +477,9 @@ __global__ void atb_reduce_kernel(const float* __restrict__ ws, int splits, int 
 template <int BN>
 int launch_atb(const CUtensorMap& a, const CUtensorMap& b, int64_t K, float* C, int64_t ldc, int M, int N, float* ws,
                size_t ws_bytes, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tf32_atb_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             AtbSmem<BN>::kBytes) != cudaSuccess)
-      return -1;
-    configured = true;
-  }
+  if (cudaFuncSetAttribute(gemm_tf32_atb_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           AtbSmem<BN>::kBytes) != cudaSuccess)
+    return -1;
   const int tn = (N + BN - 1) / BN, tm = (M + BM - 1) / BM, tiles = tn * tm;
   const int total_kb = (int)((K + BKN - 1) / BKN);
   int splits = (kNumSMs + tiles - 1) / tiles;
