@@ -78,3 +78,27 @@ def test_two_ranks_match_one(world):
     pred = np.concatenate([o["pred"] for o in outs])
     assert (pred != eng.tensor(gatx.T_PRED)).mean() < 0.01
     eng.close()
+
+
+def test_cli_two_gpus_matches_one(tmp_path):
+    """train_gatx --gpus 2 (two host threads, two contexts in one process) prints the same curve as --gpus 1."""
+    import re
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(HERE, "..", "graph-attention-network-gatv2-_b200"))
+    import build as gatx_build
+    import datasets
+    cli = gatx_build.build_cli()
+    ds = datasets.make_dataset("arxiv", 0.05)
+    datasets.write_txt(str(tmp_path / "g"), ds)
+    base = [cli, "--num-layers", "3", "--heads", "4,4,1", "--outdims", "64,64,64", "--epochs", "6", "--optimizer", "adam",
+            "--lr", "0.01", "--dataset", "g", "--data-root", str(tmp_path), "--seed", "3", "--gemm", "fp32"]
+    curves = []
+    for gpus in ("1", "2"):
+        r = subprocess.run(base + ["--gpus", gpus], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        curves.append([float(x) for x in re.findall(r"Avg Loss: ([0-9.]+)", r.stdout)])
+    assert len(curves[0]) == 6 and len(curves[1]) == 6
+    for a, b in zip(*curves):
+        assert abs(a - b) < 2e-4 * max(1.0, a)
