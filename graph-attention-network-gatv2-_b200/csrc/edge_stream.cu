@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace gatx {
 namespace {
 
@@ -789,6 +791,8 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
   }
 }
 
+#include "edge_stream_pair.inc"
+
 bool make_stream_shape(int H, int D, Shape* sh, int* nv) {
   if (H < 1 || D < 4 || D % 4 || D > 128 || H > 8) return false;
   const int lph = D / 4;
@@ -815,6 +819,11 @@ int stream_grid(const void* kernel, size_t smem, int n_chunks) {
 
 template <int NV>
 constexpr int ring_depth() { return NV == 4 ? 8 : (NV == 2 ? 8 : 16); }
+
+bool use_pair(int nv, const Shape& sh) {
+  static const bool off = getenv("GATX_NO_PAIR") != nullptr;
+  return !off && nv == 1 && sh.H == 1 && sh.lph == 32;
+}
 
 #define STREAM_DISPATCH_NV(nv, ...)                          \
   do {                                                       \
@@ -855,6 +864,22 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   ++launches;
   if (eg.E == 0) return launches;
   StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
+  if (use_pair(nv, sh)) {  // one head of 128 floats: two edges per loop iteration
+    constexpr int R = 16;
+    const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
+    auto kern = edge_fwd_pair_kernel<R>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
+    if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
+    kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, Hout, hpre, score, mx, sinv, part);
+    if (eg.kernel_events) cudaEventRecord(eg.kernel_events[1], st);
+    ++launches;
+    if (g.n_chunks > 1) {
+      edge_fwd_fixup_kernel<1><<<(g.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(g, sh, part, Hout, hpre, mx, sinv);
+      ++launches;
+    }
+    return launches;
+  }
   STREAM_DISPATCH(nv, sh.lph, {
     constexpr int R = ring_depth<NV>();
     const size_t smem = (size_t)kSW * R * NV * 128 * 4 + (size_t)kSW * R * 8;
@@ -884,6 +909,52 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   if (eg.n_rows <= 0) return 0;
   StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
   StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src};
+  if (use_pair(nv, sh)) {
+    constexpr int R = 16, F = kPF;
+    {
+      int blocks = (eg.n_rows + 7) / 8;
+      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+      edge_bwd_prep_kernel<1><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+      ++launches;
+    }
+    fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);
+    fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
+    launches += 2;
+    if (eg.E > 0) {
+      {
+        const size_t per_warp = (size_t)(R * F + 2 * F + 64) * 4;
+        const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
+        auto kern = edge_bwd_dst_pair_kernel<R>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
+        kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, gH, cdot, score, mx, sinv, gPr, rec, part,
+                                             ga_partials, galpha_dbg);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[3], st);
+        *n_partials = blocks;
+        ++launches;
+        if (gd.n_chunks > 1) {
+          edge_sum_fixup_kernel<1><<<(gd.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gd, part, gPr);
+          ++launches;
+        }
+      }
+      {
+        const size_t smem = (size_t)kSW * R * (F + 32) * 4 + (size_t)kSW * R * 8;
+        auto kern = edge_bwd_src_pair_kernel<R>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[4], st);
+        kern<<<blocks, kSW * 32, smem, st>>>(gs, eg.csc_dst, eg.csc_eid, a, gH, rec, gPl, part);
+        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[5], st);
+        ++launches;
+        if (gs.n_chunks > 1) {
+          edge_sum_fixup_kernel<1><<<(gs.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gs, part, gPl);
+          ++launches;
+        }
+      }
+    }
+    return launches;
+  }
   STREAM_DISPATCH(nv, sh.lph, {
     constexpr int F = NV * 128;
     {
