@@ -116,10 +116,11 @@ int launch_unpack_rec_generic(const uint32_t* rec, int64_t E, int H, float* alph
 constexpr int kHeadBlocks = kNumSMs * 2;
 int launch_head(const float* HL, const float* Wo, const int* labels, int N, int C, int DL, int ldc, float* y, float* dz,
                 float* z_dbg, int* pred, float* gH, double* loss_partials, int* correct_partials, int* n_partials,
-                cudaStream_t st);
+                const unsigned char* mask, cudaStream_t st);
 // tensor-core head: z = H_L W_o^T and gH = dz W_o run as tcgen05 GEMMs around this kernel
 int launch_softmax_ce(const float* z, const int* labels, int N, int C, int ldc, float* y, float* dz, int* pred,
-                      double* loss_partials, int* correct_partials, int* n_partials, cudaStream_t st);
+                      double* loss_partials, int* correct_partials, int* n_partials, const unsigned char* mask,
+                      cudaStream_t st);
 int launch_transpose_wo(const float* Wo, int C, int DL, int ldc, float* WoT, cudaStream_t st);
 int launch_loss_finalize(const double* loss_partials, const int* correct_partials, int n_partials,
                          double* loss_sum, long long* correct, cudaStream_t st);

@@ -93,6 +93,12 @@ struct gatx_ctx {
   int I0 = 0, ld0 = 0, C = 0;
   float* X0 = nullptr;
   int* labels = nullptr;
+  // optional node masks (extension): local rows, 1 = node counts; nullptr = every node (the reference)
+  unsigned char *train_mask = nullptr, *eval_mask = nullptr;
+  int64_t train_count = 0, eval_count = 0;  // GLOBAL number of counted nodes
+  int64_t last_count = 0;                   // denominator of the last forward's loss / accuracy
+  bool fwd_valid = false;                   // a training forward is the most recent forward
+  bool eval_mode = false;                   // forward only: eval_mask in the loss, no output gradients
   // params: flat [W_0..W_{L-1} | a_0..a_{L-1} | W_o]
   int64_t n_params = 0, wo_off = 0;
   OptimGroups grp{};
@@ -422,6 +428,7 @@ int comm_reduce_rows(gatx_ctx* ctx, float* full, int F) {
 
 int do_forward(gatx_ctx* ctx) {
   int rc = ensure_buffers(ctx);
+  const unsigned char* mask = ctx->eval_mode ? ctx->eval_mask : ctx->train_mask;
   if (rc) return rc;
   if (!ctx->have_params) return fail(ctx, GATX_ERR_INVALID, "parameters not initialised");
   const EdgeGraph g = edge_graph(ctx);
@@ -481,28 +488,34 @@ int do_forward(gatx_ctx* ctx) {
       if (n1 >= 0) {
         ctx->launches += n1;
         LAUNCHED(launch_softmax_ce(ctx->z_dbg, ctx->labels, ctx->n_rows, ctx->C, ctx->ldc, ctx->y, ctx->dz, ctx->pred,
-                                   ctx->loss_partials, ctx->correct_partials, &n_part, ctx->st));
-        LAUNCHED(launch_transpose_wo(Wo, ctx->C, last.D, ctx->ldc, ctx->WoT, ctx->st));
-        int n2 = launch_gemm_tc_tn(ctx->dz, ctx->ldc, ctx->WoT, ctx->ldc, gH_out, last.D, ctx->n_rows, last.D, ctx->C,
-                                   false, ctx->st);
-        if (n2 < 0) return fail(ctx, GATX_ERR_UNSUPPORTED, "tensor-core head gradient GEMM rejected its shape");
-        ctx->launches += n2;
+                                   ctx->loss_partials, ctx->correct_partials, &n_part, mask, ctx->st));
+        if (!ctx->eval_mode) {
+          LAUNCHED(launch_transpose_wo(Wo, ctx->C, last.D, ctx->ldc, ctx->WoT, ctx->st));
+          int n2 = launch_gemm_tc_tn(ctx->dz, ctx->ldc, ctx->WoT, ctx->ldc, gH_out, last.D, ctx->n_rows, last.D, ctx->C,
+                                     false, ctx->st);
+          if (n2 < 0) return fail(ctx, GATX_ERR_UNSUPPORTED, "tensor-core head gradient GEMM rejected its shape");
+          ctx->launches += n2;
+        }
         tc_done = true;
       }
     }
     if (!tc_done)
       LAUNCHED(launch_head(last.Hout, Wo, ctx->labels, ctx->n_rows, ctx->C, last.D, ctx->ldc, ctx->y, ctx->dz,
                            ctx->keep_debug ? ctx->z_dbg : nullptr, ctx->pred, gH_out, ctx->loss_partials,
-                           ctx->correct_partials, &n_part, ctx->st));
+                           ctx->correct_partials, &n_part, mask, ctx->st));
     LAUNCHED(launch_loss_finalize(ctx->loss_partials, ctx->correct_partials, n_part, ctx->loss_sum, ctx->correct,
                                   ctx->st));
-    if (last.gHout) LAUNCHED(launch_head_bcast_grad(last.gHout, ctx->n_rows, last.H, last.D, last.gH, ctx->st));
+    if (last.gHout && !ctx->eval_mode)
+      LAUNCHED(launch_head_bcast_grad(last.gHout, ctx->n_rows, last.H, last.D, last.gH, ctx->st));
   }
+  ctx->fwd_valid = !ctx->eval_mode;
+  ctx->last_count = mask ? (ctx->eval_mode ? ctx->eval_count : ctx->train_count) : (int64_t)ctx->N;
   return GATX_OK;
 }
 
 int do_backward(gatx_ctx* ctx) {
-  if (!ctx->have_bufs) return fail(ctx, GATX_ERR_INVALID, "forward must run before backward");
+  if (!ctx->have_bufs || !ctx->fwd_valid)
+    return fail(ctx, GATX_ERR_INVALID, "gatx_forward must run before gatx_backward (gatx_evaluate does not count)");
   const EdgeGraph g = edge_graph(ctx);
   int rc;
   {
@@ -601,7 +614,7 @@ __global__ void pack_loss_kernel(const double* loss_sum, const long long* correc
   out2[1] = (double)*correct;
 }
 
-int read_loss(gatx_ctx* ctx, float* avg_loss, float* accuracy) {
+int read_loss(gatx_ctx* ctx, float* avg_loss, float* accuracy, int64_t count) {
   pack_loss_kernel<<<1, 1, 0, ctx->st>>>(ctx->loss_sum, ctx->correct, ctx->red2);
   ctx->launches += 1;
   if (ctx->world > 1) {
@@ -611,8 +624,9 @@ int read_loss(gatx_ctx* ctx, float* avg_loss, float* accuracy) {
   double h[2];
   CK(cudaMemcpyAsync(h, ctx->red2, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
-  if (avg_loss) *avg_loss = (float)(h[0] / (double)ctx->N);  // EB:544
-  if (accuracy) *accuracy = (float)(h[1] / (double)ctx->N);  // EB:546
+  const double den = (double)(count > 0 ? count : 1);
+  if (avg_loss) *avg_loss = (float)(h[0] / den);  // EB:544 (count = N without a mask)
+  if (accuracy) *accuracy = (float)(h[1] / den);  // EB:546
   return GATX_OK;
 }
 
@@ -664,6 +678,8 @@ void gatx_destroy(gatx_ctx* ctx) {
   free_graph(ctx);
   dfree(ctx->X0);
   dfree(ctx->labels);
+  dfree(ctx->train_mask);
+  dfree(ctx->eval_mask);
   for (auto& s : ctx->spans) {
     cudaEventDestroy(s.a);
     cudaEventDestroy(s.b);
@@ -701,6 +717,9 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   free_graph(ctx);
   dfree(ctx->X0);
   dfree(ctx->labels);
+  dfree(ctx->train_mask);  // masks are per node: a new graph drops them
+  dfree(ctx->eval_mask);
+  ctx->fwd_valid = false;
   ctx->have_feat = ctx->have_labels = false;
   ctx->N = N;
   ctx->Eg = E;
@@ -812,6 +831,44 @@ int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes) {
   return GATX_OK;
 }
 
+// Uploads this rank's rows of a global 0/1 node mask (or drops the mask when `mask` is NULL).
+static int upload_mask(gatx_ctx* ctx, const uint8_t* mask, unsigned char** dev, int64_t* count) {
+  if (!ctx->have_graph) return fail(ctx, GATX_ERR_INVALID, "set the graph before a mask");
+  CK(cudaSetDevice(ctx->device));
+  if (!mask) {
+    dfree(*dev);
+    *count = ctx->N;
+    return GATX_OK;
+  }
+  int64_t cnt = 0;
+  for (int i = 0; i < ctx->N; ++i) cnt += mask[i] != 0;
+  if (!*dev) CK(dalloc(dev, (size_t)ctx->n_rows));
+  if (ctx->n_rows) {
+    CK(cudaMemcpyAsync(*dev, mask + ctx->r0, (size_t)ctx->n_rows, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+  }
+  *count = cnt;
+  return GATX_OK;
+}
+
+int gatx_set_train_mask(gatx_ctx* ctx, const uint8_t* mask) {
+  if (!ctx) return GATX_ERR_INVALID;
+  return upload_mask(ctx, mask, &ctx->train_mask, &ctx->train_count);
+}
+
+int gatx_evaluate(gatx_ctx* ctx, const uint8_t* mask, float* avg_loss, float* accuracy) {
+  if (!ctx) return GATX_ERR_INVALID;
+  int rc = upload_mask(ctx, mask, &ctx->eval_mask, &ctx->eval_count);
+  if (rc) return rc;
+  ctx->spans_used = 0;
+  ctx->eval_mode = true;
+  rc = do_forward(ctx);
+  ctx->eval_mode = false;
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return read_loss(ctx, avg_loss, accuracy, ctx->last_count);
+}
+
 int gatx_graph_info(gatx_ctx* ctx, int32_t* max_degree, int32_t* num_classes, int32_t* row_begin, int32_t* row_end) {
   if (!ctx || !ctx->have_graph) return fail(ctx, GATX_ERR_INVALID, "no graph");
   if (max_degree) *max_degree = ctx->max_degree;
@@ -877,7 +934,7 @@ int gatx_forward(gatx_ctx* ctx) {
 int gatx_loss_acc(gatx_ctx* ctx, float* avg_loss, float* accuracy) {
   if (!ctx || !ctx->have_bufs) return fail(ctx, GATX_ERR_INVALID, "forward must run first");
   CK(cudaSetDevice(ctx->device));
-  return read_loss(ctx, avg_loss, accuracy);
+  return read_loss(ctx, avg_loss, accuracy, ctx->last_count);
 }
 
 int gatx_backward(gatx_ctx* ctx) {
@@ -910,7 +967,7 @@ int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy)
     if ((rc = do_step(ctx, t))) return rc;
   }
   CK(cudaGetLastError());
-  if (avg_loss || accuracy) return read_loss(ctx, avg_loss, accuracy);
+  if (avg_loss || accuracy) return read_loss(ctx, avg_loss, accuracy, ctx->last_count);
   return GATX_OK;
 }
 
@@ -1019,6 +1076,39 @@ int64_t gatx_tensor_size(gatx_ctx* ctx, int32_t which, int32_t layer) {
     case GATX_T_PRED: return ctx->n_rows;
     default: return -1;
   }
+}
+
+// ---- checkpoint: [params | Adam m | Adam v], each n_params floats in the flat order W_0..W_{L-1} | a_0.. | W_o --------
+int64_t gatx_state_size(gatx_ctx* ctx) {
+  if (!ctx || ensure_buffers(ctx)) return -1;
+  return 3 * ctx->n_params;
+}
+int gatx_get_state(gatx_ctx* ctx, float* dst, size_t bytes) {
+  if (!ctx || !dst) return fail(ctx, GATX_ERR_INVALID, "bad get_state");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  const size_t nb = sizeof(float) * (size_t)ctx->n_params;
+  if (bytes != 3 * nb) return fail(ctx, GATX_ERR_INVALID, "state needs %zu bytes, got %zu", 3 * nb, bytes);
+  CK(cudaMemcpyAsync(dst, ctx->params, nb, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaMemcpyAsync(dst + ctx->n_params, ctx->adam_m, nb, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaMemcpyAsync(dst + 2 * ctx->n_params, ctx->adam_v, nb, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return GATX_OK;
+}
+int gatx_set_state(gatx_ctx* ctx, const float* src, size_t bytes) {
+  if (!ctx || !src) return fail(ctx, GATX_ERR_INVALID, "bad set_state");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  const size_t nb = sizeof(float) * (size_t)ctx->n_params;
+  if (bytes != 3 * nb) return fail(ctx, GATX_ERR_INVALID, "state needs %zu bytes, got %zu", 3 * nb, bytes);
+  CK(cudaMemcpyAsync(ctx->params, src, nb, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->adam_m, src + ctx->n_params, nb, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->adam_v, src + 2 * ctx->n_params, nb, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->have_params = true;
+  return GATX_OK;
 }
 
 int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size_t bytes) {

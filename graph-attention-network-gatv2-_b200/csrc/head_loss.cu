@@ -13,13 +13,14 @@ __global__ void __launch_bounds__(256)
 head_kernel(const float* __restrict__ HL, const float* __restrict__ Wo, const int* __restrict__ labels, int N,
             int C, int DL, int ldc, float* __restrict__ y, float* __restrict__ dz, float* __restrict__ z_dbg,
             int* __restrict__ pred, float* __restrict__ gH, double* __restrict__ loss_partials,
-            int* __restrict__ correct_partials) {
+            int* __restrict__ correct_partials, const unsigned char* __restrict__ mask) {
   extern __shared__ __align__(16) float smem[];
   const int ldw = DL + 1, ldy = C + 1;
   float* Wo_s = smem;               // [C][DL+1]
   float* Ht = Wo_s + C * ldw;       // [HT][DL+1]
   float* ys = Ht + HT * ldw;        // [HT][C+1]  logits, then probabilities, then dz
   int* lab = reinterpret_cast<int*>(ys + HT * ldy);  // [HT]
+  int* msk = lab + HT;                                // [HT] 1 = node counts (extension)
   const int tid = threadIdx.x;
   for (int i = tid; i < C * DL; i += blockDim.x) Wo_s[(i / DL) * ldw + (i % DL)] = __ldg(Wo + i);
   double loss_acc = 0.0;
@@ -30,7 +31,10 @@ head_kernel(const float* __restrict__ HL, const float* __restrict__ Wo, const in
     const int nn = N - n0 < HT ? N - n0 : HT;
     __syncthreads();  // previous tile fully consumed (also orders the Wo_s fill)
     for (int i = tid; i < nn * DL; i += blockDim.x) Ht[(i / DL) * ldw + (i % DL)] = __ldg(HL + (int64_t)n0 * DL + i);
-    if (tid < nn) lab[tid] = __ldg(labels + n0 + tid);
+    if (tid < nn) {
+      lab[tid] = __ldg(labels + n0 + tid);
+      msk[tid] = mask ? (mask[n0 + tid] != 0) : 1;
+    }
     __syncthreads();
     // z = W_o h  (EB:493-500)
     for (int p = tid; p < nn * C; p += blockDim.x) {
@@ -64,8 +68,10 @@ head_kernel(const float* __restrict__ HL, const float* __restrict__ Wo, const in
           arg = c;
         }
       }
-      loss_acc += (double)(-logf(fmaxf(row[l], 1e-12f)));  // EB:527
-      correct_acc += (arg == l);
+      if (msk[tid]) {
+        loss_acc += (double)(-logf(fmaxf(row[l], 1e-12f)));  // EB:527
+        correct_acc += (arg == l);
+      }
       pred[n0 + tid] = arg;
     }
     __syncthreads();
@@ -73,7 +79,7 @@ head_kernel(const float* __restrict__ HL, const float* __restrict__ Wo, const in
     for (int p = tid; p < nn * C; p += blockDim.x) {
       const int n = p / C, c = p % C;
       const float prob = ys[n * ldy + c];
-      const float d = prob - (c == lab[n] ? 1.0f : 0.0f);
+      const float d = msk[n] ? prob - (c == lab[n] ? 1.0f : 0.0f) : 0.f;
       y[(int64_t)(n0 + n) * ldc + c] = prob;
       dz[(int64_t)(n0 + n) * ldc + c] = d;
       ys[n * ldy + c] = d;
@@ -117,12 +123,12 @@ __global__ void loss_finalize_kernel(const double* __restrict__ loss_partials, c
 }
 
 static size_t head_smem_bytes(int C, int DL) {
-  return sizeof(float) * ((size_t)C * (DL + 1) + (size_t)HT * (DL + 1) + (size_t)HT * (C + 1)) + sizeof(int) * HT;
+  return sizeof(float) * ((size_t)C * (DL + 1) + (size_t)HT * (DL + 1) + (size_t)HT * (C + 1)) + sizeof(int) * 2 * HT;
 }
 
 int launch_head(const float* HL, const float* Wo, const int* labels, int N, int C, int DL, int ldc, float* y, float* dz,
                 float* z_dbg, int* pred, float* gH, double* loss_partials, int* correct_partials, int* n_partials,
-                cudaStream_t st) {
+                const unsigned char* mask, cudaStream_t st) {
   const size_t smem = head_smem_bytes(C, DL);
   if (smem > 200 * 1024) return -1;
   if (smem > 48 * 1024) cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -130,7 +136,7 @@ int launch_head(const float* HL, const float* Wo, const int* labels, int N, int 
   if (blocks > kHeadBlocks) blocks = kHeadBlocks;
   if (blocks < 1) blocks = 1;
   head_kernel<<<blocks, 256, smem, st>>>(HL, Wo, labels, N, C, DL, ldc, y, dz, z_dbg, pred, gH, loss_partials,
-                                         correct_partials);
+                                         correct_partials, mask);
   *n_partials = blocks;
   return 1;
 }
@@ -141,7 +147,8 @@ constexpr int ST = 128;  // nodes per tile, one thread per node
 __global__ void __launch_bounds__(ST)
 softmax_ce_kernel(const float* __restrict__ z, const int* __restrict__ labels, int N, int C, int ldc,
                   float* __restrict__ y, float* __restrict__ dz, int* __restrict__ pred,
-                  double* __restrict__ loss_partials, int* __restrict__ correct_partials) {
+                  double* __restrict__ loss_partials, int* __restrict__ correct_partials,
+                  const unsigned char* __restrict__ mask) {
   extern __shared__ __align__(16) float smem[];
   const int lds = ldc + 1;  // odd pitch: a thread walking its own row is bank-conflict free
   float* zt = smem;             // [ST][ldc+1] logits -> probabilities
@@ -170,20 +177,23 @@ softmax_ce_kernel(const float* __restrict__ z, const int* __restrict__ labels, i
       }
       const double den = (double)sum + 1e-8;  // EB:140
       const int l = __ldg(labels + n0 + tid);
+      const bool counts = mask ? (mask[n0 + tid] != 0) : true;  // extension: masked-out nodes get dz = 0
       float best = 0.f;
       int arg = 0;
       for (int c = 0; c < C; ++c) {
         const float p = (float)((double)row[c] / den);
         row[c] = p;
-        drow[c] = p - (c == l ? 1.0f : 0.0f);  // EB:572
+        drow[c] = counts ? p - (c == l ? 1.0f : 0.0f) : 0.f;  // EB:572
         if (c == 0 || p > best) {              // EB:530-535
           best = p;
           arg = c;
         }
       }
       for (int c = C; c < ldc; ++c) row[c] = drow[c] = 0.f;
-      loss_acc += (double)(-logf(fmaxf(row[l], 1e-12f)));  // EB:527
-      correct_acc += (arg == l);
+      if (counts) {
+        loss_acc += (double)(-logf(fmaxf(row[l], 1e-12f)));  // EB:527
+        correct_acc += (arg == l);
+      }
       pred[n0 + tid] = arg;
     }
     __syncthreads();
@@ -214,14 +224,15 @@ softmax_ce_kernel(const float* __restrict__ z, const int* __restrict__ labels, i
 }
 
 int launch_softmax_ce(const float* z, const int* labels, int N, int C, int ldc, float* y, float* dz, int* pred,
-                      double* loss_partials, int* correct_partials, int* n_partials, cudaStream_t st) {
+                      double* loss_partials, int* correct_partials, int* n_partials, const unsigned char* mask,
+                      cudaStream_t st) {
   const size_t smem = sizeof(float) * 2 * ST * (ldc + 1);
   if (smem > 200 * 1024) return -1;
   if (smem > 48 * 1024) cudaFuncSetAttribute(softmax_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int blocks = (N + ST - 1) / ST;
   if (blocks > kHeadBlocks) blocks = kHeadBlocks;
   if (blocks < 1) blocks = 1;
-  softmax_ce_kernel<<<blocks, ST, smem, st>>>(z, labels, N, C, ldc, y, dz, pred, loss_partials, correct_partials);
+  softmax_ce_kernel<<<blocks, ST, smem, st>>>(z, labels, N, C, ldc, y, dz, pred, loss_partials, correct_partials, mask);
   *n_partials = blocks;
   return 1;
 }

@@ -9,7 +9,13 @@
 //            "\nEpoch %d\n", "\nAvg Loss: %f, Accuracy: %.2f%%\n", " total time: <ms> ms" (EB:1372, 547, 1641)
 // Additions that do not change the defaults: --seed S, --gemm tf32|fp32, --gpus N (destination-row partition,
 // one host thread + one context per GPU), --load-weights DIR / --dump-weights DIR (W.bin a.bin Wo.bin, raw fp32
-// in the reference's layouts), --quiet-epochs (print only every k-th epoch).
+// in the reference's layouts), --save-checkpoint FILE / --resume FILE (parameters + Adam moments + epoch counter),
+// --quiet-epochs k (print only every k-th epoch), --no-cache (do not read/write the binary dataset cache
+// <dataset>/.gatx_cache.bin, keyed by the size and mtime of the four text files), --load-only (load, report, exit),
+// --split (README.md:134's announced train/val/test split: <dataset>/split.txt holds one token per node, 0 = train,
+// 1 = validation, 2 = test; training loss / accuracy / gradients use the train nodes only, every printed epoch adds a
+// "Val Loss: %f, Val Accuracy: %.2f%%" line and the run ends with "Test Loss: ..."), --eval-only (no training: one
+// evaluation forward with the loaded weights / checkpoint, prints the "Avg Loss" line over all nodes or per split).
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -123,9 +129,65 @@ bool write_bin(const std::string& path, const std::vector<float>& v) {
   return put == v.size();
 }
 
+// ---- binary dataset cache: the text format stays the interface, parsing it happens once -------------
+struct CacheHeader {
+  char magic[8];
+  int64_t n_nodes, in_dim, n_edges;
+  int64_t fsize[4], fmtime[4];
+};
+bool stat_files(const std::string& dir, CacheHeader& h) {
+  const char* names[4] = {"features.txt", "row_ptr.txt", "col_idx.txt", "labels.txt"};
+  for (int i = 0; i < 4; ++i) {
+    struct stat st;
+    if (stat((dir + names[i]).c_str(), &st) != 0) return false;
+    h.fsize[i] = (int64_t)st.st_size;
+    h.fmtime[i] = (int64_t)st.st_mtime;
+  }
+  return true;
+}
+bool cache_load(const std::string& dir, std::vector<float>& X, std::vector<int>& rp, std::vector<int>& ci,
+                std::vector<int>& lab, int& N, int& I) {
+  CacheHeader want{}, got{};
+  if (!stat_files(dir, want)) return false;
+  FILE* f = fopen((dir + ".gatx_cache.bin").c_str(), "rb");
+  if (!f) return false;
+  bool ok = fread(&got, sizeof got, 1, f) == 1 && memcmp(got.magic, "GATXDS1", 8) == 0 &&
+            memcmp(got.fsize, want.fsize, sizeof want.fsize) == 0 && memcmp(got.fmtime, want.fmtime, sizeof want.fmtime) == 0;
+  if (ok) {
+    X.resize((size_t)got.n_nodes * got.in_dim);
+    rp.resize((size_t)got.n_nodes + 1);
+    ci.resize((size_t)got.n_edges);
+    lab.resize((size_t)got.n_nodes);
+    ok = fread(X.data(), sizeof(float), X.size(), f) == X.size() && fread(rp.data(), sizeof(int), rp.size(), f) == rp.size() &&
+         fread(ci.data(), sizeof(int), ci.size(), f) == ci.size() && fread(lab.data(), sizeof(int), lab.size(), f) == lab.size();
+    N = (int)got.n_nodes;
+    I = (int)got.in_dim;
+  }
+  fclose(f);
+  return ok;
+}
+void cache_store(const std::string& dir, const std::vector<float>& X, const std::vector<int>& rp,
+                 const std::vector<int>& ci, const std::vector<int>& lab, int N, int I) {
+  CacheHeader h{};
+  memcpy(h.magic, "GATXDS1", 8);
+  h.n_nodes = N; h.in_dim = I; h.n_edges = (int64_t)ci.size();
+  if (!stat_files(dir, h)) return;
+  const std::string tmp = dir + ".gatx_cache.bin.tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;  // read-only dataset directory: just skip the cache
+  const bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(X.data(), sizeof(float), X.size(), f) == X.size() &&
+                  fwrite(rp.data(), sizeof(int), rp.size(), f) == rp.size() &&
+                  fwrite(ci.data(), sizeof(int), ci.size(), f) == ci.size() &&
+                  fwrite(lab.data(), sizeof(int), lab.size(), f) == lab.size();
+  fclose(f);
+  if (ok) rename(tmp.c_str(), (dir + ".gatx_cache.bin").c_str());
+  else remove(tmp.c_str());
+}
+
 struct Args {
   int epochs = 200, L = 2, gpus = 1, gemm = GATX_GEMM_TF32_TC, every = 1;
-  bool clip = false;
+  bool clip = false, use_cache = true, load_only = false, split = false, eval_only = false;
+  std::string save_ckpt, resume_ckpt;
   std::string optimizer = "sgd", dataset = "pubmed", data_root = "./data", load_w, dump_w;
   float lr = 0.0001f, beta1 = 0.9f, beta2 = 0.999f;
   unsigned long long seed = 0;
@@ -193,6 +255,12 @@ int main(int argc, char** argv) {
     else if (arg == "--load-weights" && i + 1 < argc) a.load_w = argv[++i];
     else if (arg == "--dump-weights" && i + 1 < argc) a.dump_w = argv[++i];
     else if (arg == "--quiet-epochs" && i + 1 < argc) a.every = std::max(1, std::atoi(argv[++i]));
+    else if (arg == "--save-checkpoint" && i + 1 < argc) a.save_ckpt = argv[++i];
+    else if (arg == "--resume" && i + 1 < argc) a.resume_ckpt = argv[++i];
+    else if (arg == "--no-cache") a.use_cache = false;
+    else if (arg == "--load-only") a.load_only = true;
+    else if (arg == "--split") a.split = true;
+    else if (arg == "--eval-only") a.eval_only = true;
     // anything else is ignored, like the reference
   }
   if (!have_heads || !have_outdims) {
@@ -231,14 +299,20 @@ int main(int argc, char** argv) {
   std::vector<float> X;
   std::vector<int> row_ptr, col_idx, labels;
   int N = 0, I = 0;
-  load_features(path + "features.txt", X, N, I);
-  load_int_array(path + "row_ptr.txt", row_ptr);
+  const auto t_load0 = std::chrono::high_resolution_clock::now();
+  const bool from_cache = a.use_cache && cache_load(path, X, row_ptr, col_idx, labels, N, I);
+  if (!from_cache) {
+    load_features(path + "features.txt", X, N, I);
+    load_int_array(path + "row_ptr.txt", row_ptr);
+  }
   if ((int)row_ptr.size() != N + 1) {
     std::cerr << "Invalid row_ptr length\n";
     return 1;
   }
-  load_int_array(path + "col_idx.txt", col_idx);
-  load_int_array(path + "labels.txt", labels);
+  if (!from_cache) {
+    load_int_array(path + "col_idx.txt", col_idx);
+    load_int_array(path + "labels.txt", labels);
+  }
   if ((int)labels.size() != N) {
     std::cerr << "Invalid labels length\n";
     return 1;
@@ -254,6 +328,29 @@ int main(int argc, char** argv) {
   std::cout << "Number of classes = " << C << std::endl;
   std::cout << "Graph loaded: " << N << " nodes, " << col_idx.size() << " edges, "
             << "input_feature_vector_dim = " << I << std::endl;
+  if (a.use_cache && !from_cache) cache_store(path, X, row_ptr, col_idx, labels, N, I);
+  {
+    const std::chrono::duration<double, std::milli> dt = std::chrono::high_resolution_clock::now() - t_load0;
+    std::cerr << "[loader] " << (from_cache ? "binary cache" : "text files") << ": " << dt.count() << " ms\n";
+  }
+  if (a.load_only) return 0;
+  std::vector<unsigned char> mask[3];  // train / validation / test
+  if (a.split) {
+    std::vector<int> part;
+    load_int_array(path + "split.txt", part);
+    if ((int)part.size() != N) {
+      std::cerr << "Invalid split length\n";
+      return 1;
+    }
+    for (int k = 0; k < 3; ++k) mask[k].assign((size_t)N, 0);
+    for (int i = 0; i < N; ++i) {
+      if (part[i] < 0 || part[i] > 2) {
+        std::cerr << "Invalid split value on line " << i + 1 << " (0 = train, 1 = validation, 2 = test)\n";
+        return 1;
+      }
+      mask[part[i]][i] = 1;
+    }
+  }
 
   const int world = a.gpus;
   std::vector<gatx_ctx*> ctx(world, nullptr);
@@ -278,6 +375,7 @@ int main(int argc, char** argv) {
     if ((rc = gatx_set_graph_csr(ctx[r], N, (int64_t)col_idx.size(), row_ptr.data(), col_idx.data()))) { failed = fail_ctx(ctx[r], "gatx_set_graph_csr", rc); return; }
     if ((rc = gatx_set_features(ctx[r], X.data(), I))) { failed = fail_ctx(ctx[r], "gatx_set_features", rc); return; }
     if ((rc = gatx_set_labels(ctx[r], labels.data(), C))) { failed = fail_ctx(ctx[r], "gatx_set_labels", rc); return; }
+    if (a.split && (rc = gatx_set_train_mask(ctx[r], mask[0].data()))) { failed = fail_ctx(ctx[r], "gatx_set_train_mask", rc); return; }
     // the reference seeds with time(NULL) (EB:1305); --seed makes runs reproducible
     const unsigned long long seed = a.seed_given ? a.seed : (unsigned long long)time(nullptr);
     if ((rc = gatx_init_params(ctx[r], seed))) { failed = fail_ctx(ctx[r], "gatx_init_params", rc); return; }
@@ -324,9 +422,62 @@ int main(int argc, char** argv) {
     return write_bin(dir + "/W.bin", W) && write_bin(dir + "/a.bin", av) && write_bin(dir + "/Wo.bin", Wo);
   };
 
-  for (int epoch = 1; epoch <= a.epochs; ++epoch) {
+  // checkpoint file: int64 epochs_done, int64 n_floats, then [params | Adam m | Adam v]
+  int first_epoch = 1;
+  if (!a.resume_ckpt.empty()) {
+    FILE* f = fopen(a.resume_ckpt.c_str(), "rb");
+    int64_t hdr[2] = {0, 0};
+    std::vector<float> stt;
+    bool ok = f && fread(hdr, sizeof hdr, 1, f) == 1 && hdr[1] == gatx_state_size(ctx[0]);
+    if (ok) {
+      stt.resize((size_t)hdr[1]);
+      ok = fread(stt.data(), sizeof(float), stt.size(), f) == stt.size();
+    }
+    if (f) fclose(f);
+    if (!ok) {
+      std::cerr << "Error: cannot resume from " << a.resume_ckpt << " (missing or for another model)\n";
+      return 1;
+    }
+    for (int r = 0; r < world; ++r)
+      if (int rc = gatx_set_state(ctx[r], stt.data(), stt.size() * sizeof(float))) return fail_ctx(ctx[r], "gatx_set_state", rc);
+    first_epoch = (int)hdr[0] + 1;
+  }
+  // evaluation forward on every rank; returns rank 0's (already all-reduced) scalars
+  auto evaluate = [&](const unsigned char* m, float* lo, float* ac) -> int {
+    std::vector<float> l2(world, 0.f), a2(world, 0.f);
+    std::vector<int> rcs(world, 0);
+    auto run = [&](int r) { rcs[r] = gatx_evaluate(ctx[r], m, &l2[r], &a2[r]); };
+    if (world == 1) run(0);
+    else {
+      std::vector<std::thread> th;
+      for (int r = 0; r < world; ++r) th.emplace_back(run, r);
+      for (auto& t : th) t.join();
+    }
+    for (int r = 0; r < world; ++r)
+      if (rcs[r]) return fail_ctx(ctx[r], "gatx_evaluate", rcs[r]);
+    *lo = l2[0];
+    *ac = a2[0];
+    return 0;
+  };
+  if (a.eval_only) {
+    float lo = 0.f, ac = 0.f;
+    if (!a.split) {
+      if (evaluate(nullptr, &lo, &ac)) return 1;
+      printf("\nAvg Loss: %f, Accuracy: %.2f%%\n", lo, 100.0f * ac);
+    } else {
+      const char* names[3] = {"Train", "Val", "Test"};
+      for (int k = 0; k < 3; ++k) {
+        if (evaluate(mask[k].data(), &lo, &ac)) return 1;
+        printf("\n%s Loss: %f, %s Accuracy: %.2f%%\n", names[k], lo, names[k], 100.0f * ac);
+      }
+    }
+    for (auto c : ctx) gatx_destroy(c);
+    return 0;
+  }
+  const int last_epoch = first_epoch + a.epochs - 1;
+  for (int epoch = first_epoch; epoch <= last_epoch; ++epoch) {
     auto start = std::chrono::high_resolution_clock::now();
-    const bool show = (epoch % a.every) == 0 || epoch == 1 || epoch == a.epochs;
+    const bool show = (epoch % a.every) == 0 || epoch == first_epoch || epoch == last_epoch;
     if (show) printf("\nEpoch %d\n", epoch);
     std::vector<float> loss(world, 0.f), acc(world, 0.f);
     std::vector<int> rcs(world, 0);
@@ -340,9 +491,28 @@ int main(int argc, char** argv) {
     for (int r = 0; r < world; ++r)
       if (rcs[r]) return fail_ctx(ctx[r], "gatx_train_epoch", rcs[r]);
     if (show) printf("\nAvg Loss: %f, Accuracy: %.2f%%\n", loss[0], 100.0f * acc[0]);
+    if (show && a.split) {
+      float lo = 0.f, ac = 0.f;
+      if (evaluate(mask[1].data(), &lo, &ac)) return 1;
+      printf("\nVal Loss: %f, Val Accuracy: %.2f%%\n", lo, 100.0f * ac);
+    }
     auto stop = std::chrono::high_resolution_clock::now();
     std::chrono::duration<double, std::milli> elapsed = stop - start;
     if (show) std::cout << " total time: " << elapsed.count() << " ms" << std::endl;
+  }
+  if (a.split) {
+    float lo = 0.f, ac = 0.f;
+    if (evaluate(mask[2].data(), &lo, &ac)) return 1;
+    printf("\nTest Loss: %f, Test Accuracy: %.2f%%\n", lo, 100.0f * ac);
+  }
+  if (!a.save_ckpt.empty()) {
+    const int64_t n = gatx_state_size(ctx[0]);
+    std::vector<float> stt((size_t)(n > 0 ? n : 0));
+    int64_t hdr[2] = {(int64_t)last_epoch, n};
+    FILE* f = n > 0 && gatx_get_state(ctx[0], stt.data(), stt.size() * sizeof(float)) == GATX_OK ? fopen(a.save_ckpt.c_str(), "wb") : nullptr;
+    if (!f || fwrite(hdr, sizeof hdr, 1, f) != 1 || fwrite(stt.data(), sizeof(float), stt.size(), f) != stt.size())
+      std::cerr << "Warning: could not write checkpoint " << a.save_ckpt << "\n";
+    if (f) fclose(f);
   }
   if (!a.dump_w.empty() && !dump_weights(a.dump_w)) std::cerr << "Warning: could not write weights to " << a.dump_w << "\n";
   for (auto c : ctx) gatx_destroy(c);

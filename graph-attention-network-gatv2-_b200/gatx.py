@@ -22,7 +22,7 @@ EXPORTS = [
     "gatx_set_features", "gatx_set_labels", "gatx_graph_info", "gatx_partition_rows", "gatx_init_params",
     "gatx_set_params", "gatx_set_wo", "gatx_forward", "gatx_loss_acc", "gatx_backward", "gatx_step",
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
-    "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_op_gemm",
+    "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init",
 ]
 
@@ -256,6 +256,37 @@ class Engine:
         f, b = C.c_double(), C.c_double()
         self._ck(self.lib.gatx_edge_bytes(self.ctx, layer, C.byref(f), C.byref(b)), "gatx_edge_bytes")
         return f.value, b.value
+
+    def get_state(self):
+        self.lib.gatx_state_size.restype = C.c_int64
+        self.lib.gatx_state_size.argtypes = [C.c_void_p]
+        n = self.lib.gatx_state_size(self.ctx)
+        if n < 0:
+            raise GatxError("gatx_state_size failed")
+        out = np.empty(n, np.float32)
+        self.lib.gatx_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        self._ck(self.lib.gatx_get_state(self.ctx, out.ctypes.data, out.nbytes), "gatx_get_state")
+        return out
+
+    def set_state(self, state):
+        state = np.ascontiguousarray(state, np.float32)
+        self.lib.gatx_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        self._ck(self.lib.gatx_set_state(self.ctx, state.ctypes.data, state.nbytes), "gatx_set_state")
+
+    def set_train_mask(self, mask):
+        """mask: uint8 [N] global (1 = node counts towards loss / accuracy / gradients) or None."""
+        self.lib.gatx_set_train_mask.argtypes = [C.c_void_p, C.c_void_p]
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self._ck(self.lib.gatx_set_train_mask(self.ctx, None if m is None else m.ctypes.data), "gatx_set_train_mask")
+
+    def evaluate(self, mask=None):
+        """Forward only; (avg_loss, accuracy) over the nodes of mask (None = all)."""
+        self.lib.gatx_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lo, ac = C.c_float(), C.c_float()
+        self._ck(self.lib.gatx_evaluate(self.ctx, None if m is None else m.ctypes.data, C.byref(lo), C.byref(ac)),
+                 "gatx_evaluate")
+        return lo.value, ac.value
 
     def comm_init(self, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)

@@ -111,6 +111,11 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t num_nodes, int64_t num_edges,
 int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim);
 /* Replaces EB:1169-1172 + EB:1106-1107 (num_classes <= 0: derived as max(label)+1). */
 int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes);
+/* Extension (README.md:134 announces train/val/test splits "later"; the reference trains and scores on every
+ * node, EB:514-550).  mask is a GLOBAL uint8 [N]: nodes with mask[n] == 0 contribute nothing to the loss, the
+ * accuracy (both averaged over the counted nodes) or the gradients (dz = 0).  NULL restores the reference
+ * behaviour.  A new graph drops the mask. */
+int gatx_set_train_mask(gatx_ctx* ctx, const uint8_t* mask);
 /* max row length (EB:89-99) and number of classes (EB:1106-1107) as the reference prints them */
 int gatx_graph_info(gatx_ctx* ctx, int32_t* max_degree, int32_t* num_classes,
                     int32_t* row_begin, int32_t* row_end);
@@ -138,6 +143,11 @@ int gatx_step(gatx_ctx* ctx, int32_t t);
 /* forward + loss/accuracy + backward + step in one call, asynchronous until the scalars are
  * read; avg_loss/accuracy may be NULL (then no host sync at all). */
 int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy);
+/* Evaluation-only forward (extension): all layers + classifier + softmax, loss / accuracy over the
+ * nodes of `mask` (GLOBAL uint8 [N], NULL = every node); no attention-coefficient storage, no output gradients,
+ * parameters and optimizer state untouched.  It overwrites the activations, so gatx_backward needs a new
+ * gatx_forward afterwards (GATX_ERR_INVALID otherwise).  Synchronises. */
+int gatx_evaluate(gatx_ctx* ctx, const uint8_t* mask, float* avg_loss, float* accuracy);
 int gatx_sync(gatx_ctx* ctx);
 
 /* ---- introspection (parity tests, checkpoints) ------------------------------------------- */
@@ -160,6 +170,12 @@ int gatx_timer_stop(gatx_ctx* ctx, float* elapsed_ms); /* records, synchronises,
 int64_t gatx_launch_count(const gatx_ctx* ctx);
 /* Algorithmic bytes of the fused edge forward / backward of one layer (SURVEY 8d formulas). */
 int gatx_edge_bytes(gatx_ctx* ctx, int32_t layer, double* fwd_bytes, double* bwd_bytes);
+
+/* ---- checkpoint (the reference only has dead dump/load helpers, NB:39-68) ------ */
+/* Flat state = [parameters | Adam m | Adam v], each in the order W_0..W_{L-1} | a_0..a_{L-1} | W_o. */
+int64_t gatx_state_size(gatx_ctx* ctx); /* floats, <0 on error */
+int gatx_get_state(gatx_ctx* ctx, float* dst, size_t bytes);
+int gatx_set_state(gatx_ctx* ctx, const float* src, size_t bytes);
 
 /* ---- op-level entry point (per-kernel parity tests, ncu) ---------------------------------- */
 /* Dense contraction on host buffers with the engine's GEMM kernels (mode = GATX_GEMM_*):

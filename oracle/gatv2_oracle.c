@@ -211,10 +211,18 @@ void orc_head_forward(int N, int C, int DL, const float* Wo, const float* HL, fl
 
 /* Per-node CE loss, first-max argmax (EB:514-537) and their reductions (EB:539-550).
  * Returns the summed loss; avg_loss = sum/N, accuracy = correct/N. */
+double orc_loss_acc_masked(int N, int C, const float* y, const int* labels, const unsigned char* mask,
+                           float* losses, int* pred, int* correct, float* avg_loss, float* accuracy);
 double orc_loss_acc(int N, int C, const float* y, const int* labels, float* losses, int* pred,
                     int* correct, float* avg_loss, float* accuracy) {
+  return orc_loss_acc_masked(N, C, y, labels, NULL, losses, pred, correct, avg_loss, accuracy);
+}
+/* Extension (README.md:134 promises train/val/test splits "later"): nodes with mask[n] == 0 do not count towards
+ * loss, accuracy (both averaged over the masked nodes) or gradients. mask == NULL is the reference behaviour. */
+double orc_loss_acc_masked(int N, int C, const float* y, const int* labels, const unsigned char* mask,
+                           float* losses, int* pred, int* correct, float* avg_loss, float* accuracy) {
   double total = 0.0;
-  int64_t ok = 0;
+  int64_t ok = 0, cnt = 0;
   for (int n = 0; n < N; ++n) {
     const float* yn = y + (size_t)n * C;
     float p = yn[labels[n]];
@@ -229,11 +237,14 @@ double orc_loss_acc(int N, int C, const float* y, const int* labels, float* loss
     if (losses) losses[n] = loss;
     if (pred) pred[n] = arg;
     if (correct) correct[n] = (arg == labels[n]);
+    if (mask && !mask[n]) continue;
+    ++cnt;
     total += (double)loss;
     ok += (arg == labels[n]);
   }
-  if (avg_loss) *avg_loss = (float)(total / (double)N);
-  if (accuracy) *accuracy = (float)((double)ok / (double)N);
+  if (cnt == 0) cnt = 1;
+  if (avg_loss) *avg_loss = (float)(total / (double)cnt);
+  if (accuracy) *accuracy = (float)((double)ok / (double)cnt);
   return total;
 }
 
@@ -244,14 +255,22 @@ double orc_loss_acc(int N, int C, const float* y, const int* labels, float* loss
  * For Hl == 1 this is exactly the reference; for Hl > 1 the reference indexes the
  * pre-activations with the wrong stride (EB:598) and the per-head
  * derivative used here is the true gradient of EB's forward (extension). */
+void orc_output_grads_masked(int N, int C, int DL, int Hl, const float* y, const int* labels,
+                             const unsigned char* mask, const float* hpre_last, const float* HL, const float* Wo,
+                             float* gWo, float* g_h);
 void orc_output_grads(int N, int C, int DL, int Hl, const float* y, const int* labels,
                       const float* hpre_last, const float* HL, const float* Wo, float* gWo,
                       float* g_h) {
+  orc_output_grads_masked(N, C, DL, Hl, y, labels, NULL, hpre_last, HL, Wo, gWo, g_h);
+}
+void orc_output_grads_masked(int N, int C, int DL, int Hl, const float* y, const int* labels,
+                             const unsigned char* mask, const float* hpre_last, const float* HL, const float* Wo,
+                             float* gWo, float* g_h) {
   double* acc = (double*)calloc((size_t)C * DL, sizeof(double));
   double* dz = (double*)malloc(sizeof(double) * (size_t)C);
   for (int n = 0; n < N; ++n) {
     for (int c = 0; c < C; ++c)
-      dz[c] = (double)(float)(y[(size_t)n * C + c] - (c == labels[n] ? 1.0f : 0.0f));
+      dz[c] = (mask && !mask[n]) ? 0.0 : (double)(float)(y[(size_t)n * C + c] - (c == labels[n] ? 1.0f : 0.0f));
     for (int c = 0; c < C; ++c)
       for (int d = 0; d < DL; ++d) acc[(size_t)c * DL + d] += dz[c] * (double)HL[(size_t)n * DL + d];
     for (int d = 0; d < DL; ++d) {
@@ -529,6 +548,7 @@ typedef struct orc_model {
   int *heads, *outdims, *indims;
   const int *row_ptr, *col_idx, *labels; /* borrowed */
   const float* X0;                       /* borrowed */
+  const unsigned char* mask;             /* borrowed, NULL = every node (reference behaviour) */
   float **W, **a, *Wo;                   /* params per layer */
   float **gW, **ga, *gWo;
   float **mW, **vW, **ma, **va, *mWo, *vWo;
@@ -640,15 +660,17 @@ void orc_model_forward(orc_model* m) {
   orc_head_forward(m->N, m->C, m->outdims[m->L - 1], m->Wo, X, m->z, m->y);
 }
 
+void orc_model_set_mask(orc_model* m, const unsigned char* mask) { m->mask = mask; }
+
 double orc_model_loss(orc_model* m, float* avg_loss, float* accuracy, int* pred) {
-  return orc_loss_acc(m->N, m->C, m->y, m->labels, NULL, pred, NULL, avg_loss, accuracy);
+  return orc_loss_acc_masked(m->N, m->C, m->y, m->labels, m->mask, NULL, pred, NULL, avg_loss, accuracy);
 }
 
 /* Backward of all layers (EB:1463-1557); gradients accumulate into gW/ga/gWo. */
 void orc_model_backward(orc_model* m) {
   int L = m->L;
-  orc_output_grads(m->N, m->C, m->outdims[L - 1], m->heads[L - 1], m->y, m->labels, m->hpre[L - 1],
-                   m->Hout[L - 1], m->Wo, m->gWo, m->g_h[L - 1]);
+  orc_output_grads_masked(m->N, m->C, m->outdims[L - 1], m->heads[L - 1], m->y, m->labels, m->mask, m->hpre[L - 1],
+                          m->Hout[L - 1], m->Wo, m->gWo, m->g_h[L - 1]);
   for (int l = L - 1; l >= 0; --l) {
     int H = m->heads[l], D = m->outdims[l], I = m->indims[l];
     const float* X = l > 0 ? m->Hout[l - 1] : m->X0;

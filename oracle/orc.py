@@ -219,6 +219,11 @@ class Model:
     def set_wo(self, Wo):
         lib().orc_model_set_wo(self._m, fp(f32(Wo)))
 
+    def set_mask(self, mask):
+        """mask: uint8 [N] (1 = node counts towards loss / accuracy / gradients) or None."""
+        self._mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().orc_model_set_mask(self._m, None if mask is None else self._mask.ctypes.data_as(C.c_void_p))
+
     def forward(self):
         lib().orc_model_forward(self._m)
 

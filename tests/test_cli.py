@@ -65,6 +65,125 @@ def test_inconsistent_feature_line(cli, tmp_path):
     assert r.returncode == 1 and "Inconsistent input_dim on line 1" in r.stderr                  # EB:42-45
 
 
+def test_binary_dataset_cache(cli, tmp_path):
+    """--load-only: the first run parses the text files and writes <dataset>/.gatx_cache.bin, the second run reads
+    it; both print the same dataset lines; editing a text file invalidates the cache (size / mtime key)."""
+    sys.path.insert(0, PKG)
+    import datasets
+    ds = datasets.make_dataset("sample")
+    d = tmp_path / "sample"
+    datasets.write_txt(str(d), ds)
+    args = ["--heads", "8,1", "--outdims", "8,8", "--dataset", "sample", "--data-root", str(tmp_path), "--load-only"]
+    r1 = run(cli, *args)
+    assert r1.returncode == 0 and "[loader] text files" in r1.stderr and (d / ".gatx_cache.bin").exists()
+    r2 = run(cli, *args)
+    assert r2.returncode == 0 and "[loader] binary cache" in r2.stderr and r2.stdout == r1.stdout
+    assert "Max degree = %d\n" % int(np.diff(ds["row_ptr"]).max()) in r2.stdout
+    assert "Graph loaded: 64 nodes, 512 edges, input_feature_vector_dim = 16\n" in r2.stdout
+    lab = ds["labels"].copy()
+    lab[0] = 9  # a new class: file size and class count change
+    np.savetxt(str(d / "labels.txt"), np.concatenate([lab, []]).astype(int), fmt="%d")
+    open(str(d / "labels.txt"), "a").write("\n")
+    r3 = run(cli, *args)
+    assert "[loader] text files" in r3.stderr and "Number of classes = 10\n" in r3.stdout
+    r4 = run(cli, *(args + ["--no-cache"]))
+    assert "[loader] text files" in r4.stderr and r4.stdout == r3.stdout
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_is_bit_exact(cli, tmp_path):
+    """6 epochs straight == 3 epochs + --save-checkpoint, then --resume for 3 more (Adam moments and t restored)."""
+    sys.path.insert(0, PKG)
+    import datasets
+    ds = datasets.make_dataset("sample")
+    datasets.write_txt(str(tmp_path / "sample"), ds)
+    base = ["--heads", "8,1", "--outdims", "8,8", "--optimizer", "adam", "--lr", "0.01", "--clip", "--dataset", "sample",
+            "--data-root", str(tmp_path), "--seed", "5"]
+    for name in ("a", "b"):
+        (tmp_path / name).mkdir()
+    r = run(cli, *(base + ["--epochs", "6", "--dump-weights", str(tmp_path / "a")]))
+    assert r.returncode == 0, r.stderr
+    r = run(cli, *(base + ["--epochs", "3", "--save-checkpoint", str(tmp_path / "ck.bin")]))
+    assert r.returncode == 0, r.stderr
+    r = run(cli, *(base + ["--epochs", "3", "--resume", str(tmp_path / "ck.bin"), "--dump-weights", str(tmp_path / "b")]))
+    assert r.returncode == 0 and "\nEpoch 4\n" in r.stdout and "\nEpoch 6\n" in r.stdout, r.stderr
+    for f in ("W.bin", "a.bin", "Wo.bin"):
+        assert (tmp_path / "a" / f).read_bytes() == (tmp_path / "b" / f).read_bytes(), f
+
+
+def test_split_file_errors(cli, tmp_path):
+    """--split: <dataset>/split.txt must hold one token in {0, 1, 2} per node (checked before any GPU work)."""
+    sys.path.insert(0, PKG)
+    import datasets
+    ds = datasets.make_dataset("sample")
+    d = tmp_path / "sample"
+    datasets.write_txt(str(d), ds)
+    args = ["--heads", "8,1", "--outdims", "8,8", "--dataset", "sample", "--data-root", str(tmp_path), "--split", "--no-cache"]
+    (d / "split.txt").write_text("0\n1\n2\n")
+    r = run(cli, *args)
+    assert r.returncode == 1 and "Invalid split length" in r.stderr
+    (d / "split.txt").write_text("\n".join(["0"] * 10 + ["3"] + ["1"] * 53) + "\n")
+    r = run(cli, *args)
+    assert r.returncode == 1 and "Invalid split value on line 11" in r.stderr
+
+
+@pytest.mark.gpu
+def test_split_training_and_eval_only_match_oracle(cli, tmp_path):
+    """--split trains on the train nodes and reports validation / test metrics; --eval-only re-scores the dumped
+    weights.  The printed numbers are checked against the oracle's masked variant with the same injected weights."""
+    sys.path.insert(0, PKG)
+    import datasets
+    import orc
+    from helpers import make_oracle, make_problem
+    p = make_problem(64, 512, 16, 4, (8, 1), (8, 8), "uniform", seed=11)
+    d = tmp_path / "data" / "s"
+    datasets.write_txt(str(d), dict(X=p["X"], row_ptr=p["row_ptr"], col_idx=p["col_idx"], labels=p["labels"]))
+    part = np.random.default_rng(4).integers(0, 3, 64)
+    np.savetxt(str(d / "split.txt"), part, fmt="%d")
+    w = tmp_path / "w"
+    w.mkdir()
+    np.concatenate([x.ravel() for x in p["Ws"]]).astype(np.float32).tofile(str(w / "W.bin"))
+    np.concatenate([x.ravel() for x in p["As"]]).astype(np.float32).tofile(str(w / "a.bin"))
+    p["Wo"].astype(np.float32).tofile(str(w / "Wo.bin"))
+    out = tmp_path / "out"
+    out.mkdir()
+    base = ["--heads", "8,1", "--outdims", "8,8", "--optimizer", "adam", "--lr", "0.01", "--dataset", "s", "--data-root",
+            str(tmp_path / "data"), "--gemm", "fp32", "--split"]
+    r = run(cli, *(base + ["--epochs", "5", "--load-weights", str(w), "--dump-weights", str(out)]))
+    assert r.returncode == 0, r.stderr
+    masks = [(part == k).astype(np.uint8) for k in range(3)]
+    ref = make_oracle(orc, p, optimizer="adam", lr=0.01)
+    got = re.findall(r"\nAvg Loss: ([0-9.]+), Accuracy: ([0-9.]+)%\n\nVal Loss: ([0-9.]+), Val Accuracy: ([0-9.]+)%\n", r.stdout)
+    assert len(got) == 5, r.stdout[-600:]
+
+    def score(mask):
+        ref.set_mask(mask)
+        ref.forward()
+        o = ref.loss()
+        return o["avg"], 100.0 * o["acc"]
+
+    for t, (tl, ta, vl, va) in enumerate(got, 1):
+        ref.set_mask(masks[0])
+        ol, oa = ref.epoch(t)
+        assert abs(float(tl) - ol) < 5e-4 * max(1.0, ol) and abs(float(ta) - 100.0 * oa) < 0.011, (t, tl, ol)
+        rvl, rva = score(masks[1])
+        assert abs(float(vl) - rvl) < 5e-4 * max(1.0, rvl) and abs(float(va) - rva) < 0.011, (t, vl, rvl)
+    m = re.search(r"\nTest Loss: ([0-9.]+), Test Accuracy: ([0-9.]+)%\n", r.stdout)
+    rtl, rta = score(masks[2])
+    assert m and abs(float(m.group(1)) - rtl) < 5e-4 * max(1.0, rtl) and abs(float(m.group(2)) - rta) < 0.011
+    # evaluation only, from the dumped weights: the three splits, then all nodes without --split
+    r2 = run(cli, *(base + ["--eval-only", "--load-weights", str(out)]))
+    assert r2.returncode == 0 and "Epoch" not in r2.stdout, r2.stderr
+    for k, name in enumerate(("Train", "Val", "Test")):
+        m = re.search(r"\n%s Loss: ([0-9.]+), %s Accuracy: ([0-9.]+)%%\n" % (name, name), r2.stdout)
+        el, ea = score(masks[k])
+        assert m and abs(float(m.group(1)) - el) < 5e-4 * max(1.0, el) and abs(float(m.group(2)) - ea) < 0.011, name
+    r3 = run(cli, *([a for a in base if a != "--split"] + ["--eval-only", "--load-weights", str(out)]))
+    el, ea = score(None)
+    m = re.search(r"\nAvg Loss: ([0-9.]+), Accuracy: ([0-9.]+)%\n", r3.stdout)
+    assert r3.returncode == 0 and m and abs(float(m.group(1)) - el) < 5e-4 * max(1.0, el)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,gemm,tol", [("sample_adam", "fp32", 5e-4), ("three_layer_adam", "fp32", 5e-4),
                                            ("sample_adam", "tf32", 1e-2)])

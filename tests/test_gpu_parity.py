@@ -239,3 +239,83 @@ def test_gemm_atb(gatx, M, N, K):
     except gatx.GatxError:
         pytest.skip("tensor-core A^T B kernel does not cover this shape")
     assert rel_err(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_train_mask_and_evaluate(gatx, orc, mode):
+    """Extension: masked training (loss / accuracy / gradients over the train nodes only) and the
+    evaluation-only forward over a validation mask, against the oracle's masked variant; gatx_backward refuses to
+    run on an evaluation forward; clearing the mask restores the reference behaviour."""
+    p = make_problem(400, 3000, 14, 5, (4, 1), (32, 16), "rmat", seed=21)
+    rng = np.random.default_rng(9)
+    part = rng.integers(0, 3, 400)
+    train, val = (part == 0).astype(np.uint8), (part == 1).astype(np.uint8)
+    eng = make_engine(gatx, p, gemm_mode=mode, optimizer="adam", lr=0.01)
+    ref = make_oracle(orc, p, optimizer="adam", lr=0.01)
+    ft, bt = FWD_TOL[mode], BWD_TOL[mode]
+    eng.set_train_mask(train)
+    ref.set_mask(train)
+    eng.forward()
+    ref.forward()
+    loss, acc = eng.loss_acc()
+    rl = ref.loss()
+    assert abs(loss - rl["avg"]) < max(ft * 5, 1e-5) * max(1.0, rl["avg"])
+    if mode == 1:
+        assert acc == pytest.approx(rl["acc"], abs=1e-7)
+    eng.backward()
+    ref.backward()
+    for l in range(2):
+        assert rel_err(eng.tensor(gatx.T_GW, l), ref.tensor(orc.T_GW, l).ravel()) < bt, ("gW", l)
+        assert rel_err(eng.tensor(gatx.T_GA, l), ref.tensor(orc.T_GA, l).ravel(), floor=1e-2) < bt, ("ga", l)
+    assert rel_err(eng.tensor(gatx.T_GWO), ref.tensor(orc.T_GWO).ravel()) < bt
+    eng.step(1)
+    ref.step(1)
+    # validation forward: other mask, same parameters on both sides
+    vl, va = eng.evaluate(val)
+    ref.set_mask(val)
+    ref.forward()
+    rv = ref.loss()
+    assert abs(vl - rv["avg"]) < max(ft * 5, 1e-5) * max(1.0, rv["avg"])
+    if mode == 1:
+        assert va == pytest.approx(rv["acc"], abs=1e-7)
+        assert np.array_equal(eng.tensor(gatx.T_PRED), rv["pred"])
+    with pytest.raises(gatx.GatxError):
+        eng.backward()  # the activations now belong to an evaluation forward
+    # a few masked epochs track the oracle, evaluation in between does not disturb training
+    ref.set_mask(train)
+    for t in (2, 3, 4):
+        gl, _ = eng.train_epoch(t)
+        eng.evaluate(val)
+        ol, _ = ref.epoch(t)
+        assert abs(gl - ol) < (2e-3 if mode == 1 else 1e-2) * max(1.0, ol), (t, gl, ol)
+    # no mask == all-ones mask == reference behaviour
+    eng.set_train_mask(None)
+    eng.forward()
+    l_none = eng.loss_acc()
+    eng.set_train_mask(np.ones(400, np.uint8))
+    eng.forward()
+    assert eng.loss_acc() == l_none
+    all_l, all_a = eng.evaluate(None)
+    assert (all_l, all_a) == l_none
+    eng.close()
+
+
+def test_state_roundtrip(gatx, orc):
+    """gatx_get_state / gatx_set_state (parameters + Adam moments): a second engine continues bit-exactly."""
+    p = make_problem(300, 2400, 24, 5, (4, 1), (32, 16), "rmat", seed=7)
+    a = make_engine(gatx, p, optimizer="adam", lr=0.01, clip=True)
+    for t in (1, 2, 3):
+        a.train_epoch(t)
+    st = a.get_state()
+    assert st.size == 3 * sum(a.tensor(k, l).size for k in (gatx.T_W, gatx.T_A) for l in range(2)) + 3 * a.tensor(gatx.T_WO).size
+    b = make_engine(gatx, p, optimizer="adam", lr=0.01, clip=True)
+    b.set_state(st)
+    for t in (4, 5):
+        la = a.train_epoch(t)
+        lb = b.train_epoch(t)
+        assert la == lb
+    assert np.array_equal(a.get_state(), b.get_state())
+    with pytest.raises(gatx.GatxError):
+        b.set_state(st[:-1])
+    a.close()
+    b.close()

@@ -133,6 +133,36 @@ def test_forward_backward_vs_torch_autograd(orc, heads, outdims):
     assert rel_err(m.tensor(orc.T_GWO), grads["gWo"]) < 2e-5
 
 
+def test_masked_loss_and_gradients_vs_torch_autograd(orc):
+    """Extension: nodes outside the mask do not enter loss, accuracy or gradients."""
+    row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(7)
+    heads, outdims = (3, 1), (4, 6)
+    mask = (np.random.default_rng(3).random(len(y)) < 0.4).astype(np.uint8)
+    m = orc.Model(heads, outdims, row_ptr, col_idx, X, y)
+    for l in range(2):
+        m.set_params(l, Ws[l], As[l])
+    m.set_wo(Wo)
+    m.set_mask(mask)
+    m.forward()
+    loss = m.loss()
+    m.backward()
+    vals, grads = torch_ref.forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, y, mask=mask)
+    cnt = int(mask.sum())
+    assert abs(loss["total"] - vals["loss_sum"]) / vals["loss_sum"] < 1e-6
+    assert abs(loss["avg"] - vals["loss_sum"] / cnt) < 1e-5 * vals["loss_sum"] / cnt
+    assert abs(loss["acc"] - float((vals["pred"] == y)[mask != 0].mean())) < 1e-6
+    for l in range(2):
+        assert rel_err(m.tensor(orc.T_GW, l), grads["gW"][l]) < 2e-5, l
+        assert rel_err(m.tensor(orc.T_GA, l), grads["ga"][l]) < 2e-5, l
+    assert rel_err(m.tensor(orc.T_GWO), grads["gWo"]) < 2e-5
+    # an all-ones mask is the reference behaviour
+    m.set_mask(np.ones(len(y), np.uint8))
+    m.forward()
+    full = m.loss()
+    m.set_mask(None)
+    assert m.loss()["total"] == full["total"] and m.loss()["avg"] == full["avg"]
+
+
 def test_literal_fp32_matches_factored(orc):
     row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(2)
     H, D = 3, 4

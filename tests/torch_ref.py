@@ -14,7 +14,7 @@ def lrelu(x):
     return torch.where(x > 0, x, SLOPE * x)
 
 
-def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch.float64):
+def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch.float64, mask=None):
     N = len(row_ptr) - 1
     deg = np.diff(row_ptr)
     src = torch.as_tensor(np.asarray(col_idx), dtype=torch.long)
@@ -51,15 +51,17 @@ def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch
     lab = torch.as_tensor(np.asarray(labels), dtype=torch.long)
     p = y[torch.arange(N), lab]
     losses = -torch.log(torch.clamp(p, min=1e-12))
+    if mask is not None:  # extension: only counted nodes enter the (summed) loss
+        losses = losses * torch.as_tensor(np.asarray(mask) != 0, dtype=dtype)
     out.update(z=z, y=y, losses=losses, loss_sum=losses.sum(), pred=y.argmax(1))
     return out
 
 
-def forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels):
+def forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, mask=None):
     tW = [torch.tensor(np.asarray(w, np.float64), requires_grad=True) for w in Ws]
     tA = [torch.tensor(np.asarray(a, np.float64), requires_grad=True) for a in As]
     tWo = torch.tensor(np.asarray(Wo, np.float64), requires_grad=True)
-    out = forward(tW, tA, tWo, np.asarray(X, np.float64), row_ptr, col_idx, heads, outdims, labels)
+    out = forward(tW, tA, tWo, np.asarray(X, np.float64), row_ptr, col_idx, heads, outdims, labels, mask=mask)
     out["loss_sum"].backward()
     grads = dict(gW=[w.grad.numpy() for w in tW], ga=[a.grad.numpy() for a in tA], gWo=tWo.grad.numpy())
     vals = {k: ([t.detach().numpy() for t in v] if isinstance(v, list) else v.detach().numpy())
