@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "libgatx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]
-SOURCES = ["gatx_api.cu", "graph_prep.cu", "gemm_simt.cu", "gemm_tc.cu", "edge_kernels.cu", "edge_stream.cu", "edge_generic.cu", "head_loss.cu", "optim.cu"]
+SOURCES = ["gatx_api.cu", "graph_prep.cu", "gemm_simt.cu", "gemm_tc.cu", "edge_kernels.cu", "edge_stream.cu", "edge_generic.cu", "head_loss.cu", "optim.cu", "halo_p2p.cu"]
 
 
 def _stale(target, deps):

@@ -125,6 +125,16 @@ int launch_transpose_wo(const float* Wo, int C, int DL, int ldc, float* WoT, cud
 int launch_loss_finalize(const double* loss_partials, const int* correct_partials, int n_partials,
                          double* loss_sum, long long* correct, cudaStream_t st);
 
+// halo_p2p.cu : halo exchange through NVLink peer memory (destination-row partition, world > 1)
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+  float* p[kMaxPeers];  // base of the peer's [N][F] buffer (this rank's own slot is unused)
+};
+int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
+                     int me, cudaStream_t st);
+int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
+                     int world, cudaStream_t st);
+
 // optim.cu
 struct OptimGroups {
   int64_t begin[3], end[3];  // {all W}, {all a}, {W_o} ranges of the flat parameter buffer

@@ -24,7 +24,8 @@ namespace {
 constexpr int kSW = 4;  // warps per CTA
 
 struct Shape {
-  int H, D, F, lph, lg_lph;
+  int H, D, F, lph, lg_lph;  // lph = D / 4: lanes per head in the node-wise kernels' layout (lane + 32 j)
+  int lc, lg_lc;             // lc = 32 / H: lanes per head in the lane-contiguous layout of the edge passes
 };
 
 struct StreamGraph {
@@ -64,117 +65,99 @@ __device__ __forceinline__ void st_pred_v4(uint32_t* p, uint32_t a, uint32_t b, 
       : "memory");
 }
 
-// Sums p[j] (j < NV, one partial per 128-float chunk row) over the LPH lanes of a head; afterwards every
-// lane holds all NV totals of its own lane group.  LPH is compile-time (0 = run-time sh.lph).  With several
-// values the reduction is transposed (reduce-scatter over the top xor offsets, butterfly over the rest,
-// all-gather back): 9 shuffles instead of 20 for NV = 4, LPH = 32.
-template <int NV, int LPH>
-__device__ __forceinline__ void reduce_heads(float (&p)[NV], int lane, int lph_rt) {
-  if constexpr (LPH == 0) {
-#pragma unroll
-    for (int j = 0; j < NV; ++j) p[j] = head_reduce(p[j], lph_rt);
-  } else if constexpr (NV == 4 && LPH >= 4) {
-    constexpr int o1 = LPH / 2, o2 = LPH / 4;
-    const bool b1 = lane & o1, b2 = lane & o2;
-    float k0 = b1 ? p[2] : p[0], k1 = b1 ? p[3] : p[1];
-    const float s0 = b1 ? p[0] : p[2], s1 = b1 ? p[1] : p[3];
-    k0 += shx(s0, o1);
-    k1 += shx(s1, o1);
-    float k = b2 ? k1 : k0;
-    k += shx(b2 ? k0 : k1, o2);
-#pragma unroll
-    for (int off = o2 / 2; off > 0; off >>= 1) k += shx(k, off);
-    const float y = shx(k, o2);
-    const float lo = b2 ? y : k, hi = b2 ? k : y;
-    const float z0 = shx(lo, o1), z1 = shx(hi, o1);
-    p[0] = b1 ? z0 : lo; p[1] = b1 ? z1 : hi; p[2] = b1 ? lo : z0; p[3] = b1 ? hi : z1;
-  } else if constexpr (NV == 2 && LPH >= 2) {
-    constexpr int o1 = LPH / 2;
-    const bool b1 = lane & o1;
-    float k = b1 ? p[1] : p[0];
-    k += shx(b1 ? p[0] : p[1], o1);
-#pragma unroll
-    for (int off = o1 / 2; off > 0; off >>= 1) k += shx(k, off);
-    const float y = shx(k, o1);
-    p[0] = b1 ? y : k; p[1] = b1 ? k : y;
+// Lane-contiguous row layout of the streaming kernels: lane l owns the 4*NV consecutive floats
+// [l*4NV, (l+1)*4NV) of a row, so it belongs to exactly ONE head (lanes per head = 32 / H) and a per-head sum is a
+// single butterfly over 32/H lanes (3 shuffles for 4 heads, against 9 shuffles + 14 selects when every lane held a
+// slice of every head); exp / alpha / ge are evaluated once per lane instead of once per head.  The j-th float4 a
+// lane holds is piece (j ^ swizzle(l)) of its span: with a 16*NV-byte lane stride, a quarter-warp of plain LDS.128
+// would hit the same banks NV times; the xor makes the eight 16-byte pieces of every quarter-warp distinct.
+template <int NV>
+__device__ __forceinline__ int lc_off(int lane, int j) {
+  constexpr int kShift = NV == 4 ? 1 : (NV == 2 ? 2 : 0);
+  const int sw = NV == 1 ? 0 : (lane >> kShift) & (NV - 1);
+  return lane * (4 * NV) + 4 * (j ^ sw);
+}
+// sum over the LC lanes of a head (LC compile-time, 0 = run-time lc_rt); every lane ends with its head's total
+template <int LC>
+__device__ __forceinline__ float head_sum(float p, int lc_rt) {
+  if constexpr (LC == 0) {
+    for (int off = lc_rt >> 1; off > 0; off >>= 1) p += shx(p, off);
   } else {
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-#pragma unroll
-      for (int off = LPH / 2; off > 0; off >>= 1) p[j] += shx(p[j], off);
+    for (int off = LC / 2; off > 0; off >>= 1) p += shx(p, off);
   }
+  return p;
 }
-template <int LPH>
-__device__ __forceinline__ int head_of(int lane, int j, const Shape& sh) {
-  if constexpr (LPH == 0) return (lane + 32 * j) >> sh.lg_lph;
-  else return lane / LPH + j * (32 / LPH);
+template <int LC>
+__device__ __forceinline__ int lc_head(int lane, const Shape& sh) {
+  if constexpr (LC == 0) return lane >> sh.lg_lc;
+  else return lane / LC;
 }
-template <int LPH>
-__device__ __forceinline__ bool is_head_lane(int lane, const Shape& sh) {
-  if constexpr (LPH == 0) return (lane & (sh.lph - 1)) == 0;
-  else return (lane & (LPH - 1)) == 0;
+template <int LC>
+__device__ __forceinline__ bool lc_head_lane(int lane, const Shape& sh) {
+  if constexpr (LC == 0) return (lane & (sh.lc - 1)) == 0;
+  else return (lane & (LC - 1)) == 0;
 }
 
 template <int NV>
 __device__ __forceinline__ void load_row(float4 (&x)[NV], const float* __restrict__ base, int row, int lane) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) x[j] = ldg4(base + (int64_t)row * (NV * 128) + 4 * (lane + 32 * j));
+  for (int j = 0; j < NV; ++j) x[j] = ldg4(base + (int64_t)row * (NV * 128) + lc_off<NV>(lane, j));
 }
 
 // Partial-state slots: [chunk][2][PF] floats.  Slot 0: the segment that starts at the first edge of the chunk,
 // slot 1: a segment that starts later and runs past the end of the chunk.
 template <int NV>
 struct FwdState {
-  float m[NV], s[NV];
+  float m, s;  // one head per lane
   float4 acc[NV];
   __device__ __forceinline__ void init() {
+    m = -1e9f;  // EB:336
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void merge(float m2, float s2, const float4 (&a2)[NV]) {
+    const float mn = fmaxf(m, m2);
+    const float c1 = __expf(m - mn), c2 = __expf(m2 - mn);
+    s = s * c1 + s2 * c2;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      m[j] = -1e9f;  // EB:336
-      s[j] = 0.f;
-      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[j].x = acc[j].x * c1 + a2[j].x * c2;
+      acc[j].y = acc[j].y * c1 + a2[j].y * c2;
+      acc[j].z = acc[j].z * c1 + a2[j].z * c2;
+      acc[j].w = acc[j].w * c1 + a2[j].w * c2;
     }
-  }
-  __device__ __forceinline__ void merge(int j, float m2, float s2, float4 a2) {
-    const float mn = fmaxf(m[j], m2);
-    const float c1 = __expf(m[j] - mn), c2 = __expf(m2 - mn);
-    s[j] = s[j] * c1 + s2 * c2;
-    acc[j].x = acc[j].x * c1 + a2.x * c2;
-    acc[j].y = acc[j].y * c1 + a2.y * c2;
-    acc[j].z = acc[j].z * c1 + a2.z * c2;
-    acc[j].w = acc[j].w * c1 + a2.w * c2;
-    m[j] = mn;
+    m = mn;
   }
 };
+// partial state of a row segment: [F floats acc, natural element order][32 m][32 s] (per lane)
 template <int NV>
 constexpr int fwd_part_floats() { return NV * 128 + 2 * NV * 32; }
 
 template <int NV>
 __device__ __forceinline__ void fwd_store_partial(const FwdState<NV>& st, float* __restrict__ p, int lane) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    st4(p + 4 * (lane + 32 * j), st.acc[j]);
-    p[NV * 128 + j * 32 + lane] = st.m[j];
-    p[NV * 128 + NV * 32 + j * 32 + lane] = st.s[j];
-  }
+  for (int j = 0; j < NV; ++j) st4(p + lc_off<NV>(lane, j), st.acc[j]);
+  p[NV * 128 + lane] = st.m;
+  p[NV * 128 + 32 + lane] = st.s;
 }
 template <int NV>
 __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, const Shape sh, float* __restrict__ Hout,
                                              float* __restrict__ hpre, float* __restrict__ mx,
                                              float* __restrict__ sinv, int lane) {
-  const bool head_lane = (lane & (sh.lph - 1)) == 0;
+  const float inv = 1.0f / (st.s + 1e-8f);  // EB:379
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const float inv = 1.0f / (st.s[j] + 1e-8f);  // EB:379
     const float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
-    const int64_t off = (int64_t)row * sh.F + 4 * (lane + 32 * j);
+    const int64_t off = (int64_t)row * sh.F + lc_off<NV>(lane, j);
     if (hpre) st4(hpre + off, h);
     st4(Hout + off, make_float4(lrelu(h.x), lrelu(h.y), lrelu(h.z), lrelu(h.w)));  // EB:440-457
-    if (head_lane) {
-      const int hd = (lane + 32 * j) >> sh.lg_lph;
-      mx[(int64_t)row * sh.H + hd] = st.m[j];
-      sinv[(int64_t)row * sh.H + hd] = inv;
-    }
+  }
+  if ((lane & (sh.lc - 1)) == 0) {
+    const int hd = lane >> sh.lg_lc;
+    mx[(int64_t)row * sh.H + hd] = st.m;
+    sinv[(int64_t)row * sh.H + hd] = inv;
   }
 }
 
@@ -198,8 +181,12 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
   __syncwarp();
   float4 av[NV];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) av[j] = ldg4(a + 4 * (lane + 32 * j));
-  const bool head_lane = is_head_lane<LPH>(lane, sh);
+  for (int j = 0; j < NV; ++j) av[j] = ldg4(a + lc_off<NV>(lane, j));
+  const bool head_lane = lc_head_lane<LPH>(lane, sh);
+  const int hd = lc_head<LPH>(lane, sh);
+  int voff[NV];  // byte-free float offsets of this lane's pieces inside a ring slot
+#pragma unroll
+  for (int j = 0; j < NV; ++j) voff[j] = lc_off<NV>(lane, j);
   const int total_warps = gridDim.x * kSW;
   uint32_t it = 0;  // ring position: edges consumed by this warp so far
   for (int chunk = blockIdx.x * kSW + warp; chunk < g.n_chunks; chunk += total_warps) {
@@ -258,7 +245,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       mbar_wait(&bar[slot], ph);
       float4 v[NV];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + 4 * (lane + 32 * j));
+      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + voff[j]);
       __syncwarp();  // every lane has read the slot before it is refilled
       {
         const int ni = i + R;
@@ -268,25 +255,24 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
           bulk_g2s(ring + slot * F, Pl + (int64_t)srcn * F, kRowBytes, &bar[slot]);
         }
       }
-      float p[NV];
+      float p = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j)  // EB:303-320
-        p[j] = av[j].x * lrelu_fast(v[j].x + pr[j].x) + av[j].y * lrelu_fast(v[j].y + pr[j].y) +
-               av[j].z * lrelu_fast(v[j].z + pr[j].z) + av[j].w * lrelu_fast(v[j].w + pr[j].w);
-      reduce_heads<NV, LPH>(p, lane, sh.lph);
-      float* sce = score + (int64_t)e * sh.H;
+        p += av[j].x * lrelu_fast(v[j].x + pr[j].x) + av[j].y * lrelu_fast(v[j].y + pr[j].y) +
+             av[j].z * lrelu_fast(v[j].z + pr[j].z) + av[j].w * lrelu_fast(v[j].w + pr[j].w);
+      p = head_sum<LPH>(p, sh.lc);
+      st_pred_u32(reinterpret_cast<uint32_t*>(score + (int64_t)e * sh.H + hd), __float_as_uint(p), head_lane);
+      const float mn = fmaxf(st.m, p);
+      const float corr = __expf(st.m - mn), w = __expf(p - mn);  // online form of EB:336-349
+      st.s = st.s * corr + w;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        st_pred_u32(reinterpret_cast<uint32_t*>(sce + head_of<LPH>(lane, j, sh)), __float_as_uint(p[j]), head_lane);
-        const float mn = fmaxf(st.m[j], p[j]);
-        const float corr = __expf(st.m[j] - mn), w = __expf(p[j] - mn);  // online form of EB:336-349
-        st.s[j] = st.s[j] * corr + w;
         st.acc[j].x = st.acc[j].x * corr + w * v[j].x;  // EB:415-422 without atomics
         st.acc[j].y = st.acc[j].y * corr + w * v[j].y;
         st.acc[j].z = st.acc[j].z * corr + w * v[j].z;
         st.acc[j].w = st.acc[j].w * corr + w * v[j].w;
-        st.m[j] = mn;
       }
+      st.m = mn;
     }
     // the segment that reaches the end of the chunk
     {
@@ -320,17 +306,16 @@ edge_fwd_fixup_kernel(StreamGraph g, Shape sh, const float* __restrict__ part, f
   {
     const float* p = part + ((int64_t)c * 2 + (rs == c * g.T ? 0 : 1)) * PF;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      st.acc[j] = lds4(p + 4 * (lane + 32 * j));
-      st.m[j] = p[NV * 128 + j * 32 + lane];
-      st.s[j] = p[NV * 128 + NV * 32 + j * 32 + lane];
-    }
+    for (int j = 0; j < NV; ++j) st.acc[j] = lds4(p + lc_off<NV>(lane, j));
+    st.m = p[NV * 128 + lane];
+    st.s = p[NV * 128 + 32 + lane];
   }
   for (int cc = c + 1; cc <= c_last; ++cc) {
     const float* p = part + ((int64_t)cc * 2 + 0) * PF;
+    float4 a2[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-      st.merge(j, p[NV * 128 + j * 32 + lane], p[NV * 128 + NV * 32 + j * 32 + lane], lds4(p + 4 * (lane + 32 * j)));
+    for (int j = 0; j < NV; ++j) a2[j] = lds4(p + lc_off<NV>(lane, j));
+    st.merge(p[NV * 128 + lane], p[NV * 128 + 32 + lane], a2);
   }
   fwd_finalize<NV>(st, rr, sh, Hout, hpre, mx, sinv, lane);
 }
@@ -394,20 +379,15 @@ edge_bwd_prep_kernel(int n_rows, Shape sh, const float* __restrict__ Hout, float
 // ------------------------------------------------------------------------- backward, pass 1
 __host__ __device__ inline int rec_words(int H, int NV) { return (4 * NV + 2 * H + 3) / 4 * 4; }
 
-template <int NV>
 struct RowScalars {
-  float c[NV], m[NV], inv[NV];
+  float c, m, inv;  // of this lane's head
 };
-template <int NV>
-__device__ __forceinline__ void load_scalars(RowScalars<NV>& q, int row, const Shape sh, const float* __restrict__ cdot,
-                                             const float* __restrict__ mx, const float* __restrict__ sinv, int lane) {
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int64_t o = (int64_t)row * sh.H + ((lane + 32 * j) >> sh.lg_lph);
-    q.c[j] = __ldg(cdot + o);
-    q.m[j] = __ldg(mx + o);
-    q.inv[j] = __ldg(sinv + o);
-  }
+__device__ __forceinline__ void load_scalars(RowScalars& q, int row, int H, int hd, const float* __restrict__ cdot,
+                                             const float* __restrict__ mx, const float* __restrict__ sinv) {
+  const int64_t o = (int64_t)row * H + hd;
+  q.c = __ldg(cdot + o);
+  q.m = __ldg(mx + o);
+  q.inv = __ldg(sinv + o);
 }
 
 // smem per warp: ring [R][F] | rowbuf [2F] (g_h row, P_r row) | score window [2][32*H] | barriers [R + 1]
@@ -439,9 +419,13 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
   float4 ga[NV];  // the attention vector a is only needed when a row segment is written: read it there (L1 hit)
 #pragma unroll
   for (int j = 0; j < NV; ++j) ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int H = LPH > 0 ? NV * 32 / (LPH > 0 ? LPH : 1) : sh.H;  // compile-time when the head width is
+  const int H = LPH > 0 ? 32 / (LPH > 0 ? LPH : 1) : sh.H;  // compile-time when the head width is
   const int RW = rec_words(H, NV);
-  const bool head_lane = is_head_lane<LPH>(lane, sh);
+  const bool head_lane = lc_head_lane<LPH>(lane, sh);
+  const int hd = lc_head<LPH>(lane, sh);
+  int voff[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) voff[j] = lc_off<NV>(lane, j);
   const int total_warps = gridDim.x * kSW;
   uint32_t it = 0;   // ring position
   uint32_t rk = 0;   // row-buffer position: row loads issued so far
@@ -485,19 +469,20 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       const int t = 32 * H + lane + 32 * k;
       scp[k] = (k < H && t < n * H) ? __ldg(score + (int64_t)e0 * H + t) : 0.f;
     }
-    RowScalars<NV> q, qn;
-    load_scalars<NV>(q, r, sh, cdot, mx, sinv, lane);
+    RowScalars q, qn;
+    load_scalars(q, r, H, hd, cdot, mx, sinv);
+    qn = q;
     int next_end = 0x7fffffff;
     if (r + 1 < g.n_rows) {
-      load_scalars<NV>(qn, r + 1, sh, cdot, mx, sinv, lane);
+      load_scalars(qn, r + 1, H, hd, cdot, mx, sinv);
       next_end = __ldg(g.row_ptr + r + 2);
     }
     float4 ghr[NV], pr[NV], gpr[NV];
     mbar_wait(rbar, rk & 1);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      ghr[j] = lds4(rowbuf + 4 * (lane + 32 * j));
-      pr[j] = lds4(rowbuf + F + 4 * (lane + 32 * j));
+      ghr[j] = lds4(rowbuf + voff[j]);
+      pr[j] = lds4(rowbuf + F + voff[j]);
       gpr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
@@ -516,8 +501,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         if (e > e0 || !first_row) {
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
-            const float4 avj = ldg4(a + 4 * (lane + 32 * j));
-            st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * avj.x, gpr[j].y * avj.y, gpr[j].z * avj.z,
+            const float4 avj = ldg4(a + voff[j]);
+            st4(dst + voff[j], make_float4(gpr[j].x * avj.x, gpr[j].y * avj.y, gpr[j].z * avj.z,
                                                        gpr[j].w * avj.w));
           }
         }
@@ -530,8 +515,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         mbar_wait(rbar, rk & 1);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          ghr[j] = lds4(rowbuf + 4 * (lane + 32 * j));
-          pr[j] = lds4(rowbuf + F + 4 * (lane + 32 * j));
+          ghr[j] = lds4(rowbuf + voff[j]);
+          pr[j] = lds4(rowbuf + F + voff[j]);
           gpr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
@@ -542,7 +527,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
             bulk_g2s(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar);
             bulk_g2s(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar);
           }
-          load_scalars<NV>(qn, r + 1, sh, cdot, mx, sinv, lane);
+          load_scalars(qn, r + 1, H, hd, cdot, mx, sinv);
           next_end = __ldg(g.row_ptr + r + 2);
         }
       }
@@ -565,7 +550,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       mbar_wait(&bar[slot], ph);
       float4 v[NV];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + 4 * (lane + 32 * j));
+      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + voff[j]);
       __syncwarp();
       {
         const int ni = i + R;
@@ -577,16 +562,15 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       }
       const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
       uint32_t* re = rec + (int64_t)e * RW;
-      float galpha[NV];
+      float galpha = 0.f;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) galpha[j] = dot4(ghr[j], v[j]);  // EB:636-646
-      reduce_heads<NV, LPH>(galpha, lane, sh.lph);
+      for (int j = 0; j < NV; ++j) galpha += dot4(ghr[j], v[j]);  // EB:636-646
+      galpha = head_sum<LPH>(galpha, sh.lc);
+      const float alpha = __expf(sc[hd] - q.m) * q.inv;  // EB:378-379
+      const float ge = alpha * (galpha - q.c);           // EB:689-690 in closed form
+      const float ges = ge * kSlope;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const int hd = head_of<LPH>(lane, j, sh);
-        const float alpha = __expf(sc[hd] - q.m[j]) * q.inv[j];  // EB:378-379
-        const float ge = alpha * (galpha[j] - q.c[j]);           // EB:689-690 in closed form
-        const float ges = ge * kSlope;
         const float sx = v[j].x + pr[j].x, sy = v[j].y + pr[j].y, sz = v[j].z + pr[j].z, sw = v[j].w + pr[j].w;
         const bool px = sx > 0.f, py = sy > 0.f, pz = sz > 0.f, pw = sw > 0.f;
         // u = ge * LReLU'(s);  ga += u * s = ge * LReLU(s) (EB:769);  gP_r += a * u (EB:774-781, a applied per row)
@@ -596,12 +580,12 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         gpr[j].x += ux; gpr[j].y += uy; gpr[j].z += uz; gpr[j].w += uw;
         const uint32_t bx = __ballot_sync(0xffffffffu, px), by = __ballot_sync(0xffffffffu, py),
                        bz = __ballot_sync(0xffffffffu, pz), bw = __ballot_sync(0xffffffffu, pw);
-        // predicated stores (no divergence regions): lane 0 writes the sign words, head lanes write alpha / ge
+        // predicated stores (no divergence regions): lane 0 writes the sign words (bit = lane, word = 4 j + component)
         st_pred_v4(re + 4 * j, bx, by, bz, bw, lane == 0);
-        st_pred_u32(re + 4 * NV + hd, __float_as_uint(alpha), head_lane);
-        st_pred_u32(re + 4 * NV + H + hd, __float_as_uint(ge), head_lane);
-        if (galpha_dbg && head_lane) galpha_dbg[(int64_t)e * H + hd] = galpha[j];
       }
+      st_pred_u32(re + 4 * NV + hd, __float_as_uint(alpha), head_lane);
+      st_pred_u32(re + 4 * NV + H + hd, __float_as_uint(ge), head_lane);
+      if (galpha_dbg && head_lane) galpha_dbg[(int64_t)e * H + hd] = galpha;
     }
     {
       const bool ended = row_end == e1;
@@ -609,8 +593,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       float* dst = complete ? gPr + (int64_t)r * F : part + ((int64_t)chunk * 2 + (first_row ? 0 : 1)) * F;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float4 avj = ldg4(a + 4 * (lane + 32 * j));
-        st4(dst + 4 * (lane + 32 * j), make_float4(gpr[j].x * avj.x, gpr[j].y * avj.y, gpr[j].z * avj.z,
+        const float4 avj = ldg4(a + voff[j]);
+        st4(dst + voff[j], make_float4(gpr[j].x * avj.x, gpr[j].y * avj.y, gpr[j].z * avj.z,
                                                    gpr[j].w * avj.w));
       }
     }
@@ -626,7 +610,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
   __syncthreads();
   float4* sm = reinterpret_cast<float4*>(smem_raw);
 #pragma unroll
-  for (int j = 0; j < NV; ++j) sm[warp * (NV * 32) + lane + 32 * j] = ga[j];
+  for (int j = 0; j < NV; ++j) sm[warp * (NV * 32) + lane + 32 * j] = ga[j];  // staging order is private
   __syncthreads();
   if (warp == 0) {
 #pragma unroll
@@ -636,7 +620,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         const float4 o = sm[w * (NV * 32) + lane + 32 * j];
         t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
       }
-      st4(ga_partials + (int64_t)blockIdx.x * F + 4 * (lane + 32 * j), t);
+      st4(ga_partials + (int64_t)blockIdx.x * F + voff[j], t);
     }
   }
 }
@@ -692,7 +676,11 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
   __syncwarp();
   float4 av[NV];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) av[j] = ldg4(a + 4 * (lane + 32 * j));
+  for (int j = 0; j < NV; ++j) av[j] = ldg4(a + lc_off<NV>(lane, j));
+  int voff[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) voff[j] = lc_off<NV>(lane, j);
+  const int hd = lane >> sh.lg_lc;
   const int RW = rec_words(sh.H, NV);
   const uint32_t kRecBytes = RW * 4;
   const int total_warps = gridDim.x * kSW;
@@ -728,7 +716,7 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
         float* dstp = (first_row && started_before) ? part + ((int64_t)chunk * 2 + 0) * F : gPl + (int64_t)r * F;
         if (e > e0 || !first_row) {
 #pragma unroll
-          for (int j = 0; j < NV; ++j) st4(dstp + 4 * (lane + 32 * j), acc[j]);
+          for (int j = 0; j < NV; ++j) st4(dstp + voff[j], acc[j]);
         }
         first_row = false;
         ++r;
@@ -750,15 +738,14 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
       const uint32_t* rw = reinterpret_cast<const uint32_t*>(sl + F);
       float4 gv[NV];
       uint4 kk[NV];
-      float al[NV], ge[NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const int hd = (lane + 32 * j) >> sh.lg_lph;
-        gv[j] = lds4(sl + 4 * (lane + 32 * j));
+        gv[j] = lds4(sl + voff[j]);
         kk[j] = *reinterpret_cast<const uint4*>(rw + 4 * j);
-        al[j] = __uint_as_float(rw[4 * NV + hd]);
-        ge[j] = __uint_as_float(rw[4 * NV + sh.H + hd]);
       }
+      const float al = __uint_as_float(rw[4 * NV + hd]);  // this lane's head
+      const float ge = __uint_as_float(rw[4 * NV + sh.H + hd]);
+      const float ges = ge * kSlope;
       __syncwarp();
       {
         const int ni = i + R;
@@ -774,10 +761,10 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         // EB:865-866: g_h[dst] * alpha + ge * a * LReLU'(s), LReLU'(s) from the recorded sign bit
-        acc[j].x += al[j] * gv[j].x + ge[j] * av[j].x * (((kk[j].x >> lane) & 1u) ? 1.f : kSlope);
-        acc[j].y += al[j] * gv[j].y + ge[j] * av[j].y * (((kk[j].y >> lane) & 1u) ? 1.f : kSlope);
-        acc[j].z += al[j] * gv[j].z + ge[j] * av[j].z * (((kk[j].z >> lane) & 1u) ? 1.f : kSlope);
-        acc[j].w += al[j] * gv[j].w + ge[j] * av[j].w * (((kk[j].w >> lane) & 1u) ? 1.f : kSlope);
+        acc[j].x = fmaf(((kk[j].x >> lane) & 1u) ? ge : ges, av[j].x, fmaf(al, gv[j].x, acc[j].x));
+        acc[j].y = fmaf(((kk[j].y >> lane) & 1u) ? ge : ges, av[j].y, fmaf(al, gv[j].y, acc[j].y));
+        acc[j].z = fmaf(((kk[j].z >> lane) & 1u) ? ge : ges, av[j].z, fmaf(al, gv[j].z, acc[j].z));
+        acc[j].w = fmaf(((kk[j].w >> lane) & 1u) ? ge : ges, av[j].w, fmaf(al, gv[j].w, acc[j].w));
       }
     }
     {
@@ -785,7 +772,7 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
       const bool complete = ended && !(first_row && started_before);
       float* dstp = complete ? gPl + (int64_t)r * F : part + ((int64_t)chunk * 2 + (first_row ? 0 : 1)) * F;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) st4(dstp + 4 * (lane + 32 * j), acc[j]);
+      for (int j = 0; j < NV; ++j) st4(dstp + voff[j], acc[j]);
     }
     it += n;
   }
@@ -803,7 +790,11 @@ bool make_stream_shape(int H, int D, Shape* sh, int* nv) {
   if (NV != 1 && NV != 2 && NV != 4) return false;
   int lg = 0;
   while ((1 << lg) < lph) ++lg;
-  *sh = Shape{H, D, F, lph, lg};
+  if (32 % H) return false;  // lane-contiguous layout: 32 / H lanes per head
+  const int lc = 32 / H;
+  int lgc = 0;
+  while ((1 << lgc) < lc) ++lgc;
+  *sh = Shape{H, D, F, lph, lg, lc, lgc};
   *nv = NV;
   return true;
 }
@@ -831,12 +822,12 @@ bool use_pair(int nv, const Shape& sh) {
     else if (nv == 2) { constexpr int NV = 2; __VA_ARGS__; } \
     else { constexpr int NV = 1; __VA_ARGS__; }              \
   } while (0)
-// lanes per head: 32 (D = 128) and 16 (D = 64) are compile-time fast paths, anything else is run-time
-#define STREAM_DISPATCH(nv, lph, ...)                                           \
+// lanes per head (32 / H): 8 (4 heads) and 16 (2 heads) are compile-time fast paths, anything else is run-time
+#define STREAM_DISPATCH(nv, lc, ...)                                           \
   do {                                                                          \
-    if (lph == 32) { constexpr int LPH = 32; STREAM_DISPATCH_NV(nv, __VA_ARGS__); }      \
-    else if (lph == 16) { constexpr int LPH = 16; STREAM_DISPATCH_NV(nv, __VA_ARGS__); } \
-    else { constexpr int LPH = 0; STREAM_DISPATCH_NV(nv, __VA_ARGS__); }                 \
+    if (lc == 8) { constexpr int LPH = 8; STREAM_DISPATCH_NV(nv, __VA_ARGS__); }        \
+    else if (lc == 16) { constexpr int LPH = 16; STREAM_DISPATCH_NV(nv, __VA_ARGS__); } \
+    else { constexpr int LPH = 0; STREAM_DISPATCH_NV(nv, __VA_ARGS__); }                \
   } while (0)
 
 }  // namespace
@@ -880,7 +871,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
     }
     return launches;
   }
-  STREAM_DISPATCH(nv, sh.lph, {
+  STREAM_DISPATCH(nv, sh.lc, {
     constexpr int R = ring_depth<NV>();
     const size_t smem = (size_t)kSW * R * NV * 128 * 4 + (size_t)kSW * R * 8;
     auto kern = edge_fwd_stream_kernel<NV, R, LPH>;
@@ -955,7 +946,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
     }
     return launches;
   }
-  STREAM_DISPATCH(nv, sh.lph, {
+  STREAM_DISPATCH(nv, sh.lc, {
     constexpr int F = NV * 128;
     {
       int blocks = (eg.n_rows + 7) / 8;

@@ -4,6 +4,7 @@
 // two loss/accuracy scalars).
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -118,6 +119,14 @@ struct gatx_ctx {
   double* red2 = nullptr;  // [2] all-reduce staging
   // comm
   ncclComm_t comm = nullptr;
+  // NVLink peer-memory halo exchange (gatx_peer_export / gatx_peer_import); NCCL collectives when not set up
+  uint16_t* ref_mask = nullptr;  // [n_rows] bit p: rank p's edge slice references this (own) source row
+  int64_t halo_rows = 0;         // sum over own rows of the number of OTHER ranks referencing them
+  bool peers_ready = false;
+  std::vector<PeerPtrs> peer_Pl;  // per layer
+  PeerPtrs peer_gPl{};
+  std::vector<void*> ipc_opened;
+  float* barrier_word = nullptr;
   // timing
   cudaEvent_t sw_a = nullptr, sw_b = nullptr;
   bool timing = false;
@@ -196,10 +205,14 @@ struct PhaseTimer {
 void free_graph(gatx_ctx* c) {
   dfree(c->row_ptr); dfree(c->col_idx); dfree(c->coo_src); dfree(c->coo_dst); dfree(c->in_deg);
   dfree(c->csc_ptr); dfree(c->csc_dst); dfree(c->csc_eid); dfree(c->heavy_rows); dfree(c->heavy_srcs);
-  dfree(c->chunk_row); dfree(c->chunk_src);
+  dfree(c->chunk_row); dfree(c->chunk_src); dfree(c->ref_mask);
   c->have_graph = false;
 }
 void free_bufs(gatx_ctx* c) {
+  for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+  c->ipc_opened.clear();
+  c->peers_ready = false;
+  dfree(c->barrier_word);
   for (auto& l : c->layers) {
     dfree(l.Wcat); dfree(l.WcatT); dfree(l.Pl); dfree(l.Pr);
     if (l.Hout != l.Hfull) dfree(l.Hout);
@@ -399,10 +412,26 @@ int gemm_nt_reduce(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, i
   return GATX_OK;
 }
 
-int comm_allgather_rows(gatx_ctx* ctx, float* full, int F) {
+// Stream-ordered barrier across ranks: a 4-byte all-reduce.  A rank leaves it only after every rank's stream has
+// reached it, i.e. after every kernel the peers enqueued before it (and its peer-memory stores) completed.
+int comm_barrier(gatx_ctx* ctx) {
+  NK(g_nccl.AllReduce(ctx->barrier_word, ctx->barrier_word, 1, ncclFloat, ncclSum, ctx->comm, ctx->st));
+  return GATX_OK;
+}
+bool halo_p2p(const gatx_ctx* ctx, int F) { return ctx->peers_ready && F % 4 == 0; }
+
+// Forward exchange: every rank ends with the P_l rows its edges gather (all rows on the NCCL path).
+int comm_allgather_rows(gatx_ctx* ctx, float* full, int F, int layer) {
   if (ctx->world == 1) return GATX_OK;
   if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
   PhaseTimer t(ctx, PH_COMM);
+  if (halo_p2p(ctx, F)) {
+    int rc = comm_barrier(ctx);  // the peers are done reading the previous contents of their P_l
+    if (rc) return rc;
+    LAUNCHED(launch_halo_push(full + (int64_t)ctx->r0 * F, ctx->r0, ctx->n_rows, F, ctx->ref_mask, ctx->peer_Pl[layer],
+                              ctx->rank, ctx->st));
+    return comm_barrier(ctx);    // every push has landed
+  }
   NK(g_nccl.GroupStart());
   for (int r = 0; r < ctx->world; ++r) {
     float* p = full + (int64_t)ctx->bounds[r] * F;
@@ -412,10 +441,18 @@ int comm_allgather_rows(gatx_ctx* ctx, float* full, int F) {
   NK(g_nccl.GroupEnd());
   return GATX_OK;
 }
+// Backward exchange: the owner of a source row ends with the sum of all ranks' partial gP_l rows.
 int comm_reduce_rows(gatx_ctx* ctx, float* full, int F) {
   if (ctx->world == 1) return GATX_OK;
   if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
   PhaseTimer t(ctx, PH_COMM);
+  if (halo_p2p(ctx, F)) {
+    int rc = comm_barrier(ctx);  // every rank's partial sums are complete
+    if (rc) return rc;
+    LAUNCHED(launch_halo_pull(full + (int64_t)ctx->r0 * F, ctx->r0, ctx->n_rows, F, ctx->ref_mask, ctx->peer_gPl,
+                              ctx->rank, ctx->world, ctx->st));
+    return comm_barrier(ctx);    // the peers may overwrite their scratch again
+  }
   NK(g_nccl.GroupStart());
   for (int r = 0; r < ctx->world; ++r) {
     float* p = full + (int64_t)ctx->bounds[r] * F;
@@ -449,7 +486,7 @@ int do_forward(gatx_ctx* ctx) {
       if (rc) return rc;
     }
     if (!replicated) {
-      rc = comm_allgather_rows(ctx, ly.Pl, ly.F);
+      rc = comm_allgather_rows(ctx, ly.Pl, ly.F, l);
       if (rc) return rc;
     }
     {
@@ -738,6 +775,26 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
     if (d > maxdeg) maxdeg = d;  // EB:89-99
   }
   ctx->max_degree = maxdeg;
+  if (ctx->world > 1 && ctx->world <= kMaxPeers) {
+    // which ranks' edge slices reference each source (integer work, identical on every rank): the halo lists
+    std::vector<uint16_t> ref((size_t)N, 0);
+    for (int p = 0; p < ctx->world; ++p) {
+      const uint16_t bit = (uint16_t)(1u << p);
+      const int64_t a = row_ptr[ctx->bounds[p]], b = row_ptr[ctx->bounds[p + 1]];
+      for (int64_t e = a; e < b; ++e) {
+        const int sidx = col_idx[e];
+        if (sidx >= 0 && sidx < N) ref[sidx] |= bit;
+      }
+    }
+    int64_t halo = 0;
+    for (int i = ctx->r0; i < ctx->r1; ++i) halo += __builtin_popcount((unsigned)(ref[i] & ~(1u << ctx->rank)));
+    ctx->halo_rows = halo;
+    CK(dalloc(&ctx->ref_mask, (size_t)ctx->n_rows));
+    if (ctx->n_rows)
+      CK(cudaMemcpyAsync(ctx->ref_mask, ref.data() + ctx->r0, sizeof(uint16_t) * (size_t)ctx->n_rows,
+                         cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));  // `ref` goes out of scope
+  }
   for (int i = 0; i <= ctx->n_rows; ++i) local_ptr[i] = (int)(row_ptr[ctx->r0 + i] - e0);
   for (int i = 0; i < ctx->n_rows; ++i)
     if (local_ptr[i + 1] - local_ptr[i] > kHeavyDeg) heavy.push_back(i);
@@ -1217,5 +1274,97 @@ int gatx_comm_init(gatx_ctx* ctx, const void* id128) {
   NK(g_nccl.CommInitRank(&ctx->comm, ctx->world, id, ctx->rank));
   return GATX_OK;
 }
+
+// ---- NVLink peer-memory halo exchange: handle exchange ------------------------------------------------------------
+namespace {
+constexpr int kPeerMaxBufs = 24;
+struct PeerInfo {  // what one rank publishes; sizeof <= GATX_PEER_INFO_BYTES
+  int32_t magic, pid, device, n_bufs;  // buffers: P_l of layer 0..L-1, then the gP_l scratch
+  int64_t n_floats[kPeerMaxBufs];
+  uint64_t raw[kPeerMaxBufs];
+  cudaIpcMemHandle_t handle[kPeerMaxBufs];
+};
+static_assert(sizeof(PeerInfo) <= GATX_PEER_INFO_BYTES, "PeerInfo must fit the public blob");
+constexpr int32_t kPeerMagic = 0x47585031;  // "GXP1"
+}  // namespace
+
+int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes) {
+  if (!ctx || !out || bytes < GATX_PEER_INFO_BYTES) return fail(ctx, GATX_ERR_INVALID, "bad peer_export");
+  if (ctx->world < 2 || ctx->world > kMaxPeers) return fail(ctx, GATX_ERR_INVALID, "peer exchange needs 2..%d ranks", kMaxPeers);
+  if (ctx->L + 1 > kPeerMaxBufs) return fail(ctx, GATX_ERR_UNSUPPORTED, "too many layers for the peer blob");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  PeerInfo info{};
+  info.magic = kPeerMagic;
+  info.pid = (int32_t)getpid();
+  info.device = ctx->device;
+  info.n_bufs = ctx->L + 1;
+  int64_t Fmax = 0;
+  for (int l = 0; l < ctx->L; ++l) Fmax = ctx->layers[l].F > Fmax ? ctx->layers[l].F : Fmax;
+  for (int b = 0; b <= ctx->L; ++b) {
+    float* ptr = b < ctx->L ? ctx->layers[b].Pl : ctx->gPl;
+    info.n_floats[b] = (int64_t)ctx->N * (b < ctx->L ? ctx->layers[b].F : Fmax);
+    info.raw[b] = (uint64_t)(uintptr_t)ptr;
+    CK(cudaIpcGetMemHandle(&info.handle[b], ptr));
+  }
+  memset(out, 0, GATX_PEER_INFO_BYTES);
+  memcpy(out, &info, sizeof info);
+  return GATX_OK;
+}
+
+int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
+  if (!ctx || !all) return fail(ctx, GATX_ERR_INVALID, "bad peer_import");
+  if (ctx->world < 2 || ctx->world > kMaxPeers || bytes != (size_t)ctx->world * GATX_PEER_INFO_BYTES)
+    return fail(ctx, GATX_ERR_INVALID, "peer_import needs world * GATX_PEER_INFO_BYTES bytes in rank order");
+  if (!ctx->have_bufs || !ctx->ref_mask) return fail(ctx, GATX_ERR_INVALID, "call gatx_peer_export first");
+  if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "gatx_comm_init must come first (barriers)");
+  CK(cudaSetDevice(ctx->device));
+  ctx->peer_Pl.assign(ctx->L, PeerPtrs{});
+  ctx->peer_gPl = PeerPtrs{};
+  int64_t Fmax = 0;
+  for (int l = 0; l < ctx->L; ++l) Fmax = ctx->layers[l].F > Fmax ? ctx->layers[l].F : Fmax;
+  for (int p = 0; p < ctx->world; ++p) {
+    PeerInfo info;
+    memcpy(&info, (const char*)all + (size_t)p * GATX_PEER_INFO_BYTES, sizeof info);
+    if (info.magic != kPeerMagic || info.n_bufs != ctx->L + 1)
+      return fail(ctx, GATX_ERR_INVALID, "peer blob of rank %d does not match this model", p);
+    for (int b = 0; b <= ctx->L; ++b)
+      if (info.n_floats[b] != (int64_t)ctx->N * (b < ctx->L ? ctx->layers[b].F : Fmax))
+        return fail(ctx, GATX_ERR_INVALID, "peer blob of rank %d: buffer %d has another size", p, b);
+    if (p == ctx->rank) continue;
+    const bool same_process = info.pid == (int32_t)getpid();
+    if (same_process) {
+      // contexts driven by threads of one process (train_gatx --gpus N): plain peer access on the raw pointers
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, ctx->device, info.device));
+      if (!can) return fail(ctx, GATX_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, info.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(info.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(ctx, GATX_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    for (int b = 0; b <= ctx->L; ++b) {
+      void* q = nullptr;
+      if (same_process) {
+        q = (void*)(uintptr_t)info.raw[b];
+      } else {
+        CK(cudaIpcOpenMemHandle(&q, info.handle[b], cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened.push_back(q);
+      }
+      if (b < ctx->L) ctx->peer_Pl[b].p[p] = (float*)q;
+      else ctx->peer_gPl.p[p] = (float*)q;
+    }
+  }
+  if (!ctx->barrier_word) {
+    CK(dalloc(&ctx->barrier_word, 1));
+    CK(cudaMemsetAsync(ctx->barrier_word, 0, sizeof(float), ctx->st));
+  }
+  ctx->peers_ready = getenv("GATX_NO_P2P") == nullptr;
+  return GATX_OK;
+}
+
+int64_t gatx_halo_rows(const gatx_ctx* ctx) { return ctx ? ctx->halo_rows : -1; }
+int gatx_halo_active(const gatx_ctx* ctx) { return ctx && ctx->peers_ready ? 1 : 0; }
 
 }  // extern "C"

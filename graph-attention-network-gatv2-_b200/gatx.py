@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libgatx.so")
  T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR, T_GALPHA, T_GE) = range(26)
 _INT_TENSORS = {T_PRED, T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID}
 GEMM_TF32_TC, GEMM_FP32_SIMT = 0, 1
+PEER_INFO_BYTES = 2048
 PHASES = ("gemm_fwd", "edge_fwd", "head", "edge_bwd", "gemm_bwd", "optimizer", "comm", "epoch")
 
 EXPORTS = [
@@ -23,7 +24,7 @@ EXPORTS = [
     "gatx_set_params", "gatx_set_wo", "gatx_forward", "gatx_loss_acc", "gatx_backward", "gatx_step",
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
-    "gatx_comm_unique_id", "gatx_comm_init",
+    "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
 ]
 
 
@@ -287,6 +288,28 @@ class Engine:
         self._ck(self.lib.gatx_evaluate(self.ctx, None if m is None else m.ctypes.data, C.byref(lo), C.byref(ac)),
                  "gatx_evaluate")
         return lo.value, ac.value
+
+    def peer_export(self):
+        """This rank's GATX_PEER_INFO_BYTES blob (IPC handles of P_l / gP_l) for the NVLink halo exchange."""
+        buf = (C.c_char * PEER_INFO_BYTES)()
+        self.lib.gatx_peer_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        self._ck(self.lib.gatx_peer_export(self.ctx, buf, PEER_INFO_BYTES), "gatx_peer_export")
+        return bytes(buf)
+
+    def peer_import(self, blobs):
+        """blobs: list of every rank's peer_export() in rank order."""
+        data = b"".join(blobs)
+        self.lib.gatx_peer_import.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        self._ck(self.lib.gatx_peer_import(self.ctx, data, len(data)), "gatx_peer_import")
+
+    def halo_rows(self):
+        self.lib.gatx_halo_rows.restype = C.c_int64
+        self.lib.gatx_halo_rows.argtypes = [C.c_void_p]
+        return int(self.lib.gatx_halo_rows(self.ctx))
+
+    def halo_active(self):
+        self.lib.gatx_halo_active.argtypes = [C.c_void_p]
+        return bool(self.lib.gatx_halo_active(self.ctx))
 
     def comm_init(self, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)

@@ -189,6 +189,24 @@ int gatx_op_gemm(int32_t mode, int32_t form, const float* A, int64_t lda, const 
 int gatx_comm_unique_id(void* out128);
 int gatx_comm_init(gatx_ctx* ctx, const void* id128);
 
+/* ---- halo exchange through NVLink peer memory (optional) --------------------------------- */
+/* With the destination-row partition a rank only needs the projected features of the sources its own edges gather
+ * (the halo), and only the ranks that reference a source hold a partial gradient for it.  After these two calls the
+ * per-layer exchange steps stop being NCCL collectives over whole [N][F] matrices: the owner of a row stores it
+ * straight into the P_l buffers of the peers that reference it, and reads their partial gP_l rows back in a fixed
+ * rank order (deterministic), all over NVLink load/store.  Call order: gatx_comm_init, graph / features / labels,
+ * gatx_peer_export on every rank, exchange the GATX_PEER_INFO_BYTES blobs (any transport: files, MPI, torchrun
+ * store), gatx_peer_import with all blobs in rank order.  Ranks may be processes (CUDA IPC handles) or threads of
+ * one process (peer access on raw pointers).  Without these calls, or with GATX_NO_P2P set, the NCCL collectives run.
+ * Changing the graph, features or labels invalidates the exchange (export / import again). */
+#define GATX_PEER_INFO_BYTES 2048
+int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes);
+int gatx_peer_import(gatx_ctx* ctx, const void* all_blobs, size_t bytes);
+/* Rows this rank pushes per layer (sum over own rows of the number of other ranks referencing them); an all-gather
+ * would move (world - 1) * own rows.  Integer, identical to oracle/orc_halo_rows. */
+int64_t gatx_halo_rows(const gatx_ctx* ctx);
+int gatx_halo_active(const gatx_ctx* ctx); /* 1 when the peer-memory path is in use */
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,7 +173,7 @@ def test_split_training_and_eval_only_match_oracle(cli, tmp_path):
     assert m and abs(float(m.group(1)) - rtl) < 5e-4 * max(1.0, rtl) and abs(float(m.group(2)) - rta) < 0.011
     # evaluation only, from the dumped weights: the three splits, then all nodes without --split
     r2 = run(cli, *(base + ["--eval-only", "--load-weights", str(out)]))
-    assert r2.returncode == 0 and "Epoch" not in r2.stdout, r2.stderr
+    assert r2.returncode == 0 and "\nEpoch " not in r2.stdout, r2.stderr
     for k, name in enumerate(("Train", "Val", "Test")):
         m = re.search(r"\n%s Loss: ([0-9.]+), %s Accuracy: ([0-9.]+)%%\n" % (name, name), r2.stdout)
         el, ea = score(masks[k])
