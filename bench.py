@@ -180,6 +180,8 @@ def run_gatx(args):
     import gatx
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("gloo", rank=rank, world_size=world)
 
@@ -207,6 +209,17 @@ def run_gatx(args):
     eng.set_labels_ptr(yp.data_ptr(), cfg["C"])
     eng.init_params(1234)
     info = eng.graph_info()
+    halo = None
+    if world > 1:
+        # NVLink peer-memory halo exchange: every rank publishes the IPC handles of its P_l / gP_l buffers
+        push_rows = eng.halo_rows()
+        if not args.no_p2p:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, eng.peer_export())
+            eng.peer_import(blobs)
+        halo = {"exchange": "nvlink peer-memory push/pull kernels" if eng.halo_active() else "nccl broadcast/reduce",
+                "rows_pushed_per_layer_rank0": push_rows,
+                "allgather_rows_rank0": (world - 1) * (info["row_end"] - info["row_begin"])}
     t = 0
     for _ in range(args.warmup):
         t += 1
@@ -320,6 +333,7 @@ def run_gatx(args):
             "config": {"workload": "%s-shaped synthetic graph N=%d E=%d feats=%d classes=%d, %s, lr %g"
                                    % (args.workload, N, E, cfg["I"], cfg["C"], flags_of(cfg), cfg["lr"]),
                        "max_in_degree": info["max_degree"], "parallelism": "dst-row partition x%d" % world,
+                       "halo": halo,
                        "l2": "inputs exceed L2 (per-epoch working set >> 126 MB)" if E * 4 * 64 > 126e6 else
                              "working set may fit L2 (small workload)"},
             "e2e": {"value": E * e2e_steps / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": h2d,
@@ -342,6 +356,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gatx", choices=["gatx", "reference"])
+    ap.add_argument("--no-p2p", action="store_true", help="N > 1: NCCL collectives instead of the peer-memory halo kernels")
     ap.add_argument("--workload", default="products", choices=list(datasets.CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--fp32", action="store_true", help="fp32 CUDA-core GEMMs instead of TF32 tensor cores")

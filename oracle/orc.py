@@ -83,6 +83,23 @@ def partition_rows(row_ptr, R):
 
 
 # ------------------------------------------------------------- layer-level ops
+def halo_rows(row_ptr, col_idx, R):
+    """Per rank: number of (own source row, other rank) pairs where that rank's edge slice gathers the row -- the
+    rows a rank sends per layer in the halo exchange (new work; bit-exact target for
+    gatx_halo_rows).  Independent numpy formulation: unique (rank-of-edge, source) pairs."""
+    b = partition_rows(row_ptr, R).astype(np.int64)
+    row_ptr = np.asarray(row_ptr, np.int64)
+    col_idx = np.asarray(col_idx, np.int64)
+    N = len(row_ptr) - 1
+    dst = np.repeat(np.arange(N, dtype=np.int64), np.diff(row_ptr))
+    edge_rank = np.searchsorted(b[1:], dst, side="right")      # rank that owns the destination row
+    pairs = np.unique(edge_rank * N + col_idx)
+    ref_rank, src = pairs // N, pairs % N
+    owner = np.searchsorted(b[1:], src, side="right")
+    keep = owner != ref_rank
+    return np.bincount(owner[keep], minlength=R).astype(np.int64)
+
+
 def project(X, W, F):
     N, I = X.shape
     Pl, Pr = np.empty((N, F), np.float32), np.empty((N, F), np.float32)

@@ -20,7 +20,21 @@ def _problem():
     return make_problem(3000, 40000, 24, 6, (4, 4, 1), (32, 32, 128), "rmat", seed=17, hub=1500)
 
 
-def _worker(rank, world, idfile, q, mode):
+def _exchange(d, name, rank, world, payload):
+    """File-based all-gather of one bytes object per rank (the tests' stand-in for MPI / a torchrun store)."""
+    tmp = os.path.join(d, "%s.%d.tmp" % (name, rank))
+    open(tmp, "wb").write(payload)
+    os.rename(tmp, os.path.join(d, "%s.%d" % (name, rank)))
+    out = []
+    for r in range(world):
+        f = os.path.join(d, "%s.%d" % (name, r))
+        while not os.path.exists(f):
+            time.sleep(0.05)
+        out.append(open(f, "rb").read())
+    return out
+
+
+def _worker(rank, world, idfile, q, mode, p2p):
     for p in (os.path.join(HERE, "..", "graph-attention-network-gatv2-_b200"), HERE):
         sys.path.insert(0, p)
     import gatx
@@ -39,16 +53,23 @@ def _worker(rank, world, idfile, q, mode):
     for l in range(len(p["heads"])):
         eng.set_params(l, p["Ws"][l], p["As"][l])
     eng.set_wo(p["Wo"])
+    if p2p:
+        eng.peer_import(_exchange(os.path.dirname(idfile), "peer", rank, world, eng.peer_export()))
+        assert eng.halo_active()
     losses = [eng.train_epoch(t) for t in range(1, 5)]
+    ev = eng.evaluate(None)  # two evaluation forwards back to back: the exchange must not race with itself
+    ev2 = eng.evaluate(None)
+    assert ev == ev2
     info = eng.graph_info()
-    out = dict(rank=rank, losses=losses, W=[eng.tensor(gatx.T_W, l) for l in range(3)], Wo=eng.tensor(gatx.T_WO),
+    out = dict(rank=rank, losses=losses, halo_rows=eng.halo_rows(), W=[eng.tensor(gatx.T_W, l) for l in range(3)], Wo=eng.tensor(gatx.T_WO),
                rows=(info["row_begin"], info["row_end"]), pred=eng.tensor(gatx.T_PRED))
     q.put(out)
     eng.close()
 
 
+@pytest.mark.parametrize("p2p", [True, False], ids=["nvlink-peer-halo", "nccl"])
 @pytest.mark.parametrize("world", [2])
-def test_two_ranks_match_one(world):
+def test_two_ranks_match_one(world, p2p):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     sys.path.insert(0, os.path.join(HERE, "..", "graph-attention-network-gatv2-_b200"))
@@ -58,7 +79,7 @@ def test_two_ranks_match_one(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     idfile = os.path.join(tempfile.mkdtemp(), "nccl_id")
-    procs = [ctx.Process(target=_worker, args=(r, world, idfile, q, mode)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, idfile, q, mode, p2p)) for r in range(world)]
     for pr in procs:
         pr.start()
     outs = sorted([q.get(timeout=300) for _ in range(world)], key=lambda o: o["rank"])
@@ -66,8 +87,11 @@ def test_two_ranks_match_one(world):
         pr.join(timeout=60)
         assert pr.exitcode == 0
     p = _problem()
+    import orc
+    assert [o["halo_rows"] for o in outs] == orc.halo_rows(p["row_ptr"], p["col_idx"], world).tolist()  # bit-exact
     eng = make_engine(gatx, p, optimizer="adam", lr=0.01, clip=True, gemm_mode=mode)
     ref_losses = [eng.train_epoch(t) for t in range(1, 5)]
+    eng.evaluate(None)  # the workers' predictions come from an evaluation forward after the last update
     for o in outs:
         for (l, a), (rl, ra) in zip(o["losses"], ref_losses):
             assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 2e-3

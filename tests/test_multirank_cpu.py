@@ -17,7 +17,7 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, halo_only=False):
     for p in (os.path.join(HERE, "..", "graph-attention-network-gatv2-_b200"), os.path.join(HERE, "..", "oracle"), HERE):
         sys.path.insert(0, p)
     import gatx
@@ -39,11 +39,32 @@ def _worker(rank, world, port, q):
         Pl_loc, Pr_loc = orc.project(Xl, p["Ws"][l], F)
         # all-gather of P_l with unequal row counts: one broadcast per owner, like the NCCL group in libgatx
         Pl = np.zeros((N, F), np.float32)
-        for r in range(world):
-            t = torch.from_numpy(Pl[bounds[r]:bounds[r + 1]])
-            if r == rank:
-                t.copy_(torch.from_numpy(Pl_loc))
-            dist.broadcast(t, src=r)
+        if halo_only:
+            # halo exchange (halo_p2p.cu): an owner sends a row only to the ranks whose edge slice gathers it; rows
+            # nobody here references stay poisoned, so a wrong mask shows up as NaNs in the result
+            Pl[:] = np.nan
+            Pl[r0:r1] = Pl_loc
+            ref = [np.unique(ci[rp[bounds[q_]]:rp[bounds[q_ + 1]]]) for q_ in range(world)]
+            sent = 0
+            for src_rank in range(world):
+                for dst_rank in range(world):
+                    if src_rank == dst_rank:
+                        continue
+                    rows = ref[dst_rank][(ref[dst_rank] >= bounds[src_rank]) & (ref[dst_rank] < bounds[src_rank + 1])]
+                    if rank == src_rank:
+                        dist.send(torch.from_numpy(np.ascontiguousarray(Pl[rows])), dst=dst_rank)
+                        sent += len(rows)
+                    elif rank == dst_rank:
+                        buf = torch.empty((len(rows), F), dtype=torch.float32)
+                        dist.recv(buf, src=src_rank)
+                        Pl[rows] = buf.numpy()
+            assert sent == int(orc.halo_rows(rp, ci, world)[rank])  # the integer the library reports as gatx_halo_rows
+        else:
+            for r in range(world):
+                t = torch.from_numpy(Pl[bounds[r]:bounds[r + 1]])
+                if r == rank:
+                    t.copy_(torch.from_numpy(Pl_loc))
+                dist.broadcast(t, src=r)
         out = orc.layer_forward(rp_loc, ci_loc, H, D, Pl, Pr_loc, p["As"][l], l == len(p["heads"]) - 1)
         Xl = out["Hout"]
     z, yprob = orc.head_forward(p["Wo"], Xl)
@@ -58,13 +79,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("halo_only", [False, True], ids=["allgather", "halo-only"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_row_partition_forward_matches_single_process(world, orc):
+def test_row_partition_forward_matches_single_process(world, halo_only, orc):
     from helpers import make_oracle, make_problem
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + world + (os.getpid() % 200)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29600 + world + 10 * int(halo_only) + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, halo_only)) for r in range(world)]
     for pr in procs:
         pr.start()
     red, parts = q.get(timeout=240)
