@@ -60,6 +60,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA store of a box from (swizzled) shared memory; completion is tracked by bulk async-groups of the issuing thread
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -132,7 +147,9 @@ struct TnSmem {
   static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
   static constexpr int kABytes = BM * BK * 4, kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingFloats = 4 * 32 * 33;  // epilogue transpose buffers alias the drained pipeline stages
+  // epilogue buffers alias the drained pipeline stages: 4 warps x 2 x (32 rows x 128 B) for the TMA-store path,
+  // 4 x 32 x 33 floats for the scalar path
+  static constexpr int kStagingFloats = 4 * 2 * 32 * 32;
   static_assert(kStages * kStageBytes >= kStagingFloats * 4, "staging must fit in the pipeline buffers");
   static constexpr int kBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256;
 };
@@ -142,9 +159,10 @@ struct TnSmem {
 template <int BN>
 __global__ void __launch_bounds__(kThreads)
 gemm_tf32_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, int K0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1, int K0,
                     int K1, float* __restrict__ C0, float* __restrict__ C1, int n_split, int64_t ldc, int M, int N,
-                    int accumulate) {
+                    int accumulate, int tma_store) {
   using S = TnSmem<BN>;
   constexpr int kTmemCols = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
@@ -166,6 +184,10 @@ gemm_tf32_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (K1 > 0) {
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmB1);
+    }
+    if (tma_store) {
+      tma_prefetch_desc(&tmC0);
+      tma_prefetch_desc(&tmC1);
     }
     for (int s = 0; s < S::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -223,38 +245,77 @@ gemm_tf32_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global stores =====
+    // ===== epilogue =====
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    float* st = staging + (warp - 2) * 32 * 33;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (tma_store) {
+      // TMEM -> registers -> 128B-swizzled shared-memory box (32 rows x 32 floats) -> TMA store.  Lane = tile row, so
+      // a lane writes its 128-byte row as eight 16-byte chunks at chunk ^ (row & 7): the quarter-warps of every
+      // st.shared.v4 hit distinct banks, and the tensor map (SWIZZLE_128B) undoes the permutation.  Two boxes per
+      // warp alternate, so the store engine drains one while the next 32 columns are read from TMEM.  Rows / columns
+      // past M / N are clipped by the tensor map.
+      const uint32_t box0 = smem_u32(staging) + (uint32_t)(warp - 2) * 8192u;
+      const bool to_c1 = n0 >= n_split;
+      const CUtensorMap* tmc = to_c1 ? &tmC1 : &tmC0;
+      const int ccol0 = to_c1 ? n0 - n_split : n0;
+      const int row0 = m0 + q * 32;
+      const uint32_t rsw = (uint32_t)(lane & 7);
+      int buf = 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= N) break;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (lane == 0) bulk_wait_read<1>();  // the store that last read this box (two chunks ago) is done with it
+        __syncwarp();
+        const uint32_t box = box0 + (uint32_t)buf * 4096u;
+        const uint32_t rowaddr = box + (uint32_t)lane * 128u;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
-      __syncwarp();
-      const int col = n0 + c0 + lane;
-      float* Cb = C0;
-      int ccol = col;
-      if (col >= n_split) {
-        Cb = C1;
-        ccol = col - n_split;
+        for (int c = 0; c < 8; ++c)
+          sts4(rowaddr + ((((uint32_t)c) ^ rsw) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          tma_store_2d(tmc, reinterpret_cast<const void*>(staging + ((warp - 2) * 8192 + buf * 4096) / 4), ccol0 + c0, row0);
+          bulk_commit();
+        }
+        buf ^= 1;
       }
-      if (col < N && c0 + lane < BN) {
+      if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the last store has read it
+      __syncwarp();
+    } else {
+      // scalar path (accumulate mode, or an output whose pitch / base no tensor map can describe):
+      // per-warp smem transpose -> 128-byte row stores
+      float* st = staging + (warp - 2) * 32 * 33;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        float* Cb = C0;
+        int ccol = col;
+        if (col >= n_split) {
+          Cb = C1;
+          ccol = col - n_split;
+        }
+        if (col < N && c0 + lane < BN) {
 #pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int row = m0 + q * 32 + r;
-          if (row < M) {
-            float* p = Cb + (int64_t)row * ldc + ccol;
-            const float val = st[r * 33 + lane];
-            *p = accumulate ? *p + val : val;
+          for (int r = 0; r < 32; ++r) {
+            const int row = m0 + q * 32 + r;
+            if (row < M) {
+              float* p = Cb + (int64_t)row * ldc + ccol;
+              const float val = st[r * 33 + lane];
+              *p = accumulate ? *p + val : val;
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
     tc_fence_before();
   }
@@ -300,15 +361,16 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
 }
 
 template <int BN>
-int launch_tn(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, int K0,
+int launch_tn(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
+              const CUtensorMap& c0, const CUtensorMap& c1, bool tma_store, int K0,
               int K1, float* C0, float* C1, int n_split, int64_t ldc, int M, int N, bool accumulate, cudaStream_t st) {
   // per launch: the attribute is per device, and one process may drive several devices (train_gatx --gpus N)
   if (cudaFuncSetAttribute(gemm_tf32_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TnSmem<BN>::kBytes) !=
       cudaSuccess)
     return -1;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_tf32_tn_kernel<BN><<<grid, kThreads, TnSmem<BN>::kBytes, st>>>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M,
-                                                                      N, accumulate ? 1 : 0);
+  gemm_tf32_tn_kernel<BN><<<grid, kThreads, TnSmem<BN>::kBytes, st>>>(a0, b0, a1, b1, c0, c1, K0, K1, C0, C1, n_split,
+                                                                      ldc, M, N, accumulate ? 1 : 0, tma_store ? 1 : 0);
   return 1;
 }
 
@@ -520,12 +582,26 @@ int launch_gemm_tc_tn2(const float* A0, int64_t lda0, const float* B0, int64_t l
     a1 = a0;
     b1 = b0;
   }
+  // output tensor maps for the TMA-store epilogue (32 x 32 boxes, 128B swizzle); the scalar epilogue takes over when
+  // the kernel must accumulate or an output cannot be described (pitch / base not 16-byte aligned)
+  static const bool no_tma_store = getenv("GATX_GEMM_NO_TMA_STORE") != nullptr;
+  CUtensorMap c0, c1;
+  bool tma_store = !accumulate && !no_tma_store && bn >= 32;
+  if (tma_store) {
+    tma_store = make_map(&c0, C0, M, n_split, ldc, 32, 32);
+    if (tma_store && n_split < N) tma_store = make_map(&c1, C1, M, N - n_split, ldc, 32, 32);
+    else if (tma_store) c1 = c0;
+  }
+  if (!tma_store) {
+    c0 = a0;
+    c1 = a0;
+  }
   switch (bn) {
-    case 256: return launch_tn<256>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
-    case 128: return launch_tn<128>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
-    case 64: return launch_tn<64>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
-    case 32: return launch_tn<32>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
-    default: return launch_tn<16>(a0, b0, a1, b1, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    case 256: return launch_tn<256>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    case 128: return launch_tn<128>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    case 64: return launch_tn<64>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    case 32: return launch_tn<32>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
+    default: return launch_tn<16>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
   }
 }
 
