@@ -275,7 +275,8 @@ def run_gatx(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     rows = info["row_end"] - info["row_begin"]
-    h2d = N * cfg["I"] * 4 + rows * 4  # every rank keeps all input-feature rows (layer 0 then needs no collective)
+    # a rank copies its own feature rows and labels; the row blocks are all-gathered over NVLink inside set_features
+    h2d = (rows if world > 1 else N) * cfg["I"] * 4 + rows * 4
     d2h = 16
 
     # Roofline (HBM-bound edge passes).  Algorithmic bytes per launch are SURVEY 8(d)'s formulas split by kernel

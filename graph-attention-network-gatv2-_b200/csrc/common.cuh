@@ -58,6 +58,11 @@ struct EdgeGraph {
   int chunk_T, n_chunks;
   const int* chunk_row;  // [n_chunks] destination row containing edge c*chunk_T
   const int* chunk_src;  // [n_chunks] source row containing transposed position c*chunk_T
+  // L2 residency hints for the gathers (nullptr = off): copies of col_idx / csc_dst whose two top bits mark the
+  // nodes gathered most often (bit 31: the hot set sized for rows of hot_wide_F floats, bit 30: for narrower rows)
+  const int* col_idx_hot;
+  const int* csc_dst_hot;
+  int hot_wide_F;
   // optional CUDA-event pairs around the three main streaming kernels of the layer being launched
   // (fwd, bwd pass 1, bwd pass 2); null = no timing
   cudaEvent_t* kernel_events;  // [6] = {fwd_a, fwd_b, dst_a, dst_b, src_a, src_b}
@@ -134,6 +139,9 @@ int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uin
                      int me, cudaStream_t st);
 int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
                      int world, cudaStream_t st);
+
+// graph_prep.cu: out[e] = idx[e] | bit31 if degree(idx[e]) >= thr_wide | bit30 if degree(idx[e]) >= thr_narrow
+int launch_mark_hot(const int* idx, const int* ptr, int64_t E, int thr_wide, int thr_narrow, int* out, cudaStream_t st);
 
 // optim.cu
 struct OptimGroups {

@@ -32,6 +32,19 @@ struct StreamGraph {
   int E, T, n_chunks, n_rows;
   const int* row_ptr;    // [n_rows + 1]
   const int* chunk_row;  // [n_chunks] row that contains edge c*T
+  uint32_t hot;          // bit of a gather index that marks an L2-resident ("hot") row; 0 = no hints in the indices
+  uint32_t idx_mask;     // gather index = raw & idx_mask
+};
+// L2 policies of the gathers: hot rows evict_last, everything streamed once evict_first (plain when hints are off)
+struct GatherPolicy {
+  uint64_t hot, cold;
+  uint32_t bit, mask;
+  __device__ __forceinline__ GatherPolicy(const StreamGraph& g) : bit(g.hot), mask(g.idx_mask) {
+    hot = g.hot ? l2_policy_evict_last() : l2_policy_evict_normal();
+    cold = g.hot ? l2_policy_evict_first() : l2_policy_evict_normal();
+  }
+  __device__ __forceinline__ uint64_t of(int raw) const { return ((uint32_t)raw & bit) ? hot : cold; }
+  __device__ __forceinline__ int64_t id(int raw) const { return (int64_t)((uint32_t)raw & mask); }
 };
 
 __device__ __forceinline__ float head_reduce(float p, int lph) {
@@ -179,6 +192,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
     fence_mbar_init();
   }
   __syncwarp();
+  const GatherPolicy gp(g);
   float4 av[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) av[j] = ldg4(a + lc_off<NV>(lane, j));
@@ -204,7 +218,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       if (s < n && lane == 0) {
         const uint32_t slot = (it + s) % R;
         mbar_expect_tx(&bar[slot], kRowBytes);
-        bulk_g2s(ring + slot * F, Pl + (int64_t)src * F, kRowBytes, &bar[slot]);
+        bulk_g2s_hint(ring + slot * F, Pl + gp.id(src) * F, kRowBytes, &bar[slot], gp.of(src));
       }
     }
     float4 pr[NV], pr_n[NV];
@@ -252,7 +266,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
         if (ni < n && lane == 0) {
           mbar_expect_tx(&bar[slot], kRowBytes);
-          bulk_g2s(ring + slot * F, Pl + (int64_t)srcn * F, kRowBytes, &bar[slot]);
+          bulk_g2s_hint(ring + slot * F, Pl + gp.id(srcn) * F, kRowBytes, &bar[slot], gp.of(srcn));
         }
       }
       float p = 0.f;
@@ -416,6 +430,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     fence_mbar_init();
   }
   __syncwarp();
+  const GatherPolicy gp(g);
   float4 ga[NV];  // the attention vector a is only needed when a row segment is written: read it there (L1 hit)
 #pragma unroll
   for (int j = 0; j < NV; ++j) ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -444,15 +459,15 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       if (s < n && lane == 0) {
         const uint32_t slot = (it + s) % R;
         mbar_expect_tx(&bar[slot], kRowBytes);
-        bulk_g2s(ring + slot * F, Pl + (int64_t)src * F, kRowBytes, &bar[slot]);
+        bulk_g2s_hint(ring + slot * F, Pl + gp.id(src) * F, kRowBytes, &bar[slot], gp.of(src));
       }
     }
     // row data (g_h row, P_r row) of r goes through the row buffer; once it sits in registers the buffer is free,
     // so row r + 1 is prefetched into the same buffer while row r is being processed
     if (lane == 0) {
       mbar_expect_tx(rbar, 2 * kRowBytes);
-      bulk_g2s(rowbuf, gh + (int64_t)r * F, kRowBytes, rbar);
-      bulk_g2s(rowbuf + F, Pr + (int64_t)r * F, kRowBytes, rbar);
+      bulk_g2s_hint(rowbuf, gh + (int64_t)r * F, kRowBytes, rbar, gp.cold);
+      bulk_g2s_hint(rowbuf + F, Pr + (int64_t)r * F, kRowBytes, rbar, gp.cold);
     }
     // score window: the scores of 32 consecutive edges are contiguous ([E][H]); the next window is
     // prefetched into registers while the current one is consumed from shared memory
@@ -489,8 +504,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     ++rk;
     if (r + 1 < g.n_rows && lane == 0) {
       mbar_expect_tx(rbar, 2 * kRowBytes);
-      bulk_g2s(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar);
-      bulk_g2s(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar);
+      bulk_g2s_hint(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
+      bulk_g2s_hint(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
     }
     bool first_row = true;
     for (int i = 0; i < n; ++i) {
@@ -524,8 +539,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         if (r + 1 < g.n_rows) {
           if (lane == 0) {
             mbar_expect_tx(rbar, 2 * kRowBytes);
-            bulk_g2s(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar);
-            bulk_g2s(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar);
+            bulk_g2s_hint(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
+            bulk_g2s_hint(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
           }
           load_scalars(qn, r + 1, H, hd, cdot, mx, sinv);
           next_end = __ldg(g.row_ptr + r + 2);
@@ -557,7 +572,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
         if (ni < n && lane == 0) {
           mbar_expect_tx(&bar[slot], kRowBytes);
-          bulk_g2s(ring + slot * F, Pl + (int64_t)srcn * F, kRowBytes, &bar[slot]);
+          bulk_g2s_hint(ring + slot * F, Pl + gp.id(srcn) * F, kRowBytes, &bar[slot], gp.of(srcn));
         }
       }
       const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
@@ -674,6 +689,7 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
     fence_mbar_init();
   }
   __syncwarp();
+  const GatherPolicy gp(g);
   float4 av[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) av[j] = ldg4(a + lc_off<NV>(lane, j));
@@ -702,8 +718,8 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
       if (s < n && lane == 0) {
         const uint32_t slot = (it + s) % R;
         mbar_expect_tx(&bar[slot], kRowBytes + kRecBytes);
-        bulk_g2s(ring + slot * slot_floats, gh + (int64_t)d * F, kRowBytes, &bar[slot]);
-        bulk_g2s(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot]);
+        bulk_g2s_hint(ring + slot * slot_floats, gh + gp.id(d) * F, kRowBytes, &bar[slot], gp.of(d));
+        bulk_g2s_hint(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot], gp.cold);
       }
     }
     float4 acc[NV];
@@ -754,8 +770,8 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
         const int ee = __shfl_sync(0xffffffffu, same ? eid_cur : eid_nxt, ni & 31);
         if (ni < n && lane == 0) {
           mbar_expect_tx(&bar[slot], kRowBytes + kRecBytes);
-          bulk_g2s(ring + slot * slot_floats, gh + (int64_t)d * F, kRowBytes, &bar[slot]);
-          bulk_g2s(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot]);
+          bulk_g2s_hint(ring + slot * slot_floats, gh + gp.id(d) * F, kRowBytes, &bar[slot], gp.of(d));
+          bulk_g2s_hint(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot], gp.cold);
         }
       }
 #pragma unroll
@@ -811,6 +827,16 @@ int stream_grid(const void* kernel, size_t smem, int n_chunks) {
 template <int NV>
 constexpr int ring_depth() { return NV == 4 ? 8 : (NV == 2 ? 8 : 16); }
 
+// which hot-set bit of the hinted index arrays a layer with F-float rows uses (wide rows: the smaller hot set)
+struct HotSel {
+  bool on;
+  uint32_t bit, mask;
+};
+HotSel hot_select(const EdgeGraph& eg, int F) {
+  if (!eg.col_idx_hot || !eg.csc_dst_hot) return HotSel{false, 0u, 0xffffffffu};
+  return HotSel{true, 2 * F > eg.hot_wide_F ? 0x80000000u : 0x40000000u, 0x3fffffffu};
+}
+
 bool use_pair(int nv, const Shape& sh) {
   static const bool off = getenv("GATX_NO_PAIR") != nullptr;
   return !off && nv == 1 && sh.H == 1 && sh.lph == 32;
@@ -854,7 +880,9 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   fill_empty_fwd_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, sh.F, H, Hout, hpre, mx, sinv);
   ++launches;
   if (eg.E == 0) return launches;
-  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
+  const HotSel hs = hot_select(eg, sh.F);
+  const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
+  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask};
   if (use_pair(nv, sh)) {  // one head of 128 floats: two edges per loop iteration
     constexpr int R = 16;
     const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
@@ -862,6 +890,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
+    // 512-byte rows: the cache-hint form of the bulk copy is slower than the plain one at this size (measured), no hints
     kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, Hout, hpre, score, mx, sinv, part);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[1], st);
     ++launches;
@@ -878,7 +907,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
-    kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, sh, Hout, hpre, score, mx, sinv, part);
+    kern<<<blocks, kSW * 32, smem, st>>>(g, colx, Pl, Pr, a, sh, Hout, hpre, score, mx, sinv, part);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[1], st);
     ++launches;
     if (g.n_chunks > 1) {
@@ -898,8 +927,11 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
   *n_partials = 0;
   if (eg.n_rows <= 0) return 0;
-  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row};
-  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src};
+  const HotSel hs = hot_select(eg, sh.F);
+  const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
+  const int* cdstx = hs.on ? eg.csc_dst_hot : eg.csc_dst;
+  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask};
+  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask};
   if (use_pair(nv, sh)) {
     constexpr int R = 16, F = kPF;
     {
@@ -966,7 +998,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
-        kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, sh, gH, cdot, score, mx, sinv, gPr, rec, part,
+        kern<<<blocks, kSW * 32, smem, st>>>(gd, colx, Pl, Pr, a, sh, gH, cdot, score, mx, sinv, gPr, rec, part,
                                              ga_partials, galpha_dbg, H);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[3], st);
         *n_partials = blocks;
@@ -984,7 +1016,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[4], st);
-        kern<<<blocks, kSW * 32, smem, st>>>(gs, eg.csc_dst, eg.csc_eid, a, sh, gH, rec, gPl, part, slot_floats);
+        kern<<<blocks, kSW * 32, smem, st>>>(gs, cdstx, eg.csc_eid, a, sh, gH, rec, gPl, part, slot_floats);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[5], st);
         ++launches;
         if (gs.n_chunks > 1) {

@@ -6,6 +6,7 @@
 #include <nccl.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -88,6 +89,9 @@ struct gatx_ctx {
   int n_heavy_rows = 0, n_heavy_srcs = 0;
   int chunk_T = 256, n_chunks = 0;
   int *chunk_row = nullptr, *chunk_src = nullptr;
+  // L2 residency hints: index copies whose top bits mark the most frequently gathered nodes (nullptr = off)
+  int *col_idx_hot = nullptr, *csc_dst_hot = nullptr;
+  int hot_wide_F = 0;
   bool use_stream = true;
   bool have_graph = false, have_feat = false, have_labels = false, have_bufs = false, have_params = false;
   // data
@@ -205,7 +209,7 @@ struct PhaseTimer {
 void free_graph(gatx_ctx* c) {
   dfree(c->row_ptr); dfree(c->col_idx); dfree(c->coo_src); dfree(c->coo_dst); dfree(c->in_deg);
   dfree(c->csc_ptr); dfree(c->csc_dst); dfree(c->csc_eid); dfree(c->heavy_rows); dfree(c->heavy_srcs);
-  dfree(c->chunk_row); dfree(c->chunk_src); dfree(c->ref_mask);
+  dfree(c->chunk_row); dfree(c->chunk_src); dfree(c->ref_mask); dfree(c->col_idx_hot); dfree(c->csc_dst_hot);
   c->have_graph = false;
 }
 void free_bufs(gatx_ctx* c) {
@@ -347,6 +351,7 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   g.heavy_srcs = c->heavy_srcs; g.n_heavy_srcs = c->n_heavy_srcs;
   g.E = c->E;
   g.chunk_T = c->chunk_T; g.n_chunks = c->n_chunks; g.chunk_row = c->chunk_row; g.chunk_src = c->chunk_src;
+  g.col_idx_hot = c->col_idx_hot; g.csc_dst_hot = c->csc_dst_hot; g.hot_wide_F = c->hot_wide_F;
   g.kernel_events = nullptr;
   return g;
 }
@@ -420,6 +425,18 @@ int comm_barrier(gatx_ctx* ctx) {
 }
 bool halo_p2p(const gatx_ctx* ctx, int F) { return ctx->peers_ready && F % 4 == 0; }
 
+// All-gather of row blocks with unequal counts: one NCCL broadcast per owner inside a group.
+int nccl_allgather_rows(gatx_ctx* ctx, float* full, int64_t F) {
+  NK(g_nccl.GroupStart());
+  for (int r = 0; r < ctx->world; ++r) {
+    float* p = full + (int64_t)ctx->bounds[r] * F;
+    const size_t cnt = (size_t)(ctx->bounds[r + 1] - ctx->bounds[r]) * F;
+    if (cnt) NK(g_nccl.Broadcast(p, p, cnt, ncclFloat, r, ctx->comm, ctx->st));
+  }
+  NK(g_nccl.GroupEnd());
+  return GATX_OK;
+}
+
 // Forward exchange: every rank ends with the P_l rows its edges gather (all rows on the NCCL path).
 int comm_allgather_rows(gatx_ctx* ctx, float* full, int F, int layer) {
   if (ctx->world == 1) return GATX_OK;
@@ -432,15 +449,9 @@ int comm_allgather_rows(gatx_ctx* ctx, float* full, int F, int layer) {
                               ctx->rank, ctx->st));
     return comm_barrier(ctx);    // every push has landed
   }
-  NK(g_nccl.GroupStart());
-  for (int r = 0; r < ctx->world; ++r) {
-    float* p = full + (int64_t)ctx->bounds[r] * F;
-    const size_t cnt = (size_t)(ctx->bounds[r + 1] - ctx->bounds[r]) * F;
-    if (cnt) NK(g_nccl.Broadcast(p, p, cnt, ncclFloat, r, ctx->comm, ctx->st));
-  }
-  NK(g_nccl.GroupEnd());
-  return GATX_OK;
+  return nccl_allgather_rows(ctx, full, F);
 }
+
 // Backward exchange: the owner of a source row ends with the sum of all ranks' partial gP_l rows.
 int comm_reduce_rows(gatx_ctx* ctx, float* full, int F) {
   if (ctx->world == 1) return GATX_OK;
@@ -840,6 +851,40 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   CK(dalloc(&ctx->heavy_srcs, heavy_s.size()));
   if (!heavy_s.empty())
     CK(cudaMemcpyAsync(ctx->heavy_srcs, heavy_s.data(), sizeof(int) * heavy_s.size(), cudaMemcpyHostToDevice, ctx->st));
+  {
+    // L2 residency hints for the gathers (edge_stream.cu): on a power-law graph a few percent of the nodes take a
+    // large share of the gathers (products shape: the 50 000 most referenced sources, 2 % of the nodes, are 25 % of
+    // all gathers).  Mark as many of the most-gathered nodes as fit a budget of the 126 MB L2; their rows are
+    // fetched evict_last, all other traffic evict_first.  GATX_HOT_MB sets the budget (0 = off).
+    int wideF = 0, narrowF = 0;
+    for (int l = 0; l < ctx->L; ++l) {
+      const int F = ctx->heads[l] * ctx->outdims[l];
+      if (!edge_stream_supported(ctx->heads[l], ctx->outdims[l]) || F < 256) continue;  // 128-float rows: no hints
+      if (F > wideF) wideF = F;
+      if (narrowF == 0 || F < narrowF) narrowF = F;
+    }
+    double budget_mb = 96.0;
+    if (const char* ev = getenv("GATX_HOT_MB")) budget_mb = atof(ev);
+    if (wideF > 0 && budget_mb > 0.0 && N < (1 << 30) && ctx->E > 0) {
+      auto threshold = [](std::vector<int> deg, int64_t k) {  // k-th largest degree, at least 2 (a row used once is not hot)
+        if (k <= 0) return 0x7fffffff;
+        if (k >= (int64_t)deg.size()) return 2;
+        std::nth_element(deg.begin(), deg.begin() + (k - 1), deg.end(), [](int a, int b) { return a > b; });
+        return deg[k - 1] > 2 ? deg[k - 1] : 2;
+      };
+      std::vector<int> outdeg((size_t)N), indeg((size_t)ctx->n_rows);
+      for (int j = 0; j < N; ++j) outdeg[j] = cptr[j + 1] - cptr[j];
+      for (int i = 0; i < ctx->n_rows; ++i) indeg[i] = local_ptr[i + 1] - local_ptr[i];
+      const int64_t k_wide = (int64_t)(budget_mb * 1e6 / (4.0 * wideF)), k_narrow = (int64_t)(budget_mb * 1e6 / (4.0 * narrowF));
+      const int to_w = threshold(outdeg, k_wide), to_n = threshold(outdeg, k_narrow);
+      const int ti_w = threshold(indeg, k_wide), ti_n = threshold(indeg, k_narrow);
+      CK(dalloc(&ctx->col_idx_hot, (size_t)ctx->E));
+      CK(dalloc(&ctx->csc_dst_hot, (size_t)ctx->E));
+      LAUNCHED(launch_mark_hot(ctx->col_idx, ctx->csc_ptr, ctx->E, to_w, to_n, ctx->col_idx_hot, ctx->st));
+      LAUNCHED(launch_mark_hot(ctx->csc_dst, ctx->row_ptr, ctx->E, ti_w, ti_n, ctx->csc_dst_hot, ctx->st));
+      ctx->hot_wide_F = wideF;
+    }
+  }
   CK(cudaStreamSynchronize(ctx->st));
   ctx->have_graph = true;
   return GATX_OK;
@@ -859,11 +904,23 @@ int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim) {
     ctx->I0 = in_dim;
     ctx->ld0 = ld;
   }
-  if (ld == in_dim)  // no padding: one contiguous DMA
-    CK(cudaMemcpyAsync(ctx->X0, X, sizeof(float) * (size_t)ctx->N * in_dim, cudaMemcpyHostToDevice, ctx->st));
-  else
-    CK(cudaMemcpy2DAsync(ctx->X0, sizeof(float) * ld, X, sizeof(float) * in_dim, sizeof(float) * in_dim, ctx->N,
-                         cudaMemcpyHostToDevice, ctx->st));
+  // With a communicator every rank copies only ITS rows over PCIe and the row blocks are all-gathered over NVLink
+  // (the call is then collective: every rank must make it); without one each rank uploads the whole matrix.
+  const bool scatter = ctx->world > 1 && ctx->comm != nullptr;
+  const int64_t first = scatter ? ctx->r0 : 0, count = scatter ? ctx->n_rows : ctx->N;
+  if (count > 0) {
+    float* dst = ctx->X0 + first * ld;
+    const float* src = X + first * in_dim;
+    if (ld == in_dim)  // no padding: one contiguous DMA
+      CK(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)count * in_dim, cudaMemcpyHostToDevice, ctx->st));
+    else
+      CK(cudaMemcpy2DAsync(dst, sizeof(float) * ld, src, sizeof(float) * in_dim, sizeof(float) * in_dim, count,
+                           cudaMemcpyHostToDevice, ctx->st));
+  }
+  if (scatter) {
+    int rc = nccl_allgather_rows(ctx, ctx->X0, ld);
+    if (rc) return rc;
+  }
   ctx->have_feat = true;
   return GATX_OK;
 }

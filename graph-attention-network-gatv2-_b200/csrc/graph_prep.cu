@@ -123,4 +123,23 @@ int launch_philox_uniform(float* out, int64_t n, float limit, uint64_t seed, uin
   return 1;
 }
 
+__global__ void mark_hot_kernel(const int* __restrict__ idx, const int* __restrict__ ptr, int64_t E, int thr_wide,
+                                int thr_narrow, int* __restrict__ out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    const int v = idx[e];
+    const int deg = ptr[v + 1] - ptr[v];
+    uint32_t o = (uint32_t)v;
+    if (deg >= thr_wide) o |= 0x80000000u;
+    if (deg >= thr_narrow) o |= 0x40000000u;
+    out[e] = (int)o;
+  }
+}
+int launch_mark_hot(const int* idx, const int* ptr, int64_t E, int thr_wide, int thr_narrow, int* out, cudaStream_t st) {
+  if (E <= 0) return 0;
+  int64_t blocks = (E + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  mark_hot_kernel<<<(int)blocks, 256, 0, st>>>(idx, ptr, E, thr_wide, thr_narrow, out);
+  return 1;
+}
+
 }  // namespace gatx

@@ -107,7 +107,9 @@ const char* gatx_version(void);
  * rank; a rank keeps rows [bounds[rank], bounds[rank+1]). */
 int gatx_set_graph_csr(gatx_ctx* ctx, int32_t num_nodes, int64_t num_edges,
                        const int32_t* row_ptr, const int32_t* col_idx);
-/* Replaces EB:1151-1155.  X is the GLOBAL row-major [N][in_dim] matrix. */
+/* Replaces EB:1151-1155.  X is the GLOBAL row-major [N][in_dim] matrix.  With world > 1 and an initialised
+ * communicator the call is COLLECTIVE: every rank copies only its own rows host->device and the row blocks are
+ * all-gathered over NVLink (every rank keeps all input rows, so layer 0 needs no exchange step). */
 int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim);
 /* Replaces EB:1169-1172 + EB:1106-1107 (num_classes <= 0: derived as max(label)+1). */
 int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes);
