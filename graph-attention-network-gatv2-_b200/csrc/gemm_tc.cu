@@ -53,6 +53,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -327,6 +330,171 @@ gemm_tf32_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   }
 }
 
+// ---- persistent variant for 256-column tiles ---------------------------------------------------------------
+// One CTA per SM walks the tile list (n fastest, so the CTAs that run at the same time share the A tile in L2):
+// a 4-stage TMA ring (4 x 48 KB) feeds the MMA thread across tile boundaries, the accumulator is double-buffered
+// in TMEM (2 x 256 columns), and the four epilogue warps drain tile i (TMEM -> swizzled smem boxes -> TMA store)
+// while the tensor core already works on tile i + 1.  Compared with one tile per CTA (two co-resident CTAs with a
+// 2-stage ring each) this removes the per-tile TMEM allocation / barrier setup and keeps four k-blocks in flight
+// for a single main loop.
+struct TnPersist {
+  static constexpr int BN = 256, kStages = 4;
+  static constexpr int kABytes = BM * BK * 4, kBBytes = BN * BK * 4, kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, each takes one half of the 256 columns
+  static constexpr int kThreadsP = 64 + 32 * kEpiWarps;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+};
+
+__global__ void __launch_bounds__(TnPersist::kThreadsP)
+gemm_tf32_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                               const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
+                               int K0, int K1, int n_split, int M, int N, int tiles_n, int num_tiles) {
+  using S = TnPersist;
+  constexpr int BN = S::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  uint8_t* staging = smem + S::kStages * S::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::kStagingBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb0 = (K0 + BK - 1) / BK, kb1 = (K1 + BK - 1) / BK, num_kb = kb0 + kb1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (K1 > 0) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    tma_prefetch_desc(&tmC0);
+    tma_prefetch_desc(&tmC1);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], S::kEpiWarps);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t kbg = 0;  // k-blocks issued so far (ring position)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % S::kStages;
+          const uint32_t ph = (kbg / S::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = tiles + s * S::kStageBytes;
+          uint8_t* b_dst = a_dst + S::kABytes;
+          mbar_expect_tx(&full_bar[s], S::kStageBytes);
+          if (kb < kb0) {
+            tma_load_2d(&tmA0, &full_bar[s], a_dst, kb * BK, m0);
+            tma_load_2d(&tmB0, &full_bar[s], b_dst, kb * BK, n0);
+          } else {
+            tma_load_2d(&tmA1, &full_bar[s], a_dst, (kb - kb0) * BK, m0);
+            tma_load_2d(&tmB1, &full_bar[s], b_dst, (kb - kb0) * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+      uint32_t kbg = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % S::kStages;
+          const uint32_t ph = (kbg / S::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + s * S::kStageBytes);
+          const uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 4, 16, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 4, 16, 1024);
+            umma_tf32(tmem_d, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue (see gemm_tf32_tn_kernel): TMEM -> registers -> swizzled smem box -> TMA store =====
+    // Eight warps: warp w may only touch TMEM lanes 32 (w % 4) .. + 31, so warps w and w + 4 share a lane quadrant
+    // and split the tile's columns.  Draining a 128 x 256 fp32 tile with four warps took longer than its main loop.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint8_t* box_ptr = staging + (warp - 2) * 4096;
+    const uint32_t box = smem_u32(box_ptr);
+    const uint32_t rsw = (uint32_t)(lane & 7);
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      const bool to_c1 = n0 >= n_split;
+      const CUtensorMap* tmc = to_c1 ? &tmC1 : &tmC0;
+      const int ccol0 = to_c1 ? n0 - n_split : n0;
+      const int row0 = m0 + q * 32;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        if (n0 + c0 >= N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, v);
+        if (lane == 0) bulk_wait_read<0>();  // the previous store of this warp has read the box
+        __syncwarp();
+        const uint32_t rowaddr = box + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          sts4(rowaddr + ((((uint32_t)c) ^ rsw) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          tma_store_2d(tmc, box_ptr, ccol0 + c0, row0);
+          bulk_commit();
+        }
+      }
+      // every tcgen05.ld of this accumulator has completed (tmem_ld32 waits): hand it back to the MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ---- host side: tensor maps -------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -595,6 +763,18 @@ int launch_gemm_tc_tn2(const float* A0, int64_t lda0, const float* B0, int64_t l
   if (!tma_store) {
     c0 = a0;
     c1 = a0;
+  }
+  static const bool no_persist = getenv("GATX_GEMM_NO_PERSISTENT") != nullptr;
+  if (bn == 256 && tma_store && !no_persist) {
+    if (cudaFuncSetAttribute(gemm_tf32_tn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TnPersist::kBytes) != cudaSuccess)
+      return -1;
+    const int tiles_n = (N + 255) / 256, tiles_m = (M + BM - 1) / BM;
+    const int num_tiles = tiles_n * tiles_m;
+    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    gemm_tf32_tn_persistent_kernel<<<grid, TnPersist::kThreadsP, TnPersist::kBytes, st>>>(a0, b0, a1, b1, c0, c1, K0, K1, n_split, M, N,
+                                                                              tiles_n, num_tiles);
+    return 1;
   }
   switch (bn) {
     case 256: return launch_tn<256>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
