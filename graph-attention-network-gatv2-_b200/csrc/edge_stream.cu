@@ -276,8 +276,12 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
              av[j].z * lrelu_fast(v[j].z + pr[j].z) + av[j].w * lrelu_fast(v[j].w + pr[j].w);
       p = head_sum<LPH>(p, sh.lc);
       st_pred_u32(reinterpret_cast<uint32_t*>(score + (int64_t)e * sh.H + hd), __float_as_uint(p), head_lane);
-      const float mn = fmaxf(st.m, p);
-      const float corr = __expf(st.m - mn), w = __expf(p - mn);  // online form of EB:336-349
+      // online form of EB:336-349.  Of exp(m - max) and exp(p - max) one is exp(0) = 1: a single exponential
+      const float dlt = p - st.m;
+      const bool up = dlt > 0.f;
+      const float ex = __expf(-fabsf(dlt));
+      const float corr = up ? ex : 1.f, w = up ? 1.f : ex;
+      const float mn = up ? p : st.m;
       st.s = st.s * corr + w;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
