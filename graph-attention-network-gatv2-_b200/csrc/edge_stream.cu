@@ -193,6 +193,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
   }
   __syncwarp();
   const GatherPolicy gp(g);
+  const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(bar);
   float4 av[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) av[j] = ldg4(a + lc_off<NV>(lane, j));
@@ -212,13 +213,14 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
     int row_end = __ldg(g.row_ptr + r + 1);
     int idx_cur = lane < n ? __ldg(col_idx + e0 + lane) : 0;
     int idx_nxt = 32 + lane < n ? __ldg(col_idx + e0 + 32 + lane) : 0;
+    int idx_nn = 64 + lane < n ? __ldg(col_idx + e0 + 64 + lane) : 0;  // two windows ahead: its latency is never exposed
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int src = __shfl_sync(0xffffffffu, idx_cur, s);
       if (s < n && lane == 0) {
         const uint32_t slot = (it + s) % R;
-        mbar_expect_tx(&bar[slot], kRowBytes);
-        bulk_g2s_hint(ring + slot * F, Pl + gp.id(src) * F, kRowBytes, &bar[slot], gp.of(src));
+        mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
+        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(src) * F, kRowBytes, bar_s + slot * 8u, gp.of(src));
       }
     }
     float4 pr[NV], pr_n[NV];
@@ -252,11 +254,12 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       }
       if ((i & 31) == 0 && i > 0) {
         idx_cur = idx_nxt;
-        const int p = i + 32 + lane;
-        idx_nxt = p < n ? __ldg(col_idx + e0 + p) : 0;
+        idx_nxt = idx_nn;
+        const int p = i + 64 + lane;
+        idx_nn = p < n ? __ldg(col_idx + e0 + p) : 0;
       }
       const uint32_t pos = it + i, slot = pos % R, ph = (pos / R) & 1;
-      mbar_wait(&bar[slot], ph);
+      mbar_wait_s(bar_s + slot * 8u, ph);
       float4 v[NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + voff[j]);
@@ -265,8 +268,8 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
         const int ni = i + R;
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
         if (ni < n && lane == 0) {
-          mbar_expect_tx(&bar[slot], kRowBytes);
-          bulk_g2s_hint(ring + slot * F, Pl + gp.id(srcn) * F, kRowBytes, &bar[slot], gp.of(srcn));
+          mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
+          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
         }
       }
       float p = 0.f;
@@ -435,6 +438,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
   }
   __syncwarp();
   const GatherPolicy gp(g);
+  const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(bar);
   float4 ga[NV];  // the attention vector a is only needed when a row segment is written: read it there (L1 hit)
 #pragma unroll
   for (int j = 0; j < NV; ++j) ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -457,13 +461,14 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     int row_end = __ldg(g.row_ptr + r + 1);
     int idx_cur = lane < n ? __ldg(col_idx + e0 + lane) : 0;
     int idx_nxt = 32 + lane < n ? __ldg(col_idx + e0 + 32 + lane) : 0;
+    int idx_nn = 64 + lane < n ? __ldg(col_idx + e0 + 64 + lane) : 0;  // two windows ahead: its latency is never exposed
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int src = __shfl_sync(0xffffffffu, idx_cur, s);
       if (s < n && lane == 0) {
         const uint32_t slot = (it + s) % R;
-        mbar_expect_tx(&bar[slot], kRowBytes);
-        bulk_g2s_hint(ring + slot * F, Pl + gp.id(src) * F, kRowBytes, &bar[slot], gp.of(src));
+        mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
+        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(src) * F, kRowBytes, bar_s + slot * 8u, gp.of(src));
       }
     }
     // row data (g_h row, P_r row) of r goes through the row buffer; once it sits in registers the buffer is free,
@@ -552,8 +557,9 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       }
       if ((i & 31) == 0 && i > 0) {
         idx_cur = idx_nxt;
-        const int p = i + 32 + lane;
-        idx_nxt = p < n ? __ldg(col_idx + e0 + p) : 0;
+        idx_nxt = idx_nn;
+        const int p = i + 64 + lane;
+        idx_nn = p < n ? __ldg(col_idx + e0 + p) : 0;
         float* w = scwin + ((i >> 5) & 1) * 32 * H;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -566,7 +572,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         }
       }
       const uint32_t pos = it + i, slot = pos % R, ph = (pos / R) & 1;
-      mbar_wait(&bar[slot], ph);
+      mbar_wait_s(bar_s + slot * 8u, ph);
       float4 v[NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + voff[j]);
@@ -575,8 +581,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         const int ni = i + R;
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
         if (ni < n && lane == 0) {
-          mbar_expect_tx(&bar[slot], kRowBytes);
-          bulk_g2s_hint(ring + slot * F, Pl + gp.id(srcn) * F, kRowBytes, &bar[slot], gp.of(srcn));
+          mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
+          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
         }
       }
       const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
@@ -694,6 +700,7 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
   }
   __syncwarp();
   const GatherPolicy gp(g);
+  const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(bar);
   float4 av[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) av[j] = ldg4(a + lc_off<NV>(lane, j));
@@ -716,14 +723,16 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
     int dst_cur = lane < n ? __ldg(csc_dst + e0 + lane) : 0, eid_cur = lane < n ? __ldg(csc_eid + e0 + lane) : 0;
     int dst_nxt = 32 + lane < n ? __ldg(csc_dst + e0 + 32 + lane) : 0;
     int eid_nxt = 32 + lane < n ? __ldg(csc_eid + e0 + 32 + lane) : 0;
+    int dst_nn = 64 + lane < n ? __ldg(csc_dst + e0 + 64 + lane) : 0;  // two windows ahead
+    int eid_nn = 64 + lane < n ? __ldg(csc_eid + e0 + 64 + lane) : 0;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int d = __shfl_sync(0xffffffffu, dst_cur, s), ee = __shfl_sync(0xffffffffu, eid_cur, s);
       if (s < n && lane == 0) {
         const uint32_t slot = (it + s) % R;
-        mbar_expect_tx(&bar[slot], kRowBytes + kRecBytes);
-        bulk_g2s_hint(ring + slot * slot_floats, gh + gp.id(d) * F, kRowBytes, &bar[slot], gp.of(d));
-        bulk_g2s_hint(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot], gp.cold);
+        mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes + kRecBytes);
+        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats) * 4u, gh + gp.id(d) * F, kRowBytes, bar_s + slot * 8u, gp.of(d));
+        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats + F) * 4u, rec + (int64_t)ee * RW, kRecBytes, bar_s + slot * 8u, gp.cold);
       }
     }
     float4 acc[NV];
@@ -748,12 +757,14 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
       if ((i & 31) == 0 && i > 0) {
         dst_cur = dst_nxt;
         eid_cur = eid_nxt;
-        const int p = i + 32 + lane;
-        dst_nxt = p < n ? __ldg(csc_dst + e0 + p) : 0;
-        eid_nxt = p < n ? __ldg(csc_eid + e0 + p) : 0;
+        dst_nxt = dst_nn;
+        eid_nxt = eid_nn;
+        const int p = i + 64 + lane;
+        dst_nn = p < n ? __ldg(csc_dst + e0 + p) : 0;
+        eid_nn = p < n ? __ldg(csc_eid + e0 + p) : 0;
       }
       const uint32_t pos = it + i, slot = pos % R, ph = (pos / R) & 1;
-      mbar_wait(&bar[slot], ph);
+      mbar_wait_s(bar_s + slot * 8u, ph);
       const float* sl = ring + slot * slot_floats;
       const uint32_t* rw = reinterpret_cast<const uint32_t*>(sl + F);
       float4 gv[NV];
@@ -773,9 +784,9 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
         const int d = __shfl_sync(0xffffffffu, same ? dst_cur : dst_nxt, ni & 31);
         const int ee = __shfl_sync(0xffffffffu, same ? eid_cur : eid_nxt, ni & 31);
         if (ni < n && lane == 0) {
-          mbar_expect_tx(&bar[slot], kRowBytes + kRecBytes);
-          bulk_g2s_hint(ring + slot * slot_floats, gh + gp.id(d) * F, kRowBytes, &bar[slot], gp.of(d));
-          bulk_g2s_hint(ring + slot * slot_floats + F, rec + (int64_t)ee * RW, kRecBytes, &bar[slot], gp.cold);
+          mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes + kRecBytes);
+          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats) * 4u, gh + gp.id(d) * F, kRowBytes, bar_s + slot * 8u, gp.of(d));
+          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats + F) * 4u, rec + (int64_t)ee * RW, kRecBytes, bar_s + slot * 8u, gp.cold);
         }
       }
 #pragma unroll

@@ -40,6 +40,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// Variants on precomputed 32-bit shared-memory addresses: the streaming loops compute `smem_u32(base)` once and then
+// only add slot offsets (the generic-pointer forms re-derive the shared window address -- an S2R plus a few integer
+// instructions -- on every trip).
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint_s(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar,
+                                                uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
 // Same copy with an L2 eviction-priority hint (createpolicy): rows of frequently gathered nodes are kept
 // (evict_last), rows touched once are dropped first (evict_first) so they cannot push the hot set out.
 __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
