@@ -138,6 +138,13 @@ struct gatx_ctx {
   std::vector<Span> spans;
   size_t spans_used = 0;
   float phase_ms[PH_COUNT] = {0};
+  // CUDA-graph replay of forward + backward (launch-bound shapes: tens of microsecond-sized kernels per epoch)
+  int graph_mode = -1;            // -1 auto (single rank, at most kGraphAutoMaxEdges edges), 0 off, 1 on
+  uint64_t gen = 1;               // bumped by everything that changes device pointers or the launch sequence
+  cudaGraphExec_t epoch_exec = nullptr;
+  uint64_t epoch_exec_gen = 0;
+  int64_t epoch_exec_launches = 0, epoch_exec_count = 0;
+  bool epoch_replayed = false;    // the last gatx_train_epoch ran as a graph launch
 };
 
 namespace {
@@ -211,8 +218,10 @@ void free_graph(gatx_ctx* c) {
   dfree(c->csc_ptr); dfree(c->csc_dst); dfree(c->csc_eid); dfree(c->heavy_rows); dfree(c->heavy_srcs);
   dfree(c->chunk_row); dfree(c->chunk_src); dfree(c->ref_mask); dfree(c->col_idx_hot); dfree(c->csc_dst_hot);
   c->have_graph = false;
+  ++c->gen;
 }
 void free_bufs(gatx_ctx* c) {
+  ++c->gen;
   for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
   c->ipc_opened.clear();
   c->peers_ready = false;
@@ -340,6 +349,7 @@ int ensure_buffers(gatx_ctx* ctx) {
   CK(dalloc(&ctx->correct, 1));
   CK(dalloc(&ctx->red2, 2));
   ctx->have_bufs = true;
+  ++ctx->gen;
   return GATX_OK;
 }
 
@@ -678,6 +688,63 @@ int read_loss(gatx_ctx* ctx, float* avg_loss, float* accuracy, int64_t count) {
   return GATX_OK;
 }
 
+// ---- CUDA-graph replay of the epoch ----------------------------------------------------------------------------
+// Small graphs (cora / pubmed class) run ~50 kernels of a few microseconds each per epoch: the epoch is bound by
+// launch latency, not by the GPU.  Forward + backward are captured once per (buffers, graph, mask) generation and
+// replayed with one cudaGraphLaunch.  Single rank only (the multi-rank epoch interleaves NCCL and peer-memory
+// barriers), not while per-phase timing is on (event records change the launch sequence).
+constexpr int64_t kGraphAutoMaxEdges = 8 << 20;  // beyond this the kernels are long enough to hide the launches
+
+bool epoch_graph_wanted(const gatx_ctx* ctx) {
+  if (ctx->world != 1 || ctx->timing || ctx->graph_mode == 0) return false;
+  if (ctx->graph_mode == 1) return true;
+  static const int env = [] {
+    const char* e = getenv("GATX_CUDA_GRAPH");
+    return e ? atoi(e) : -1;
+  }();
+  if (env == 0) return false;
+  return env == 1 || ctx->E <= kGraphAutoMaxEdges;
+}
+
+// Captures do_forward + do_backward into ctx->epoch_exec.  A capture that fails leaves epoch_exec null and turns the
+// replay off for this context (the eager path then runs the epoch); a genuine launch error is reported as usual.
+int capture_epoch(gatx_ctx* ctx) {
+  if (ctx->epoch_exec) {
+    cudaGraphExecDestroy(ctx->epoch_exec);
+    ctx->epoch_exec = nullptr;
+  }
+  CK(cudaStreamSynchronize(ctx->st));
+  const int64_t before = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->graph_mode = 0;
+    return GATX_OK;
+  }
+  int rc = do_forward(ctx);
+  if (!rc) rc = do_backward(ctx);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->st, &graph);
+  const int64_t n = ctx->launches - before;
+  ctx->launches = before;
+  ctx->fwd_valid = false;
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (ce != cudaSuccess || !graph || cudaGraphInstantiate(&ctx->epoch_exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    ctx->epoch_exec = nullptr;
+    ctx->graph_mode = 0;
+    return GATX_OK;
+  }
+  cudaGraphDestroy(graph);
+  ctx->epoch_exec_gen = ctx->gen;
+  ctx->epoch_exec_launches = n;
+  ctx->epoch_exec_count = ctx->last_count;
+  return GATX_OK;
+}
+
 }  // namespace
 
 // =============================================================================== C ABI
@@ -722,6 +789,7 @@ void gatx_destroy(gatx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->epoch_exec) cudaGraphExecDestroy(ctx->epoch_exec);
   free_bufs(ctx);
   free_graph(ctx);
   dfree(ctx->X0);
@@ -887,6 +955,7 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   }
   CK(cudaStreamSynchronize(ctx->st));
   ctx->have_graph = true;
+  ++ctx->gen;
   return GATX_OK;
 }
 
@@ -903,6 +972,7 @@ int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim) {
     CK(cudaMemsetAsync(ctx->X0, 0, sizeof(float) * (size_t)ctx->N * ld, ctx->st));
     ctx->I0 = in_dim;
     ctx->ld0 = ld;
+    ++ctx->gen;
   }
   // With a communicator every rank copies only ITS rows over PCIe and the row blocks are all-gathered over NVLink
   // (the call is then collective: every rank must make it); without one each rank uploads the whole matrix.
@@ -937,7 +1007,10 @@ int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes) {
   }
   if (ctx->have_bufs && C != ctx->C) free_bufs(ctx);
   ctx->C = C;
-  if (!ctx->labels) CK(dalloc(&ctx->labels, (size_t)ctx->n_rows));
+  if (!ctx->labels) {
+    CK(dalloc(&ctx->labels, (size_t)ctx->n_rows));
+    ++ctx->gen;
+  }
   if (ctx->n_rows)
     CK(cudaMemcpyAsync(ctx->labels, labels + ctx->r0, sizeof(int) * (size_t)ctx->n_rows, cudaMemcpyHostToDevice,
                        ctx->st));
@@ -967,6 +1040,7 @@ static int upload_mask(gatx_ctx* ctx, const uint8_t* mask, unsigned char** dev, 
 
 int gatx_set_train_mask(gatx_ctx* ctx, const uint8_t* mask) {
   if (!ctx) return GATX_ERR_INVALID;
+  ++ctx->gen;  // the mask pointer and the loss denominator are baked into a captured epoch
   return upload_mask(ctx, mask, &ctx->train_mask, &ctx->train_count);
 }
 
@@ -1073,7 +1147,26 @@ int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy)
   if (!ctx || t < 1) return fail(ctx, GATX_ERR_INVALID, "epoch index is 1-based");
   CK(cudaSetDevice(ctx->device));
   ctx->spans_used = 0;
+  ctx->epoch_replayed = false;
   int rc;
+  if (epoch_graph_wanted(ctx)) {
+    // forward + backward replayed as one CUDA graph; the optimizer (its bias correction depends on t) and the
+    // loss read-back stay ordinary launches behind it
+    if ((rc = ensure_buffers(ctx))) return rc;
+    if (!ctx->have_params) return fail(ctx, GATX_ERR_INVALID, "parameters not initialised");
+    if ((!ctx->epoch_exec || ctx->epoch_exec_gen != ctx->gen) && (rc = capture_epoch(ctx))) return rc;
+    if (ctx->epoch_exec) {
+      CK(cudaGraphLaunch(ctx->epoch_exec, ctx->st));
+      ctx->launches += ctx->epoch_exec_launches;
+      ctx->fwd_valid = true;
+      ctx->last_count = ctx->epoch_exec_count;
+      ctx->epoch_replayed = true;
+      if ((rc = do_step(ctx, t))) return rc;
+      CK(cudaGetLastError());
+      if (avg_loss || accuracy) return read_loss(ctx, avg_loss, accuracy, ctx->last_count);
+      return GATX_OK;
+    }
+  }
   {
     PhaseTimer whole(ctx, PH_EPOCH);
     if ((rc = do_forward(ctx))) return rc;
@@ -1084,6 +1177,13 @@ int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy)
   if (avg_loss || accuracy) return read_loss(ctx, avg_loss, accuracy, ctx->last_count);
   return GATX_OK;
 }
+
+int gatx_set_cuda_graph(gatx_ctx* ctx, int32_t mode) {
+  if (!ctx || mode < -1 || mode > 1) return fail(ctx, GATX_ERR_INVALID, "mode is -1 (auto), 0 (off) or 1 (on)");
+  ctx->graph_mode = mode;
+  return GATX_OK;
+}
+int gatx_cuda_graph_active(const gatx_ctx* ctx) { return ctx && ctx->epoch_replayed ? 1 : 0; }
 
 int gatx_sync(gatx_ctx* ctx) {
   if (!ctx) return GATX_ERR_INVALID;
@@ -1096,6 +1196,7 @@ int gatx_enable_timing(gatx_ctx* ctx, int32_t on) {
   if (!ctx) return GATX_ERR_INVALID;
   ctx->timing = on != 0;
   ctx->spans_used = 0;
+  ++ctx->gen;
   for (auto& l : ctx->layers) l.kev_fwd = l.kev_bwd = false;
   return GATX_OK;
 }

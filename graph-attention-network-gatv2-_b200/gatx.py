@@ -25,6 +25,7 @@ EXPORTS = [
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
+    "gatx_set_cuda_graph", "gatx_cuda_graph_active",
 ]
 
 
@@ -252,6 +253,15 @@ class Engine:
 
     def launch_count(self):
         return self.lib.gatx_launch_count(self.ctx)
+
+    def set_cuda_graph(self, mode):
+        """-1 auto, 0 eager launches, 1 replay forward + backward of train_epoch as one CUDA graph"""
+        self.lib.gatx_set_cuda_graph.argtypes = [C.c_void_p, C.c_int32]
+        self._ck(self.lib.gatx_set_cuda_graph(self.ctx, mode), "gatx_set_cuda_graph")
+
+    def cuda_graph_active(self):
+        self.lib.gatx_cuda_graph_active.argtypes = [C.c_void_p]
+        return bool(self.lib.gatx_cuda_graph_active(self.ctx))
 
     def edge_bytes(self, layer):
         f, b = C.c_double(), C.c_double()

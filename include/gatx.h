@@ -151,6 +151,14 @@ int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy)
  * gatx_forward afterwards (GATX_ERR_INVALID otherwise).  Synchronises. */
 int gatx_evaluate(gatx_ctx* ctx, const uint8_t* mask, float* avg_loss, float* accuracy);
 int gatx_sync(gatx_ctx* ctx);
+/* CUDA-graph replay of gatx_train_epoch (replaces the ~20 cudaDeviceSynchronize-separated launches per layer of
+ * EB:1375-1557 with ONE graph launch per epoch).  Small graphs run tens of microsecond-sized kernels per epoch and
+ * are bound by launch latency; forward + backward are captured once and replayed, the optimizer (t-dependent) and
+ * the loss read-back follow as ordinary launches.  mode: -1 auto (default: single rank, <= 8 Mi edges, timing off;
+ * env GATX_CUDA_GRAPH=0/1 overrides), 0 off, 1 on.  Results are bit-identical to the eager launches.  A new graph,
+ * feature matrix, label set or train mask re-captures automatically. */
+int gatx_set_cuda_graph(gatx_ctx* ctx, int32_t mode);
+int gatx_cuda_graph_active(const gatx_ctx* ctx); /* 1 when the last gatx_train_epoch was a graph replay */
 
 /* ---- introspection (parity tests, checkpoints) ------------------------------------------- */
 int64_t gatx_tensor_size(gatx_ctx* ctx, int32_t which, int32_t layer); /* elements, <0 on error */

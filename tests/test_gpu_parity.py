@@ -319,3 +319,53 @@ def test_state_roundtrip(gatx, orc):
         b.set_state(st[:-1])
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cuda_graph_replay_is_bit_identical(gatx, mode):
+    """gatx_set_cuda_graph: forward + backward replayed as one CUDA graph give the eager launches' bits, across
+    everything that forces a re-capture (train mask, new features / labels, timing on and off) and with
+    evaluation forwards and state reloads in between."""
+    p = make_problem(700, 9000, 40, 6, (4, 4, 1), (32, 32, 16), "rmat", seed=21, hub=300)
+    eager = make_engine(gatx, p, optimizer="adam", lr=0.01, clip=True, gemm_mode=mode)
+    graph = make_engine(gatx, p, optimizer="adam", lr=0.01, clip=True, gemm_mode=mode)
+    eager.set_cuda_graph(0)
+    graph.set_cuda_graph(1)
+    mask = (np.arange(700) % 3 != 0).astype(np.uint8)
+    t = 0
+
+    def both(n):
+        nonlocal t
+        for _ in range(n):
+            t += 1
+            le, lg = eager.train_epoch(t), graph.train_epoch(t)
+            assert le == lg, (t, le, lg)
+            assert graph.cuda_graph_active() and not eager.cuda_graph_active()
+
+    both(3)
+    assert graph.launch_count() == eager.launch_count()  # a replay counts the kernels inside the graph
+    assert eager.evaluate(mask) == graph.evaluate(mask)  # an eager forward between two replays
+    both(2)
+    for e in (eager, graph):
+        e.set_train_mask(mask)
+    both(2)
+    for e in (eager, graph):
+        e.set_train_mask(None)
+        e.set_features(p["X"][:, ::-1].copy())
+        e.set_labels((p["labels"] + 1) % p["C"], p["C"])
+    both(2)
+    graph.enable_timing(True)  # event records change the launch sequence: eager while timing is on
+    t += 1
+    le, lg = eager.train_epoch(t), graph.train_epoch(t)
+    assert le == lg and not graph.cuda_graph_active()
+    graph.enable_timing(False)
+    both(2)
+    st = eager.get_state()
+    assert np.array_equal(st, graph.get_state())
+    graph.set_state(st)
+    both(1)
+    for l in range(3):
+        assert np.array_equal(eager.tensor(gatx.T_W, l), graph.tensor(gatx.T_W, l))
+    assert np.array_equal(eager.tensor(gatx.T_PRED), graph.tensor(gatx.T_PRED))
+    eager.close()
+    graph.close()

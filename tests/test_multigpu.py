@@ -60,8 +60,15 @@ def _worker(rank, world, idfile, q, mode, p2p):
     ev = eng.evaluate(None)  # two evaluation forwards back to back: the exchange must not race with itself
     ev2 = eng.evaluate(None)
     assert ev == ev2
+    # masks are global arrays, every rank keeps its own rows: masked training + masked evaluation across ranks
+    mask = (np.arange(len(p["labels"])) % 3 == 0).astype(np.uint8)
+    eng.set_train_mask(mask)
+    masked = [eng.train_epoch(t) for t in range(5, 7)]
+    masked_eval = eng.evaluate(1 - mask)
+    eng.set_train_mask(None)
+    eng.evaluate(None)
     info = eng.graph_info()
-    out = dict(rank=rank, losses=losses, halo_rows=eng.halo_rows(), W=[eng.tensor(gatx.T_W, l) for l in range(3)], Wo=eng.tensor(gatx.T_WO),
+    out = dict(rank=rank, losses=losses, halo_rows=eng.halo_rows(), masked=masked, masked_eval=masked_eval, W=[eng.tensor(gatx.T_W, l) for l in range(3)], Wo=eng.tensor(gatx.T_WO),
                rows=(info["row_begin"], info["row_end"]), pred=eng.tensor(gatx.T_PRED))
     q.put(out)
     eng.close()
@@ -91,9 +98,17 @@ def test_two_ranks_match_one(world, p2p):
     assert [o["halo_rows"] for o in outs] == orc.halo_rows(p["row_ptr"], p["col_idx"], world).tolist()  # bit-exact
     eng = make_engine(gatx, p, optimizer="adam", lr=0.01, clip=True, gemm_mode=mode)
     ref_losses = [eng.train_epoch(t) for t in range(1, 5)]
+    eng.evaluate(None)
+    mask = (np.arange(len(p["labels"])) % 3 == 0).astype(np.uint8)
+    eng.set_train_mask(mask)
+    ref_masked = [eng.train_epoch(t) for t in range(5, 7)]
+    ref_masked_eval = eng.evaluate(1 - mask)
+    eng.set_train_mask(None)
     eng.evaluate(None)  # the workers' predictions come from an evaluation forward after the last update
     for o in outs:
         for (l, a), (rl, ra) in zip(o["losses"], ref_losses):
+            assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 2e-3
+        for (l, a), (rl, ra) in zip(o["masked"] + [o["masked_eval"]], ref_masked + [ref_masked_eval]):
             assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 2e-3
         for l in range(3):
             assert rel_err(o["W"][l], eng.tensor(gatx.T_W, l)) < 2e-3
