@@ -5,11 +5,16 @@
 
 namespace gatx {
 
-constexpr float kSlope = 0.01f;  // LeakyReLU slope of the reference (EB:1143, EB:1428)
+constexpr float kSlope = 0.01f;  // LeakyReLU slope of the reference (EB:1143, EB:1428): the default of both slopes
 constexpr int kNumSMs = 148;     // B200
 
-__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : kSlope * x; }
-__device__ __forceinline__ float lrelu_grad(float x) { return x > 0.f ? 1.f : kSlope; }
+// The two LeakyReLU slopes of a layer: `attn` inside the attention score a . LReLU(W_l x_j + W_r x_i) (EB:1143; GATv2's
+// negative_slope) and `act` of the layer activation (EB:1428).  The reference fixes both at 0.01; 0 <= slope < 1.
+struct Slopes {
+  float attn, act;
+};
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : slope * x; }
+__device__ __forceinline__ float lrelu_grad(float x, float slope) { return x > 0.f ? 1.f : slope; }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // streaming 128-bit load that does not allocate in L1 (gathered rows are used once per warp)
@@ -33,6 +38,10 @@ int build_csc(const int* col_idx, const int* coo_dst, int64_t E, int n_src, int*
               int* csc_eid, cudaStream_t st);
 int launch_philox_uniform(float* out, int64_t n, float limit, uint64_t seed, uint64_t stream_id,
                           cudaStream_t st);
+// Y[n][c] = keep(n, c) ? X[n][c] / (1 - p) : 0 for rows [row0, row0 + n_rows) of a layer input (Y == X: in place);
+// keep() is a pure function of (seed, layer, step, global row, column), see dropout_kernel
+int launch_dropout(const float* X, int64_t ldx, float* Y, int64_t ldy, int n_rows, int cols, int row0, float p,
+                   uint64_t seed, int layer, int64_t step, cudaStream_t st);
 
 // gemm_simt.cu : C[m][n] (ldc) (+)= sum_k A(m,k) B(n,k), A(m,k) = A[m*sAm + k*sAk], same for B.
 int launch_gemm_simt(const float* A, int64_t sAm, int64_t sAk, const float* B, int64_t sBn, int64_t sBk,
@@ -66,6 +75,7 @@ struct EdgeGraph {
   // optional CUDA-event pairs around the three main streaming kernels of the layer being launched
   // (fwd, bwd pass 1, bwd pass 2); null = no timing
   cudaEvent_t* kernel_events;  // [6] = {fwd_a, fwd_b, dst_a, dst_b, src_a, src_b}
+  Slopes slopes;               // LeakyReLU slopes of the layer being launched
 };
 constexpr int kHeavyDeg = 1024;
 bool edge_shape_supported(int H, int D);

@@ -34,7 +34,7 @@ template <int T>
 __global__ void __launch_bounds__(kGW * 32)
 edge_fwd_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                         const float* __restrict__ Pl, const float* __restrict__ Pr, const float* __restrict__ a, int H,
-                        int D, float* __restrict__ Hout, float* __restrict__ hpre, float* __restrict__ score,
+                        int D, Slopes sl, float* __restrict__ Hout, float* __restrict__ hpre, float* __restrict__ score,
                         float* __restrict__ mx, float* __restrict__ sinv) {
   __shared__ float sc_s[kGW][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, F = H * D;
@@ -61,7 +61,7 @@ edge_fwd_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* 
     for (int t = 0; t < T; ++t) {
       const int k = lane + 32 * t;
       v[t] = k < F ? __ldg(Pl + (int64_t)src * F + k) : 0.f;
-      part[t] = av[t] * lrelu(v[t] + pr[t]);  // EB:303-320
+      part[t] = av[t] * lrelu(v[t] + pr[t], sl.attn);  // EB:303-320
     }
     head_sums<T>(part, hd, H, sc_s[warp], lane);
     if (lane < H) score[(int64_t)e * H + lane] = sc_s[warp][lane];
@@ -85,7 +85,7 @@ edge_fwd_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* 
       const float inv = 1.0f / (s[t] + 1e-8f);  // EB:379
       const float h = acc[t] * inv;
       if (hpre) hpre[(int64_t)row * F + k] = h;
-      Hout[(int64_t)row * F + k] = lrelu(h);
+      Hout[(int64_t)row * F + k] = lrelu(h, sl.act);
       if (k % D == 0) {
         mx[(int64_t)row * H + hd[t]] = m[t];
         sinv[(int64_t)row * H + hd[t]] = inv;
@@ -99,7 +99,7 @@ template <int T>
 __global__ void __launch_bounds__(kGW * 32)
 edge_bwd_dst_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                             const float* __restrict__ Pl, const float* __restrict__ Pr, const float* __restrict__ a,
-                            int H, int D, const float* __restrict__ Hout, float* __restrict__ gH,
+                            int H, int D, Slopes sl, const float* __restrict__ Hout, float* __restrict__ gH,
                             const float* __restrict__ score, const float* __restrict__ mx,
                             const float* __restrict__ sinv, float* __restrict__ gPr, float* __restrict__ rec, int RW,
                             float* __restrict__ ga_partials, float* __restrict__ galpha_dbg) {
@@ -124,7 +124,7 @@ edge_bwd_dst_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const i
       const float ho = k < F ? __ldg(Hout + (int64_t)row * F + k) : 0.f;
       pr[t] = k < F ? __ldg(Pr + (int64_t)row * F + k) : 0.f;
       cdot[t] = g * ho;                 // sum over the segment of alpha*galpha = gH . Hout
-      gh[t] = g * lrelu_grad(ho);       // EB:879-893 / EB:599
+      gh[t] = g * lrelu_grad(ho, sl.act);      // EB:879-893 / EB:599
       gpr[t] = 0.f;
       if (k < F) gH[(int64_t)row * F + k] = gh[t];
     }
@@ -156,8 +156,8 @@ edge_bwd_dst_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const i
         const float ge = __shfl_sync(0xffffffffu, ge_l, hd[t] >= 0 ? hd[t] : 0);
         if (hd[t] >= 0) {
           const float sx = v[t] + pr[t];
-          ga[t] += ge * lrelu(sx);                     // EB:769
-          gpr[t] += ge * av[t] * lrelu_grad(sx);       // EB:774-781
+          ga[t] += ge * lrelu(sx, sl.attn);                    // EB:769
+          gpr[t] += ge * av[t] * lrelu_grad(sx, sl.attn);      // EB:774-781
         }
       }
     }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kGW * 32)
 edge_bwd_src_generic_kernel(int n_src, const int* __restrict__ csc_ptr, const int* __restrict__ csc_dst,
                             const int* __restrict__ csc_eid, const float* __restrict__ Pl,
                             const float* __restrict__ Pr, const float* __restrict__ a, int H, int D,
-                            const float* __restrict__ gh, const float* __restrict__ rec, int RW,
+                            Slopes sl, const float* __restrict__ gh, const float* __restrict__ rec, int RW,
                             float* __restrict__ gPl) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, F = H * D;
   const int row = blockIdx.x * kGW + warp;
@@ -213,7 +213,7 @@ edge_bwd_src_generic_kernel(int n_src, const int* __restrict__ csc_ptr, const in
       if (k < F) {
         const float g = __ldg(gh + (int64_t)d * F + k);
         const float sx = pl[t] + __ldg(Pr + (int64_t)d * F + k);
-        acc[t] += alh * g + geh * av[t] * lrelu_grad(sx);  // EB:865-866
+        acc[t] += alh * g + geh * av[t] * lrelu_grad(sx, sl.attn);  // EB:865-866
       }
     }
   }
@@ -265,7 +265,7 @@ int launch_edge_forward_generic(const EdgeGraph& g, int H, int D, const float* P
   if (!edge_generic_supported(H, D) || tv < 0) return -1;
   if (g.n_rows <= 0) return 0;
   GENERIC_DISPATCH(tv, edge_fwd_generic_kernel<T><<<(g.n_rows + kGW - 1) / kGW, kGW * 32, 0, st>>>(
-                           g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, Hout, hpre, score, mx, sinv));
+                           g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, Hout, hpre, score, mx, sinv));
   return 1;
 }
 
@@ -281,11 +281,13 @@ int launch_edge_backward_generic(const EdgeGraph& g, int H, int D, const float* 
   int blocks = (g.n_rows + kGW - 1) / kGW;
   if (blocks > kGenericBwdBlocks) blocks = kGenericBwdBlocks;
   GENERIC_DISPATCH(tv, {
-    edge_bwd_dst_generic_kernel<T><<<blocks, kGW * 32, 0, st>>>(g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, Hout, gH,
+    edge_bwd_dst_generic_kernel<T><<<blocks, kGW * 32, 0, st>>>(g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, Hout,
+                                                                gH,
                                                                 score, mx, sinv, gPr, reinterpret_cast<float*>(rec), RW,
                                                                 ga_partials, galpha_dbg);
     edge_bwd_src_generic_kernel<T><<<(g.n_src + kGW - 1) / kGW, kGW * 32, 0, st>>>(
-        g.n_src, g.csc_ptr, g.csc_dst, g.csc_eid, Pl, Pr, a, H, D, gH, reinterpret_cast<const float*>(rec), RW, gPl);
+        g.n_src, g.csc_ptr, g.csc_dst, g.csc_eid, Pl, Pr, a, H, D, g.slopes, gH, reinterpret_cast<const float*>(rec), RW,
+        gPl);
   });
   *n_partials = blocks * kGW;
   return 2;

@@ -32,6 +32,7 @@ constexpr int kHeavyWarps = 16;  // warps per CTA for the CTA-per-heavy-row kern
 
 struct Shape {
   int H, D, F, lph, lg_lph;  // lph = D/4 chunks (lanes) per head
+  Slopes sl;                 // LeakyReLU slopes (set by the launchers from EdgeGraph::slopes)
 };
 
 __device__ __forceinline__ float head_reduce(float p, int lph) {
@@ -97,8 +98,9 @@ __device__ __forceinline__ void fwd_range(FwdState<NV>& st, int first, int end, 
       if (u == 1 && base + step >= end) break;  // warp-uniform
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        float p = av[j].x * lrelu(v[j].x + pr[j].x) + av[j].y * lrelu(v[j].y + pr[j].y) +
-                  av[j].z * lrelu(v[j].z + pr[j].z) + av[j].w * lrelu(v[j].w + pr[j].w);
+        const float sa = sh.sl.attn;
+        float p = av[j].x * lrelu(v[j].x + pr[j].x, sa) + av[j].y * lrelu(v[j].y + pr[j].y, sa) +
+                  av[j].z * lrelu(v[j].z + pr[j].z, sa) + av[j].w * lrelu(v[j].w + pr[j].w, sa);
         p = head_reduce(p, sh.lph);
         if (ok) {
           if (head_lane) score[(int64_t)e * sh.H + ((li + j * LPR) >> sh.lg_lph)] = p;
@@ -144,7 +146,8 @@ __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, co
     float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
     const int64_t off = (int64_t)row * sh.F + 4 * (li + j * LPR);
     if (hpre) st4(hpre + off, h);
-    st4(Hout + off, make_float4(lrelu(h.x), lrelu(h.y), lrelu(h.z), lrelu(h.w)));
+    const float sc = sh.sl.act;
+    st4(Hout + off, make_float4(lrelu(h.x, sc), lrelu(h.y, sc), lrelu(h.z, sc), lrelu(h.w, sc)));
     if (head_lane) {
       const int hd = (li + j * LPR) >> sh.lg_lph;
       mx[(int64_t)row * sh.H + hd] = st.m[j];
@@ -246,8 +249,9 @@ __device__ __forceinline__ void bwd1_load_row(Bwd1Row<NV>& r, int row, const Sha
     // sum_seg alpha*galpha = gH . Hout  because LReLU'(h) * h = LReLU(h)
     r.c[j] = head_reduce(dot4(g, ho), sh.lph);
     // EB:879-893 / EB:599: gradient through the activation, LReLU'(h) has the sign of LReLU(h)
-    r.gh[j] = make_float4(g.x * lrelu_grad(ho.x), g.y * lrelu_grad(ho.y), g.z * lrelu_grad(ho.z),
-                          g.w * lrelu_grad(ho.w));
+    const float sc = sh.sl.act;
+    r.gh[j] = make_float4(g.x * lrelu_grad(ho.x, sc), g.y * lrelu_grad(ho.y, sc), g.z * lrelu_grad(ho.z, sc),
+                          g.w * lrelu_grad(ho.w, sc));
     const int hd = (li + j * LPR) >> sh.lg_lph;
     r.m[j] = __ldg(mx + (int64_t)row * sh.H + hd);
     r.inv[j] = __ldg(sinv + (int64_t)row * sh.H + hd);
@@ -298,11 +302,12 @@ __device__ __forceinline__ void bwd1_range(Bwd1Row<NV>& r, float4 (&ga)[NV], int
         const float sx = v[j].x + r.pr[j].x, sy = v[j].y + r.pr[j].y, sz = v[j].z + r.pr[j].z,
                     sw = v[j].w + r.pr[j].w;
         // ga += ge * LReLU(s)  (EB:769)
-        ga[j].x += ge * lrelu(sx); ga[j].y += ge * lrelu(sy);
-        ga[j].z += ge * lrelu(sz); ga[j].w += ge * lrelu(sw);
+        const float sa = sh.sl.attn;
+        ga[j].x += ge * lrelu(sx, sa); ga[j].y += ge * lrelu(sy, sa);
+        ga[j].z += ge * lrelu(sz, sa); ga[j].w += ge * lrelu(sw, sa);
         // m = ge * a * LReLU'(s)  (EB:774-775) accumulated for the destination
-        r.gpr[j].x += ge * av[j].x * lrelu_grad(sx); r.gpr[j].y += ge * av[j].y * lrelu_grad(sy);
-        r.gpr[j].z += ge * av[j].z * lrelu_grad(sz); r.gpr[j].w += ge * av[j].w * lrelu_grad(sw);
+        r.gpr[j].x += ge * av[j].x * lrelu_grad(sx, sa); r.gpr[j].y += ge * av[j].y * lrelu_grad(sy, sa);
+        r.gpr[j].z += ge * av[j].z * lrelu_grad(sz, sa); r.gpr[j].w += ge * av[j].w * lrelu_grad(sw, sa);
         const uint32_t bx = __ballot_sync(0xffffffffu, sx > 0.f), by = __ballot_sync(0xffffffffu, sy > 0.f),
                        bz = __ballot_sync(0xffffffffu, sz > 0.f), bw = __ballot_sync(0xffffffffu, sw > 0.f);
         if (ok) {
@@ -475,17 +480,17 @@ __device__ __forceinline__ void bwd2_range(float4 (&acc)[NV], int first, int end
       if (ok0) {
         const float al = al0[j], ge = ge0[j];
         // EB:865-866: g_h[dst] * alpha + ge * a * LReLU'(s), LReLU'(s) from the recorded sign bit
-        acc[j].x += al * g0[j].x + ge * av[j].x * (((k0[j].x >> li) & 1u) ? 1.f : kSlope);
-        acc[j].y += al * g0[j].y + ge * av[j].y * (((k0[j].y >> li) & 1u) ? 1.f : kSlope);
-        acc[j].z += al * g0[j].z + ge * av[j].z * (((k0[j].z >> li) & 1u) ? 1.f : kSlope);
-        acc[j].w += al * g0[j].w + ge * av[j].w * (((k0[j].w >> li) & 1u) ? 1.f : kSlope);
+        acc[j].x += al * g0[j].x + ge * av[j].x * (((k0[j].x >> li) & 1u) ? 1.f : sh.sl.attn);
+        acc[j].y += al * g0[j].y + ge * av[j].y * (((k0[j].y >> li) & 1u) ? 1.f : sh.sl.attn);
+        acc[j].z += al * g0[j].z + ge * av[j].z * (((k0[j].z >> li) & 1u) ? 1.f : sh.sl.attn);
+        acc[j].w += al * g0[j].w + ge * av[j].w * (((k0[j].w >> li) & 1u) ? 1.f : sh.sl.attn);
       }
       if (ok1) {
         const float al = al1[j], ge = ge1[j];
-        acc[j].x += al * g1[j].x + ge * av[j].x * (((k1[j].x >> li) & 1u) ? 1.f : kSlope);
-        acc[j].y += al * g1[j].y + ge * av[j].y * (((k1[j].y >> li) & 1u) ? 1.f : kSlope);
-        acc[j].z += al * g1[j].z + ge * av[j].z * (((k1[j].z >> li) & 1u) ? 1.f : kSlope);
-        acc[j].w += al * g1[j].w + ge * av[j].w * (((k1[j].w >> li) & 1u) ? 1.f : kSlope);
+        acc[j].x += al * g1[j].x + ge * av[j].x * (((k1[j].x >> li) & 1u) ? 1.f : sh.sl.attn);
+        acc[j].y += al * g1[j].y + ge * av[j].y * (((k1[j].y >> li) & 1u) ? 1.f : sh.sl.attn);
+        acc[j].z += al * g1[j].z + ge * av[j].z * (((k1[j].z >> li) & 1u) ? 1.f : sh.sl.attn);
+        acc[j].w += al * g1[j].w + ge * av[j].w * (((k1[j].w >> li) & 1u) ? 1.f : sh.sl.attn);
       }
     }
   }
@@ -604,7 +609,7 @@ bool make_shape(int H, int D, Shape* sh, int* nv, int* lpr) {
   }
   int lg = 0;
   while ((1 << lg) < lph) ++lg;
-  if (sh) *sh = Shape{H, D, F, lph, lg};
+  if (sh) *sh = Shape{H, D, F, lph, lg, Slopes{kSlope, kSlope}};
   if (nv) *nv = NV;
   if (lpr) *lpr = LPR;
   return true;
@@ -644,6 +649,7 @@ int launch_edge_forward(const EdgeGraph& g, int H, int D, const float* Pl, const
   Shape sh;
   int nv, lpr, launches = 0;
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
+  sh.sl = g.slopes;
   if (g.n_rows <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
     edge_fwd_kernel<NV, LPR><<<(g.n_rows + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(
@@ -667,6 +673,7 @@ int launch_edge_backward_dst(const EdgeGraph& g, int H, int D, const float* Pl, 
   Shape sh;
   int nv, lpr, launches = 0;
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
+  sh.sl = g.slopes;
   *n_partials = 0;
   if (g.n_rows <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
@@ -700,6 +707,7 @@ int launch_edge_backward_src(const EdgeGraph& g, int H, int D, const float* a, c
   Shape sh;
   int nv, lpr, launches = 0;
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
+  sh.sl = g.slopes;
   if (g.n_src <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
     edge_bwd_src_kernel<NV, LPR><<<(g.n_src + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(

@@ -26,6 +26,7 @@ constexpr int kSW = 4;  // warps per CTA
 struct Shape {
   int H, D, F, lph, lg_lph;  // lph = D / 4: lanes per head in the node-wise kernels' layout (lane + 32 j)
   int lc, lg_lc;             // lc = 32 / H: lanes per head in the lane-contiguous layout of the edge passes
+  Slopes slopes;             // LeakyReLU slopes (set by the launchers from EdgeGraph::slopes)
 };
 
 struct StreamGraph {
@@ -34,6 +35,7 @@ struct StreamGraph {
   const int* chunk_row;  // [n_chunks] row that contains edge c*T
   uint32_t hot;          // bit of a gather index that marks an L2-resident ("hot") row; 0 = no hints in the indices
   uint32_t idx_mask;     // gather index = raw & idx_mask
+  Slopes slopes;         // LeakyReLU slopes: attention score / layer activation
 };
 // L2 policies of the gathers: hot rows evict_last, everything streamed once evict_first (plain when hints are off)
 struct GatherPolicy {
@@ -54,7 +56,8 @@ __device__ __forceinline__ float head_reduce(float p, int lph) {
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 // LeakyReLU with 0 < slope < 1 is max(x, slope*x): FMUL + FMNMX
-__device__ __forceinline__ float lrelu_fast(float x) { return fmaxf(x, kSlope * x); }
+// LeakyReLU for 0 <= slope < 1 (gatx_create rejects anything else): two instructions, no select
+__device__ __forceinline__ float lrelu_fast(float x, float slope) { return fmaxf(x, slope * x); }
 __device__ __forceinline__ float shx(float v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
 // predicated global stores: one STG with a predicate instead of a divergent branch region per store
 __device__ __forceinline__ void st_pred_u32(uint32_t* p, uint32_t v, bool pred) {
@@ -165,7 +168,8 @@ __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, co
     const float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
     const int64_t off = (int64_t)row * sh.F + lc_off<NV>(lane, j);
     if (hpre) st4(hpre + off, h);
-    st4(Hout + off, make_float4(lrelu(h.x), lrelu(h.y), lrelu(h.z), lrelu(h.w)));  // EB:440-457
+    const float sc = sh.slopes.act;
+    st4(Hout + off, make_float4(lrelu(h.x, sc), lrelu(h.y, sc), lrelu(h.z, sc), lrelu(h.w, sc)));  // EB:440-457
   }
   if ((lane & (sh.lc - 1)) == 0) {
     const int hd = lane >> sh.lg_lc;
@@ -275,8 +279,8 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       float p = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j)  // EB:303-320
-        p += av[j].x * lrelu_fast(v[j].x + pr[j].x) + av[j].y * lrelu_fast(v[j].y + pr[j].y) +
-             av[j].z * lrelu_fast(v[j].z + pr[j].z) + av[j].w * lrelu_fast(v[j].w + pr[j].w);
+        p += av[j].x * lrelu_fast(v[j].x + pr[j].x, g.slopes.attn) + av[j].y * lrelu_fast(v[j].y + pr[j].y, g.slopes.attn) +
+             av[j].z * lrelu_fast(v[j].z + pr[j].z, g.slopes.attn) + av[j].w * lrelu_fast(v[j].w + pr[j].w, g.slopes.attn);
       p = head_sum<LPH>(p, sh.lc);
       st_pred_u32(reinterpret_cast<uint32_t*>(score + (int64_t)e * sh.H + hd), __float_as_uint(p), head_lane);
       // online form of EB:336-349.  Of exp(m - max) and exp(p - max) one is exp(0) = 1: a single exponential
@@ -390,8 +394,9 @@ edge_bwd_prep_kernel(int n_rows, Shape sh, const float* __restrict__ Hout, float
       const float4 g = *reinterpret_cast<const float4*>(gH + off);
       const float4 ho = ldg4(Hout + off);
       const float c = head_reduce(dot4(g, ho), sh.lph);
-      st4(gH + off, make_float4(g.x * lrelu_grad(ho.x), g.y * lrelu_grad(ho.y), g.z * lrelu_grad(ho.z),
-                                g.w * lrelu_grad(ho.w)));
+      const float sc = sh.slopes.act;
+      st4(gH + off, make_float4(g.x * lrelu_grad(ho.x, sc), g.y * lrelu_grad(ho.y, sc), g.z * lrelu_grad(ho.z, sc),
+                                g.w * lrelu_grad(ho.w, sc)));
       if (head_lane) cdot[(int64_t)row * sh.H + ((lane + 32 * j) >> sh.lg_lph)] = c;
     }
   }
@@ -593,7 +598,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       galpha = head_sum<LPH>(galpha, sh.lc);
       const float alpha = __expf(sc[hd] - q.m) * q.inv;  // EB:378-379
       const float ge = alpha * (galpha - q.c);           // EB:689-690 in closed form
-      const float ges = ge * kSlope;
+      const float ges = ge * g.slopes.attn;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const float sx = v[j].x + pr[j].x, sy = v[j].y + pr[j].y, sz = v[j].z + pr[j].z, sw = v[j].w + pr[j].w;
@@ -776,7 +781,7 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
       }
       const float al = __uint_as_float(rw[4 * NV + hd]);  // this lane's head
       const float ge = __uint_as_float(rw[4 * NV + sh.H + hd]);
-      const float ges = ge * kSlope;
+      const float ges = ge * g.slopes.attn;
       __syncwarp();
       {
         const int ni = i + R;
@@ -825,7 +830,7 @@ bool make_stream_shape(int H, int D, Shape* sh, int* nv) {
   const int lc = 32 / H;
   int lgc = 0;
   while ((1 << lgc) < lc) ++lgc;
-  *sh = Shape{H, D, F, lph, lg, lc, lgc};
+  *sh = Shape{H, D, F, lph, lg, lc, lgc, Slopes{kSlope, kSlope}};
   *nv = NV;
   return true;
 }
@@ -891,13 +896,14 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   Shape sh;
   int nv, launches = 0;
   if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
+  sh.slopes = eg.slopes;
   if (eg.n_rows <= 0) return 0;
   fill_empty_fwd_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, sh.F, H, Hout, hpre, mx, sinv);
   ++launches;
   if (eg.E == 0) return launches;
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
-  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask};
+  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes};
   if (use_pair(nv, sh)) {  // one head of 128 floats: two edges per loop iteration
     constexpr int R = 16;
     const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
@@ -940,13 +946,14 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   Shape sh;
   int nv, launches = 0;
   if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
+  sh.slopes = eg.slopes;
   *n_partials = 0;
   if (eg.n_rows <= 0) return 0;
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
   const int* cdstx = hs.on ? eg.csc_dst_hot : eg.csc_dst;
-  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask};
-  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask};
+  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes};
+  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask, eg.slopes};
   if (use_pair(nv, sh)) {
     constexpr int R = 16, F = kPF;
     {

@@ -59,6 +59,7 @@ struct Layer {
   bool vec = true;
   int64_t w_off = 0, a_off = 0;
   float *Wcat = nullptr, *WcatT = nullptr;
+  float* Xd = nullptr;  // dropped input of the last training forward (gatx_set_dropout), allocated on first use
   float *Pl = nullptr, *Pr = nullptr, *Hfull = nullptr, *Hout = nullptr, *hpre = nullptr;
   float *score = nullptr, *mx = nullptr, *sinv = nullptr, *gH = nullptr, *gHout = nullptr;
   float *galpha_dbg = nullptr, *gPl_dbg = nullptr, *gPr_dbg = nullptr, *alpha_dbg = nullptr, *ge_dbg = nullptr;
@@ -72,6 +73,12 @@ struct gatx_ctx {
   // config
   int L = 0, optimizer = 0, clip = 0, device = 0, gemm_mode = 0, keep_debug = 0, rank = 0, world = 1;
   float lr = 1e-4f, b1 = 0.9f, b2 = 0.999f;
+  Slopes slopes{kSlope, kSlope};  // gatx_set_slopes; the reference's 0.01 / 0.01 by default
+  // dropout on every layer's input in training forwards (gatx_set_dropout; the reference has none)
+  float p_drop = 0.f;
+  uint64_t drop_seed = 0;
+  int64_t drop_step = 0;     // training forwards since gatx_set_dropout
+  bool fwd_dropped = false;  // the last training forward used dropout (the backward must use the same inputs / mask)
   std::vector<int> heads, outdims;
   std::string err;
   cudaStream_t st = nullptr;
@@ -227,7 +234,7 @@ void free_bufs(gatx_ctx* c) {
   c->peers_ready = false;
   dfree(c->barrier_word);
   for (auto& l : c->layers) {
-    dfree(l.Wcat); dfree(l.WcatT); dfree(l.Pl); dfree(l.Pr);
+    dfree(l.Wcat); dfree(l.WcatT); dfree(l.Pl); dfree(l.Pr); dfree(l.Xd);
     if (l.Hout != l.Hfull) dfree(l.Hout);
     l.Hout = nullptr;
     dfree(l.Hfull); dfree(l.hpre); dfree(l.score); dfree(l.mx); dfree(l.sinv); dfree(l.gH); dfree(l.gHout);
@@ -363,6 +370,7 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   g.chunk_T = c->chunk_T; g.n_chunks = c->n_chunks; g.chunk_row = c->chunk_row; g.chunk_src = c->chunk_src;
   g.col_idx_hot = c->col_idx_hot; g.csc_dst_hot = c->csc_dst_hot; g.hot_wide_F = c->hot_wide_F;
   g.kernel_events = nullptr;
+  g.slopes = c->slopes;
   return g;
 }
 
@@ -491,15 +499,32 @@ int do_forward(gatx_ctx* ctx) {
   if (!ctx->have_params) return fail(ctx, GATX_ERR_INVALID, "parameters not initialised");
   const EdgeGraph g = edge_graph(ctx);
   const float* X = ctx->X0 + (int64_t)ctx->r0 * ctx->ld0;
+  const float* X0all = ctx->X0;
+  const bool drop = !ctx->eval_mode && ctx->p_drop > 0.f;
+  if (drop) ++ctx->drop_step;
+  if (!ctx->eval_mode) ctx->fwd_dropped = drop;
   for (int l = 0; l < ctx->L; ++l) {
     Layer& ly = ctx->layers[l];
     const bool replicated = l == 0 && ctx->world > 1;  // layer 0 with the input features on every rank
     {
       PhaseTimer t(ctx, PH_GEMM_FWD);
+      if (drop) {
+        // layer 0 keeps every rank's copy of ALL input rows dropped identically (the mask is a pure function of the
+        // global row); deeper layers drop their own rows of the previous layer's output
+        const int rows = l == 0 ? ctx->N : ctx->n_rows, row0 = l == 0 ? 0 : ctx->r0;
+        if (!ly.Xd) {
+          CK(dalloc(&ly.Xd, (size_t)rows * ly.ldx));
+          CK(cudaMemsetAsync(ly.Xd, 0, sizeof(float) * (size_t)rows * ly.ldx, ctx->st));  // zero padding columns
+        }
+        LAUNCHED(launch_dropout(l == 0 ? ctx->X0 : X, ly.ldx, ly.Xd, ly.ldx, rows, ly.I, row0, ctx->p_drop,
+                                ctx->drop_seed, l, ctx->drop_step, ctx->st));
+        X = l == 0 ? ly.Xd + (int64_t)ctx->r0 * ly.ldx : ly.Xd;
+        X0all = ly.Xd;
+      }
       LAUNCHED(launch_pack_weights(ctx->params + ly.w_off, ly.F, ly.I, ly.Wcat, ly.ldk, ly.WcatT, ctx->st));
       // P_l = X W_l^T, P_r = X W_r^T : the only dense contraction of the forward (EB:303-316)
       if (replicated) {
-        rc = gemm_tn_any(ctx, ctx->X0, ly.ldx, ly.Wcat, ly.ldk, ly.Pl, ly.F, ctx->N, ly.F, ly.I);
+        rc = gemm_tn_any(ctx, X0all, ly.ldx, ly.Wcat, ly.ldk, ly.Pl, ly.F, ctx->N, ly.F, ly.I);
         if (!rc) rc = gemm_tn_any(ctx, X, ly.ldx, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, ly.Pr, ly.F, ctx->n_rows, ly.F, ly.I);
       } else {
         rc = gemm_project(ctx, X, ly.ldx, ly);
@@ -586,7 +611,9 @@ int do_backward(gatx_ctx* ctx) {
   }
   for (int l = ctx->L - 1; l >= 0; --l) {
     Layer& ly = ctx->layers[l];
-    const float* X = l == 0 ? ctx->X0 + (int64_t)ctx->r0 * ctx->ld0 : ctx->layers[l - 1].Hout;
+    const bool drop = ctx->fwd_dropped && ly.Xd;
+    const float* Xall = drop ? ly.Xd : ctx->X0;  // layer 0: all input rows
+    const float* X = l == 0 ? Xall + (int64_t)ctx->r0 * ctx->ld0 : (drop ? ly.Xd : ctx->layers[l - 1].Hout);
     const bool replicated = l == 0 && ctx->world > 1;
     {
       PhaseTimer t(ctx, PH_EDGE_BWD);
@@ -636,7 +663,7 @@ int do_backward(gatx_ctx* ctx) {
       // Replicated layer 0: this rank's PARTIAL gP_l over all sources is contracted with the full X; the
       // all-reduce of the weight gradients completes the sum, so gP_l itself is never exchanged.
       if (replicated)
-        rc = gemm_nt_reduce(ctx, ctx->gPl, ly.F, ctx->X0, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->N);
+        rc = gemm_nt_reduce(ctx, ctx->gPl, ly.F, Xall, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->N);
       else
         rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
@@ -648,6 +675,10 @@ int do_backward(gatx_ctx* ctx) {
         Layer& prev = ctx->layers[l - 1];
         rc = gemm_input_grad(ctx, gPl_own, ctx->gPr, ly, prev.gH, prev.F);
         if (rc) return rc;
+        // gradient w.r.t. the dropped input -> w.r.t. the previous layer's output: same mask, same scale
+        if (drop)
+          LAUNCHED(launch_dropout(prev.gH, prev.F, prev.gH, prev.F, ctx->n_rows, ly.I, ctx->r0, ctx->p_drop,
+                                  ctx->drop_seed, l, ctx->drop_step, ctx->st));
       }
     }
   }
@@ -696,7 +727,8 @@ int read_loss(gatx_ctx* ctx, float* avg_loss, float* accuracy, int64_t count) {
 constexpr int64_t kGraphAutoMaxEdges = 8 << 20;  // beyond this the kernels are long enough to hide the launches
 
 bool epoch_graph_wanted(const gatx_ctx* ctx) {
-  if (ctx->world != 1 || ctx->timing || ctx->graph_mode == 0) return false;
+  // dropout: the step counter is a kernel argument that changes every epoch
+  if (ctx->world != 1 || ctx->timing || ctx->graph_mode == 0 || ctx->p_drop > 0.f) return false;
   if (ctx->graph_mode == 1) return true;
   static const int env = [] {
     const char* e = getenv("GATX_CUDA_GRAPH");
@@ -1175,6 +1207,25 @@ int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy)
   }
   CK(cudaGetLastError());
   if (avg_loss || accuracy) return read_loss(ctx, avg_loss, accuracy, ctx->last_count);
+  return GATX_OK;
+}
+
+int gatx_set_slopes(gatx_ctx* ctx, float attn_slope, float act_slope) {
+  // the streaming kernels evaluate LeakyReLU as max(x, slope * x), valid for 0 <= slope < 1
+  if (!ctx || !(attn_slope >= 0.f && attn_slope < 1.f) || !(act_slope >= 0.f && act_slope < 1.f))
+    return fail(ctx, GATX_ERR_INVALID, "LeakyReLU slopes must lie in [0, 1)");
+  ctx->slopes = Slopes{attn_slope, act_slope};
+  ctx->fwd_valid = false;  // activations of an earlier forward no longer match
+  ++ctx->gen;              // kernel arguments of a captured epoch
+  return GATX_OK;
+}
+
+int gatx_set_dropout(gatx_ctx* ctx, float p, uint64_t seed) {
+  if (!ctx || !(p >= 0.f && p < 1.f)) return fail(ctx, GATX_ERR_INVALID, "dropout probability must lie in [0, 1)");
+  ctx->p_drop = p;
+  ctx->drop_seed = seed;
+  ctx->drop_step = 0;
+  ctx->fwd_valid = false;
   return GATX_OK;
 }
 

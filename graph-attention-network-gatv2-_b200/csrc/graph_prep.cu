@@ -123,6 +123,43 @@ int launch_philox_uniform(float* out, int64_t n, float limit, uint64_t seed, uin
   return 1;
 }
 
+// Inverted dropout (extension).  Thread per (row, 4-column group): element (n, 4q + t) is kept iff word t
+// of Philox4x32-10(counter = {q, global row, layer, step}, key = seed) >= thresh = floor(p * 2^32); kept elements are
+// scaled by 1 / (1 - p).  The backward pass re-generates the same words to mask the gradient (Y == X: in place).
+__global__ void dropout_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy, int n_rows,
+                               int cols, int row0, uint32_t thresh, float scale, uint64_t seed, uint32_t layer,
+                               uint32_t step) {
+  const int quads = (cols + 3) / 4;
+  const int64_t total = (int64_t)n_rows * quads;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / quads), q = (int)(i - (int64_t)n * quads);
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(row0 + n), layer, step};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    const float* x = X + (int64_t)n * ldx + 4 * q;
+    float* y = Y + (int64_t)n * ldy + 4 * q;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (4 * q + t < cols) y[t] = c[t] >= thresh ? x[t] * scale : 0.f;
+  }
+}
+int launch_dropout(const float* X, int64_t ldx, float* Y, int64_t ldy, int n_rows, int cols, int row0, float p,
+                   uint64_t seed, int layer, int64_t step, cudaStream_t st) {
+  if (n_rows <= 0 || cols <= 0) return 0;
+  const int64_t total = (int64_t)n_rows * ((cols + 3) / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  dropout_kernel<<<(int)blocks, 256, 0, st>>>(X, ldx, Y, ldy, n_rows, cols, row0, thresh, 1.0f / (1.0f - p), seed,
+                                             (uint32_t)layer, (uint32_t)step);
+  return 1;
+}
+
 __global__ void mark_hot_kernel(const int* __restrict__ idx, const int* __restrict__ ptr, int64_t E, int thr_wide,
                                 int thr_narrow, int* __restrict__ out) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {

@@ -190,6 +190,8 @@ struct Args {
   std::string save_ckpt, resume_ckpt;
   std::string optimizer = "sgd", dataset = "pubmed", data_root = "./data", load_w, dump_w;
   float lr = 0.0001f, beta1 = 0.9f, beta2 = 0.999f;
+  // opt-in extensions; the defaults are the reference's fixed behaviour (slopes 0.01 / 0.01, no dropout)
+  float attn_slope = 0.01f, act_slope = 0.01f, dropout = 0.0f;
   unsigned long long seed = 0;
   bool seed_given = false;
   std::vector<int> heads, outdims;
@@ -261,6 +263,9 @@ int main(int argc, char** argv) {
     else if (arg == "--load-only") a.load_only = true;
     else if (arg == "--split") a.split = true;
     else if (arg == "--eval-only") a.eval_only = true;
+    else if (arg == "--attn-slope" && i + 1 < argc) a.attn_slope = std::strtof(argv[++i], nullptr);
+    else if (arg == "--act-slope" && i + 1 < argc) a.act_slope = std::strtof(argv[++i], nullptr);
+    else if (arg == "--dropout" && i + 1 < argc) a.dropout = std::strtof(argv[++i], nullptr);
     // anything else is ignored, like the reference
   }
   if (!have_heads || !have_outdims) {
@@ -376,6 +381,7 @@ int main(int argc, char** argv) {
     if ((rc = gatx_set_features(ctx[r], X.data(), I))) { failed = fail_ctx(ctx[r], "gatx_set_features", rc); return; }
     if ((rc = gatx_set_labels(ctx[r], labels.data(), C))) { failed = fail_ctx(ctx[r], "gatx_set_labels", rc); return; }
     if (a.split && (rc = gatx_set_train_mask(ctx[r], mask[0].data()))) { failed = fail_ctx(ctx[r], "gatx_set_train_mask", rc); return; }
+    if ((a.attn_slope != 0.01f || a.act_slope != 0.01f) && (rc = gatx_set_slopes(ctx[r], a.attn_slope, a.act_slope))) { failed = fail_ctx(ctx[r], "gatx_set_slopes", rc); return; }
     // the reference seeds with time(NULL) (EB:1305); --seed makes runs reproducible
     const unsigned long long seed = a.seed_given ? a.seed : (unsigned long long)time(nullptr);
     if ((rc = gatx_init_params(ctx[r], seed))) { failed = fail_ctx(ctx[r], "gatx_init_params", rc); return; }
@@ -449,6 +455,14 @@ int main(int argc, char** argv) {
     for (int r = 0; r < world; ++r)
       if (int rc = gatx_set_state(ctx[r], stt.data(), stt.size() * sizeof(float))) return fail_ctx(ctx[r], "gatx_set_state", rc);
     first_epoch = (int)hdr[0] + 1;
+  }
+  if (a.dropout != 0.0f) {
+    // every rank draws the same mask (a function of seed, layer, step, global row, column); a resumed run continues
+    // with a fresh stream
+    const unsigned long long dseed = (a.seed_given ? a.seed : (unsigned long long)time(nullptr)) + 7919ull * (unsigned long long)first_epoch;
+    for (int r = 0; r < world; ++r)
+      if (int rc = gatx_set_dropout(ctx[r], a.dropout, dseed)) return fail_ctx(ctx[r], "gatx_set_dropout", rc);
+    std::cout << "Dropout: " << a.dropout << " on every layer's input (training forwards only)\n";
   }
   // evaluation forward on every rank; returns rank 0's (already all-reduced) scalars
   auto evaluate = [&](const unsigned char* m, float* lo, float* ac) -> int {

@@ -25,7 +25,7 @@ EXPORTS = [
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
-    "gatx_set_cuda_graph", "gatx_cuda_graph_active",
+    "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout",
 ]
 
 
@@ -253,6 +253,16 @@ class Engine:
 
     def launch_count(self):
         return self.lib.gatx_launch_count(self.ctx)
+
+    def set_slopes(self, attn_slope=0.01, act_slope=0.01):
+        """LeakyReLU slopes of the attention score / the layer activation (the reference fixes both at 0.01)"""
+        self.lib.gatx_set_slopes.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        self._ck(self.lib.gatx_set_slopes(self.ctx, attn_slope, act_slope), "gatx_set_slopes")
+
+    def set_dropout(self, p, seed=0):
+        """Inverted dropout on every layer's input in training forwards (Philox, reproducible); p = 0 switches it off"""
+        self.lib.gatx_set_dropout.argtypes = [C.c_void_p, C.c_float, C.c_uint64]
+        self._ck(self.lib.gatx_set_dropout(self.ctx, p, seed), "gatx_set_dropout")
 
     def set_cuda_graph(self, mode):
         """-1 auto, 0 eager launches, 1 replay forward + backward of train_epoch as one CUDA graph"""

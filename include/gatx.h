@@ -132,6 +132,18 @@ int gatx_init_params(gatx_ctx* ctx, uint64_t seed);
 int gatx_set_params(gatx_ctx* ctx, int32_t layer, const float* W, const float* a);
 int gatx_set_wo(gatx_ctx* ctx, const float* Wo);
 
+/* Extension: the two LeakyReLU slopes, both fixed at 0.01 in the reference -- attn_slope inside the
+ * attention score a . LReLU(W_l x_j + W_r x_i) (EB:1143; GATv2's negative_slope, 0.2 in the paper) and act_slope of
+ * the layer activation (EB:1428).  0 <= slope < 1 (0 = ReLU).  Not calling it keeps the reference behaviour. */
+int gatx_set_slopes(gatx_ctx* ctx, float attn_slope, float act_slope);
+/* Extension (the reference has no dropout): inverted dropout with probability p on the INPUT of every
+ * layer (features, then each hidden representation) in training forwards -- gatx_forward / gatx_train_epoch; never in
+ * gatx_evaluate.  Element (global node n, column c) of layer l in the k-th training forward since this call is kept
+ * iff word c % 4 of Philox4x32-10(counter {c / 4, n, l, k}, key seed) >= floor(p * 2^32), and scaled by 1 / (1 - p):
+ * reproducible, identical on every rank of a partitioned run, re-generated (not stored) by the backward pass.
+ * p = 0 switches it off.  0 <= p < 1. */
+int gatx_set_dropout(gatx_ctx* ctx, float p, uint64_t seed);
+
 /* ---- the epoch (EB:1370-1642) ----------------------------------------------------------- */
 /* EB:1375-1452: per layer projection + score + segmented softmax + aggregation + activation,
  * then classifier + softmax. */

@@ -34,8 +34,17 @@
 
 #define ORC_SLOPE 0.01f
 
-static inline float lrelu_f(float x) { return x > 0.0f ? x : ORC_SLOPE * x; }
-static inline double lrelu_d(double x) { return x > 0.0 ? x : (double)ORC_SLOPE * x; }
+/* Extension: the reference hard-codes 0.01 for both LeakyReLUs; the engine's opt-in gatx_set_slopes is
+ * checked against the same formulas with these two values (process-wide: the oracle is a test fixture). */
+static float g_attn_slope = ORC_SLOPE; /* inside the attention score, EB:1143 */
+static float g_act_slope = ORC_SLOPE;  /* layer activation, EB:1428 */
+void orc_set_slopes(float attn, float act) {
+  g_attn_slope = attn;
+  g_act_slope = act;
+}
+
+static inline float lrelu_f(float x, float slope) { return x > 0.0f ? x : slope * x; }
+static inline double lrelu_d(double x, float slope) { return x > 0.0 ? x : (double)slope * x; }
 
 /* ------------------------------------------------------------------ graph prep */
 
@@ -152,7 +161,7 @@ void orc_layer_forward(int N, const int* row_ptr, const int* col_idx, int H, int
       for (int e = beg; e < end; ++e) {
         const float* pl = Pl + (size_t)col_idx[e] * F + (size_t)h * D;
         double acc = 0.0;
-        for (int k = 0; k < D; ++k) acc += (double)ah[k] * lrelu_d((double)pl[k] + (double)pr[k]);
+        for (int k = 0; k < D; ++k) acc += (double)ah[k] * lrelu_d((double)pl[k] + (double)pr[k], g_attn_slope);
         float sc = (float)acc;
         score[(size_t)h * E + e] = sc;
         if (sc > m) m = sc;
@@ -177,11 +186,11 @@ void orc_layer_forward(int N, const int* row_ptr, const int* col_idx, int H, int
     if (is_last) {
       for (int k = 0; k < D; ++k) {
         double acc = 0.0;
-        for (int h = 0; h < H; ++h) acc += lrelu_d((double)hpre[((size_t)i * H + h) * D + k]);
+        for (int h = 0; h < H; ++h) acc += lrelu_d((double)hpre[((size_t)i * H + h) * D + k], g_act_slope);
         Hout[(size_t)i * D + k] = (float)(acc / (double)H);
       }
     } else {
-      for (int r = 0; r < F; ++r) Hout[(size_t)i * F + r] = lrelu_f(hpre[(size_t)i * F + r]);
+      for (int r = 0; r < F; ++r) Hout[(size_t)i * F + r] = lrelu_f(hpre[(size_t)i * F + r], g_act_slope);
     }
   }
 }
@@ -278,7 +287,7 @@ void orc_output_grads_masked(int N, int C, int DL, int Hl, const float* y, const
       for (int c = 0; c < C; ++c) s += (double)Wo[(size_t)c * DL + d] * dz[c];
       for (int h = 0; h < Hl; ++h) {
         float hv = hpre_last[((size_t)n * Hl + h) * DL + d];
-        double der = hv > 0.0f ? 1.0 : (double)ORC_SLOPE;
+        double der = hv > 0.0f ? 1.0 : (double)g_act_slope;
         g_h[((size_t)n * Hl + h) * DL + d] = (float)(s * der / (double)Hl);
       }
     }
@@ -333,8 +342,8 @@ void orc_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, in
         const double gee = (double)gef;
         for (int k = 0; k < D; ++k) {
           double s = (double)pl[k] + (double)pr[k];
-          gad[(size_t)h * D + k] += gee * lrelu_d(s);
-          double mk = gee * (double)ah[k] * (s > 0.0 ? 1.0 : (double)ORC_SLOPE);
+          gad[(size_t)h * D + k] += gee * lrelu_d(s, g_attn_slope);
+          double mk = gee * (double)ah[k] * (s > 0.0 ? 1.0 : (double)g_attn_slope);
           gPr[(size_t)i * F + (size_t)h * D + k] += mk;
           gPl[(size_t)j * F + (size_t)h * D + k] += al * (double)gh[k] + mk;
         }
@@ -381,7 +390,7 @@ void orc_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, in
 
 /* EB:879-893: g[n][d] *= LReLU'(h_pre_prev[n][d]). */
 void orc_preact_grad(int N, int I, const float* hpre_prev, float* g) {
-  for (size_t t = 0; t < (size_t)N * I; ++t) g[t] = g[t] * (hpre_prev[t] > 0.0f ? 1.0f : ORC_SLOPE);
+  for (size_t t = 0; t < (size_t)N * I; ++t) g[t] = g[t] * (hpre_prev[t] > 0.0f ? 1.0f : g_act_slope);
 }
 
 /* ---------------------------------------------------------------------- update */
@@ -440,7 +449,7 @@ void orc_lit_layer_forward(int N, const int* row_ptr, const int* col_idx, int H,
           float acc = 0.f;
           for (int d = 0; d < I; ++d) acc += wk[d] * xs[d];
           for (int d = 0; d < I; ++d) acc += wk[I + d] * xd[d];
-          ev += a[(size_t)h * D + k] * lrelu_f(acc);
+          ev += a[(size_t)h * D + k] * lrelu_f(acc, g_attn_slope);
         }
         score[(size_t)h * E + e] = ev;
       }
@@ -470,11 +479,11 @@ void orc_lit_layer_forward(int N, const int* row_ptr, const int* col_idx, int H,
     if (is_last) {
       for (int k = 0; k < D; ++k) {
         float sum = 0.f;
-        for (int h = 0; h < H; ++h) sum += lrelu_f(hpre[((size_t)i * H + h) * D + k]);
+        for (int h = 0; h < H; ++h) sum += lrelu_f(hpre[((size_t)i * H + h) * D + k], g_act_slope);
         Hout[(size_t)i * D + k] = sum / (float)H;
       }
     } else {
-      for (int r = 0; r < F; ++r) Hout[(size_t)i * F + r] = lrelu_f(hpre[(size_t)i * F + r]);
+      for (int r = 0; r < F; ++r) Hout[(size_t)i * F + r] = lrelu_f(hpre[(size_t)i * F + r], g_act_slope);
     }
   }
 }
@@ -523,8 +532,8 @@ void orc_lit_layer_backward(int N, const int* row_ptr, const int* col_idx, int H
           float s = 0.f;
           for (int q = 0; q < I; ++q) s += wk[q] * xs[q];
           for (int q = 0; q < I; ++q) s += wk[I + q] * xd[q];
-          ga[(size_t)h * D + k] += dl * lrelu_f(s);
-          float der = s > 0.f ? 1.f : ORC_SLOPE;
+          ga[(size_t)h * D + k] += dl * lrelu_f(s, g_attn_slope);
+          float der = s > 0.f ? 1.f : g_attn_slope;
           float common = dl * a[(size_t)h * D + k] * der;
           float gd = g_h[((size_t)i * H + h) * D + k];
           float* gw = gW + ((size_t)h * D + k) * 2 * I;
@@ -557,6 +566,11 @@ typedef struct orc_model {
   int optimizer; /* 0 sgd, 1 adam */
   int clip;
   float lr, b1, b2;
+  /* extension: dropout on every layer's input during training forwards */
+  float p_drop;
+  uint64_t drop_seed;
+  int64_t drop_step; /* number of training forwards since orc_model_set_dropout */
+  float** Xd;        /* per layer: the dropped, rescaled input [N][indims[l]] (allocated on first use) */
 } orc_model;
 
 static float* falloc(size_t n) { return (float*)calloc(n > 0 ? n : 1, sizeof(float)); }
@@ -574,7 +588,7 @@ orc_model* orc_model_create(int L, const int* heads, const int* outdims, int N, 
   m->indims = (int*)malloc(sizeof(int) * L);
 #define PP(field) m->field = (float**)calloc(L, sizeof(float*))
   PP(W); PP(a); PP(gW); PP(ga); PP(mW); PP(vW); PP(ma); PP(va);
-  PP(Pl); PP(Pr); PP(score); PP(alpha); PP(mx); PP(sm); PP(hpre); PP(Hout); PP(g_h);
+  PP(Pl); PP(Pr); PP(score); PP(alpha); PP(mx); PP(sm); PP(hpre); PP(Hout); PP(g_h); PP(Xd);
 #undef PP
   for (int l = 0; l < L; ++l) {
     m->heads[l] = heads[l];
@@ -602,11 +616,11 @@ void orc_model_destroy(orc_model* m) {
     free(m->W[l]); free(m->gW[l]); free(m->mW[l]); free(m->vW[l]);
     free(m->a[l]); free(m->ga[l]); free(m->ma[l]); free(m->va[l]);
     free(m->Pl[l]); free(m->Pr[l]); free(m->score[l]); free(m->alpha[l]);
-    free(m->mx[l]); free(m->sm[l]); free(m->hpre[l]); free(m->Hout[l]); free(m->g_h[l]);
+    free(m->mx[l]); free(m->sm[l]); free(m->hpre[l]); free(m->Hout[l]); free(m->g_h[l]); free(m->Xd[l]);
   }
   free(m->W); free(m->a); free(m->gW); free(m->ga); free(m->mW); free(m->vW); free(m->ma);
   free(m->va); free(m->Pl); free(m->Pr); free(m->score); free(m->alpha); free(m->mx); free(m->sm);
-  free(m->hpre); free(m->Hout); free(m->g_h);
+  free(m->hpre); free(m->Hout); free(m->g_h); free(m->Xd);
   free(m->Wo); free(m->gWo); free(m->mWo); free(m->vWo); free(m->z); free(m->y);
   free(m->heads); free(m->outdims); free(m->indims);
   free(m);
@@ -646,11 +660,61 @@ float* orc_model_tensor(orc_model* m, int which, int l) {
   }
 }
 
-/* Forward of all layers + classifier (EB:1375-1452). */
-void orc_model_forward(orc_model* m) {
+/* ---- dropout (extension; the reference has none) --------------------------------------------------
+ * Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11), restated from the
+ * paper: multipliers 0xD2511F53 / 0xCD9E8D57, Weyl key increments 0x9E3779B9 / 0xBB67AE85, ten rounds.
+ * Pinned by the Random123 known-answer vectors in tests/test_oracle.py. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* Inverted dropout of a row-major [n_rows][cols] block whose first row is global row `row0`:
+ * element (n, 4q + t) is kept iff word t of Philox(counter = {q, n, layer, step}, key = seed) >= floor(p * 2^32),
+ * kept elements are scaled by 1 / (1 - p).  The same rule masks the gradient in the backward pass. */
+void orc_dropout(const float* X, float* Y, int n_rows, int cols, int row0, float p, uint64_t seed, int layer,
+                 int64_t step) {
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  const float scale = 1.0f / (1.0f - p);
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int n = 0; n < n_rows; ++n)
+    for (int q = 0; q * 4 < cols; ++q) {
+      uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(row0 + n), (uint32_t)layer, (uint32_t)step}, r[4];
+      orc_philox4x32_10(ctr, key, r);
+      for (int t = 0; t < 4 && q * 4 + t < cols; ++t) {
+        size_t i = (size_t)n * cols + (size_t)q * 4 + t;
+        Y[i] = r[t] >= thresh ? X[i] * scale : 0.0f;
+      }
+    }
+}
+
+void orc_model_set_dropout(orc_model* m, float p, uint64_t seed) {
+  m->p_drop = p;
+  m->drop_seed = seed;
+  m->drop_step = 0;
+}
+
+static void model_forward(orc_model* m, int training) {
   const float* X = m->X0;
+  const int drop = training && m->p_drop > 0.0f;
+  if (drop) ++m->drop_step;
   for (int l = 0; l < m->L; ++l) {
     int H = m->heads[l], D = m->outdims[l], I = m->indims[l];
+    if (drop) {
+      if (!m->Xd[l]) m->Xd[l] = falloc((size_t)m->N * I);
+      orc_dropout(X, m->Xd[l], m->N, I, 0, m->p_drop, m->drop_seed, l, m->drop_step);
+      X = m->Xd[l];
+    }
     orc_project(m->N, I, H * D, X, m->W[l], m->Pl[l], m->Pr[l]);
     orc_layer_forward(m->N, m->row_ptr, m->col_idx, H, D, m->Pl[l], m->Pr[l], m->a[l],
                       l == m->L - 1, m->score[l], m->alpha[l], m->mx[l], m->sm[l], m->hpre[l],
@@ -659,6 +723,11 @@ void orc_model_forward(orc_model* m) {
   }
   orc_head_forward(m->N, m->C, m->outdims[m->L - 1], m->Wo, X, m->z, m->y);
 }
+
+/* Forward of all layers + classifier (EB:1375-1452); a training forward (dropout active when set). */
+void orc_model_forward(orc_model* m) { model_forward(m, 1); }
+/* Evaluation forward: never any dropout. */
+void orc_model_forward_eval(orc_model* m) { model_forward(m, 0); }
 
 void orc_model_set_mask(orc_model* m, const unsigned char* mask) { m->mask = mask; }
 
@@ -673,11 +742,14 @@ void orc_model_backward(orc_model* m) {
                           m->Hout[L - 1], m->Wo, m->gWo, m->g_h[L - 1]);
   for (int l = L - 1; l >= 0; --l) {
     int H = m->heads[l], D = m->outdims[l], I = m->indims[l];
-    const float* X = l > 0 ? m->Hout[l - 1] : m->X0;
+    const int drop = m->p_drop > 0.0f && m->drop_step > 0 && m->Xd[l];
+    const float* X = drop ? m->Xd[l] : (l > 0 ? m->Hout[l - 1] : m->X0);
     float* gX = l > 0 ? m->g_h[l - 1] : NULL;
     orc_layer_backward(m->N, m->row_ptr, m->col_idx, H, D, I, X, m->W[l], m->a[l], m->Pl[l],
                        m->Pr[l], m->alpha[l], m->g_h[l], m->gW[l], m->ga[l], gX, NULL, NULL, NULL,
                        NULL);
+    /* gradient w.r.t. the dropped input -> w.r.t. the previous layer's output: same mask, same scale */
+    if (l > 0 && drop) orc_dropout(gX, gX, m->N, I, 0, m->p_drop, m->drop_seed, l, m->drop_step);
     if (l > 0) orc_preact_grad(m->N, I, m->hpre[l - 1], gX);
   }
 }

@@ -241,8 +241,12 @@ class Model:
         self._mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         lib().orc_model_set_mask(self._m, None if mask is None else self._mask.ctypes.data_as(C.c_void_p))
 
-    def forward(self):
-        lib().orc_model_forward(self._m)
+    def set_dropout(self, p, seed):
+        """Dropout on every layer's input in training forwards; resets the step counter."""
+        lib().orc_model_set_dropout(self._m, C.c_float(p), C.c_uint64(seed))
+
+    def forward(self, train=True):
+        (lib().orc_model_forward if train else lib().orc_model_forward_eval)(self._m)
 
     def loss(self):
         avg, acc = C.c_float(), C.c_float()
@@ -260,6 +264,28 @@ class Model:
         avg, acc = C.c_float(), C.c_float()
         lib().orc_model_epoch(self._m, t, C.byref(avg), C.byref(acc))
         return avg.value, acc.value
+
+
+def set_slopes(attn=0.01, act=0.01):
+    """LeakyReLU slopes of the attention score / layer activation (process-wide; the reference fixes 0.01 / 0.01)."""
+    lib().orc_set_slopes(C.c_float(attn), C.c_float(act))
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in ctr])
+    k = (C.c_uint32 * 2)(*[int(v) & 0xFFFFFFFF for v in key])
+    out = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, out)
+    return [int(v) for v in out]
+
+
+def dropout(X, p, seed, layer, step, row0=0):
+    """Inverted dropout of a [rows][cols] block (keep rule and scale documented at orc_dropout)."""
+    X = f32(X)
+    Y = np.empty_like(X)
+    lib().orc_dropout(fp(X), fp(Y), X.shape[0], X.shape[1], row0, C.c_float(p), C.c_uint64(seed), layer,
+                      C.c_int64(step))
+    return Y
 
 
 def num_threads():

@@ -111,6 +111,33 @@ def test_checkpoint_resume_is_bit_exact(cli, tmp_path):
         assert (tmp_path / "a" / f).read_bytes() == (tmp_path / "b" / f).read_bytes(), f
 
 
+@pytest.mark.gpu
+def test_extension_flags(cli, tmp_path):
+    """--attn-slope / --act-slope / --dropout are opt-in: absent (or at the reference values) the loss curve is the
+    default one bit for bit; present they change it, reproducibly for a fixed --seed."""
+    sys.path.insert(0, PKG)
+    import datasets
+    datasets.write_txt(str(tmp_path / "sample"), datasets.make_dataset("sample"))
+    base = ["--heads", "8,1", "--outdims", "8,8", "--optimizer", "adam", "--lr", "0.01", "--dataset", "sample",
+            "--data-root", str(tmp_path), "--seed", "5", "--epochs", "5"]
+
+    def losses(*extra):
+        r = run(cli, *(base + list(extra)))
+        assert r.returncode == 0, r.stderr
+        return re.findall(r"Avg Loss: ([0-9.]+)", r.stdout), r.stdout
+
+    default, out = losses()
+    assert len(default) == 5 and "Dropout" not in out
+    assert losses("--attn-slope", "0.01", "--act-slope", "0.01", "--dropout", "0")[0] == default
+    slope, _ = losses("--attn-slope", "0.2")
+    assert slope != default and slope[0] != default[0]  # the very first forward already differs
+    drop, out = losses("--dropout", "0.4")
+    assert "Dropout: 0.4" in out and drop != default
+    assert losses("--dropout", "0.4")[0] == drop
+    r = run(cli, *(base + ["--dropout", "1.5"]))
+    assert r.returncode == 1 and "gatx_set_dropout" in r.stderr
+
+
 def test_split_file_errors(cli, tmp_path):
     """--split: <dataset>/split.txt must hold one token in {0, 1, 2} per node (checked before any GPU work)."""
     sys.path.insert(0, PKG)

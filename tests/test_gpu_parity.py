@@ -369,3 +369,76 @@ def test_cuda_graph_replay_is_bit_identical(gatx, mode):
     assert np.array_equal(eager.tensor(gatx.T_PRED), graph.tensor(gatx.T_PRED))
     eager.close()
     graph.close()
+
+
+# one shape per edge-kernel family: narrow rows, streaming (128 / 512-float rows) + pair (single head x 128), generic
+EXT_SHAPES = [SHAPES[0], SHAPES[7], SHAPES[6], SHAPES[8]]
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("shape", EXT_SHAPES, ids=["narrow", "stream", "pair", "generic"])
+def test_slopes_and_dropout_parity(gatx, orc, shape, mode):
+    """Opt-in extensions: gatx_set_slopes (attention / activation LeakyReLU slopes) and gatx_set_dropout
+    (Philox input dropout) against the oracle's same-named variants: two training epochs, so the second uses new
+    masks and updated weights, then an evaluation forward without dropout."""
+    N, E, I, C, heads, outdims, kind, hub = shape
+    p = make_problem(N, E, I, C, heads, outdims, kind, seed=N + 1, hub=hub)
+    ft, bt = FWD_TOL[mode], BWD_TOL[mode]
+    L = len(heads)
+    try:
+        orc.set_slopes(0.2, 0.05)
+        eng = make_engine(gatx, p, gemm_mode=mode, keep_debug=True, optimizer="sgd", lr=1e-4)
+        ref = make_oracle(orc, p, optimizer="sgd", lr=1e-4)
+        eng.set_slopes(0.2, 0.05)
+        eng.set_dropout(0.3, 4242)
+        ref.set_dropout(0.3, 4242)
+        for t in (1, 2):
+            eng.forward()
+            loss, _ = eng.loss_acc()
+            ref.forward()
+            rl = ref.loss()
+            for l in range(L):
+                # P_l = dropout(X) W_l^T: one wrong mask bit would move an element by O(1)
+                assert rel_err(eng.tensor(gatx.T_PL, l), ref.tensor(orc.T_PL, l).ravel()) < ft * t, ("Pl", l, t)
+                assert rel_err(eng.tensor(gatx.T_HOUT, l), ref.tensor(orc.T_HOUT, l).ravel()) < ft * 2 * t, ("Hout", l, t)
+            assert abs(loss - rl["avg"]) < max(ft * 5, 1e-5) * t * max(1.0, abs(rl["avg"]))
+            eng.backward()
+            ref.backward()
+            for l in range(L):
+                assert rel_err(eng.tensor(gatx.T_GW, l), ref.tensor(orc.T_GW, l).ravel()) < bt * t, ("gW", l, t)
+                assert rel_err(eng.tensor(gatx.T_GA, l), ref.tensor(orc.T_GA, l).ravel(), floor=1e-2) < bt * t, ("ga", l, t)
+            assert rel_err(eng.tensor(gatx.T_GWO), ref.tensor(orc.T_GWO).ravel()) < bt * t
+            eng.step(t)
+            ref.step(t)
+        ev = eng.evaluate(None)
+        ref.forward(train=False)
+        rl = ref.loss()
+        assert abs(ev[0] - rl["avg"]) < max(ft * 10, 1e-4) * max(1.0, abs(rl["avg"]))
+        with pytest.raises(gatx.GatxError):
+            eng.backward()  # an evaluation forward does not feed a backward
+        # dropout off again == never switched on (same weights, same forward)
+        eng.set_dropout(0.0)
+        eng.forward()
+        assert eng.loss_acc() == ev
+        with pytest.raises(gatx.GatxError):
+            eng.set_slopes(1.5, 0.01)
+        with pytest.raises(gatx.GatxError):
+            eng.set_dropout(1.0)
+        eng.close()
+    finally:
+        orc.set_slopes(0.01, 0.01)
+
+
+def test_dropout_reproducible_and_graph_free(gatx):
+    """Same seed -> bit-identical training; another seed -> another trajectory; dropout keeps the epoch off the CUDA-graph
+    replay (its step counter is a kernel argument)."""
+    p = make_problem(400, 3000, 24, 5, (4, 1), (32, 16), "rmat", seed=9)
+    runs = []
+    for seed in (5, 5, 6):
+        eng = make_engine(gatx, p, optimizer="adam", lr=0.01)
+        eng.set_dropout(0.5, seed)
+        runs.append([eng.train_epoch(t) for t in range(1, 6)])
+        assert not eng.cuda_graph_active()
+        eng.close()
+    assert runs[0] == runs[1]
+    assert runs[0] != runs[2]

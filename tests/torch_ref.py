@@ -10,11 +10,13 @@ import torch
 SLOPE = 0.01
 
 
-def lrelu(x):
-    return torch.where(x > 0, x, SLOPE * x)
+def lrelu(x, slope=SLOPE):
+    return torch.where(x > 0, x, slope * x)
 
 
-def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch.float64, mask=None):
+def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch.float64, mask=None,
+            attn_slope=SLOPE, act_slope=SLOPE, in_scale=None):
+    """in_scale: optional per-layer [N][I_l] arrays multiplied into each layer's input (a dropout mask / (1 - p))."""
     N = len(row_ptr) - 1
     deg = np.diff(row_ptr)
     src = torch.as_tensor(np.asarray(col_idx), dtype=torch.long)
@@ -26,10 +28,12 @@ def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch
     for l, (H, D) in enumerate(zip(heads, outdims)):
         I = x.shape[1]
         W, a = Ws[l], As[l]
+        if in_scale is not None:
+            x = x * torch.as_tensor(np.asarray(in_scale[l], np.float64), dtype=dtype)
         Pl = x @ W[:, :I].T
         Pr = x @ W[:, I:].T
         s = (Pl[src] + Pr[dst]).view(E, H, D)
-        score = (lrelu(s) * a.view(1, H, D)).sum(-1)  # [E, H]
+        score = (lrelu(s, attn_slope) * a.view(1, H, D)).sum(-1)  # [E, H]
         m = torch.full((N, H), -1e9, dtype=dtype).scatter_reduce(
             0, dst[:, None].expand(E, H), score.detach(), "amax", include_self=True)
         ex = torch.exp(score - m[dst])
@@ -37,9 +41,9 @@ def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch
         alpha = ex / (ssum[dst] + 1e-8)
         h = torch.zeros((N, H, D), dtype=dtype).index_add(0, dst, alpha[:, :, None] * Pl[src].view(E, H, D))
         if l == L - 1:
-            Hout = lrelu(h).mean(1)
+            Hout = lrelu(h, act_slope).mean(1)
         else:
-            Hout = lrelu(h).reshape(N, H * D)
+            Hout = lrelu(h, act_slope).reshape(N, H * D)
         for k, v in (("Pl", Pl), ("Pr", Pr), ("score", score.T), ("alpha", alpha.T),
                      ("hpre", h.reshape(N, H * D)), ("Hout", Hout)):
             out[k].append(v)
@@ -57,11 +61,11 @@ def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch
     return out
 
 
-def forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, mask=None):
+def forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, mask=None, **kw):
     tW = [torch.tensor(np.asarray(w, np.float64), requires_grad=True) for w in Ws]
     tA = [torch.tensor(np.asarray(a, np.float64), requires_grad=True) for a in As]
     tWo = torch.tensor(np.asarray(Wo, np.float64), requires_grad=True)
-    out = forward(tW, tA, tWo, np.asarray(X, np.float64), row_ptr, col_idx, heads, outdims, labels, mask=mask)
+    out = forward(tW, tA, tWo, np.asarray(X, np.float64), row_ptr, col_idx, heads, outdims, labels, mask=mask, **kw)
     out["loss_sum"].backward()
     grads = dict(gW=[w.grad.numpy() for w in tW], ga=[a.grad.numpy() for a in tA], gWo=tWo.grad.numpy())
     vals = {k: ([t.detach().numpy() for t in v] if isinstance(v, list) else v.detach().numpy())
