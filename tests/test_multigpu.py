@@ -119,8 +119,11 @@ def test_two_ranks_match_one(world, p2p):
     eng.close()
 
 
-def test_cli_two_gpus_matches_one(tmp_path):
-    """train_gatx --gpus 2 (two host threads, two contexts in one process) prints the same curve as --gpus 1."""
+@pytest.mark.parametrize("extra", [[], ["--dropout", "0.3", "--attn-slope", "0.2", "--act-slope", "0.05"]],
+                         ids=["reference-model", "slopes+dropout"])
+def test_cli_two_gpus_matches_one(tmp_path, extra):
+    """train_gatx --gpus 2 (two host threads, two contexts in one process) prints the same curve as --gpus 1; with
+    dropout every rank must draw the mask of the GLOBAL row (layer 0 drops its replicated copy of all input rows)."""
     import re
     import subprocess
     if torch.cuda.device_count() < 2:
@@ -132,7 +135,7 @@ def test_cli_two_gpus_matches_one(tmp_path):
     ds = datasets.make_dataset("arxiv", 0.05)
     datasets.write_txt(str(tmp_path / "g"), ds)
     base = [cli, "--num-layers", "3", "--heads", "4,4,1", "--outdims", "64,64,64", "--epochs", "6", "--optimizer", "adam",
-            "--lr", "0.01", "--dataset", "g", "--data-root", str(tmp_path), "--seed", "3", "--gemm", "fp32"]
+            "--lr", "0.01", "--dataset", "g", "--data-root", str(tmp_path), "--seed", "3", "--gemm", "fp32"] + extra
     curves = []
     for gpus in ("1", "2"):
         r = subprocess.run(base + ["--gpus", gpus], capture_output=True, text=True, timeout=300)
