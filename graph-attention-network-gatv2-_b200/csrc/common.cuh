@@ -76,6 +76,7 @@ struct EdgeGraph {
   // (fwd, bwd pass 1, bwd pass 2); null = no timing
   cudaEvent_t* kernel_events;  // [6] = {fwd_a, fwd_b, dst_a, dst_b, src_a, src_b}
   Slopes slopes;               // LeakyReLU slopes of the layer being launched
+  const float* bias;           // [F] added to the aggregate before the activation (extension); nullptr = none (reference)
 };
 constexpr int kHeavyDeg = 1024;
 bool edge_shape_supported(int H, int D);
@@ -99,6 +100,9 @@ int launch_reduce_partials(const float* partials, int n_partials, int n, float* 
 int launch_unpack_rec(const uint32_t* rec, int64_t E, int H, int D, float* alpha, float* ge, cudaStream_t st);
 int launch_alpha_from_score(const float* score, const int* coo_dst, const float* mx, const float* sinv, int64_t E,
                             int H, float* alpha, cudaStream_t st);
+// out[c] (+)= sum over rows of M[row][c] (fixed order: per-block partials in `partials`, >= kColsumBlocks * cols floats)
+constexpr int kColsumBlocks = kNumSMs * 2;
+int launch_colsum(const float* M, int n_rows, int cols, float* partials, float* out, bool accumulate, cudaStream_t st);
 int launch_head_mean(const float* Hfull, int N, int H, int D, float* Hout, cudaStream_t st);
 int launch_head_bcast_grad(const float* gHout, int N, int H, int D, float* gHfull, cudaStream_t st);
 

@@ -34,7 +34,7 @@ template <int T>
 __global__ void __launch_bounds__(kGW * 32)
 edge_fwd_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                         const float* __restrict__ Pl, const float* __restrict__ Pr, const float* __restrict__ a, int H,
-                        int D, Slopes sl, float* __restrict__ Hout, float* __restrict__ hpre, float* __restrict__ score,
+                        int D, Slopes sl, const float* __restrict__ bias, float* __restrict__ Hout, float* __restrict__ hpre, float* __restrict__ score,
                         float* __restrict__ mx, float* __restrict__ sinv) {
   __shared__ float sc_s[kGW][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, F = H * D;
@@ -83,7 +83,7 @@ edge_fwd_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* 
     const int k = lane + 32 * t;
     if (k < F) {
       const float inv = 1.0f / (s[t] + 1e-8f);  // EB:379
-      const float h = acc[t] * inv;
+      const float h = acc[t] * inv + (bias ? bias[k] : 0.f);
       if (hpre) hpre[(int64_t)row * F + k] = h;
       Hout[(int64_t)row * F + k] = lrelu(h, sl.act);
       if (k % D == 0) {
@@ -99,7 +99,8 @@ template <int T>
 __global__ void __launch_bounds__(kGW * 32)
 edge_bwd_dst_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                             const float* __restrict__ Pl, const float* __restrict__ Pr, const float* __restrict__ a,
-                            int H, int D, Slopes sl, const float* __restrict__ Hout, float* __restrict__ gH,
+                            int H, int D, Slopes sl, const float* __restrict__ bias, const float* __restrict__ Hout,
+                            float* __restrict__ gH,
                             const float* __restrict__ score, const float* __restrict__ mx,
                             const float* __restrict__ sinv, float* __restrict__ gPr, float* __restrict__ rec, int RW,
                             float* __restrict__ ga_partials, float* __restrict__ galpha_dbg) {
@@ -123,8 +124,9 @@ edge_bwd_dst_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const i
       const float g = k < F ? gH[(int64_t)row * F + k] : 0.f;
       const float ho = k < F ? __ldg(Hout + (int64_t)row * F + k) : 0.f;
       pr[t] = k < F ? __ldg(Pr + (int64_t)row * F + k) : 0.f;
-      cdot[t] = g * ho;                 // sum over the segment of alpha*galpha = gH . Hout
       gh[t] = g * lrelu_grad(ho, sl.act);      // EB:879-893 / EB:599
+      // sum over the segment of alpha*galpha = g_pre . h = gH . Hout  (- g_pre . bias when the aggregate carries one)
+      cdot[t] = g * ho - ((bias && k < F) ? gh[t] * __ldg(bias + k) : 0.f);
       gpr[t] = 0.f;
       if (k < F) gH[(int64_t)row * F + k] = gh[t];
     }
@@ -265,7 +267,7 @@ int launch_edge_forward_generic(const EdgeGraph& g, int H, int D, const float* P
   if (!edge_generic_supported(H, D) || tv < 0) return -1;
   if (g.n_rows <= 0) return 0;
   GENERIC_DISPATCH(tv, edge_fwd_generic_kernel<T><<<(g.n_rows + kGW - 1) / kGW, kGW * 32, 0, st>>>(
-                           g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, Hout, hpre, score, mx, sinv));
+                           g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, g.bias, Hout, hpre, score, mx, sinv));
   return 1;
 }
 
@@ -281,8 +283,8 @@ int launch_edge_backward_generic(const EdgeGraph& g, int H, int D, const float* 
   int blocks = (g.n_rows + kGW - 1) / kGW;
   if (blocks > kGenericBwdBlocks) blocks = kGenericBwdBlocks;
   GENERIC_DISPATCH(tv, {
-    edge_bwd_dst_generic_kernel<T><<<blocks, kGW * 32, 0, st>>>(g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, Hout,
-                                                                gH,
+    edge_bwd_dst_generic_kernel<T><<<blocks, kGW * 32, 0, st>>>(g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, g.bias,
+                                                                Hout, gH,
                                                                 score, mx, sinv, gPr, reinterpret_cast<float*>(rec), RW,
                                                                 ga_partials, galpha_dbg);
     edge_bwd_src_generic_kernel<T><<<(g.n_src + kGW - 1) / kGW, kGW * 32, 0, st>>>(

@@ -33,6 +33,7 @@ constexpr int kHeavyWarps = 16;  // warps per CTA for the CTA-per-heavy-row kern
 struct Shape {
   int H, D, F, lph, lg_lph;  // lph = D/4 chunks (lanes) per head
   Slopes sl;                 // LeakyReLU slopes (set by the launchers from EdgeGraph::slopes)
+  const float* bias;         // [F] or nullptr (EdgeGraph::bias)
 };
 
 __device__ __forceinline__ float head_reduce(float p, int lph) {
@@ -144,6 +145,10 @@ __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, co
   for (int j = 0; j < NV; ++j) {
     const float inv = 1.0f / (st.s[j] + 1e-8f);  // EB:379
     float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
+    if (sh.bias) {
+      const float4 b = ldg4(sh.bias + 4 * (li + j * LPR));
+      h = make_float4(h.x + b.x, h.y + b.y, h.z + b.z, h.w + b.w);
+    }
     const int64_t off = (int64_t)row * sh.F + 4 * (li + j * LPR);
     if (hpre) st4(hpre + off, h);
     const float sc = sh.sl.act;
@@ -246,12 +251,14 @@ __device__ __forceinline__ void bwd1_load_row(Bwd1Row<NV>& r, int row, const Sha
     const float4 g = *reinterpret_cast<const float4*>(gH + off);  // rewritten in place: no nc path
     const float4 ho = ldg4(Hout + off);
     r.pr[j] = ldg4(Pr + off);
-    // sum_seg alpha*galpha = gH . Hout  because LReLU'(h) * h = LReLU(h)
-    r.c[j] = head_reduce(dot4(g, ho), sh.lph);
     // EB:879-893 / EB:599: gradient through the activation, LReLU'(h) has the sign of LReLU(h)
     const float sc = sh.sl.act;
     r.gh[j] = make_float4(g.x * lrelu_grad(ho.x, sc), g.y * lrelu_grad(ho.y, sc), g.z * lrelu_grad(ho.z, sc),
                           g.w * lrelu_grad(ho.w, sc));
+    // sum_seg alpha*galpha = g_pre . (h - bias) = gH . Hout - g_pre . bias  because LReLU'(h) * h = LReLU(h)
+    float cd = dot4(g, ho);
+    if (sh.bias) cd -= dot4(r.gh[j], ldg4(sh.bias + 4 * (li + j * LPR)));
+    r.c[j] = head_reduce(cd, sh.lph);
     const int hd = (li + j * LPR) >> sh.lg_lph;
     r.m[j] = __ldg(mx + (int64_t)row * sh.H + hd);
     r.inv[j] = __ldg(sinv + (int64_t)row * sh.H + hd);
@@ -552,6 +559,15 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
   out[i] = accumulate ? out[i] + s : s;
 }
 
+// column sums of a row-major [n_rows][cols] matrix: block b sums rows b, b + gridDim.x, ... into partials[b][cols]
+__global__ void colsum_partial_kernel(const float* __restrict__ M, int n_rows, int cols, float* __restrict__ partials) {
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) s += M[(int64_t)r * cols + c];
+    partials[(int64_t)blockIdx.x * cols + c] = s;
+  }
+}
+
 __global__ void unpack_rec_kernel(const uint32_t* __restrict__ rec, int64_t E, int H, int NV, int RW,
                                   float* __restrict__ alpha, float* __restrict__ ge) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E * H; i += (int64_t)gridDim.x * blockDim.x) {
@@ -609,7 +625,7 @@ bool make_shape(int H, int D, Shape* sh, int* nv, int* lpr) {
   }
   int lg = 0;
   while ((1 << lg) < lph) ++lg;
-  if (sh) *sh = Shape{H, D, F, lph, lg, Slopes{kSlope, kSlope}};
+  if (sh) *sh = Shape{H, D, F, lph, lg, Slopes{kSlope, kSlope}, nullptr};
   if (nv) *nv = NV;
   if (lpr) *lpr = LPR;
   return true;
@@ -650,6 +666,7 @@ int launch_edge_forward(const EdgeGraph& g, int H, int D, const float* Pl, const
   int nv, lpr, launches = 0;
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
   sh.sl = g.slopes;
+  sh.bias = g.bias;
   if (g.n_rows <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
     edge_fwd_kernel<NV, LPR><<<(g.n_rows + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(
@@ -674,6 +691,7 @@ int launch_edge_backward_dst(const EdgeGraph& g, int H, int D, const float* Pl, 
   int nv, lpr, launches = 0;
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
   sh.sl = g.slopes;
+  sh.bias = g.bias;
   *n_partials = 0;
   if (g.n_rows <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
@@ -708,6 +726,7 @@ int launch_edge_backward_src(const EdgeGraph& g, int H, int D, const float* a, c
   int nv, lpr, launches = 0;
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
   sh.sl = g.slopes;
+  sh.bias = g.bias;
   if (g.n_src <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
     edge_bwd_src_kernel<NV, LPR><<<(g.n_src + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(
@@ -729,6 +748,13 @@ int launch_reduce_partials(const float* partials, int n_partials, int n, float* 
   if (n <= 0) return 0;
   reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(partials, n_partials, n, out, accumulate ? 1 : 0);
   return 1;
+}
+
+int launch_colsum(const float* M, int n_rows, int cols, float* partials, float* out, bool accumulate, cudaStream_t st) {
+  if (cols <= 0) return 0;
+  int blocks = n_rows < kColsumBlocks ? (n_rows > 0 ? n_rows : 1) : kColsumBlocks;
+  colsum_partial_kernel<<<blocks, 256, 0, st>>>(M, n_rows, cols, partials);
+  return 1 + launch_reduce_partials(partials, blocks, cols, out, accumulate, st);
 }
 
 int launch_unpack_rec(const uint32_t* rec, int64_t E, int H, int D, float* alpha, float* ge, cudaStream_t st) {

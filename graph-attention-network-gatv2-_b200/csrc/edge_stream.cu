@@ -27,6 +27,7 @@ struct Shape {
   int H, D, F, lph, lg_lph;  // lph = D / 4: lanes per head in the node-wise kernels' layout (lane + 32 j)
   int lc, lg_lc;             // lc = 32 / H: lanes per head in the lane-contiguous layout of the edge passes
   Slopes slopes;             // LeakyReLU slopes (set by the launchers from EdgeGraph::slopes)
+  const float* bias;         // [F] or nullptr (EdgeGraph::bias)
 };
 
 struct StreamGraph {
@@ -36,6 +37,7 @@ struct StreamGraph {
   uint32_t hot;          // bit of a gather index that marks an L2-resident ("hot") row; 0 = no hints in the indices
   uint32_t idx_mask;     // gather index = raw & idx_mask
   Slopes slopes;         // LeakyReLU slopes: attention score / layer activation
+  const float* bias;     // [F] added to the aggregate before the activation, or nullptr
 };
 // L2 policies of the gathers: hot rows evict_last, everything streamed once evict_first (plain when hints are off)
 struct GatherPolicy {
@@ -165,7 +167,11 @@ __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, co
   const float inv = 1.0f / (st.s + 1e-8f);  // EB:379
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
+    float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
+    if (sh.bias) {
+      const float4 b = ldg4(sh.bias + lc_off<NV>(lane, j));
+      h = make_float4(h.x + b.x, h.y + b.y, h.z + b.z, h.w + b.w);
+    }
     const int64_t off = (int64_t)row * sh.F + lc_off<NV>(lane, j);
     if (hpre) st4(hpre + off, h);
     const float sc = sh.slopes.act;
@@ -348,12 +354,13 @@ edge_fwd_fixup_kernel(StreamGraph g, Shape sh, const float* __restrict__ part, f
 // rows without any edge: h = 0, m = -1e9, 1/(s+eps) = 1e8
 __global__ void fill_empty_fwd_kernel(const int* __restrict__ row_ptr, int n_rows, int F, int H,
                                       float* __restrict__ Hout, float* __restrict__ hpre, float* __restrict__ mx,
-                                      float* __restrict__ sinv) {
+                                      float* __restrict__ sinv, const float* __restrict__ bias, float act_slope) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows || row_ptr[r + 1] != row_ptr[r]) return;
   for (int k = 0; k < F; ++k) {
-    Hout[(int64_t)r * F + k] = 0.f;
-    if (hpre) hpre[(int64_t)r * F + k] = 0.f;
+    const float h = bias ? bias[k] : 0.f;
+    Hout[(int64_t)r * F + k] = lrelu(h, act_slope);
+    if (hpre) hpre[(int64_t)r * F + k] = h;
   }
   for (int h = 0; h < H; ++h) {
     mx[(int64_t)r * H + h] = -1e9f;
@@ -393,10 +400,14 @@ edge_bwd_prep_kernel(int n_rows, Shape sh, const float* __restrict__ Hout, float
       const int64_t off = (int64_t)row * sh.F + 4 * (lane + 32 * j);
       const float4 g = *reinterpret_cast<const float4*>(gH + off);
       const float4 ho = ldg4(Hout + off);
-      const float c = head_reduce(dot4(g, ho), sh.lph);
       const float sc = sh.slopes.act;
-      st4(gH + off, make_float4(g.x * lrelu_grad(ho.x, sc), g.y * lrelu_grad(ho.y, sc), g.z * lrelu_grad(ho.z, sc),
-                                g.w * lrelu_grad(ho.w, sc)));
+      const float4 gp = make_float4(g.x * lrelu_grad(ho.x, sc), g.y * lrelu_grad(ho.y, sc), g.z * lrelu_grad(ho.z, sc),
+                                    g.w * lrelu_grad(ho.w, sc));
+      // sum_seg alpha*galpha = g_pre . (h - bias) = gH . Hout - g_pre . bias  (LReLU'(h) h = LReLU(h))
+      float cd = dot4(g, ho);
+      if (sh.bias) cd -= dot4(gp, ldg4(sh.bias + 4 * (lane + 32 * j)));
+      const float c = head_reduce(cd, sh.lph);
+      st4(gH + off, gp);
       if (head_lane) cdot[(int64_t)row * sh.H + ((lane + 32 * j) >> sh.lg_lph)] = c;
     }
   }
@@ -830,7 +841,7 @@ bool make_stream_shape(int H, int D, Shape* sh, int* nv) {
   const int lc = 32 / H;
   int lgc = 0;
   while ((1 << lgc) < lc) ++lgc;
-  *sh = Shape{H, D, F, lph, lg, lc, lgc, Slopes{kSlope, kSlope}};
+  *sh = Shape{H, D, F, lph, lg, lc, lgc, Slopes{kSlope, kSlope}, nullptr};
   *nv = NV;
   return true;
 }
@@ -897,13 +908,15 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   int nv, launches = 0;
   if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
   sh.slopes = eg.slopes;
+  sh.bias = eg.bias;
   if (eg.n_rows <= 0) return 0;
-  fill_empty_fwd_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, sh.F, H, Hout, hpre, mx, sinv);
+  fill_empty_fwd_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, sh.F, H, Hout, hpre, mx, sinv, eg.bias,
+                                                                       eg.slopes.act);
   ++launches;
   if (eg.E == 0) return launches;
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
-  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes};
+  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias};
   if (use_pair(nv, sh)) {  // one head of 128 floats: two edges per loop iteration
     constexpr int R = 16;
     const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
@@ -947,13 +960,14 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   int nv, launches = 0;
   if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
   sh.slopes = eg.slopes;
+  sh.bias = eg.bias;
   *n_partials = 0;
   if (eg.n_rows <= 0) return 0;
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
   const int* cdstx = hs.on ? eg.csc_dst_hot : eg.csc_dst;
-  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes};
-  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask, eg.slopes};
+  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias};
+  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask, eg.slopes, eg.bias};
   if (use_pair(nv, sh)) {
     constexpr int R = 16, F = kPF;
     {

@@ -57,7 +57,7 @@ enum Phase { PH_GEMM_FWD = 0, PH_EDGE_FWD, PH_HEAD, PH_EDGE_BWD, PH_GEMM_BWD, PH
 struct Layer {
   int H = 0, D = 0, F = 0, I = 0, Fout = 0, ldx = 0, ldk = 0, recw = 0;
   bool vec = true;
-  int64_t w_off = 0, a_off = 0;
+  int64_t w_off = 0, a_off = 0, b_off = -1;  // b_off: bias of this layer in the flat buffer (gatx_set_bias), -1 = none
   float *Wcat = nullptr, *WcatT = nullptr;
   float* Xd = nullptr;  // dropped input of the last training forward (gatx_set_dropout), allocated on first use
   float *Pl = nullptr, *Pr = nullptr, *Hfull = nullptr, *Hout = nullptr, *hpre = nullptr;
@@ -79,6 +79,10 @@ struct gatx_ctx {
   uint64_t drop_seed = 0;
   int64_t drop_step = 0;     // training forwards since gatx_set_dropout
   bool fwd_dropped = false;  // the last training forward used dropout (the backward must use the same inputs / mask)
+  // per-layer bias on the aggregate (gatx_set_bias): extra parameters [b_0 .. b_{L-1}] appended after W_o
+  int use_bias = 0;
+  int64_t bias_begin = 0, bias_end = 0;
+  float* colsum_partials = nullptr;
   std::vector<int> heads, outdims;
   std::string err;
   cudaStream_t st = nullptr;
@@ -246,7 +250,7 @@ void free_bufs(gatx_ctx* c) {
     l.kev_fwd = l.kev_bwd = false;
   }
   dfree(c->params); dfree(c->grads); dfree(c->adam_m); dfree(c->adam_v);
-  dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials);
+  dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials); dfree(c->colsum_partials);
   dfree(c->rec); dfree(c->part); dfree(c->cdot); dfree(c->y); dfree(c->dz); dfree(c->z_dbg); dfree(c->WoT); dfree(c->pred);
   dfree(c->loss_partials); dfree(c->loss_sum); dfree(c->correct_partials); dfree(c->correct); dfree(c->red2);
   c->have_bufs = false;
@@ -295,6 +299,12 @@ int ensure_buffers(gatx_ctx* ctx) {
   const int DL = ctx->outdims[L - 1];
   off += (int64_t)ctx->C * DL;
   ctx->grp.end[2] = off;
+  ctx->bias_begin = off;
+  for (int l = 0; l < L; ++l) {
+    ctx->layers[l].b_off = ctx->use_bias ? off : -1;
+    if (ctx->use_bias) off += ctx->layers[l].F;
+  }
+  ctx->bias_end = off;
   ctx->n_params = off;
   CK(dalloc(&ctx->params, off));
   CK(dalloc(&ctx->grads, off));
@@ -343,7 +353,8 @@ int ensure_buffers(gatx_ctx* ctx) {
   CK(dalloc(&ctx->ga_partials, (size_t)(kNumSMs * 8 + ctx->n_heavy_rows + 1) * Fmax));
   ctx->splitk_ws_bytes = (size_t)256 << 20;
   CK(dalloc(&ctx->splitk_ws, ctx->splitk_ws_bytes / sizeof(float)));
-  CK(dalloc(&ctx->norm_partials, (size_t)3 * kOptimBlocks));
+  CK(dalloc(&ctx->norm_partials, (size_t)6 * kOptimBlocks));  // [0, 3): the reference's groups, [3, 6): the bias group
+  if (ctx->use_bias) CK(dalloc(&ctx->colsum_partials, (size_t)kColsumBlocks * Fmax));
   ctx->ldc = (ctx->C + 3) / 4 * 4;
   CK(dalloc(&ctx->y, (size_t)nr * ctx->ldc));
   CK(dalloc(&ctx->dz, (size_t)nr * ctx->ldc));
@@ -371,6 +382,7 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   g.col_idx_hot = c->col_idx_hot; g.csc_dst_hot = c->csc_dst_hot; g.hot_wide_F = c->hot_wide_F;
   g.kernel_events = nullptr;
   g.slopes = c->slopes;
+  g.bias = nullptr;
   return g;
 }
 
@@ -538,6 +550,7 @@ int do_forward(gatx_ctx* ctx) {
     {
       PhaseTimer t(ctx, PH_EDGE_FWD);
       EdgeGraph gl = g;
+      gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
       if (ctx->timing) {
         for (auto& e : ly.kev)
           if (!e) cudaEventCreate(&e);
@@ -545,13 +558,13 @@ int do_forward(gatx_ctx* ctx) {
         ly.kev_fwd = true;
       }
       if (!ly.vec)
-        LAUNCHED(launch_edge_forward_generic(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
+        LAUNCHED(launch_edge_forward_generic(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
                                              ly.score, ly.mx, ly.sinv, ctx->st));
       else if (ctx->use_stream && edge_stream_supported(ly.H, ly.D))
         LAUNCHED(launch_edge_forward_stream(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
                                             ly.score, ly.mx, ly.sinv, ctx->part, ctx->st));
       else
-        LAUNCHED(launch_edge_forward(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre, ly.score,
+        LAUNCHED(launch_edge_forward(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre, ly.score,
                                      ly.mx, ly.sinv, ctx->st));
       if (ly.Hout != ly.Hfull) LAUNCHED(launch_head_mean(ly.Hfull, ctx->n_rows, ly.H, ly.D, ly.Hout, ctx->st));
     }
@@ -619,6 +632,7 @@ int do_backward(gatx_ctx* ctx) {
       PhaseTimer t(ctx, PH_EDGE_BWD);
       int n_part = 0;
       EdgeGraph gl = g;
+      gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
       if (ctx->timing) {
         for (auto& e : ly.kev)
           if (!e) cudaEventCreate(&e);
@@ -626,7 +640,7 @@ int do_backward(gatx_ctx* ctx) {
         ly.kev_bwd = true;
       }
       if (!ly.vec) {
-        LAUNCHED(launch_edge_backward_generic(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
+        LAUNCHED(launch_edge_backward_generic(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
                                               ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->gPl, ctx->rec, ctx->ga_partials,
                                               &n_part, ly.galpha_dbg, ctx->st));
         LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
@@ -636,12 +650,15 @@ int do_backward(gatx_ctx* ctx) {
                                              ctx->part, ctx->ga_partials, &n_part, ly.galpha_dbg, ctx->st));
         LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
       } else {
-        LAUNCHED(launch_edge_backward_dst(g, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
+        LAUNCHED(launch_edge_backward_dst(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
                                           ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->rec, ctx->ga_partials, &n_part,
                                           ly.galpha_dbg, ctx->st));
         LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
         LAUNCHED(launch_edge_backward_src(g, ly.H, ly.D, ctx->params + ly.a_off, ly.gH, ctx->rec, ctx->gPl, ctx->st));
       }
+      // gb = column sums of the pre-activation gradient (own rows; the all-reduce of the flat gradients adds the ranks)
+      if (ly.b_off >= 0)
+        LAUNCHED(launch_colsum(ly.gH, ctx->n_rows, ly.F, ctx->colsum_partials, ctx->grads + ly.b_off, true, ctx->st));
       if (ctx->keep_debug) {
         if (ly.vec) LAUNCHED(launch_unpack_rec(ctx->rec, ctx->E, ly.H, ly.D, ly.alpha_dbg, ly.ge_dbg, ctx->st));
         else LAUNCHED(launch_unpack_rec_generic(ctx->rec, ctx->E, ly.H, ly.alpha_dbg, ly.ge_dbg, ctx->st));
@@ -693,8 +710,17 @@ int do_step(gatx_ctx* ctx, int t) {
     NK(g_nccl.AllReduce(ctx->grads, ctx->grads, (size_t)ctx->n_params, ncclFloat, ncclSum, ctx->comm, ctx->st));
   }
   PhaseTimer tm(ctx, PH_OPT);
-  LAUNCHED(launch_optimizer(ctx->params, ctx->grads, ctx->adam_m, ctx->adam_v, ctx->n_params, ctx->grp, ctx->clip != 0,
+  LAUNCHED(launch_optimizer(ctx->params, ctx->grads, ctx->adam_m, ctx->adam_v, ctx->bias_begin, ctx->grp, ctx->clip != 0,
                             ctx->optimizer, ctx->lr, ctx->b1, ctx->b2, t, ctx->norm_partials, ctx->st));
+  if (ctx->bias_end > ctx->bias_begin) {  // the biases are a clip group of their own
+    const int64_t o = ctx->bias_begin, n = ctx->bias_end - ctx->bias_begin;
+    OptimGroups one{};
+    one.begin[0] = 0;
+    one.end[0] = one.begin[1] = one.end[1] = one.begin[2] = one.end[2] = n;
+    LAUNCHED(launch_optimizer(ctx->params + o, ctx->grads + o, ctx->adam_m + o, ctx->adam_v + o, n, one, ctx->clip != 0,
+                              ctx->optimizer, ctx->lr, ctx->b1, ctx->b2, t, ctx->norm_partials + 3 * kOptimBlocks,
+                              ctx->st));
+  }
   return GATX_OK;
 }
 
@@ -1112,6 +1138,8 @@ int gatx_init_params(gatx_ctx* ctx, uint64_t seed) {
   const int DL = ctx->outdims[ctx->L - 1];
   const float limit = sqrtf(6.0f / (float)(ctx->C + DL));  // EB:236
   LAUNCHED(launch_philox_uniform(ctx->params + ctx->wo_off, (int64_t)ctx->C * DL, limit, seed, 1000, ctx->st));
+  if (ctx->bias_end > ctx->bias_begin)  // biases start at zero
+    CK(cudaMemsetAsync(ctx->params + ctx->bias_begin, 0, sizeof(float) * (size_t)(ctx->bias_end - ctx->bias_begin), ctx->st));
   ctx->have_params = true;
   return GATX_OK;
 }
@@ -1217,6 +1245,29 @@ int gatx_set_slopes(gatx_ctx* ctx, float attn_slope, float act_slope) {
   ctx->slopes = Slopes{attn_slope, act_slope};
   ctx->fwd_valid = false;  // activations of an earlier forward no longer match
   ++ctx->gen;              // kernel arguments of a captured epoch
+  return GATX_OK;
+}
+
+int gatx_set_bias(gatx_ctx* ctx, int32_t on) {
+  if (!ctx) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if ((on != 0) == (ctx->use_bias != 0)) return GATX_OK;
+  if (ctx->have_bufs) free_bufs(ctx);  // the parameter layout changes: parameters must be set / initialised again
+  ctx->use_bias = on != 0;
+  ctx->fwd_valid = false;
+  ++ctx->gen;
+  return GATX_OK;
+}
+
+int gatx_set_bias_values(gatx_ctx* ctx, int32_t layer, const float* b) {
+  if (!ctx || layer < 0 || layer >= ctx->L || !b) return fail(ctx, GATX_ERR_INVALID, "bad set_bias_values");
+  if (!ctx->use_bias) return fail(ctx, GATX_ERR_INVALID, "gatx_set_bias(ctx, 1) first");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_buffers(ctx);
+  if (rc) return rc;
+  const Layer& ly = ctx->layers[layer];
+  CK(cudaMemcpyAsync(ctx->params + ly.b_off, b, sizeof(float) * (size_t)ly.F, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
   return GATX_OK;
 }
 
@@ -1333,6 +1384,7 @@ int64_t gatx_tensor_size(gatx_ctx* ctx, int32_t which, int32_t layer) {
   switch (which) {
     case GATX_T_W: case GATX_T_GW: return (int64_t)ly->F * 2 * ly->I;
     case GATX_T_A: case GATX_T_GA: return ly->F;
+    case GATX_T_B: case GATX_T_GB: return ly->b_off >= 0 ? ly->F : -1;
     case GATX_T_WO: case GATX_T_GWO: return (int64_t)ctx->C * DL;
     case GATX_T_PL: case GATX_T_GPL: return (int64_t)ctx->N * ly->F;
     case GATX_T_PR: case GATX_T_GPR: case GATX_T_HPRE: case GATX_T_GH: return (int64_t)ctx->n_rows * ly->F;
@@ -1392,6 +1444,8 @@ int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size
     case GATX_T_WO: src = ctx->params + ctx->wo_off; break;
     case GATX_T_GW: src = ctx->grads + ly->w_off; break;
     case GATX_T_GA: src = ctx->grads + ly->a_off; break;
+    case GATX_T_B: src = ctx->params + ly->b_off; break;
+    case GATX_T_GB: src = ctx->grads + ly->b_off; break;
     case GATX_T_GWO: src = ctx->grads + ctx->wo_off; break;
     case GATX_T_PL: src = ly->Pl; break;
     case GATX_T_PR: src = ly->Pr; break;

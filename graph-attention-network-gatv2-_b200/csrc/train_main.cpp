@@ -186,7 +186,7 @@ void cache_store(const std::string& dir, const std::vector<float>& X, const std:
 
 struct Args {
   int epochs = 200, L = 2, gpus = 1, gemm = GATX_GEMM_TF32_TC, every = 1;
-  bool clip = false, use_cache = true, load_only = false, split = false, eval_only = false;
+  bool clip = false, use_cache = true, load_only = false, split = false, eval_only = false, bias = false;
   std::string save_ckpt, resume_ckpt;
   std::string optimizer = "sgd", dataset = "pubmed", data_root = "./data", load_w, dump_w;
   float lr = 0.0001f, beta1 = 0.9f, beta2 = 0.999f;
@@ -266,6 +266,7 @@ int main(int argc, char** argv) {
     else if (arg == "--attn-slope" && i + 1 < argc) a.attn_slope = std::strtof(argv[++i], nullptr);
     else if (arg == "--act-slope" && i + 1 < argc) a.act_slope = std::strtof(argv[++i], nullptr);
     else if (arg == "--dropout" && i + 1 < argc) a.dropout = std::strtof(argv[++i], nullptr);
+    else if (arg == "--bias") a.bias = true;
     // anything else is ignored, like the reference
   }
   if (!have_heads || !have_outdims) {
@@ -381,6 +382,7 @@ int main(int argc, char** argv) {
     if ((rc = gatx_set_features(ctx[r], X.data(), I))) { failed = fail_ctx(ctx[r], "gatx_set_features", rc); return; }
     if ((rc = gatx_set_labels(ctx[r], labels.data(), C))) { failed = fail_ctx(ctx[r], "gatx_set_labels", rc); return; }
     if (a.split && (rc = gatx_set_train_mask(ctx[r], mask[0].data()))) { failed = fail_ctx(ctx[r], "gatx_set_train_mask", rc); return; }
+    if (a.bias && (rc = gatx_set_bias(ctx[r], 1))) { failed = fail_ctx(ctx[r], "gatx_set_bias", rc); return; }
     if ((a.attn_slope != 0.01f || a.act_slope != 0.01f) && (rc = gatx_set_slopes(ctx[r], a.attn_slope, a.act_slope))) { failed = fail_ctx(ctx[r], "gatx_set_slopes", rc); return; }
     // the reference seeds with time(NULL) (EB:1305); --seed makes runs reproducible
     const unsigned long long seed = a.seed_given ? a.seed : (unsigned long long)time(nullptr);

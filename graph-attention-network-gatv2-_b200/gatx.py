@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgatx.so")
 
 (T_W, T_A, T_WO, T_GW, T_GA, T_GWO, T_PL, T_PR, T_SCORE, T_ALPHA, T_HPRE, T_HOUT, T_Y, T_GH, T_Z, T_PRED,
- T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR, T_GALPHA, T_GE) = range(26)
+ T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR, T_GALPHA, T_GE, T_B, T_GB) = range(28)
 _INT_TENSORS = {T_PRED, T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID}
 GEMM_TF32_TC, GEMM_FP32_SIMT = 0, 1
 PEER_INFO_BYTES = 2048
@@ -25,7 +25,7 @@ EXPORTS = [
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
-    "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout",
+    "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_bias", "gatx_set_bias_values",
 ]
 
 
@@ -258,6 +258,16 @@ class Engine:
         """LeakyReLU slopes of the attention score / the layer activation (the reference fixes both at 0.01)"""
         self.lib.gatx_set_slopes.argtypes = [C.c_void_p, C.c_float, C.c_float]
         self._ck(self.lib.gatx_set_slopes(self.ctx, attn_slope, act_slope), "gatx_set_slopes")
+
+    def set_bias(self, on=True):
+        """Learnable per-layer bias on the aggregate (call before the parameters are set)"""
+        self.lib.gatx_set_bias.argtypes = [C.c_void_p, C.c_int32]
+        self._ck(self.lib.gatx_set_bias(self.ctx, int(on)), "gatx_set_bias")
+
+    def set_bias_values(self, layer, b):
+        b = np.ascontiguousarray(b, np.float32)
+        self.lib.gatx_set_bias_values.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        self._ck(self.lib.gatx_set_bias_values(self.ctx, layer, b.ctypes.data), "gatx_set_bias_values")
 
     def set_dropout(self, p, seed=0):
         """Inverted dropout on every layer's input in training forwards (Philox, reproducible); p = 0 switches it off"""

@@ -90,7 +90,9 @@ enum {
   GATX_T_GPL = 22,   /* [N][F] grad wrt projected source features */
   GATX_T_GPR = 23,   /* [N][F] grad wrt projected destination features */
   GATX_T_GALPHA = 24, /* [E][H] grad wrt attention coefficients (EB grad_attn_coeff, transposed) -- keep_debug */
-  GATX_T_GE = 25     /* [E][H] grad wrt attention logits (EB grad_attn_score, transposed) -- keep_debug */
+  GATX_T_GE = 25,    /* [E][H] grad wrt attention logits (EB grad_attn_score, transposed) -- keep_debug */
+  GATX_T_B = 26,     /* [H*D] layer bias (extension, gatx_set_bias) */
+  GATX_T_GB = 27     /* grad of the layer bias */
 };
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
@@ -143,6 +145,13 @@ int gatx_set_slopes(gatx_ctx* ctx, float attn_slope, float act_slope);
  * reproducible, identical on every rank of a partitioned run, re-generated (not stored) by the backward pass.
  * p = 0 switches it off.  0 <= p < 1. */
 int gatx_set_dropout(gatx_ctx* ctx, float p, uint64_t seed);
+/* Extension (the reference has no bias): a learnable bias b_l [H*D] per layer added to the aggregate
+ * before the activation, h_i = sum_j alpha_ij W_l x_j + b_l (rows without in-edges give LReLU(b_l)).  The biases are
+ * appended to the flat parameter / state buffer after W_o ([.. | W_o | b_0 .. b_{L-1}]), start at zero in
+ * gatx_init_params, form a clip group of their own and are updated by the same Adam / SGD rule.  Switching it changes
+ * the parameter layout: call it before the parameters are set (it drops them otherwise). */
+int gatx_set_bias(gatx_ctx* ctx, int32_t on);
+int gatx_set_bias_values(gatx_ctx* ctx, int32_t layer, const float* b /* [H*D] */);
 
 /* ---- the epoch (EB:1370-1642) ----------------------------------------------------------- */
 /* EB:1375-1452: per layer projection + score + segmented softmax + aggregation + activation,

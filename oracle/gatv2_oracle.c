@@ -146,9 +146,18 @@ void orc_project(int N, int I, int F, const float* X, const float* W, float* Pl,
  *   activation EB:426-459 hidden: LReLU(h) concat; last: mean_h LReLU(h_h)
  * Outputs score/alpha are head-major [H][E] like the reference; mx/sm are [H][N];
  * hpre is [N][H][D]; Hout is [N][H*D] (hidden) or [N][D] (last). */
+void orc_layer_forward_bias(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
+                            const float* Pr, const float* a, int is_last, float* score, float* alpha,
+                            float* mx, float* sm, float* hpre, float* Hout, const float* bias);
 void orc_layer_forward(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
                        const float* Pr, const float* a, int is_last, float* score, float* alpha,
                        float* mx, float* sm, float* hpre, float* Hout) {
+  orc_layer_forward_bias(N, row_ptr, col_idx, H, D, Pl, Pr, a, is_last, score, alpha, mx, sm, hpre, Hout, NULL);
+}
+/* Same with the optional bias extension (the reference has none): hpre = sum_j alpha_ij P_l[j] + bias, bias [H][D]. */
+void orc_layer_forward_bias(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
+                            const float* Pr, const float* a, int is_last, float* score, float* alpha,
+                            float* mx, float* sm, float* hpre, float* Hout, const float* bias) {
   const int F = H * D;
   const int64_t E = row_ptr[N];
 #pragma omp parallel for schedule(dynamic, 64)
@@ -180,6 +189,7 @@ void orc_layer_forward(int N, const int* row_ptr, const int* col_idx, int H, int
         for (int e = beg; e < end; ++e)
           acc += (double)alpha[(size_t)h * E + e] *
                  (double)Pl[(size_t)col_idx[e] * F + (size_t)h * D + k];
+        if (bias) acc += (double)bias[(size_t)h * D + k];
         hpre[((size_t)i * H + h) * D + k] = (float)acc;
       }
     }
@@ -571,6 +581,9 @@ typedef struct orc_model {
   uint64_t drop_seed;
   int64_t drop_step; /* number of training forwards since orc_model_set_dropout */
   float** Xd;        /* per layer: the dropped, rescaled input [N][indims[l]] (allocated on first use) */
+  /* extension: per-layer bias on the aggregate (NULL arrays = off, the reference) */
+  int use_bias;
+  float **b, **gb, **mb, **vb;
 } orc_model;
 
 static float* falloc(size_t n) { return (float*)calloc(n > 0 ? n : 1, sizeof(float)); }
@@ -588,7 +601,7 @@ orc_model* orc_model_create(int L, const int* heads, const int* outdims, int N, 
   m->indims = (int*)malloc(sizeof(int) * L);
 #define PP(field) m->field = (float**)calloc(L, sizeof(float*))
   PP(W); PP(a); PP(gW); PP(ga); PP(mW); PP(vW); PP(ma); PP(va);
-  PP(Pl); PP(Pr); PP(score); PP(alpha); PP(mx); PP(sm); PP(hpre); PP(Hout); PP(g_h); PP(Xd);
+  PP(Pl); PP(Pr); PP(score); PP(alpha); PP(mx); PP(sm); PP(hpre); PP(Hout); PP(g_h); PP(Xd); PP(b); PP(gb); PP(mb); PP(vb);
 #undef PP
   for (int l = 0; l < L; ++l) {
     m->heads[l] = heads[l];
@@ -617,10 +630,11 @@ void orc_model_destroy(orc_model* m) {
     free(m->a[l]); free(m->ga[l]); free(m->ma[l]); free(m->va[l]);
     free(m->Pl[l]); free(m->Pr[l]); free(m->score[l]); free(m->alpha[l]);
     free(m->mx[l]); free(m->sm[l]); free(m->hpre[l]); free(m->Hout[l]); free(m->g_h[l]); free(m->Xd[l]);
+    free(m->b[l]); free(m->gb[l]); free(m->mb[l]); free(m->vb[l]);
   }
   free(m->W); free(m->a); free(m->gW); free(m->ga); free(m->mW); free(m->vW); free(m->ma);
   free(m->va); free(m->Pl); free(m->Pr); free(m->score); free(m->alpha); free(m->mx); free(m->sm);
-  free(m->hpre); free(m->Hout); free(m->g_h); free(m->Xd);
+  free(m->hpre); free(m->Hout); free(m->g_h); free(m->Xd); free(m->b); free(m->gb); free(m->mb); free(m->vb);
   free(m->Wo); free(m->gWo); free(m->mWo); free(m->vWo); free(m->z); free(m->y);
   free(m->heads); free(m->outdims); free(m->indims);
   free(m);
@@ -656,6 +670,8 @@ float* orc_model_tensor(orc_model* m, int which, int l) {
     case 12: return m->y;
     case 13: return m->g_h[l];
     case 14: return m->z;
+    case 26: return m->b[l];
+    case 27: return m->gb[l];
     default: return NULL;
   }
 }
@@ -698,6 +714,18 @@ void orc_dropout(const float* X, float* Y, int n_rows, int cols, int row0, float
     }
 }
 
+/* Switches the bias extension on (zero-initialised biases, like the engine's gatx_init_params). */
+void orc_model_set_bias(orc_model* m, int on) {
+  m->use_bias = on;
+  for (int l = 0; l < m->L && on; ++l) {
+    size_t F = (size_t)m->heads[l] * m->outdims[l];
+    if (!m->b[l]) { m->b[l] = falloc(F); m->gb[l] = falloc(F); m->mb[l] = falloc(F); m->vb[l] = falloc(F); }
+  }
+}
+void orc_model_set_bias_values(orc_model* m, int l, const float* b) {
+  memcpy(m->b[l], b, sizeof(float) * (size_t)m->heads[l] * m->outdims[l]);
+}
+
 void orc_model_set_dropout(orc_model* m, float p, uint64_t seed) {
   m->p_drop = p;
   m->drop_seed = seed;
@@ -716,9 +744,9 @@ static void model_forward(orc_model* m, int training) {
       X = m->Xd[l];
     }
     orc_project(m->N, I, H * D, X, m->W[l], m->Pl[l], m->Pr[l]);
-    orc_layer_forward(m->N, m->row_ptr, m->col_idx, H, D, m->Pl[l], m->Pr[l], m->a[l],
-                      l == m->L - 1, m->score[l], m->alpha[l], m->mx[l], m->sm[l], m->hpre[l],
-                      m->Hout[l]);
+    orc_layer_forward_bias(m->N, m->row_ptr, m->col_idx, H, D, m->Pl[l], m->Pr[l], m->a[l],
+                           l == m->L - 1, m->score[l], m->alpha[l], m->mx[l], m->sm[l], m->hpre[l],
+                           m->Hout[l], m->use_bias ? m->b[l] : NULL);
     X = m->Hout[l];
   }
   orc_head_forward(m->N, m->C, m->outdims[m->L - 1], m->Wo, X, m->z, m->y);
@@ -742,6 +770,14 @@ void orc_model_backward(orc_model* m) {
                           m->Hout[L - 1], m->Wo, m->gWo, m->g_h[L - 1]);
   for (int l = L - 1; l >= 0; --l) {
     int H = m->heads[l], D = m->outdims[l], I = m->indims[l];
+    if (m->use_bias) { /* gb = column sums of the pre-activation gradient */
+      size_t F = (size_t)H * D;
+      for (size_t r = 0; r < F; ++r) {
+        double acc = 0.0;
+        for (int n = 0; n < m->N; ++n) acc += (double)m->g_h[l][(size_t)n * F + r];
+        m->gb[l][r] += (float)acc;
+      }
+    }
     const int drop = m->p_drop > 0.0f && m->drop_step > 0 && m->Xd[l];
     const float* X = drop ? m->Xd[l] : (l > 0 ? m->Hout[l - 1] : m->X0);
     float* gX = l > 0 ? m->g_h[l - 1] : NULL;
@@ -790,6 +826,22 @@ void orc_model_step(orc_model* m, int t) {
   if (m->optimizer == 1) orc_adam(m->Wo, m->gWo, m->mWo, m->vWo, m->lr, (int64_t)nwo, m->b1, m->b2, 1e-8f, t);
   else orc_sgd(m->Wo, m->gWo, m->lr, (int64_t)nwo);
   memset(m->gWo, 0, sizeof(float) * nwo);
+  if (m->use_bias) { /* the biases of all layers: a clip group of their own, same update rule */
+    if (m->clip) {
+      double ss = 0.0;
+      for (int l = 0; l < L; ++l)
+        for (int64_t i = 0; i < (int64_t)m->heads[l] * m->outdims[l]; ++i) ss += (double)m->gb[l][i] * (double)m->gb[l][i];
+      float nb = (float)sqrt((double)(float)ss), sb = nb > 5.0f ? 5.0f / (nb + 1e-9f) : 1.0f;
+      for (int l = 0; l < L && sb < 1.0f; ++l)
+        for (int64_t i = 0; i < (int64_t)m->heads[l] * m->outdims[l]; ++i) m->gb[l][i] *= sb;
+    }
+    for (int l = 0; l < L; ++l) {
+      int64_t nbias = (int64_t)m->heads[l] * m->outdims[l];
+      if (m->optimizer == 1) orc_adam(m->b[l], m->gb[l], m->mb[l], m->vb[l], m->lr, nbias, m->b1, m->b2, 1e-8f, t);
+      else orc_sgd(m->b[l], m->gb[l], m->lr, nbias);
+      memset(m->gb[l], 0, sizeof(float) * (size_t)nbias);
+    }
+  }
 }
 
 /* One whole epoch exactly as timed by the reference (EB:1371 -> EB:1639). */

@@ -188,6 +188,7 @@ def lit_layer_backward(row_ptr, col_idx, H, D, X, W, a, alpha, g_h, want_gx=True
 
 # tensor ids (identical to GATX_T_* in include/gatx.h)
 T_W, T_A, T_WO, T_GW, T_GA, T_GWO, T_PL, T_PR, T_SCORE, T_ALPHA, T_HPRE, T_HOUT, T_Y, T_GH, T_Z = range(15)
+T_B, T_GB = 26, 27  # bias extension (same ids as include/gatx.h)
 
 
 class Model:
@@ -219,7 +220,7 @@ class Model:
         H, D, I = self.heads[l], self.outdims[l], self.indims[l]
         F = H * D
         last = l == self.L - 1
-        return {T_W: (F, 2 * I), T_GW: (F, 2 * I), T_A: (F,), T_GA: (F,),
+        return {T_W: (F, 2 * I), T_GW: (F, 2 * I), T_A: (F,), T_GA: (F,), T_B: (F,), T_GB: (F,),
                 T_WO: (self.C, self.outdims[-1]), T_GWO: (self.C, self.outdims[-1]),
                 T_PL: (self.N, F), T_PR: (self.N, F), T_SCORE: (H, self.E), T_ALPHA: (H, self.E),
                 T_HPRE: (self.N, F), T_HOUT: (self.N, D if last else F), T_Y: (self.N, self.C),
@@ -240,6 +241,12 @@ class Model:
         """mask: uint8 [N] (1 = node counts towards loss / accuracy / gradients) or None."""
         self._mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         lib().orc_model_set_mask(self._m, None if mask is None else self._mask.ctypes.data_as(C.c_void_p))
+
+    def set_bias(self, on=True):
+        lib().orc_model_set_bias(self._m, int(on))
+
+    def set_bias_values(self, l, b):
+        lib().orc_model_set_bias_values(self._m, l, fp(f32(b)))
 
     def set_dropout(self, p, seed):
         """Dropout on every layer's input in training forwards; resets the step counter."""

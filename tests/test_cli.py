@@ -134,6 +134,8 @@ def test_extension_flags(cli, tmp_path):
     drop, out = losses("--dropout", "0.4")
     assert "Dropout: 0.4" in out and drop != default
     assert losses("--dropout", "0.4")[0] == drop
+    bias, _ = losses("--bias")
+    assert bias[0] == default[0] and bias[1:] != default[1:]  # biases start at zero, then train
     r = run(cli, *(base + ["--dropout", "1.5"]))
     assert r.returncode == 1 and "gatx_set_dropout" in r.stderr
 

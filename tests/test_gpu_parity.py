@@ -452,3 +452,67 @@ def test_dropout_reproducible_and_graph_free(gatx):
         eng.close()
     assert runs[0] == runs[1]
     assert runs[0] != runs[2]
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("shape", EXT_SHAPES + [SHAPES[4]], ids=["narrow", "stream", "pair", "generic", "two-head-last"])
+def test_bias_parity(gatx, orc, shape, mode):
+    """Opt-in per-layer bias (gatx_set_bias): forward values, gb and the updated biases against the oracle over two
+    clipped epochs, on a graph where some rows have no in-edge (their aggregate is the bias alone)."""
+    N, E, I, C, heads, outdims, kind, hub = shape
+    p = make_problem(N, E, I, C, heads, outdims, kind, seed=N + 2, hub=hub)
+    deg = np.diff(p["row_ptr"])
+    keep = np.ones(len(p["col_idx"]), bool)
+    for i in (1, 7, N - 1):
+        keep[p["row_ptr"][i]:p["row_ptr"][i + 1]] = False
+        deg[i] = 0
+    p["col_idx"] = p["col_idx"][keep]
+    p["row_ptr"] = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    ft, bt = FWD_TOL[mode], BWD_TOL[mode]
+    L = len(heads)
+    rng = np.random.default_rng(N)
+    bs = [(rng.standard_normal(h * d) * 0.3).astype(np.float32) for h, d in zip(heads, outdims)]
+    eng = gatx.Engine(p["heads"], p["outdims"], gemm_mode=mode, keep_debug=True, optimizer="sgd", lr=1e-4, clip=True)
+    eng.set_bias(True)
+    eng.set_graph(p["row_ptr"], p["col_idx"])
+    eng.set_features(p["X"])
+    eng.set_labels(p["labels"], p["C"])
+    ref = make_oracle(orc, p, optimizer="sgd", lr=1e-4, clip=True)
+    ref.set_bias(True)
+    for l in range(L):
+        eng.set_params(l, p["Ws"][l], p["As"][l])
+        eng.set_bias_values(l, bs[l])
+        ref.set_bias_values(l, bs[l])
+    eng.set_wo(p["Wo"])
+    for t in (1, 2):
+        eng.forward()
+        ref.forward()
+        loss, _ = eng.loss_acc()
+        rl = ref.loss()
+        for l in range(L):
+            assert rel_err(eng.tensor(gatx.T_HPRE, l), ref.tensor(orc.T_HPRE, l).ravel()) < ft * 2 * t, ("hpre", l, t)
+            assert rel_err(eng.tensor(gatx.T_HOUT, l), ref.tensor(orc.T_HOUT, l).ravel()) < ft * 2 * t, ("Hout", l, t)
+        F0 = heads[0] * outdims[0]
+        assert np.array_equal(eng.tensor(gatx.T_HPRE, 0).reshape(N, F0)[7], eng.tensor(gatx.T_B, 0))  # edge-less row
+        assert abs(loss - rl["avg"]) < max(ft * 5, 1e-5) * t * max(1.0, abs(rl["avg"]))
+        eng.backward()
+        ref.backward()
+        for l in range(L):
+            assert rel_err(eng.tensor(gatx.T_GB, l), ref.tensor(orc.T_GB, l).ravel(), floor=1e-2) < bt * t, ("gb", l, t)
+            assert rel_err(eng.tensor(gatx.T_GW, l), ref.tensor(orc.T_GW, l).ravel()) < bt * t, ("gW", l, t)
+        eng.step(t)
+        ref.step(t)
+        for l in range(L):
+            assert rel_err(eng.tensor(gatx.T_B, l), ref.tensor(orc.T_B, l).ravel()) < bt * t, ("b", l, t)
+            assert not eng.tensor(gatx.T_GB, l).any()
+    # the biases travel with the checkpoint state: [params | m | v], each ending with b_0 .. b_{L-1}
+    st = eng.get_state()
+    nb = sum(h * d for h, d in zip(heads, outdims))
+    assert st.size % 3 == 0 and np.array_equal(st[st.size // 3 - nb:st.size // 3],
+                                               np.concatenate([eng.tensor(gatx.T_B, l) for l in range(L)]))
+    eng.close()
+    plain = make_engine(gatx, p)
+    with pytest.raises(gatx.GatxError):
+        plain.tensor(gatx.T_B, 0)  # no bias unless switched on
+    assert plain.get_state().size == st.size - 3 * nb
+    plain.close()

@@ -119,8 +119,8 @@ def test_two_ranks_match_one(world, p2p):
     eng.close()
 
 
-@pytest.mark.parametrize("extra", [[], ["--dropout", "0.3", "--attn-slope", "0.2", "--act-slope", "0.05"]],
-                         ids=["reference-model", "slopes+dropout"])
+@pytest.mark.parametrize("extra", [[], ["--dropout", "0.3", "--attn-slope", "0.2", "--act-slope", "0.05", "--bias"]],
+                         ids=["reference-model", "slopes+dropout+bias"])
 def test_cli_two_gpus_matches_one(tmp_path, extra):
     """train_gatx --gpus 2 (two host threads, two contexts in one process) prints the same curve as --gpus 1; with
     dropout every rank must draw the mask of the GLOBAL row (layer 0 drops its replicated copy of all input rows)."""

@@ -224,6 +224,47 @@ def test_slopes_and_dropout_vs_torch_autograd(orc, heads, outdims):
         orc.set_slopes(0.01, 0.01)
 
 
+@pytest.mark.parametrize("heads,outdims", [((3, 1), (4, 6)), ((2, 2, 2), (4, 3, 5))])
+def test_bias_vs_torch_autograd(orc, heads, outdims):
+    """Extension: per-layer bias on the aggregate, values and gradients vs autograd; a graph with
+    edge-less rows (their aggregate is the bias alone)."""
+    row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(11, heads=heads, outdims=outdims)
+    keep = np.ones(len(col_idx), bool)
+    for i in (2, 5):  # strip every in-edge of two nodes
+        keep[row_ptr[i]:row_ptr[i + 1]] = False
+    deg = np.diff(row_ptr)
+    deg[[2, 5]] = 0
+    col_idx = col_idx[keep]
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    rng = np.random.default_rng(4)
+    bs = [rng.standard_normal(h * d).astype(np.float32) * 0.5 for h, d in zip(heads, outdims)]
+    m = orc.Model(heads, outdims, row_ptr, col_idx, X, y)
+    m.set_bias(True)
+    for l in range(len(heads)):
+        m.set_params(l, Ws[l], As[l])
+        m.set_bias_values(l, bs[l])
+    m.set_wo(Wo)
+    m.forward()
+    loss = m.loss()
+    m.backward()
+    vals, grads = torch_ref.forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, y, biases=bs)
+    for l in range(len(heads)):
+        assert rel_err(m.tensor(orc.T_HPRE, l), vals["hpre"][l]) < 2e-6, l
+        assert rel_err(m.tensor(orc.T_HOUT, l), vals["Hout"][l]) < 2e-6, l
+    assert np.allclose(m.tensor(orc.T_HPRE, 0)[2], bs[0]) and np.allclose(m.tensor(orc.T_HPRE, 0)[5], bs[0])
+    assert abs(loss["total"] - vals["loss_sum"]) / vals["loss_sum"] < 1e-6
+    for l in range(len(heads)):
+        assert rel_err(m.tensor(orc.T_GW, l), grads["gW"][l]) < 2e-5, l
+        assert rel_err(m.tensor(orc.T_GA, l), grads["ga"][l]) < 2e-5, l
+        assert rel_err(m.tensor(orc.T_GB, l), grads["gb"][l]) < 2e-5, l
+    assert rel_err(m.tensor(orc.T_GWO), grads["gWo"]) < 2e-5
+    # a step moves the biases (SGD: b -= lr * gb) and clears their gradient
+    gb0 = m.tensor(orc.T_GB, 0).copy()
+    m.step(1)
+    assert np.allclose(m.tensor(orc.T_B, 0), bs[0] - np.float32(1e-4) * gb0, rtol=1e-6, atol=1e-7)
+    assert not m.tensor(orc.T_GB, 0).any()
+
+
 def test_literal_fp32_matches_factored(orc):
     row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(2)
     H, D = 3, 4

@@ -15,7 +15,7 @@ def lrelu(x, slope=SLOPE):
 
 
 def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch.float64, mask=None,
-            attn_slope=SLOPE, act_slope=SLOPE, in_scale=None):
+            attn_slope=SLOPE, act_slope=SLOPE, in_scale=None, biases=None):
     """in_scale: optional per-layer [N][I_l] arrays multiplied into each layer's input (a dropout mask / (1 - p))."""
     N = len(row_ptr) - 1
     deg = np.diff(row_ptr)
@@ -40,6 +40,8 @@ def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch
         ssum = torch.zeros((N, H), dtype=dtype).index_add(0, dst, ex)
         alpha = ex / (ssum[dst] + 1e-8)
         h = torch.zeros((N, H, D), dtype=dtype).index_add(0, dst, alpha[:, :, None] * Pl[src].view(E, H, D))
+        if biases is not None:
+            h = h + biases[l].view(1, H, D)
         if l == L - 1:
             Hout = lrelu(h, act_slope).mean(1)
         else:
@@ -65,9 +67,15 @@ def forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, ma
     tW = [torch.tensor(np.asarray(w, np.float64), requires_grad=True) for w in Ws]
     tA = [torch.tensor(np.asarray(a, np.float64), requires_grad=True) for a in As]
     tWo = torch.tensor(np.asarray(Wo, np.float64), requires_grad=True)
+    tB = None
+    if kw.get("biases") is not None:
+        tB = [torch.tensor(np.asarray(b, np.float64), requires_grad=True) for b in kw["biases"]]
+        kw = dict(kw, biases=tB)
     out = forward(tW, tA, tWo, np.asarray(X, np.float64), row_ptr, col_idx, heads, outdims, labels, mask=mask, **kw)
     out["loss_sum"].backward()
     grads = dict(gW=[w.grad.numpy() for w in tW], ga=[a.grad.numpy() for a in tA], gWo=tWo.grad.numpy())
+    if tB is not None:
+        grads["gb"] = [b.grad.numpy() for b in tB]
     vals = {k: ([t.detach().numpy() for t in v] if isinstance(v, list) else v.detach().numpy())
             for k, v in out.items()}
     return vals, grads
