@@ -6,10 +6,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libgatx.so")
+# GATX_VARIANT=<name> GATX_EXTRA_FLAGS="-D..." builds an A/B variant libgatx_<name>.so next to the product library
+VARIANT = os.environ.get("GATX_VARIANT", "")
+OUT = os.path.join(HERE, "libgatx_%s.so" % VARIANT if VARIANT else "libgatx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"] + os.environ.get("GATX_EXTRA_FLAGS", "").split()
 SOURCES = ["gatx_api.cu", "graph_prep.cu", "gemm_simt.cu", "gemm_tc.cu", "edge_kernels.cu", "edge_stream.cu", "edge_generic.cu", "head_loss.cu", "optim.cu", "halo_p2p.cu"]
 
 
@@ -21,7 +23,7 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_" + VARIANT if VARIANT else "build")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "gatx.h"))

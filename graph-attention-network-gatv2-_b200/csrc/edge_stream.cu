@@ -61,6 +61,34 @@ __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cas
 // LeakyReLU for 0 <= slope < 1 (gatx_create rejects anything else): two instructions, no select
 __device__ __forceinline__ float lrelu_fast(float x, float slope) { return fmaxf(x, slope * x); }
 __device__ __forceinline__ float shx(float v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE-rn fp32 operations per issued instruction).  The
+// streaming loops are bound by instruction issue at the power-capped clock, and half of their instructions are
+// elementwise fp32 math on LDS.128 results, whose components already sit in aligned register pairs.
+// -DGATX_SCALAR_FP32 builds the same arithmetic (same operations, same rounding, bit-identical results) from scalar
+// FADD / FMUL / FFMA: the A/B baseline of tools/ab_packed_fp32.sh.
+#ifdef GATX_SCALAR_FP32
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#else
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#endif
+// Scalar forms for the kernels where packing loses.  Same-box A/B against -DGATX_SCALAR_FP32 (tools/ab_packed_fp32.sh,
+// profiles/r1_ab_packed_fp32.txt): packed is 3.5 % faster in edge_fwd_stream_kernel (512-float rows), 6-9 % in
+// edge_fwd_pair_kernel, 2-5 % in edge_bwd_dst_pair_kernel, but 2-5 % SLOWER in edge_bwd_{dst,src}_stream_kernel and
+// edge_bwd_src_pair_kernel, whose bodies interleave a select per element (FSETP / FSEL, bit tests) with the arithmetic
+// and pay for the aligned-register-pair constraint -- even with only the galpha dot product packed.  Those stay scalar.
+__device__ __forceinline__ float2 fma2_s(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 add2_s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 lrelu_fast2(float2 x, float2 slope) {
+  const float2 t = mul2(x, slope);
+  return make_float2(fmaxf(x.x, t.x), fmaxf(x.y, t.y));
+}
 // predicated global stores: one STG with a predicate instead of a divergent branch region per store
 __device__ __forceinline__ void st_pred_u32(uint32_t* p, uint32_t v, bool pred) {
   asm volatile(
@@ -212,6 +240,7 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
   int voff[NV];  // byte-free float offsets of this lane's pieces inside a ring slot
 #pragma unroll
   for (int j = 0; j < NV; ++j) voff[j] = lc_off<NV>(lane, j);
+  const float2 slope2 = splat2(g.slopes.attn);
   const int total_warps = gridDim.x * kSW;
   uint32_t it = 0;  // ring position: edges consumed by this warp so far
   for (int chunk = blockIdx.x * kSW + warp; chunk < g.n_chunks; chunk += total_warps) {
@@ -282,12 +311,13 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
           bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
         }
       }
-      float p = 0.f;
+      float2 pp = make_float2(0.f, 0.f);  // even / odd elements: two interleaved FFMA2 chains
 #pragma unroll
-      for (int j = 0; j < NV; ++j)  // EB:303-320
-        p += av[j].x * lrelu_fast(v[j].x + pr[j].x, g.slopes.attn) + av[j].y * lrelu_fast(v[j].y + pr[j].y, g.slopes.attn) +
-             av[j].z * lrelu_fast(v[j].z + pr[j].z, g.slopes.attn) + av[j].w * lrelu_fast(v[j].w + pr[j].w, g.slopes.attn);
-      p = head_sum<LPH>(p, sh.lc);
+      for (int j = 0; j < NV; ++j) {  // EB:303-320
+        pp = fma2(lo2(av[j]), lrelu_fast2(add2(lo2(v[j]), lo2(pr[j])), slope2), pp);
+        pp = fma2(hi2(av[j]), lrelu_fast2(add2(hi2(v[j]), hi2(pr[j])), slope2), pp);
+      }
+      float p = head_sum<LPH>(pp.x + pp.y, sh.lc);
       st_pred_u32(reinterpret_cast<uint32_t*>(score + (int64_t)e * sh.H + hd), __float_as_uint(p), head_lane);
       // online form of EB:336-349.  Of exp(m - max) and exp(p - max) one is exp(0) = 1: a single exponential
       const float dlt = p - st.m;
@@ -296,12 +326,12 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       const float corr = up ? ex : 1.f, w = up ? 1.f : ex;
       const float mn = up ? p : st.m;
       st.s = st.s * corr + w;
+      const float2 corr2 = splat2(corr), w2 = splat2(w);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        st.acc[j].x = st.acc[j].x * corr + w * v[j].x;  // EB:415-422 without atomics
-        st.acc[j].y = st.acc[j].y * corr + w * v[j].y;
-        st.acc[j].z = st.acc[j].z * corr + w * v[j].z;
-        st.acc[j].w = st.acc[j].w * corr + w * v[j].w;
+      for (int j = 0; j < NV; ++j) {  // acc = acc * corr + (w * v), EB:415-422 without atomics (same rounding as the scalar form)
+        const float2 a0 = fma2(lo2(st.acc[j]), corr2, mul2(w2, lo2(v[j])));
+        const float2 a1 = fma2(hi2(st.acc[j]), corr2, mul2(w2, hi2(v[j])));
+        st.acc[j] = make_float4(a0.x, a0.y, a1.x, a1.y);
       }
       st.m = mn;
     }
@@ -603,22 +633,27 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       }
       const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
       uint32_t* re = rec + (int64_t)e * RW;
-      float galpha = 0.f;
+      float2 gal2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) galpha += dot4(ghr[j], v[j]);  // EB:636-646
-      galpha = head_sum<LPH>(galpha, sh.lc);
+      for (int j = 0; j < NV; ++j) {  // EB:636-646, two interleaved FFMA2 chains (even / odd elements)
+        gal2 = fma2_s(lo2(ghr[j]), lo2(v[j]), gal2);
+        gal2 = fma2_s(hi2(ghr[j]), hi2(v[j]), gal2);
+      }
+      float galpha = head_sum<LPH>(gal2.x + gal2.y, sh.lc);
       const float alpha = __expf(sc[hd] - q.m) * q.inv;  // EB:378-379
       const float ge = alpha * (galpha - q.c);           // EB:689-690 in closed form
       const float ges = ge * g.slopes.attn;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float sx = v[j].x + pr[j].x, sy = v[j].y + pr[j].y, sz = v[j].z + pr[j].z, sw = v[j].w + pr[j].w;
+        const float2 s01 = add2_s(lo2(v[j]), lo2(pr[j])), s23 = add2_s(hi2(v[j]), hi2(pr[j]));
+        const float sx = s01.x, sy = s01.y, sz = s23.x, sw = s23.y;
         const bool px = sx > 0.f, py = sy > 0.f, pz = sz > 0.f, pw = sw > 0.f;
         // u = ge * LReLU'(s);  ga += u * s = ge * LReLU(s) (EB:769);  gP_r += a * u (EB:774-781, a applied per row)
-        const float ux = px ? ge : ges, uy = py ? ge : ges, uz = pz ? ge : ges, uw = pw ? ge : ges;
-        ga[j].x = fmaf(ux, sx, ga[j].x); ga[j].y = fmaf(uy, sy, ga[j].y);
-        ga[j].z = fmaf(uz, sz, ga[j].z); ga[j].w = fmaf(uw, sw, ga[j].w);
-        gpr[j].x += ux; gpr[j].y += uy; gpr[j].z += uz; gpr[j].w += uw;
+        const float2 u01 = make_float2(px ? ge : ges, py ? ge : ges), u23 = make_float2(pz ? ge : ges, pw ? ge : ges);
+        const float2 g01 = fma2_s(u01, s01, lo2(ga[j])), g23 = fma2_s(u23, s23, hi2(ga[j]));
+        ga[j] = make_float4(g01.x, g01.y, g23.x, g23.y);
+        const float2 r01 = add2_s(lo2(gpr[j]), u01), r23 = add2_s(hi2(gpr[j]), u23);
+        gpr[j] = make_float4(r01.x, r01.y, r23.x, r23.y);
         const uint32_t bx = __ballot_sync(0xffffffffu, px), by = __ballot_sync(0xffffffffu, py),
                        bz = __ballot_sync(0xffffffffu, pz), bw = __ballot_sync(0xffffffffu, pw);
         // predicated stores (no divergence regions): lane 0 writes the sign words (bit = lane, word = 4 j + component)
@@ -793,6 +828,7 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
       const float al = __uint_as_float(rw[4 * NV + hd]);  // this lane's head
       const float ge = __uint_as_float(rw[4 * NV + sh.H + hd]);
       const float ges = ge * g.slopes.attn;
+      const float2 al2 = splat2(al);
       __syncwarp();
       {
         const int ni = i + R;
@@ -808,10 +844,11 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         // EB:865-866: g_h[dst] * alpha + ge * a * LReLU'(s), LReLU'(s) from the recorded sign bit
-        acc[j].x = fmaf(((kk[j].x >> lane) & 1u) ? ge : ges, av[j].x, fmaf(al, gv[j].x, acc[j].x));
-        acc[j].y = fmaf(((kk[j].y >> lane) & 1u) ? ge : ges, av[j].y, fmaf(al, gv[j].y, acc[j].y));
-        acc[j].z = fmaf(((kk[j].z >> lane) & 1u) ? ge : ges, av[j].z, fmaf(al, gv[j].z, acc[j].z));
-        acc[j].w = fmaf(((kk[j].w >> lane) & 1u) ? ge : ges, av[j].w, fmaf(al, gv[j].w, acc[j].w));
+        const float2 u01 = make_float2(((kk[j].x >> lane) & 1u) ? ge : ges, ((kk[j].y >> lane) & 1u) ? ge : ges);
+        const float2 u23 = make_float2(((kk[j].z >> lane) & 1u) ? ge : ges, ((kk[j].w >> lane) & 1u) ? ge : ges);
+        const float2 a01 = fma2_s(u01, lo2(av[j]), fma2_s(al2, lo2(gv[j]), lo2(acc[j])));
+        const float2 a23 = fma2_s(u23, hi2(av[j]), fma2_s(al2, hi2(gv[j]), hi2(acc[j])));
+        acc[j] = make_float4(a01.x, a01.y, a23.x, a23.y);
       }
     }
     {

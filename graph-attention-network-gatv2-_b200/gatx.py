@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgatx.so")
+# GATX_LIB selects an A/B variant built by `GATX_VARIANT=... build.py` (tools/ab_packed_fp32.sh); default: the product
+LIB_PATH = os.environ.get("GATX_LIB") or os.path.join(HERE, "libgatx.so")
 
 (T_W, T_A, T_WO, T_GW, T_GA, T_GWO, T_PL, T_PR, T_SCORE, T_ALPHA, T_HPRE, T_HOUT, T_Y, T_GH, T_Z, T_PRED,
  T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR, T_GALPHA, T_GE, T_B, T_GB) = range(28)
