@@ -341,6 +341,8 @@ def run_gatx(args):
         line = {
             "metric": "train_edges_per_s", "value": E / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "epochs_per_s": 1e3 / ms,
+            # every (edge, head) pair is traversed once per layer in the forward and twice in the backward
+            "edge_head_traversals_per_s": E * sum(cfg["heads"]) / (ms * 1e-3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.fp32 else "f32 (tf32 tensor-core projections)", "data": "synthetic",
             "config": {"workload": "%s-shaped synthetic graph N=%d E=%d feats=%d classes=%d, %s, lr %g"
