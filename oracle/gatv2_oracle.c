@@ -146,18 +146,24 @@ void orc_project(int N, int I, int F, const float* X, const float* W, float* Pl,
  *   activation EB:426-459 hidden: LReLU(h) concat; last: mean_h LReLU(h_h)
  * Outputs score/alpha are head-major [H][E] like the reference; mx/sm are [H][N];
  * hpre is [N][H][D]; Hout is [N][H*D] (hidden) or [N][D] (last). */
+void orc_layer_forward_ex(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
+                          const float* Pr, const float* a, int is_last, float* score, float* alpha,
+                          float* mx, float* sm, float* hpre, float* Hout, const float* bias, const float* ascale);
 void orc_layer_forward_bias(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
                             const float* Pr, const float* a, int is_last, float* score, float* alpha,
-                            float* mx, float* sm, float* hpre, float* Hout, const float* bias);
+                            float* mx, float* sm, float* hpre, float* Hout, const float* bias) {
+  orc_layer_forward_ex(N, row_ptr, col_idx, H, D, Pl, Pr, a, is_last, score, alpha, mx, sm, hpre, Hout, bias, NULL);
+}
 void orc_layer_forward(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
                        const float* Pr, const float* a, int is_last, float* score, float* alpha,
                        float* mx, float* sm, float* hpre, float* Hout) {
   orc_layer_forward_bias(N, row_ptr, col_idx, H, D, Pl, Pr, a, is_last, score, alpha, mx, sm, hpre, Hout, NULL);
 }
-/* Same with the optional bias extension (the reference has none): hpre = sum_j alpha_ij P_l[j] + bias, bias [H][D]. */
-void orc_layer_forward_bias(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
-                            const float* Pr, const float* a, int is_last, float* score, float* alpha,
-                            float* mx, float* sm, float* hpre, float* Hout, const float* bias) {
+/* Same with the optional extensions (the reference has neither): hpre = sum_j alpha_ij * ascale_ij * P_l[j] + bias, with
+ * bias [H][D] and ascale [H][E] = keep / (1 - p) of attention-coefficient dropout (the stored alpha stays the softmax). */
+void orc_layer_forward_ex(int N, const int* row_ptr, const int* col_idx, int H, int D, const float* Pl,
+                          const float* Pr, const float* a, int is_last, float* score, float* alpha,
+                          float* mx, float* sm, float* hpre, float* Hout, const float* bias, const float* ascale) {
   const int F = H * D;
   const int64_t E = row_ptr[N];
 #pragma omp parallel for schedule(dynamic, 64)
@@ -187,7 +193,7 @@ void orc_layer_forward_bias(int N, const int* row_ptr, const int* col_idx, int H
       for (int k = 0; k < D; ++k) {
         double acc = 0.0;
         for (int e = beg; e < end; ++e)
-          acc += (double)alpha[(size_t)h * E + e] *
+          acc += (double)alpha[(size_t)h * E + e] * (ascale ? (double)ascale[(size_t)h * E + e] : 1.0) *
                  (double)Pl[(size_t)col_idx[e] * F + (size_t)h * D + k];
         if (bias) acc += (double)bias[(size_t)h * D + k];
         hpre[((size_t)i * H + h) * D + k] = (float)acc;
@@ -317,10 +323,25 @@ void orc_output_grads_masked(int N, int C, int DL, int Hl, const float* y, const
  * and contracted with X and W once.  gW/ga are accumulated (+=) like the reference's
  * atomics; gX (may be NULL for layer 0, EB:1528) is overwritten. gPl/gPr/galpha/ge
  * are optional outputs for per-kernel parity tests. */
+void orc_layer_backward_ex(int N, const int* row_ptr, const int* col_idx, int H, int D, int I,
+                           const float* X, const float* W, const float* a, const float* Pl,
+                           const float* Pr, const float* alpha, const float* g_h, float* gW, float* ga,
+                           float* gX, float* galpha_out, float* ge_out, float* gPl_out, float* gPr_out,
+                           const float* ascale);
 void orc_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, int D, int I,
                         const float* X, const float* W, const float* a, const float* Pl,
                         const float* Pr, const float* alpha, const float* g_h, float* gW, float* ga,
                         float* gX, float* galpha_out, float* ge_out, float* gPl_out, float* gPr_out) {
+  orc_layer_backward_ex(N, row_ptr, col_idx, H, D, I, X, W, a, Pl, Pr, alpha, g_h, gW, ga, gX, galpha_out, ge_out, gPl_out,
+                        gPr_out, NULL);
+}
+/* ascale [H][E] or NULL: attention-coefficient dropout, h = sum alpha * ascale * P_l, so the gradient w.r.t. alpha and
+ * the aggregation weight of g_h both carry ascale; the softmax backward is unchanged. */
+void orc_layer_backward_ex(int N, const int* row_ptr, const int* col_idx, int H, int D, int I,
+                           const float* X, const float* W, const float* a, const float* Pl,
+                           const float* Pr, const float* alpha, const float* g_h, float* gW, float* ga,
+                           float* gX, float* galpha_out, float* ge_out, float* gPl_out, float* gPr_out,
+                           const float* ascale) {
   const int F = H * D;
   const int64_t E = row_ptr[N];
   double* gPl = (double*)calloc((size_t)N * F, sizeof(double));
@@ -337,6 +358,7 @@ void orc_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, in
         const float* pl = Pl + (size_t)col_idx[e] * F + (size_t)h * D;
         double g = 0.0;
         for (int k = 0; k < D; ++k) g += (double)gh[k] * (double)pl[k];
+        if (ascale) g *= (double)ascale[(size_t)h * E + e];
         float gf = (float)g;
         if (galpha_out) galpha_out[(size_t)h * E + e] = gf;
         dotsum += (double)alpha[(size_t)h * E + e] * (double)gf;
@@ -346,6 +368,8 @@ void orc_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, in
         const float* pl = Pl + (size_t)j * F + (size_t)h * D;
         double g = 0.0;
         for (int k = 0; k < D; ++k) g += (double)gh[k] * (double)pl[k];
+        const double asc = ascale ? (double)ascale[(size_t)h * E + e] : 1.0;
+        g *= asc;
         const double al = (double)alpha[(size_t)h * E + e];
         const float gef = (float)(al * ((double)(float)g - dotsum));
         if (ge_out) ge_out[(size_t)h * E + e] = gef;
@@ -355,7 +379,7 @@ void orc_layer_backward(int N, const int* row_ptr, const int* col_idx, int H, in
           gad[(size_t)h * D + k] += gee * lrelu_d(s, g_attn_slope);
           double mk = gee * (double)ah[k] * (s > 0.0 ? 1.0 : (double)g_attn_slope);
           gPr[(size_t)i * F + (size_t)h * D + k] += mk;
-          gPl[(size_t)j * F + (size_t)h * D + k] += al * (double)gh[k] + mk;
+          gPl[(size_t)j * F + (size_t)h * D + k] += al * asc * (double)gh[k] + mk;
         }
       }
     }
@@ -581,6 +605,11 @@ typedef struct orc_model {
   uint64_t drop_seed;
   int64_t drop_step; /* number of training forwards since orc_model_set_dropout */
   float** Xd;        /* per layer: the dropped, rescaled input [N][indims[l]] (allocated on first use) */
+  /* extension: attention-coefficient dropout (oracle only so far; the engine does not implement it yet) */
+  float p_adrop;
+  uint64_t adrop_seed;
+  int64_t adrop_step;
+  float** ascale; /* per layer [H][E] keep / (1 - p) of the last training forward */
   /* extension: per-layer bias on the aggregate (NULL arrays = off, the reference) */
   int use_bias;
   float **b, **gb, **mb, **vb;
@@ -601,7 +630,7 @@ orc_model* orc_model_create(int L, const int* heads, const int* outdims, int N, 
   m->indims = (int*)malloc(sizeof(int) * L);
 #define PP(field) m->field = (float**)calloc(L, sizeof(float*))
   PP(W); PP(a); PP(gW); PP(ga); PP(mW); PP(vW); PP(ma); PP(va);
-  PP(Pl); PP(Pr); PP(score); PP(alpha); PP(mx); PP(sm); PP(hpre); PP(Hout); PP(g_h); PP(Xd); PP(b); PP(gb); PP(mb); PP(vb);
+  PP(Pl); PP(Pr); PP(score); PP(alpha); PP(mx); PP(sm); PP(hpre); PP(Hout); PP(g_h); PP(Xd); PP(b); PP(gb); PP(mb); PP(vb); PP(ascale);
 #undef PP
   for (int l = 0; l < L; ++l) {
     m->heads[l] = heads[l];
@@ -630,11 +659,11 @@ void orc_model_destroy(orc_model* m) {
     free(m->a[l]); free(m->ga[l]); free(m->ma[l]); free(m->va[l]);
     free(m->Pl[l]); free(m->Pr[l]); free(m->score[l]); free(m->alpha[l]);
     free(m->mx[l]); free(m->sm[l]); free(m->hpre[l]); free(m->Hout[l]); free(m->g_h[l]); free(m->Xd[l]);
-    free(m->b[l]); free(m->gb[l]); free(m->mb[l]); free(m->vb[l]);
+    free(m->b[l]); free(m->gb[l]); free(m->mb[l]); free(m->vb[l]); free(m->ascale[l]);
   }
   free(m->W); free(m->a); free(m->gW); free(m->ga); free(m->mW); free(m->vW); free(m->ma);
   free(m->va); free(m->Pl); free(m->Pr); free(m->score); free(m->alpha); free(m->mx); free(m->sm);
-  free(m->hpre); free(m->Hout); free(m->g_h); free(m->Xd); free(m->b); free(m->gb); free(m->mb); free(m->vb);
+  free(m->hpre); free(m->Hout); free(m->g_h); free(m->Xd); free(m->b); free(m->gb); free(m->mb); free(m->vb); free(m->ascale);
   free(m->Wo); free(m->gWo); free(m->mWo); free(m->vWo); free(m->z); free(m->y);
   free(m->heads); free(m->outdims); free(m->indims);
   free(m);
@@ -732,10 +761,40 @@ void orc_model_set_dropout(orc_model* m, float p, uint64_t seed) {
   m->drop_step = 0;
 }
 
+/* Attention-coefficient dropout scale of layer l: element (h, e) is kept iff word h % 4 of
+ * Philox(counter {e, h / 4, 0x80000000 | l, step}, key seed) >= floor(p * 2^32); kept coefficients are scaled by 1 / (1 - p). */
+void orc_attn_dropout_scale(float* out, int H, int64_t E, float p, uint64_t seed, int layer, int64_t step) {
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  const float scale = 1.0f / (1.0f - p);
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int64_t e = 0; e < E; ++e)
+    for (int q = 0; q * 4 < H; ++q) {
+      uint32_t ctr[4] = {(uint32_t)e, (uint32_t)q, 0x80000000u | (uint32_t)layer, (uint32_t)step}, r[4];
+      orc_philox4x32_10(ctr, key, r);
+      for (int t = 0; t < 4 && q * 4 + t < H; ++t) out[(size_t)(q * 4 + t) * E + e] = r[t] >= thresh ? scale : 0.0f;
+    }
+}
+void orc_model_set_attn_dropout(orc_model* m, float p, uint64_t seed) {
+  m->p_adrop = p;
+  m->adrop_seed = seed;
+  m->adrop_step = 0;
+}
+
 static void model_forward(orc_model* m, int training) {
   const float* X = m->X0;
   const int drop = training && m->p_drop > 0.0f;
+  const int adrop = training && m->p_adrop > 0.0f;
   if (drop) ++m->drop_step;
+  if (adrop) ++m->adrop_step;
+  for (int l = 0; l < m->L; ++l) { /* an evaluation forward invalidates the scale of the last training forward */
+    if (adrop) {
+      if (!m->ascale[l]) m->ascale[l] = falloc((size_t)m->heads[l] * m->E);
+      orc_attn_dropout_scale(m->ascale[l], m->heads[l], m->E, m->p_adrop, m->adrop_seed, l, m->adrop_step);
+    } else if (m->ascale[l]) {
+      free(m->ascale[l]);
+      m->ascale[l] = NULL;
+    }
+  }
   for (int l = 0; l < m->L; ++l) {
     int H = m->heads[l], D = m->outdims[l], I = m->indims[l];
     if (drop) {
@@ -744,9 +803,9 @@ static void model_forward(orc_model* m, int training) {
       X = m->Xd[l];
     }
     orc_project(m->N, I, H * D, X, m->W[l], m->Pl[l], m->Pr[l]);
-    orc_layer_forward_bias(m->N, m->row_ptr, m->col_idx, H, D, m->Pl[l], m->Pr[l], m->a[l],
-                           l == m->L - 1, m->score[l], m->alpha[l], m->mx[l], m->sm[l], m->hpre[l],
-                           m->Hout[l], m->use_bias ? m->b[l] : NULL);
+    orc_layer_forward_ex(m->N, m->row_ptr, m->col_idx, H, D, m->Pl[l], m->Pr[l], m->a[l],
+                         l == m->L - 1, m->score[l], m->alpha[l], m->mx[l], m->sm[l], m->hpre[l],
+                         m->Hout[l], m->use_bias ? m->b[l] : NULL, m->ascale[l]);
     X = m->Hout[l];
   }
   orc_head_forward(m->N, m->C, m->outdims[m->L - 1], m->Wo, X, m->z, m->y);
@@ -781,9 +840,9 @@ void orc_model_backward(orc_model* m) {
     const int drop = m->p_drop > 0.0f && m->drop_step > 0 && m->Xd[l];
     const float* X = drop ? m->Xd[l] : (l > 0 ? m->Hout[l - 1] : m->X0);
     float* gX = l > 0 ? m->g_h[l - 1] : NULL;
-    orc_layer_backward(m->N, m->row_ptr, m->col_idx, H, D, I, X, m->W[l], m->a[l], m->Pl[l],
-                       m->Pr[l], m->alpha[l], m->g_h[l], m->gW[l], m->ga[l], gX, NULL, NULL, NULL,
-                       NULL);
+    orc_layer_backward_ex(m->N, m->row_ptr, m->col_idx, H, D, I, X, m->W[l], m->a[l], m->Pl[l],
+                          m->Pr[l], m->alpha[l], m->g_h[l], m->gW[l], m->ga[l], gX, NULL, NULL, NULL,
+                          NULL, m->ascale[l]);
     /* gradient w.r.t. the dropped input -> w.r.t. the previous layer's output: same mask, same scale */
     if (l > 0 && drop) orc_dropout(gX, gX, m->N, I, 0, m->p_drop, m->drop_seed, l, m->drop_step);
     if (l > 0) orc_preact_grad(m->N, I, m->hpre[l - 1], gX);

@@ -248,6 +248,10 @@ class Model:
     def set_bias_values(self, l, b):
         lib().orc_model_set_bias_values(self._m, l, fp(f32(b)))
 
+    def set_attn_dropout(self, p, seed):
+        """Attention-coefficient dropout in training forwards (oracle only so far); resets the step counter."""
+        lib().orc_model_set_attn_dropout(self._m, C.c_float(p), C.c_uint64(seed))
+
     def set_dropout(self, p, seed):
         """Dropout on every layer's input in training forwards; resets the step counter."""
         lib().orc_model_set_dropout(self._m, C.c_float(p), C.c_uint64(seed))
@@ -293,6 +297,12 @@ def dropout(X, p, seed, layer, step, row0=0):
     lib().orc_dropout(fp(X), fp(Y), X.shape[0], X.shape[1], row0, C.c_float(p), C.c_uint64(seed), layer,
                       C.c_int64(step))
     return Y
+
+
+def attn_dropout_scale(H, E, p, seed, layer, step):
+    out = np.empty((H, E), np.float32)
+    lib().orc_attn_dropout_scale(fp(out), H, C.c_int64(E), C.c_float(p), C.c_uint64(seed), layer, C.c_int64(step))
+    return out
 
 
 def num_threads():

@@ -265,6 +265,38 @@ def test_bias_vs_torch_autograd(orc, heads, outdims):
     assert not m.tensor(orc.T_GB, 0).any()
 
 
+def test_attention_dropout_vs_torch_autograd(orc):
+    """Attention-coefficient dropout (the pin for the engine's next model option): the aggregate uses
+    alpha * keep / (1 - p), the stored alpha stays the softmax, gradients vs autograd."""
+    heads, outdims = (2, 3, 1), (4, 3, 5)
+    row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(13, heads=heads, outdims=outdims)
+    p, seed = 0.3, 17
+    m = orc.Model(heads, outdims, row_ptr, col_idx, X, y)
+    for l in range(3):
+        m.set_params(l, Ws[l], As[l])
+    m.set_wo(Wo)
+    m.set_attn_dropout(p, seed)
+    m.forward()
+    loss = m.loss()
+    m.backward()
+    E = len(col_idx)
+    sc = [orc.attn_dropout_scale(heads[l], E, p, seed, l, 1) for l in range(3)]
+    assert all(abs((s == 0).mean() - p) < 0.06 for s in sc) and not np.array_equal(sc[0][0], sc[1][0])
+    vals, grads = torch_ref.forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, y, alpha_scale=sc)
+    assert vals["y"][np.arange(len(y)), y].min() > 1e-10  # no clamped node (see test_slopes_and_dropout_vs_torch_autograd)
+    for l in range(3):
+        assert rel_err(m.tensor(orc.T_ALPHA, l), vals["alpha"][l]) < 2e-6, l
+        assert rel_err(m.tensor(orc.T_HOUT, l), vals["Hout"][l]) < 2e-6, l
+    assert abs(loss["total"] - vals["loss_sum"]) / vals["loss_sum"] < 1e-6
+    for l in range(3):
+        assert rel_err(m.tensor(orc.T_GW, l), grads["gW"][l]) < 2e-5, l
+        assert rel_err(m.tensor(orc.T_GA, l), grads["ga"][l]) < 2e-5, l
+    assert rel_err(m.tensor(orc.T_GWO), grads["gWo"]) < 2e-5
+    m.forward(train=False)  # evaluation: plain attention
+    plain, _ = torch_ref.forward_backward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, y)
+    assert rel_err(m.tensor(orc.T_Y), plain["y"]) < 2e-6
+
+
 def test_literal_fp32_matches_factored(orc):
     row_ptr, col_idx, X, y, Ws, As, Wo = small_problem(2)
     H, D = 3, 4

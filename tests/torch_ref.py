@@ -15,7 +15,7 @@ def lrelu(x, slope=SLOPE):
 
 
 def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch.float64, mask=None,
-            attn_slope=SLOPE, act_slope=SLOPE, in_scale=None, biases=None):
+            attn_slope=SLOPE, act_slope=SLOPE, in_scale=None, biases=None, alpha_scale=None):
     """in_scale: optional per-layer [N][I_l] arrays multiplied into each layer's input (a dropout mask / (1 - p))."""
     N = len(row_ptr) - 1
     deg = np.diff(row_ptr)
@@ -39,7 +39,8 @@ def forward(Ws, As, Wo, X, row_ptr, col_idx, heads, outdims, labels, dtype=torch
         ex = torch.exp(score - m[dst])
         ssum = torch.zeros((N, H), dtype=dtype).index_add(0, dst, ex)
         alpha = ex / (ssum[dst] + 1e-8)
-        h = torch.zeros((N, H, D), dtype=dtype).index_add(0, dst, alpha[:, :, None] * Pl[src].view(E, H, D))
+        agg = alpha if alpha_scale is None else alpha * torch.as_tensor(np.asarray(alpha_scale[l], np.float64).T, dtype=dtype)
+        h = torch.zeros((N, H, D), dtype=dtype).index_add(0, dst, agg[:, :, None] * Pl[src].view(E, H, D))
         if biases is not None:
             h = h + biases[l].view(1, H, D)
         if l == L - 1:
