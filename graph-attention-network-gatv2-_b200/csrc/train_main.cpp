@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -59,57 +60,162 @@ struct Mapped {
 
 inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
 
+// One token -> float with `iss >> val` / strtof semantics.  Fast path: std::from_chars (correctly rounded, like strtof,
+// so the bits are the same); anything it does not consume completely (leading '+', "inf", hex floats ...) goes through strtof.
+inline bool parse_float(const char* t, const char* e, float& v) {
+  const auto r = std::from_chars(t, e, v);
+  if (r.ec == std::errc() && r.ptr == e) return true;
+  char buf[64];
+  const size_t n = (size_t)(e - t) < sizeof buf - 1 ? (size_t)(e - t) : sizeof buf - 1;
+  memcpy(buf, t, n);
+  buf[n] = 0;
+  char* e2 = nullptr;
+  v = strtof(buf, &e2);
+  return e2 != buf;
+}
+
+// Parses the tokens of one line; stores at most `cap` values at dst and returns the number of tokens the reference's
+// `while (iss >> val)` would have read (it stops at the first token that is not a number).
+inline int parse_line(const char* q, const char* eol, float* dst, int cap) {
+  int count = 0;
+  while (q < eol) {
+    while (q < eol && is_space(*q)) ++q;
+    if (q >= eol) break;
+    const char* t = q;
+    while (q < eol && !is_space(*q)) ++q;
+    float v;
+    if (!parse_float(t, q, v)) break;
+    if (count < cap) dst[count] = v;
+    ++count;
+  }
+  return count;
+}
+
+int loader_threads(size_t bytes) {
+  const char* e = getenv("GATX_LOADER_THREADS");
+  int t = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+  if (t < 1) t = 1;
+  if (t > 32) t = 32;
+  const size_t by_size = bytes / (4u << 20) + 1;  // at least 4 MB of text per thread
+  return (size_t)t < by_size ? t : (int)by_size;
+}
+
 // Line-oriented like the reference's load_features (EB:24-51): N = number of lines, I = tokens of the first
-// line, every line must have the same count ("Inconsistent input_dim on line k", exit 1).
+// line, every line must have the same count ("Inconsistent input_dim on line k", exit 1).  The file is cut at line
+// boundaries into one segment per host thread: pass 1 counts the lines of every segment, pass 2 parses each line
+// straight into its row of the [N][I] matrix (a products-size features.txt is 2.4 GB of text).
 bool load_features(const std::string& path, std::vector<float>& out, int& n_nodes, int& in_dim) {
   Mapped f;
   n_nodes = 0;
   in_dim = 0;
   if (!f.open(path)) return true;  // the reference silently reads nothing from a missing file
-  const char *p = f.p, *end = f.p + f.n;
-  std::string tok;
-  while (p < end) {
-    const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
-    if (!eol) eol = end;
-    int count = 0;
-    const char* q = p;
-    while (q < eol) {
-      while (q < eol && is_space(*q)) ++q;
-      if (q >= eol) break;
-      const char* t = q;
-      while (q < eol && !is_space(*q)) ++q;
-      tok.assign(t, (size_t)(q - t));
-      char* e2 = nullptr;
-      const float v = strtof(tok.c_str(), &e2);
-      if (e2 == tok.c_str()) break;  // like `iss >> val` failing: stop reading this line
-      out.push_back(v);
-      ++count;
+  const char *base = f.p, *end = f.p + f.n;
+  if (f.n == 0) return true;
+  const int T = loader_threads(f.n);
+  std::vector<const char*> cut(T + 1, end);
+  cut[0] = base;
+  for (int t = 1; t < T; ++t) {
+    const char* guess = base + f.n / T * t;
+    if (guess < cut[t - 1]) guess = cut[t - 1];
+    const char* nl = guess < end ? (const char*)memchr(guess, '\n', (size_t)(end - guess)) : nullptr;
+    cut[t] = nl ? nl + 1 : end;
+  }
+  // tokens of the first line fix I (EB:38-41)
+  {
+    const char* eol = (const char*)memchr(base, '\n', f.n);
+    in_dim = parse_line(base, eol ? eol : end, nullptr, 0);
+  }
+  std::vector<int64_t> lines(T, 0);
+  auto for_segments = [&](auto&& fn) {
+    if (T == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back(fn, t);
+    for (auto& x : th) x.join();
+  };
+  for_segments([&](int t) {
+    int64_t n = 0;
+    const char* p = cut[t];
+    while (p < cut[t + 1]) {
+      const char* eol = (const char*)memchr(p, '\n', (size_t)(cut[t + 1] - p));
+      ++n;
+      p = eol ? eol + 1 : cut[t + 1];
     }
-    if (in_dim == 0) in_dim = count;
-    else if (count != in_dim) {
-      std::cerr << "Inconsistent input_dim on line " << n_nodes << std::endl;
+    lines[t] = n;
+  });
+  std::vector<int64_t> first(T + 1, 0);
+  for (int t = 0; t < T; ++t) first[t + 1] = first[t] + lines[t];
+  const int64_t N = first[T];
+  out.resize((size_t)N * (size_t)in_dim);
+  std::vector<int64_t> bad(T, -1);  // first line of the segment whose token count differs from I
+  for_segments([&](int t) {
+    const char* p = cut[t];
+    int64_t row = first[t];
+    while (p < cut[t + 1]) {
+      const char* eol = (const char*)memchr(p, '\n', (size_t)(cut[t + 1] - p));
+      if (!eol) eol = cut[t + 1];
+      const int count = parse_line(p, eol, in_dim ? out.data() + (size_t)row * in_dim : nullptr, in_dim);
+      if (count != in_dim && bad[t] < 0) bad[t] = row;
+      ++row;
+      p = eol < cut[t + 1] ? eol + 1 : cut[t + 1];
+    }
+  });
+  for (int t = 0; t < T; ++t)
+    if (bad[t] >= 0) {
+      // in_dim == 0 (an empty first line) adopts the next line's count in the reference; not worth a fast path
+      std::cerr << "Inconsistent input_dim on line " << bad[t] << std::endl;
       exit(1);
     }
-    ++n_nodes;
-    p = eol < end ? eol + 1 : end;
-  }
+  n_nodes = (int)N;
   return true;
 }
 
-// Whitespace-separated integers (EB:53-64).
+// Whitespace-separated integers (EB:53-64), parsed by one host thread per segment of the file; `file >> int` stops at
+// the first token that is not an integer, so everything after such a token is dropped.
 void load_int_array(const std::string& path, std::vector<int>& out) {
   Mapped f;
-  if (!f.open(path)) return;
-  const char *p = f.p, *end = f.p + f.n;
-  while (p < end) {
-    while (p < end && is_space(*p)) ++p;
-    if (p >= end) break;
-    bool neg = false;
-    if (*p == '-' || *p == '+') { neg = *p == '-'; ++p; }
-    if (p >= end || *p < '0' || *p > '9') break;  // `file >> int` stops at the first non-integer
-    long long v = 0;
-    while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; }
-    out.push_back((int)(neg ? -v : v));
+  if (!f.open(path) || f.n == 0) return;
+  const char *base = f.p, *end = f.p + f.n;
+  const int T = loader_threads(f.n);
+  std::vector<const char*> cut(T + 1, end);
+  cut[0] = base;
+  for (int t = 1; t < T; ++t) {
+    const char* q = base + f.n / T * t;
+    if (q < cut[t - 1]) q = cut[t - 1];
+    while (q < end && !is_space(*q)) ++q;  // never cut inside a token
+    cut[t] = q;
+  }
+  std::vector<std::vector<int>> part(T);
+  std::vector<char> stopped(T, 0);
+  auto work = [&](int t) {
+    const char *p = cut[t], *e = cut[t + 1];
+    std::vector<int>& v = part[t];
+    v.reserve((size_t)(e - p) / 4 + 1);
+    while (p < e) {
+      while (p < e && is_space(*p)) ++p;
+      if (p >= e) break;
+      bool neg = false;
+      if (*p == '-' || *p == '+') { neg = *p == '-'; ++p; }
+      if (p >= e || *p < '0' || *p > '9') { stopped[t] = 1; break; }
+      long long x = 0;
+      while (p < e && *p >= '0' && *p <= '9') { x = x * 10 + (*p - '0'); ++p; }
+      v.push_back((int)(neg ? -x : x));
+    }
+  };
+  if (T == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  size_t total = 0;
+  for (int t = 0; t < T; ++t) {
+    total += part[t].size();
+    if (stopped[t]) break;
+  }
+  out.reserve(out.size() + total);
+  for (int t = 0; t < T; ++t) {
+    out.insert(out.end(), part[t].begin(), part[t].end());
+    if (stopped[t]) break;
   }
 }
 

@@ -90,6 +90,67 @@ def test_binary_dataset_cache(cli, tmp_path):
     assert "[loader] text files" in r4.stderr and r4.stdout == r3.stdout
 
 
+def _read_cache(path):
+    """<dataset>/.gatx_cache.bin: header (magic, N, I, E, 4 sizes, 4 mtimes) then X, row_ptr, col_idx, labels."""
+    raw = open(path, "rb").read()
+    assert raw[:7] == b"GATXDS1"
+    N, I, E = np.frombuffer(raw, np.int64, 3, 8)
+    off = 8 + 8 * 3 + 8 * 8
+    X = np.frombuffer(raw, np.float32, N * I, off).reshape(N, I)
+    off += 4 * N * I
+    rp = np.frombuffer(raw, np.int32, N + 1, off)
+    off += 4 * (N + 1)
+    ci = np.frombuffer(raw, np.int32, E, off)
+    off += 4 * E
+    return X, rp, ci, np.frombuffer(raw, np.int32, N, off)
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_parallel_text_loader_is_bit_exact(cli, tmp_path, threads):
+    """The text files are cut into one segment per host thread (lines for features.txt, tokens for the integer
+    files); whatever the thread count, the parsed arrays are the bits numpy reads from the same files, incl. tokens
+    only strtof understands ("+1.5", "inf", "1e-3", "0x1p-2") and a last line without a newline."""
+    sys.path.insert(0, PKG)
+    import datasets
+    rng = np.random.default_rng(5)
+    N, I = 30000, 40   # ~13 MB of text: several 4 MB segments
+    X = (rng.standard_normal((N, I)) * 10.0 ** rng.integers(-20, 20, (N, I))).astype(np.float32)
+    row_ptr, col_idx = datasets.make_graph(N, 200000, "rmat", 3)
+    labels = rng.integers(0, 7, N).astype(np.int32)
+    d = tmp_path / "big"
+    datasets.write_txt(str(d), dict(X=X, row_ptr=row_ptr, col_idx=col_idx, labels=labels))
+    lines = open(d / "features.txt").read().split("\n")
+    assert lines[-1] == ""
+    special = ["+1.5", "inf", "-inf", "1e-3", "0x1p-2", "1E+5", ".5", "5."]
+    toks = lines[12345].split(" ")
+    toks[:len(special)] = special
+    lines[12345] = "  ".join(toks) + " \t"          # extra blanks and trailing whitespace
+    X[12345, :len(special)] = [1.5, np.inf, -np.inf, 1e-3, 0.25, 1e5, 0.5, 5.0]
+    open(d / "features.txt", "w").write("\n".join(lines[:-1]))  # no newline after the last line
+    env = dict(os.environ, GATX_LOADER_THREADS=threads)
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", "--dataset", "big", "--data-root", str(tmp_path), "--load-only",
+            env=env)
+    assert r.returncode == 0, r.stderr
+    assert "Graph loaded: %d nodes, %d edges, input_feature_vector_dim = %d\n" % (N, len(col_idx), I) in r.stdout
+    Xc, rp, ci, lab = _read_cache(d / ".gatx_cache.bin")
+    assert np.array_equal(Xc.view(np.uint32), X.view(np.uint32))     # bit-exact floats
+    assert np.array_equal(rp, row_ptr) and np.array_equal(ci, col_idx) and np.array_equal(lab, labels)
+    # a short line deep inside a later segment is reported with its line number (EB:42-45)
+    lines[20001] = " ".join(lines[20001].split()[:-1])
+    open(d / "features.txt", "w").write("\n".join(lines))
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", "--dataset", "big", "--data-root", str(tmp_path), "--load-only",
+            "--no-cache", env=env)
+    assert r.returncode == 1 and "Inconsistent input_dim on line 20001\n" in r.stderr
+    # `file >> int` stops at the first token that is not an integer (EB:53-64): col_idx is short and the run refuses it
+    open(d / "features.txt", "w").write("\n".join(lines[:20001] + [lines[0]] + lines[20002:]))
+    ctoks = open(d / "col_idx.txt").read().split()
+    ctoks[150000] = "x7"
+    open(d / "col_idx.txt", "w").write("\n".join(ctoks) + "\n")
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", "--dataset", "big", "--data-root", str(tmp_path), "--load-only",
+            "--no-cache", env=env)
+    assert r.returncode == 1 and "Invalid col_idx length" in r.stderr
+
+
 @pytest.mark.gpu
 def test_checkpoint_resume_is_bit_exact(cli, tmp_path):
     """6 epochs straight == 3 epochs + --save-checkpoint, then --resume for 3 more (Adam moments and t restored)."""
