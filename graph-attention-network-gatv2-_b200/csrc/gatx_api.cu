@@ -808,7 +808,22 @@ int capture_epoch(gatx_ctx* ctx) {
 // =============================================================================== C ABI
 extern "C" {
 
-const char* gatx_version(void) { return "gatx 0.1 (sm_100a)"; }
+const char* gatx_version(void) { return "gatx 0.2 (sm_100a)"; }
+
+int gatx_device_count(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  int usable = 0;
+  for (int d = 0; d < ndev; ++d) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d) != cudaSuccess || prop.major < 10) break;  // contexts use ordinals 0..n-1
+    ++usable;
+  }
+  return usable;
+}
 
 int gatx_create(gatx_ctx** out, const gatx_config* cfg) {
   if (!out || !cfg || cfg->num_layers <= 0 || !cfg->heads || !cfg->outdims) return GATX_ERR_INVALID;
@@ -1063,6 +1078,10 @@ int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes) {
     for (int i = 1; i < ctx->N; ++i) mx = labels[i] > mx ? labels[i] : mx;  // EB:1106-1107
     C = mx + 1;
   }
+  // the loss / gradient kernels index a row of C class scores with the label (EB:524, EB:572): refuse anything outside
+  for (int i = 0; i < ctx->N; ++i)
+    if (labels[i] < 0 || labels[i] >= C)
+      return fail(ctx, GATX_ERR_INVALID, "label %d of node %d outside [0, %d)", labels[i], i, C);
   if (ctx->have_bufs && C != ctx->C) free_bufs(ctx);
   ctx->C = C;
   if (!ctx->labels) {
@@ -1624,6 +1643,16 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
     CK(cudaMemsetAsync(ctx->barrier_word, 0, sizeof(float), ctx->st));
   }
   ctx->peers_ready = getenv("GATX_NO_P2P") == nullptr;
+  return GATX_OK;
+}
+
+int gatx_peer_disable(gatx_ctx* ctx) {
+  if (!ctx) return GATX_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->st);
+  for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
+  ctx->ipc_opened.clear();
+  ctx->peers_ready = false;
   return GATX_OK;
 }
 

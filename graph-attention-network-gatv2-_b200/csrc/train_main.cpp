@@ -15,7 +15,8 @@
 // --split (README.md:134's announced train/val/test split: <dataset>/split.txt holds one token per node, 0 = train,
 // 1 = validation, 2 = test; training loss / accuracy / gradients use the train nodes only, every printed epoch adds a
 // "Val Loss: %f, Val Accuracy: %.2f%%" line and the run ends with "Test Loss: ..."), --eval-only (no training: one
-// evaluation forward with the loaded weights / checkpoint, prints the "Avg Loss" line over all nodes or per split).
+// evaluation forward with the loaded weights / checkpoint, prints the "Avg Loss" line over all nodes or per split),
+// --check-replicas (--gpus N: after training, compare parameters + optimizer state of all ranks bit for bit).
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -293,6 +294,7 @@ void cache_store(const std::string& dir, const std::vector<float>& X, const std:
 struct Args {
   int epochs = 200, L = 2, gpus = 1, gemm = GATX_GEMM_TF32_TC, every = 1;
   bool clip = false, use_cache = true, load_only = false, split = false, eval_only = false, bias = false;
+  bool check_replicas = false;
   std::string save_ckpt, resume_ckpt;
   std::string optimizer = "sgd", dataset = "pubmed", data_root = "./data", load_w, dump_w;
   float lr = 0.0001f, beta1 = 0.9f, beta2 = 0.999f;
@@ -301,6 +303,15 @@ struct Args {
   unsigned long long seed = 0;
   bool seed_given = false;
   std::vector<int> heads, outdims;
+};
+
+// Checkpoint header (version 2): enough of the model / optimizer description to refuse a file made for another run.
+constexpr int kCkptMaxLayers = 16;
+struct CkptHeader {
+  char magic[8];
+  int32_t version, num_layers, in_dim, num_classes, use_bias, optimizer;
+  int32_t heads[kCkptMaxLayers], outdims[kCkptMaxLayers];
+  int64_t epochs_done, n_floats;
 };
 
 int fail_ctx(gatx_ctx* c, const char* what, int rc) {
@@ -373,6 +384,7 @@ int main(int argc, char** argv) {
     else if (arg == "--act-slope" && i + 1 < argc) a.act_slope = std::strtof(argv[++i], nullptr);
     else if (arg == "--dropout" && i + 1 < argc) a.dropout = std::strtof(argv[++i], nullptr);
     else if (arg == "--bias") a.bias = true;
+    else if (arg == "--check-replicas") a.check_replicas = true;
     // anything else is ignored, like the reference
   }
   if (!have_heads || !have_outdims) {
@@ -435,6 +447,11 @@ int main(int argc, char** argv) {
   }
   int max_degree = 0;
   for (int i = 0; i < N; ++i) max_degree = std::max(max_degree, row_ptr[i + 1] - row_ptr[i]);
+  for (int i = 0; i < N; ++i)
+    if (labels[i] < 0) {  // the reference would index its class arrays out of bounds (EB:524, EB:572)
+      std::cerr << "Invalid label on line " << i + 1 << "\n";
+      return 1;
+    }
   const int C = *std::max_element(labels.begin(), labels.end()) + 1;
   std::cout << "Max degree = " << max_degree << std::endl;
   std::cout << "Number of classes = " << C << std::endl;
@@ -471,8 +488,25 @@ int main(int argc, char** argv) {
     std::cerr << "Error: NCCL is not available for --gpus " << world << "\n";
     return 1;
   }
+  {
+    int ndev = gatx_device_count();
+    if (ndev < world) {  // checked here: a rank that cannot be created would leave the others waiting in NCCL
+      std::cerr << "Error: --gpus " << world << " but " << (ndev < 0 ? 0 : ndev) << " usable CUDA device(s)\n";
+      return 1;
+    }
+  }
+  // the reference seeds with time(NULL) (EB:1305); --seed makes runs reproducible.  ONE value for every rank: the
+  // parameters are replicated, never broadcast.
+  const unsigned long long init_seed = a.seed_given ? a.seed : (unsigned long long)time(nullptr);
   std::atomic<int> failed{0};
-  auto setup = [&](int r) {
+  auto for_ranks = [&](auto&& fn) {
+    if (world == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; ++r) th.emplace_back(fn, r);
+    for (auto& t : th) t.join();
+  };
+  // phase 0: contexts, one after the other (nothing collective yet)
+  for (int r = 0; r < world; ++r) {
     gatx_config cfg{};
     cfg.num_layers = a.L;
     cfg.heads = a.heads.data();
@@ -482,17 +516,37 @@ int main(int argc, char** argv) {
     cfg.clip = a.clip ? 1 : 0;
     cfg.device = r; cfg.gemm_mode = a.gemm; cfg.keep_debug = 0; cfg.rank = r; cfg.world = world;
     int rc = gatx_create(&ctx[r], &cfg);
-    if (rc) { std::cerr << "Error: gatx_create failed (" << rc << ") on device " << r << " -- no usable sm_100 GPU?\n"; failed = 1; return; }
-    if (world > 1 && (rc = gatx_comm_init(ctx[r], nccl_id))) { failed = fail_ctx(ctx[r], "gatx_comm_init", rc); return; }
+    if (rc) {
+      std::cerr << "Error: gatx_create failed (" << rc << ") on device " << r << " -- no usable sm_100 GPU?\n";
+      for (auto c : ctx) gatx_destroy(c);
+      return 1;
+    }
+  }
+  // phase 1: everything a rank does on its own (graph preparation, labels, masks, options)
+  for_ranks([&](int r) {
+    int rc;
     if ((rc = gatx_set_graph_csr(ctx[r], N, (int64_t)col_idx.size(), row_ptr.data(), col_idx.data()))) { failed = fail_ctx(ctx[r], "gatx_set_graph_csr", rc); return; }
-    if ((rc = gatx_set_features(ctx[r], X.data(), I))) { failed = fail_ctx(ctx[r], "gatx_set_features", rc); return; }
     if ((rc = gatx_set_labels(ctx[r], labels.data(), C))) { failed = fail_ctx(ctx[r], "gatx_set_labels", rc); return; }
     if (a.split && (rc = gatx_set_train_mask(ctx[r], mask[0].data()))) { failed = fail_ctx(ctx[r], "gatx_set_train_mask", rc); return; }
     if (a.bias && (rc = gatx_set_bias(ctx[r], 1))) { failed = fail_ctx(ctx[r], "gatx_set_bias", rc); return; }
     if ((a.attn_slope != 0.01f || a.act_slope != 0.01f) && (rc = gatx_set_slopes(ctx[r], a.attn_slope, a.act_slope))) { failed = fail_ctx(ctx[r], "gatx_set_slopes", rc); return; }
-    // the reference seeds with time(NULL) (EB:1305); --seed makes runs reproducible
-    const unsigned long long seed = a.seed_given ? a.seed : (unsigned long long)time(nullptr);
-    if ((rc = gatx_init_params(ctx[r], seed))) { failed = fail_ctx(ctx[r], "gatx_init_params", rc); return; }
+  });
+  if (failed) {  // no rank has entered a collective yet: a clean exit
+    for (auto c : ctx) gatx_destroy(c);
+    return 1;
+  }
+  // phase 2: the collective part (communicator, feature all-gather) and the parameters.  A rank that fails here would
+  // leave its peers blocked inside NCCL, so the process ends at once instead of joining them.
+  auto die = [&](gatx_ctx* c, const char* what, int rc) {
+    fail_ctx(c, what, rc);
+    if (world > 1) std::_Exit(1);
+    failed = 1;
+  };
+  for_ranks([&](int r) {
+    int rc;
+    if (world > 1 && (rc = gatx_comm_init(ctx[r], nccl_id))) { die(ctx[r], "gatx_comm_init", rc); return; }
+    if ((rc = gatx_set_features(ctx[r], X.data(), I))) { die(ctx[r], "gatx_set_features", rc); return; }
+    if ((rc = gatx_init_params(ctx[r], init_seed))) { die(ctx[r], "gatx_init_params", rc); return; }
     if (!a.load_w.empty()) {
       std::vector<float> W, av, Wo;
       size_t wo = 0, ao = 0, tw = 0, ta = 0;
@@ -501,32 +555,46 @@ int main(int argc, char** argv) {
       if (!read_bin(a.load_w + "/W.bin", W, tw) || !read_bin(a.load_w + "/a.bin", av, ta) ||
           !read_bin(a.load_w + "/Wo.bin", Wo, (size_t)C * a.outdims[a.L - 1])) {
         std::cerr << "Error: cannot read W.bin / a.bin / Wo.bin from " << a.load_w << "\n";
+        if (world > 1) std::_Exit(1);
         failed = 1;
         return;
       }
       in = I;
       for (int l = 0; l < a.L; ++l) {
-        if ((rc = gatx_set_params(ctx[r], l, W.data() + wo, av.data() + ao))) { failed = fail_ctx(ctx[r], "gatx_set_params", rc); return; }
+        if ((rc = gatx_set_params(ctx[r], l, W.data() + wo, av.data() + ao))) { die(ctx[r], "gatx_set_params", rc); return; }
         wo += (size_t)a.heads[l] * a.outdims[l] * 2 * in;
         ao += (size_t)a.heads[l] * a.outdims[l];
         in = a.heads[l] * a.outdims[l];
       }
-      if ((rc = gatx_set_wo(ctx[r], Wo.data()))) { failed = fail_ctx(ctx[r], "gatx_set_wo", rc); return; }
+      if ((rc = gatx_set_wo(ctx[r], Wo.data()))) { die(ctx[r], "gatx_set_wo", rc); return; }
+      if (a.bias) {  // b.bin: the per-layer biases [b_0 | .. | b_{L-1}]; absent in dumps made without --bias (they stay zero)
+        std::vector<float> bv;
+        if (read_bin(a.load_w + "/b.bin", bv, ta)) {
+          size_t bo = 0;
+          for (int l = 0; l < a.L; ++l) {
+            if ((rc = gatx_set_bias_values(ctx[r], l, bv.data() + bo))) { die(ctx[r], "gatx_set_bias_values", rc); return; }
+            bo += (size_t)a.heads[l] * a.outdims[l];
+          }
+        }
+      }
     }
-  };
-  {
-    std::vector<std::thread> th;
-    for (int r = 0; r < world; ++r) th.emplace_back(setup, r);
-    for (auto& t : th) t.join();
-  }
+  });
   if (failed) return 1;
   if (world > 1) {
-    // halo exchange over NVLink peer memory: the contexts live in one process, so the blobs carry raw pointers
+    // halo exchange over NVLink peer memory: the contexts live in one process, so the blobs carry raw pointers.  The
+    // decision is GLOBAL: if any rank cannot export or import, every rank falls back to the NCCL collectives (ranks
+    // issuing different exchange sequences would deadlock).
     std::vector<unsigned char> blobs((size_t)world * GATX_PEER_INFO_BYTES);
     bool ok = true;
-    for (int r = 0; r < world && ok; ++r) ok = gatx_peer_export(ctx[r], blobs.data() + (size_t)r * GATX_PEER_INFO_BYTES, GATX_PEER_INFO_BYTES) == GATX_OK;
-    for (int r = 0; r < world && ok; ++r) ok = gatx_peer_import(ctx[r], blobs.data(), blobs.size()) == GATX_OK;
-    if (!ok) std::cerr << "Note: peer-memory halo exchange unavailable (" << gatx_last_error(ctx[0]) << "); using NCCL collectives\n";
+    int bad = 0;
+    for (int r = 0; r < world && ok; ++r)
+      if (gatx_peer_export(ctx[r], blobs.data() + (size_t)r * GATX_PEER_INFO_BYTES, GATX_PEER_INFO_BYTES) != GATX_OK) { ok = false; bad = r; }
+    for (int r = 0; r < world && ok; ++r)
+      if (gatx_peer_import(ctx[r], blobs.data(), blobs.size()) != GATX_OK) { ok = false; bad = r; }
+    if (!ok) {
+      std::cerr << "Note: peer-memory halo exchange unavailable (" << gatx_last_error(ctx[bad]) << "); using NCCL collectives\n";
+      for (int r = 0; r < world; ++r) gatx_peer_disable(ctx[r]);
+    }
   }
 
   auto dump_weights = [&](const std::string& dir) {
@@ -541,33 +609,64 @@ int main(int argc, char** argv) {
     }
     Wo.resize((size_t)gatx_tensor_size(ctx[0], GATX_T_WO, 0));
     gatx_get_tensor(ctx[0], GATX_T_WO, 0, Wo.data(), Wo.size() * 4);
+    if (a.bias) {
+      std::vector<float> bv;
+      for (int l = 0; l < a.L; ++l) {
+        std::vector<float> b((size_t)gatx_tensor_size(ctx[0], GATX_T_B, l));
+        gatx_get_tensor(ctx[0], GATX_T_B, l, b.data(), b.size() * 4);
+        bv.insert(bv.end(), b.begin(), b.end());
+      }
+      if (!write_bin(dir + "/b.bin", bv)) return false;
+    }
     return write_bin(dir + "/W.bin", W) && write_bin(dir + "/a.bin", av) && write_bin(dir + "/Wo.bin", Wo);
   };
 
-  // checkpoint file: int64 epochs_done, int64 n_floats, then [params | Adam m | Adam v]
+  // checkpoint file: CkptHeader (magic, version, the model / optimizer description), then [params | Adam m | Adam v].
+  // --resume refuses a file written for another architecture even when the parameter COUNT happens to match
+  // (4 heads x 64 and 8 heads x 32 have the same number of floats).
+  CkptHeader want{};
+  memcpy(want.magic, "GATXCK2", 8);
+  want.version = 2;
+  want.num_layers = a.L;
+  want.in_dim = I;
+  want.num_classes = C;
+  want.use_bias = a.bias ? 1 : 0;
+  want.optimizer = a.optimizer == "adam" ? GATX_OPT_ADAM : GATX_OPT_SGD;
+  for (int l = 0; l < a.L && l < kCkptMaxLayers; ++l) { want.heads[l] = a.heads[l]; want.outdims[l] = a.outdims[l]; }
+  want.n_floats = gatx_state_size(ctx[0]);
   int first_epoch = 1;
   if (!a.resume_ckpt.empty()) {
     FILE* f = fopen(a.resume_ckpt.c_str(), "rb");
-    int64_t hdr[2] = {0, 0};
+    CkptHeader got{};
     std::vector<float> stt;
-    bool ok = f && fread(hdr, sizeof hdr, 1, f) == 1 && hdr[1] == gatx_state_size(ctx[0]);
+    bool ok = f && fread(&got, sizeof got, 1, f) == 1;
+    const char* why = "missing or not a gatx checkpoint";
+    if (ok && (memcmp(got.magic, want.magic, 8) != 0 || got.version != want.version)) ok = false;
     if (ok) {
-      stt.resize((size_t)hdr[1]);
+      why = "written for another model";
+      ok = a.L <= kCkptMaxLayers && got.num_layers == want.num_layers && got.in_dim == want.in_dim &&
+           got.num_classes == want.num_classes && got.use_bias == want.use_bias && got.n_floats == want.n_floats &&
+           memcmp(got.heads, want.heads, sizeof want.heads) == 0 && memcmp(got.outdims, want.outdims, sizeof want.outdims) == 0;
+    }
+    if (ok && got.optimizer != want.optimizer) { ok = false; why = "written by another optimizer"; }
+    if (ok) {
+      why = "truncated";
+      stt.resize((size_t)got.n_floats);
       ok = fread(stt.data(), sizeof(float), stt.size(), f) == stt.size();
     }
     if (f) fclose(f);
     if (!ok) {
-      std::cerr << "Error: cannot resume from " << a.resume_ckpt << " (missing or for another model)\n";
+      std::cerr << "Error: cannot resume from " << a.resume_ckpt << " (" << why << ")\n";
       return 1;
     }
     for (int r = 0; r < world; ++r)
       if (int rc = gatx_set_state(ctx[r], stt.data(), stt.size() * sizeof(float))) return fail_ctx(ctx[r], "gatx_set_state", rc);
-    first_epoch = (int)hdr[0] + 1;
+    first_epoch = (int)got.epochs_done + 1;
   }
   if (a.dropout != 0.0f) {
     // every rank draws the same mask (a function of seed, layer, step, global row, column); a resumed run continues
     // with a fresh stream
-    const unsigned long long dseed = (a.seed_given ? a.seed : (unsigned long long)time(nullptr)) + 7919ull * (unsigned long long)first_epoch;
+    const unsigned long long dseed = init_seed + 7919ull * (unsigned long long)first_epoch;
     for (int r = 0; r < world; ++r)
       if (int rc = gatx_set_dropout(ctx[r], a.dropout, dseed)) return fail_ctx(ctx[r], "gatx_set_dropout", rc);
     std::cout << "Dropout: " << a.dropout << " on every layer's input (training forwards only)\n";
@@ -636,13 +735,26 @@ int main(int argc, char** argv) {
     printf("\nTest Loss: %f, Test Accuracy: %.2f%%\n", lo, 100.0f * ac);
   }
   if (!a.save_ckpt.empty()) {
-    const int64_t n = gatx_state_size(ctx[0]);
+    const int64_t n = want.n_floats;
     std::vector<float> stt((size_t)(n > 0 ? n : 0));
-    int64_t hdr[2] = {(int64_t)last_epoch, n};
-    FILE* f = n > 0 && gatx_get_state(ctx[0], stt.data(), stt.size() * sizeof(float)) == GATX_OK ? fopen(a.save_ckpt.c_str(), "wb") : nullptr;
-    if (!f || fwrite(hdr, sizeof hdr, 1, f) != 1 || fwrite(stt.data(), sizeof(float), stt.size(), f) != stt.size())
+    CkptHeader hdr = want;
+    hdr.epochs_done = last_epoch;
+    FILE* f = n > 0 && a.L <= kCkptMaxLayers && gatx_get_state(ctx[0], stt.data(), stt.size() * sizeof(float)) == GATX_OK
+                  ? fopen(a.save_ckpt.c_str(), "wb") : nullptr;
+    if (!f || fwrite(&hdr, sizeof hdr, 1, f) != 1 || fwrite(stt.data(), sizeof(float), stt.size(), f) != stt.size())
       std::cerr << "Warning: could not write checkpoint " << a.save_ckpt << "\n";
     if (f) fclose(f);
+  }
+  if (a.check_replicas && world > 1) {
+    // every rank applies the same all-reduced gradients to its own copy of the parameters: the copies must be identical
+    const int64_t n = gatx_state_size(ctx[0]);
+    std::vector<float> s0((size_t)n), sr((size_t)n);
+    bool same = n > 0 && gatx_get_state(ctx[0], s0.data(), s0.size() * sizeof(float)) == GATX_OK;
+    for (int r = 1; r < world && same; ++r)
+      same = gatx_get_state(ctx[r], sr.data(), sr.size() * sizeof(float)) == GATX_OK &&
+             memcmp(s0.data(), sr.data(), s0.size() * sizeof(float)) == 0;
+    std::cout << (same ? "Replicas identical on " : "REPLICAS DIFFER on ") << world << " ranks" << std::endl;
+    if (!same) return 1;
   }
   if (!a.dump_w.empty() && !dump_weights(a.dump_w)) std::cerr << "Warning: could not write weights to " << a.dump_w << "\n";
   for (auto c : ctx) gatx_destroy(c);

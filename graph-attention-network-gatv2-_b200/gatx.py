@@ -26,7 +26,7 @@ EXPORTS = [
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
-    "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_bias", "gatx_set_bias_values",
+    "gatx_device_count", "gatx_peer_disable", "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_bias", "gatx_set_bias_values",
 ]
 
 
@@ -332,6 +332,11 @@ class Engine:
         data = b"".join(blobs)
         self.lib.gatx_peer_import.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         self._ck(self.lib.gatx_peer_import(self.ctx, data, len(data)), "gatx_peer_import")
+
+    def peer_disable(self):
+        """Back to the NCCL collectives (call on EVERY rank when any rank failed to export / import)."""
+        self.lib.gatx_peer_disable.argtypes = [C.c_void_p]
+        self._ck(self.lib.gatx_peer_disable(self.ctx), "gatx_peer_disable")
 
     def halo_rows(self):
         self.lib.gatx_halo_rows.restype = C.c_int64

@@ -102,6 +102,10 @@ int gatx_create(gatx_ctx** out, const gatx_config* cfg);
 void gatx_destroy(gatx_ctx* ctx);
 const char* gatx_last_error(const gatx_ctx* ctx);
 const char* gatx_version(void);
+/* Number of usable devices (sm_100 class, ordinals 0..n-1); -1 when the CUDA runtime cannot be initialised.  A
+ * multi-rank host checks it BEFORE creating contexts: a rank that cannot be created would leave its peers waiting in
+ * the communicator (replaces nothing in the reference, which is single-GPU and never calls cudaSetDevice). */
+int gatx_device_count(void);
 
 /* ---- data ------------------------------------------------------------------------------- */
 /* Replaces EB:1158-1192 (H2D of CSR + csr_to_coo_kernel) and adds the transposed graph and
@@ -113,7 +117,8 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t num_nodes, int64_t num_edges,
  * communicator the call is COLLECTIVE: every rank copies only its own rows host->device and the row blocks are
  * all-gathered over NVLink (every rank keeps all input rows, so layer 0 needs no exchange step). */
 int gatx_set_features(gatx_ctx* ctx, const float* X, int32_t in_dim);
-/* Replaces EB:1169-1172 + EB:1106-1107 (num_classes <= 0: derived as max(label)+1). */
+/* Replaces EB:1169-1172 + EB:1106-1107 (num_classes <= 0: derived as max(label)+1).  Labels outside [0, num_classes)
+ * are refused with GATX_ERR_INVALID (the reference would index its class arrays out of bounds, EB:524, EB:572). */
 int gatx_set_labels(gatx_ctx* ctx, const int32_t* labels, int32_t num_classes);
 /* Extension (README.md:134 announces train/val/test splits "later"; the reference trains and scores on every
  * node, EB:514-550).  mask is a GLOBAL uint8 [N]: nodes with mask[n] == 0 contribute nothing to the loss, the
@@ -233,6 +238,10 @@ int gatx_comm_init(gatx_ctx* ctx, const void* id128);
 #define GATX_PEER_INFO_BYTES 2048
 int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes);
 int gatx_peer_import(gatx_ctx* ctx, const void* all_blobs, size_t bytes);
+/* Back to the NCCL collectives on this rank.  The choice of exchange path must be the same on EVERY rank (different
+ * sequences of barriers / collectives deadlock): when gatx_peer_export or gatx_peer_import fails on any rank, the host
+ * calls this on all of them. */
+int gatx_peer_disable(gatx_ctx* ctx);
 /* Rows this rank pushes per layer (sum over own rows of the number of other ranks referencing them); an all-gather
  * would move (world - 1) * own rows.  Integer, identical to oracle/orc_halo_rows. */
 int64_t gatx_halo_rows(const gatx_ctx* ctx);

@@ -30,18 +30,30 @@ CASES = {
     # Kept to document the defect ("D13"); only the unaffected quantities are compared.
     "tail_block_defect": (96, 600, 10, 3, [4, 1], [16, 8], "sgd", 0.001, False, "rmat", 4),
     "three_layer_adam": (80, 480, 12, 5, [4, 4, 1], [8, 8, 16], "adam", 0.005, True, "rmat", 8),
+    # BASELINE.json config 2 at its literal shape and flags (datasets.make_dataset("cora"): 2 708 nodes, 5 429 edges,
+    # 1 433 sparse features, 7 classes, --heads 8,1 --outdims 8,8, SGD).  E % 256 = 53 < 2 * in_dim of BOTH layers, so
+    # defect D13 corrupts the reference's own gW here; forward, g_h, ga and gW_o are unaffected and compared.
+    "cora_shape_defect": "cora",
 }
 
 
 def run_case(name, spec, out_dir):
-    N, E, I, C, heads, outdims, opt, lr, clip, kind, epochs = spec
     seed = 4000 + len(name)
-    row_ptr, col_idx = datasets.make_graph(N, E, kind, seed)
-    X = datasets.make_features(N, I, "uniform", seed)
-    y = datasets.make_labels(N, C, seed)
-    Ws, As, Wo = datasets.init_params(heads, outdims, I, C, seed)
-    Ws = [w * 2 for w in Ws]
-    As = [a * 2 for a in As]
+    if isinstance(spec, str):  # a literal BASELINE config of datasets.CONFIGS
+        ds0 = datasets.make_dataset(spec)
+        c0 = ds0["cfg"]
+        N, E, I, C, heads, outdims, opt, lr, clip, epochs = (c0["N"], c0["E"], c0["I"], c0["C"], c0["heads"], c0["outdims"],
+                                                             c0["optimizer"], c0["lr"], c0["clip"], 3)
+        row_ptr, col_idx, X, y = ds0["row_ptr"], ds0["col_idx"], ds0["X"], ds0["labels"]
+        Ws, As, Wo = datasets.init_params(heads, outdims, I, C, seed)
+    else:
+        N, E, I, C, heads, outdims, opt, lr, clip, kind, epochs = spec
+        row_ptr, col_idx = datasets.make_graph(N, E, kind, seed)
+        X = datasets.make_features(N, I, "uniform", seed)
+        y = datasets.make_labels(N, C, seed)
+        Ws, As, Wo = datasets.init_params(heads, outdims, I, C, seed)
+        Ws = [w * 2 for w in Ws]
+        As = [a * 2 for a in As]
     tmp = tempfile.mkdtemp(prefix="gatx_golden_")
     ds = dict(row_ptr=row_ptr, col_idx=col_idx, X=X, labels=y)
     datasets.write_txt(os.path.join(tmp, "data", name), ds)
@@ -67,7 +79,12 @@ def run_case(name, spec, out_dir):
     curve_d1 = [(float(a), float(b)) for a, b in re.findall(r"Avg Loss: ([0-9.eE+-]+), Accuracy: ([0-9.]+)%", out2.stdout)]
     m = re.search(r"Max degree = (\d+)", out.stdout)
     c = re.search(r"Number of classes = (\d+)", out.stdout)
-    rec = dict(row_ptr=row_ptr, col_idx=col_idx, X=X, labels=y, Wo=Wo, heads=np.array(heads), outdims=np.array(outdims),
+    if isinstance(spec, str):  # sparse features: keep the fixture small (non-zeros only; the loader rebuilds X)
+        nz = np.flatnonzero(X.ravel())
+        Xrec = dict(X_shape=np.array(X.shape), X_nnz_idx=nz.astype(np.int32), X_nnz_val=X.ravel()[nz])
+    else:
+        Xrec = dict(X=X)
+    rec = dict(row_ptr=row_ptr, col_idx=col_idx, labels=y, Wo=Wo, **Xrec, heads=np.array(heads), outdims=np.array(outdims),
                optimizer=np.array(opt), lr=np.array(lr), clip=np.array(clip), loss_curve=np.array(curve),
                loss_curve_unpatched_d1=np.array(curve_d1), max_degree=np.array(int(m.group(1))),
                num_classes=np.array(int(c.group(1))))
@@ -84,5 +101,7 @@ def run_case(name, spec, out_dir):
 
 if __name__ == "__main__":
     out_dir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    only = sys.argv[2:]  # optional case names
     for name, spec in CASES.items():
-        run_case(name, spec, out_dir)
+        if not only or name in only:
+            run_case(name, spec, out_dir)

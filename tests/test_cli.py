@@ -173,6 +173,38 @@ def test_checkpoint_resume_is_bit_exact(cli, tmp_path):
 
 
 @pytest.mark.gpu
+def test_checkpoint_of_another_model_is_refused(cli, tmp_path):
+    """4 heads x 16 and 8 heads x 8 have the same number of parameters: the checkpoint header (magic, version, layers,
+    heads, outdims, in_dim, classes, bias, optimizer) must refuse the file instead of reinterpreting the floats."""
+    sys.path.insert(0, PKG)
+    import datasets
+    datasets.write_txt(str(tmp_path / "sample"), datasets.make_dataset("sample"))
+    common = ["--optimizer", "adam", "--lr", "0.01", "--dataset", "sample", "--data-root", str(tmp_path), "--seed", "5",
+              "--epochs", "2"]
+    ck = str(tmp_path / "ck.bin")
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", *common, "--save-checkpoint", ck)
+    assert r.returncode == 0, r.stderr
+    r = run(cli, "--heads", "4,1", "--outdims", "16,8", *common, "--resume", ck)
+    assert r.returncode == 1 and "written for another model" in r.stderr
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", *[("sgd" if x == "adam" else x) for x in common], "--resume", ck)
+    assert r.returncode == 1 and "another optimizer" in r.stderr
+    open(tmp_path / "junk.bin", "wb").write(b"\0" * 4096)
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", *common, "--resume", str(tmp_path / "junk.bin"))
+    assert r.returncode == 1 and "not a gatx checkpoint" in r.stderr
+    # --bias: the biases travel with --dump-weights / --load-weights (b.bin)
+    (tmp_path / "w").mkdir()
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", *common, "--bias", "--dump-weights", str(tmp_path / "w"))
+    assert r.returncode == 0 and (tmp_path / "w" / "b.bin").stat().st_size == 4 * (64 + 8)
+    b = np.fromfile(tmp_path / "w" / "b.bin", np.float32)
+    assert np.abs(b).max() > 0  # trained for two epochs
+    (tmp_path / "w2").mkdir()
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", *common[:-1], "0", "--bias", "--load-weights", str(tmp_path / "w"),
+            "--dump-weights", str(tmp_path / "w2"))
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "w2" / "b.bin").read_bytes() == (tmp_path / "w" / "b.bin").read_bytes()
+
+
+@pytest.mark.gpu
 def test_extension_flags(cli, tmp_path):
     """--attn-slope / --act-slope / --dropout are opt-in: absent (or at the reference values) the loss curve is the
     default one bit for bit; present they change it, reproducibly for a fixed --seed."""
@@ -199,6 +231,23 @@ def test_extension_flags(cli, tmp_path):
     assert bias[0] == default[0] and bias[1:] != default[1:]  # biases start at zero, then train
     r = run(cli, *(base + ["--dropout", "1.5"]))
     assert r.returncode == 1 and "gatx_set_dropout" in r.stderr
+
+
+def test_invalid_label_and_gpu_count(cli, tmp_path):
+    """A negative label is refused while loading (the reference would index its class arrays out of bounds, EB:524);
+    --gpus N with fewer usable devices ends with an error instead of leaving rank threads waiting in NCCL."""
+    sys.path.insert(0, PKG)
+    import datasets
+    ds = datasets.make_dataset("sample")
+    ds["labels"] = ds["labels"].copy()
+    ds["labels"][10] = -2
+    datasets.write_txt(str(tmp_path / "neg"), ds)
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", "--dataset", "neg", "--data-root", str(tmp_path), "--load-only")
+    assert r.returncode == 1 and "Invalid label on line 11" in r.stderr
+    datasets.write_txt(str(tmp_path / "ok"), datasets.make_dataset("sample"))
+    r = run(cli, "--heads", "8,1", "--outdims", "8,8", "--dataset", "ok", "--data-root", str(tmp_path), "--gpus", "64",
+            "--epochs", "1")
+    assert r.returncode == 1 and "usable CUDA device" in r.stderr
 
 
 def test_split_file_errors(cli, tmp_path):

@@ -516,3 +516,23 @@ def test_bias_parity(gatx, orc, shape, mode):
         plain.tensor(gatx.T_B, 0)  # no bias unless switched on
     assert plain.get_state().size == st.size - 3 * nb
     plain.close()
+
+
+def test_labels_outside_class_range_are_refused(gatx):
+    """gatx_set_labels validates [0, C): the loss kernels index a row of C scores with the label (EB:524, EB:572)."""
+    p = make_problem(100, 500, 8, 4, (2, 1), (8, 8), seed=4)
+    eng = gatx.Engine(p["heads"], p["outdims"])
+    eng.set_graph(p["row_ptr"], p["col_idx"])
+    eng.set_features(p["X"])
+    bad = p["labels"].copy()
+    bad[17] = -1
+    with pytest.raises(gatx.GatxError, match="label -1 of node 17"):
+        eng.set_labels(bad, 4)
+    bad[17] = 4
+    with pytest.raises(gatx.GatxError, match="outside"):
+        eng.set_labels(bad, 4)
+    eng.set_labels(p["labels"], 4)  # the context stays usable
+    eng.init_params(1)
+    assert np.isfinite(eng.train_epoch(1)[0])
+    assert gatx.load().gatx_device_count() >= 1
+    eng.close()

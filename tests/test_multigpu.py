@@ -144,3 +144,22 @@ def test_cli_two_gpus_matches_one(tmp_path, extra):
     assert len(curves[0]) == 6 and len(curves[1]) == 6
     for a, b in zip(*curves):
         assert abs(a - b) < 2e-4 * max(1.0, a)
+
+
+def test_cli_two_gpus_without_seed_keeps_replicas_identical(tmp_path):
+    """Without --seed the parameters are drawn from time(NULL) like the reference (EB:1305).  The value is taken ONCE
+    for all ranks (the replicas are never broadcast): after training, --check-replicas compares parameters and Adam
+    moments of both ranks bit for bit."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(HERE, "..", "graph-attention-network-gatv2-_b200"))
+    import build as gatx_build
+    import datasets
+    cli = gatx_build.build_cli()
+    datasets.write_txt(str(tmp_path / "g"), datasets.make_dataset("arxiv", 0.05))
+    r = subprocess.run([cli, "--num-layers", "3", "--heads", "4,4,1", "--outdims", "64,64,64", "--epochs", "4",
+                        "--optimizer", "adam", "--lr", "0.01", "--dataset", "g", "--data-root", str(tmp_path), "--gpus", "2",
+                        "--check-replicas"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Replicas identical on 2 ranks" in r.stdout
