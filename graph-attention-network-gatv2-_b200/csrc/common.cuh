@@ -113,11 +113,13 @@ int launch_chunk_rows(const int* row_ptr, int n_rows, int64_t E, int T, int n_ch
 int launch_edge_forward_stream(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
                                float* Hout, float* hpre, float* score, float* mx, float* sinv, float* part,
                                cudaStream_t st);
-// prep (g_h in place + cdot) + pass 1 (gPr, rec, ga partials) + pass 2 (gPl)
+// phases bit 0: prep (g_h in place + cdot) + pass 1 (gPr, rec, ga partials) over g's destination rows;
+// bit 1: pass 2 (gPl) over g's sources.  The multi-GPU epoch runs pass 1 per block of destination rows (a block is
+// an EdgeGraph of its own: rebased row_ptr, its own chunks, pointers offset to the block) and pass 2 once.
 int launch_edge_backward_stream(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
                                 const float* Hout, float* gH, float* cdot, const float* score, const float* mx,
                                 const float* sinv, float* gPr, float* gPl, uint32_t* rec, float* part,
-                                float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st);
+                                float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st, int phases = 3);
 
 // edge_generic.cu : any heads <= 32, any per-head dim with heads*dim <= 1024 (scalar fallback)
 bool edge_generic_supported(int H, int D);
@@ -153,6 +155,14 @@ int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uin
                      int me, cudaStream_t st);
 int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
                      int world, cudaStream_t st);
+// Device-side barrier across ranks through flags in peer memory: rank `me` stores `seq` (release, system scope) into
+// slot `me` of every peer's flag array, then waits (acquire) until every slot of its own array has reached `seq`.
+// Stream-ordered: everything this rank enqueued before it on `st` (and its peer-memory stores) is visible to a peer
+// once that peer has left its own barrier `seq`.  A peer that never arrives trips a timeout (the kernel traps).
+struct PeerFlags {
+  uint32_t* p[kMaxPeers];  // flag array [kMaxPeers] of every rank (own slot: this rank's array)
+};
+int launch_halo_barrier(const PeerFlags& flags, int me, int world, uint32_t seq, cudaStream_t st);
 
 // graph_prep.cu: out[e] = idx[e] | bit31 if degree(idx[e]) >= thr_wide | bit30 if degree(idx[e]) >= thr_narrow
 int launch_mark_hot(const int* idx, const int* ptr, int64_t E, int thr_wide, int thr_narrow, int* out, cudaStream_t st);

@@ -992,14 +992,16 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
 int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* Pl, const float* Pr, const float* a,
                                 const float* Hout, float* gH, float* cdot, const float* score, const float* mx,
                                 const float* sinv, float* gPr, float* gPl, uint32_t* rec, float* part,
-                                float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st) {
+                                float* ga_partials, int* n_partials, float* galpha_dbg, cudaStream_t st, int phases) {
   Shape sh;
   int nv, launches = 0;
   if (!make_stream_shape(H, D, &sh, &nv) || eg.E >= 0x7fffffffLL) return -1;
   sh.slopes = eg.slopes;
   sh.bias = eg.bias;
-  *n_partials = 0;
-  if (eg.n_rows <= 0) return 0;
+  const bool do_p1 = (phases & 1) != 0, do_p2 = (phases & 2) != 0;
+  if (do_p1) *n_partials = 0;
+  if (eg.n_rows <= 0 && !do_p2) return 0;
+  if (eg.n_rows <= 0 && eg.n_src <= 0) return 0;
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
   const int* cdstx = hs.on ? eg.csc_dst_hot : eg.csc_dst;
@@ -1007,17 +1009,19 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask, eg.slopes, eg.bias};
   if (use_pair(nv, sh)) {
     constexpr int R = 16, F = kPF;
-    {
+    if (do_p1 && eg.n_rows > 0) {
       int blocks = (eg.n_rows + 7) / 8;
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
       edge_bwd_prep_kernel<1><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+      fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);
+      launches += 2;
+    }
+    if (do_p2) {
+      fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
       ++launches;
     }
-    fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);
-    fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
-    launches += 2;
     if (eg.E > 0) {
-      {
+      if (do_p1) {
         const size_t per_warp = (size_t)(R * F + 2 * F + 64) * 4;
         const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
         auto kern = edge_bwd_dst_pair_kernel<R>;
@@ -1034,7 +1038,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
           ++launches;
         }
       }
-      {
+      if (do_p2) {
         const size_t smem = (size_t)kSW * R * (F + 32) * 4 + (size_t)kSW * R * 8;
         auto kern = edge_bwd_src_pair_kernel<R>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1053,17 +1057,19 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   }
   STREAM_DISPATCH(nv, sh.lc, {
     constexpr int F = NV * 128;
-    {
+    if (do_p1 && eg.n_rows > 0) {
       int blocks = (eg.n_rows + 7) / 8;
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
       edge_bwd_prep_kernel<NV><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+      fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);  // 8 warps x 32 rows
+      launches += 2;
+    }
+    if (do_p2) {
+      fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
       ++launches;
     }
-    fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);  // 8 warps x 32 rows
-    fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
-    launches += 2;
     if (eg.E > 0) {
-      {
+      if (do_p1) {
         constexpr int R = NV == 4 ? 4 : 8;
         const size_t per_warp = (size_t)(R * F + 2 * F + 2 * 32 * H) * 4;
         const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
@@ -1081,7 +1087,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
           ++launches;
         }
       }
-      {
+      if (do_p2) {
         constexpr int R = ring_depth<NV>();
         const int slot_floats = F + (rec_words(H, NV) + 31) / 32 * 32;
         const size_t smem = (size_t)kSW * R * slot_floats * 4 + (size_t)kSW * R * 8;

@@ -100,6 +100,16 @@ struct gatx_ctx {
   int n_heavy_rows = 0, n_heavy_srcs = 0;
   int chunk_T = 256, n_chunks = 0;
   int *chunk_row = nullptr, *chunk_src = nullptr;
+  // multi-GPU pipeline: the own destination rows cut into edge-balanced blocks, each a graph of its own for the
+  // streaming kernels (rebased row_ptr, own chunk table); one block = the whole range when pipelining is off
+  struct RowBlock {
+    int r0 = 0, n_rows = 0;
+    int64_t e0 = 0, E = 0, halo_rows = 0;  // halo_rows: (own row, other rank that gathers it) pairs of the block
+    int n_chunks = 0;
+    int *row_ptr = nullptr, *chunk_row = nullptr;  // views into blk_row_ptr / blk_chunk_row
+  };
+  std::vector<RowBlock> blocks;
+  int *blk_row_ptr = nullptr, *blk_chunk_row = nullptr;
   // L2 residency hints: index copies whose top bits mark the most frequently gathered nodes (nullptr = off)
   int *col_idx_hot = nullptr, *csc_dst_hot = nullptr;
   int hot_wide_F = 0;
@@ -122,6 +132,7 @@ struct gatx_ctx {
   std::vector<Layer> layers;
   // scratch
   float *gPl = nullptr, *gPr = nullptr, *ga_partials = nullptr, *splitk_ws = nullptr, *norm_partials = nullptr;
+  float* gPr2 = nullptr;  // second gP_r scratch: the pipelined backward writes layer l - 1's while layer l's is still read
   uint32_t* rec = nullptr;
   float *part = nullptr, *cdot = nullptr;
   size_t splitk_ws_bytes = 0;
@@ -141,7 +152,16 @@ struct gatx_ctx {
   std::vector<PeerPtrs> peer_Pl;  // per layer
   PeerPtrs peer_gPl{};
   std::vector<void*> ipc_opened;
-  float* barrier_word = nullptr;
+  // exchange stream + flag barriers in peer memory (halo_p2p.cu)
+  cudaStream_t st_comm = nullptr;
+  uint32_t* halo_flags = nullptr;  // [kMaxPeers] slot p: the last barrier rank p has reached
+  PeerFlags peer_flags{};
+  uint32_t barrier_seq = 0;
+  std::vector<cudaEvent_t> ev_pool;  // cross-stream ordering events, reused every epoch
+  size_t ev_used = 0;
+  struct CommSpan { int dir; double bytes; cudaEvent_t a, b; };  // dir 0 = push, 1 = pull (timing enabled)
+  std::vector<CommSpan> comm_spans;
+  size_t comm_spans_used = 0;
   // timing
   cudaEvent_t sw_a = nullptr, sw_b = nullptr;
   bool timing = false;
@@ -228,6 +248,8 @@ void free_graph(gatx_ctx* c) {
   dfree(c->row_ptr); dfree(c->col_idx); dfree(c->coo_src); dfree(c->coo_dst); dfree(c->in_deg);
   dfree(c->csc_ptr); dfree(c->csc_dst); dfree(c->csc_eid); dfree(c->heavy_rows); dfree(c->heavy_srcs);
   dfree(c->chunk_row); dfree(c->chunk_src); dfree(c->ref_mask); dfree(c->col_idx_hot); dfree(c->csc_dst_hot);
+  dfree(c->blk_row_ptr); dfree(c->blk_chunk_row);
+  c->blocks.clear();
   c->have_graph = false;
   ++c->gen;
 }
@@ -236,7 +258,8 @@ void free_bufs(gatx_ctx* c) {
   for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
   c->ipc_opened.clear();
   c->peers_ready = false;
-  dfree(c->barrier_word);
+  dfree(c->halo_flags);
+  dfree(c->gPr2);
   for (auto& l : c->layers) {
     dfree(l.Wcat); dfree(l.WcatT); dfree(l.Pl); dfree(l.Pr); dfree(l.Xd);
     if (l.Hout != l.Hfull) dfree(l.Hout);
@@ -339,6 +362,12 @@ int ensure_buffers(gatx_ctx* ctx) {
   }
   CK(dalloc(&ctx->gPl, (size_t)N * Fmax));
   CK(dalloc(&ctx->gPr, (size_t)nr * Fmax));
+  if (ctx->blocks.size() > 1) CK(dalloc(&ctx->gPr2, (size_t)nr * Fmax));
+  if (ctx->world > 1) {
+    CK(dalloc(&ctx->halo_flags, (size_t)kMaxPeers));
+    CK(cudaMemsetAsync(ctx->halo_flags, 0, sizeof(uint32_t) * kMaxPeers, ctx->st));
+    ctx->barrier_seq = 0;
+  }
   CK(dalloc(&ctx->rec, (size_t)E * recmax));
   {
     int64_t part_floats = 1, hmax = 1;
@@ -386,21 +415,20 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   return g;
 }
 
-// P_l | P_r = X [W_l ; W_r]^T in one pass over X (Wcat is [2F][ldk], rows 0..F-1 = W_l).
-int gemm_project(gatx_ctx* ctx, const float* X, int ldx, const Layer& ly) {
-  float* Pl_own = ly.Pl + (int64_t)ctx->r0 * ly.F;
+// P_l | P_r = X [W_l ; W_r]^T in one pass over X (Wcat is [2F][ldk], rows 0..F-1 = W_l) for `rows` rows of X.
+int gemm_project(gatx_ctx* ctx, const float* X, int ldx, const Layer& ly, float* Pl_rows, float* Pr_rows, int rows) {
+  if (rows <= 0) return GATX_OK;
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
-    int n = launch_gemm_tc_tn2(X, ldx, ly.Wcat, ly.ldk, ly.I, nullptr, 0, nullptr, 0, 0, Pl_own, ly.Pr, ly.F, ly.F,
-                               ctx->n_rows, 2 * ly.F, false, ctx->st);
+    int n = launch_gemm_tc_tn2(X, ldx, ly.Wcat, ly.ldk, ly.I, nullptr, 0, nullptr, 0, 0, Pl_rows, Pr_rows, ly.F, ly.F,
+                               rows, 2 * ly.F, false, ctx->st);
     if (n >= 0) {
       ctx->launches += n;
       return GATX_OK;
     }
   }
-  LAUNCHED(launch_gemm_simt(X, ldx, 1, ly.Wcat, ly.ldk, 1, Pl_own, ly.F, ctx->n_rows, ly.F, ly.I, false, nullptr, 0,
-                            ctx->st));
-  LAUNCHED(launch_gemm_simt(X, ldx, 1, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, 1, ly.Pr, ly.F, ctx->n_rows, ly.F,
-                            ly.I, false, nullptr, 0, ctx->st));
+  LAUNCHED(launch_gemm_simt(X, ldx, 1, ly.Wcat, ly.ldk, 1, Pl_rows, ly.F, rows, ly.F, ly.I, false, nullptr, 0, ctx->st));
+  LAUNCHED(launch_gemm_simt(X, ldx, 1, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, 1, Pr_rows, ly.F, rows, ly.F, ly.I,
+                            false, nullptr, 0, ctx->st));
   return GATX_OK;
 }
 // C[M][N] = A[M][K] B[N][K]^T with the configured arithmetic
@@ -416,20 +444,22 @@ int gemm_tn_any(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int6
   LAUNCHED(launch_gemm_simt(A, lda, 1, B, ldb, 1, C, ldc, M, N, K, false, nullptr, 0, ctx->st));
   return GATX_OK;
 }
-// gX[n][i] = sum_r gP_l[n][r] W_l[r][i] + gP_r[n][r] W_r[r][i]   (WcatT is [I][2F])
-int gemm_input_grad(gatx_ctx* ctx, const float* gPl_own, const float* gPr, const Layer& ly, float* gX, int ldg) {
+// gX[n][i] = sum_r gP_l[n][r] W_l[r][i] + gP_r[n][r] W_r[r][i]   (WcatT is [I][2F]) for `rows` rows
+int gemm_input_grad(gatx_ctx* ctx, const float* gPl_rows, const float* gPr_rows, const Layer& ly, float* gX, int ldg,
+                    int rows) {
+  if (rows <= 0) return GATX_OK;
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
-    int n = launch_gemm_tc_tn2(gPl_own, ly.F, ly.WcatT, 2 * ly.F, ly.F, gPr, ly.F, ly.WcatT + ly.F, 2 * ly.F, ly.F, gX,
-                               gX, ly.I, ldg, ctx->n_rows, ly.I, false, ctx->st);
+    int n = launch_gemm_tc_tn2(gPl_rows, ly.F, ly.WcatT, 2 * ly.F, ly.F, gPr_rows, ly.F, ly.WcatT + ly.F, 2 * ly.F, ly.F,
+                               gX, gX, ly.I, ldg, rows, ly.I, false, ctx->st);
     if (n >= 0) {
       ctx->launches += n;
       return GATX_OK;
     }
   }
-  LAUNCHED(launch_gemm_simt(gPl_own, ly.F, 1, ly.WcatT, 2 * ly.F, 1, gX, ldg, ctx->n_rows, ly.I, ly.F, false, nullptr,
-                            0, ctx->st));
-  LAUNCHED(launch_gemm_simt(gPr, ly.F, 1, ly.WcatT + ly.F, 2 * ly.F, 1, gX, ldg, ctx->n_rows, ly.I, ly.F, true, nullptr,
-                            0, ctx->st));
+  LAUNCHED(launch_gemm_simt(gPl_rows, ly.F, 1, ly.WcatT, 2 * ly.F, 1, gX, ldg, rows, ly.I, ly.F, false, nullptr, 0,
+                            ctx->st));
+  LAUNCHED(launch_gemm_simt(gPr_rows, ly.F, 1, ly.WcatT + ly.F, 2 * ly.F, 1, gX, ldg, rows, ly.I, ly.F, true, nullptr, 0,
+                            ctx->st));
   return GATX_OK;
 }
 // C[M][N] (ldc) += A^T B with A [K][>=M] (lda), B [K][>=N] (ldb): contraction over the node dimension.
@@ -447,13 +477,58 @@ int gemm_nt_reduce(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, i
   return GATX_OK;
 }
 
-// Stream-ordered barrier across ranks: a 4-byte all-reduce.  A rank leaves it only after every rank's stream has
-// reached it, i.e. after every kernel the peers enqueued before it (and its peer-memory stores) completed.
+// ---- multi-GPU exchange ------------------------------------------------------------------------------------------
+// Peer-memory path (default): the exchange kernels run on a stream of their own (st_comm), one block of destination
+// rows at a time, ordered against the compute stream by events and across ranks by flag barriers in peer memory, so
+// that the NVLink traffic of block b overlaps the edge pass of block b + 1 (see do_forward / do_backward).
+// NCCL path (GATX_NO_P2P, or no peer access): whole-matrix broadcasts / reduces on the compute stream.
+bool halo_p2p(const gatx_ctx* ctx, int F) { return ctx->world > 1 && ctx->peers_ready && F % 4 == 0; }
+
+cudaEvent_t next_event(gatx_ctx* c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    c->ev_pool.push_back(e);
+  }
+  return c->ev_pool[c->ev_used++];
+}
+// `waiter` continues only after everything enqueued on `src` so far
+void stream_after(gatx_ctx* c, cudaStream_t waiter, cudaStream_t src) {
+  cudaEvent_t e = next_event(c);
+  cudaEventRecord(e, src);
+  cudaStreamWaitEvent(waiter, e, 0);
+}
+// the compute stream waits for the exchange stream; the wait is what the PH_COMM phase measures (EXPOSED exchange time)
+void compute_waits_comm(gatx_ctx* ctx) {
+  PhaseTimer t(ctx, PH_COMM);
+  stream_after(ctx, ctx->st, ctx->st_comm);
+}
 int comm_barrier(gatx_ctx* ctx) {
-  NK(g_nccl.AllReduce(ctx->barrier_word, ctx->barrier_word, 1, ncclFloat, ncclSum, ctx->comm, ctx->st));
+  ++ctx->barrier_seq;
+  LAUNCHED(launch_halo_barrier(ctx->peer_flags, ctx->rank, ctx->world, ctx->barrier_seq, ctx->st_comm));
   return GATX_OK;
 }
-bool halo_p2p(const gatx_ctx* ctx, int F) { return ctx->peers_ready && F % 4 == 0; }
+// timing of the exchange kernels themselves (on st_comm): bytes over NVLink and busy time per direction
+struct CommTimer {
+  gatx_ctx* c;
+  size_t idx = (size_t)-1;
+  CommTimer(gatx_ctx* ctx, int dir, double bytes) : c(ctx) {
+    if (!c->timing) return;
+    if (c->comm_spans_used == c->comm_spans.size()) {
+      gatx_ctx::CommSpan s{dir, 0.0, nullptr, nullptr};
+      cudaEventCreate(&s.a);
+      cudaEventCreate(&s.b);
+      c->comm_spans.push_back(s);
+    }
+    idx = c->comm_spans_used++;
+    c->comm_spans[idx].dir = dir;
+    c->comm_spans[idx].bytes = bytes;
+    cudaEventRecord(c->comm_spans[idx].a, c->st_comm);
+  }
+  ~CommTimer() {
+    if (idx != (size_t)-1) cudaEventRecord(c->comm_spans[idx].b, c->st_comm);
+  }
+};
 
 // All-gather of row blocks with unequal counts: one NCCL broadcast per owner inside a group.
 int nccl_allgather_rows(gatx_ctx* ctx, float* full, int64_t F) {
@@ -467,33 +542,19 @@ int nccl_allgather_rows(gatx_ctx* ctx, float* full, int64_t F) {
   return GATX_OK;
 }
 
-// Forward exchange: every rank ends with the P_l rows its edges gather (all rows on the NCCL path).
-int comm_allgather_rows(gatx_ctx* ctx, float* full, int F, int layer) {
+// Forward exchange, NCCL path: every rank ends with all P_l rows.
+int comm_allgather_rows(gatx_ctx* ctx, float* full, int F) {
   if (ctx->world == 1) return GATX_OK;
   if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
   PhaseTimer t(ctx, PH_COMM);
-  if (halo_p2p(ctx, F)) {
-    int rc = comm_barrier(ctx);  // the peers are done reading the previous contents of their P_l
-    if (rc) return rc;
-    LAUNCHED(launch_halo_push(full + (int64_t)ctx->r0 * F, ctx->r0, ctx->n_rows, F, ctx->ref_mask, ctx->peer_Pl[layer],
-                              ctx->rank, ctx->st));
-    return comm_barrier(ctx);    // every push has landed
-  }
   return nccl_allgather_rows(ctx, full, F);
 }
 
-// Backward exchange: the owner of a source row ends with the sum of all ranks' partial gP_l rows.
+// Backward exchange, NCCL path: the owner of a source row ends with the sum of all ranks' partial gP_l rows.
 int comm_reduce_rows(gatx_ctx* ctx, float* full, int F) {
   if (ctx->world == 1) return GATX_OK;
   if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "world > 1 but gatx_comm_init was not called");
   PhaseTimer t(ctx, PH_COMM);
-  if (halo_p2p(ctx, F)) {
-    int rc = comm_barrier(ctx);  // every rank's partial sums are complete
-    if (rc) return rc;
-    LAUNCHED(launch_halo_pull(full + (int64_t)ctx->r0 * F, ctx->r0, ctx->n_rows, F, ctx->ref_mask, ctx->peer_gPl,
-                              ctx->rank, ctx->world, ctx->st));
-    return comm_barrier(ctx);    // the peers may overwrite their scratch again
-  }
   NK(g_nccl.GroupStart());
   for (int r = 0; r < ctx->world; ++r) {
     float* p = full + (int64_t)ctx->bounds[r] * F;
@@ -504,69 +565,217 @@ int comm_reduce_rows(gatx_ctx* ctx, float* full, int F) {
   return GATX_OK;
 }
 
+// ---- views of the own destination rows: everything (b < 0) or one block of the multi-GPU pipeline ---------------
+struct RowView {
+  int rb, nb;    // rows [rb, rb + nb) of this rank's own rows
+  int64_t e0;    // first local edge of the view
+  EdgeGraph g;   // the view as a graph of its own (rebased row_ptr, own chunks, col_idx offset to e0)
+  bool whole;
+};
+RowView row_view(const gatx_ctx* ctx, int b) {
+  RowView v{0, ctx->n_rows, 0, edge_graph(ctx), true};
+  if (b < 0 || ctx->blocks.size() <= 1) return v;
+  const gatx_ctx::RowBlock& B = ctx->blocks[b];
+  v.rb = B.r0; v.nb = B.n_rows; v.e0 = B.e0; v.whole = false;
+  v.g.n_rows = B.n_rows; v.g.row_ptr = B.row_ptr; v.g.col_idx = ctx->col_idx + B.e0; v.g.E = B.E;
+  v.g.n_chunks = B.n_chunks; v.g.chunk_row = B.chunk_row;
+  v.g.col_idx_hot = ctx->col_idx_hot ? ctx->col_idx_hot + B.e0 : nullptr;
+  v.g.heavy_rows = nullptr; v.g.n_heavy_rows = 0;
+  return v;
+}
+// the streaming kernels take any view; the warp-per-row / generic kernels only the whole row range
+bool blockable(const gatx_ctx* ctx, int l) {
+  const Layer& ly = ctx->layers[l];
+  return ctx->blocks.size() > 1 && ly.vec && ctx->use_stream && edge_stream_supported(ly.H, ly.D);
+}
+float* gpr_buf(const gatx_ctx* ctx, int l) { return (ctx->gPr2 && ((ctx->L - 1 - l) & 1)) ? ctx->gPr2 : ctx->gPr; }
+
+// fused edge forward of layer l over a view (EB:279-459)
+int fwd_edge(gatx_ctx* ctx, int l, const RowView& v) {
+  Layer& ly = ctx->layers[l];
+  if (v.nb <= 0) return GATX_OK;
+  EdgeGraph gl = v.g;
+  gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
+  if (ctx->timing && v.whole) {
+    for (auto& e : ly.kev)
+      if (!e) cudaEventCreate(&e);
+    gl.kernel_events = ly.kev;
+    ly.kev_fwd = true;
+  }
+  const int64_t ro = v.rb;
+  float* Pr = ly.Pr + ro * ly.F;
+  float* Hfull = ly.Hfull + ro * ly.F;
+  float* hpre = ly.hpre ? ly.hpre + ro * ly.F : nullptr;
+  float* score = ly.score + v.e0 * ly.H;
+  float *mx = ly.mx + ro * ly.H, *sinv = ly.sinv + ro * ly.H;
+  const float* a = ctx->params + ly.a_off;
+  if (!ly.vec)
+    LAUNCHED(launch_edge_forward_generic(gl, ly.H, ly.D, ly.Pl, Pr, a, Hfull, hpre, score, mx, sinv, ctx->st));
+  else if (ctx->use_stream && edge_stream_supported(ly.H, ly.D))
+    LAUNCHED(launch_edge_forward_stream(gl, ly.H, ly.D, ly.Pl, Pr, a, Hfull, hpre, score, mx, sinv, ctx->part, ctx->st));
+  else
+    LAUNCHED(launch_edge_forward(gl, ly.H, ly.D, ly.Pl, Pr, a, Hfull, hpre, score, mx, sinv, ctx->st));
+  return GATX_OK;
+}
+
+// backward of layer l over a view: phases bit 0 = prep + destination-major pass 1 (over the view's rows),
+// bit 1 = source-major pass 2 (always over all local edges; the view must be the whole range)
+int bwd_edge(gatx_ctx* ctx, int l, const RowView& v, int phases) {
+  Layer& ly = ctx->layers[l];
+  EdgeGraph gl = v.g;
+  gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
+  if (ctx->timing && v.whole) {
+    for (auto& e : ly.kev)
+      if (!e) cudaEventCreate(&e);
+    gl.kernel_events = ly.kev;
+    ly.kev_bwd = true;
+  }
+  const int64_t ro = v.rb;
+  const float* a = ctx->params + ly.a_off;
+  float* gPr = gpr_buf(ctx, l) + ro * ly.F;
+  const float* Pr = ly.Pr + ro * ly.F;
+  const float* Hfull = ly.Hfull + ro * ly.F;
+  float* gH = ly.gH + ro * ly.F;
+  const float* score = ly.score + v.e0 * ly.H;
+  const float *mx = ly.mx + ro * ly.H, *sinv = ly.sinv + ro * ly.H;
+  uint32_t* rec = ctx->rec + v.e0 * ly.recw;
+  float* galpha = ly.galpha_dbg ? ly.galpha_dbg + v.e0 * ly.H : nullptr;
+  int n_part = 0;
+  if (ly.vec && ctx->use_stream && edge_stream_supported(ly.H, ly.D)) {
+    if ((phases & 1) && v.nb <= 0) phases &= ~1;
+    if (!phases) return GATX_OK;
+    // pass 2 walks the transposed graph of ALL local edges and reads g_h / rec by local row / edge id: whole range only
+    LAUNCHED(launch_edge_backward_stream(gl, ly.H, ly.D, ly.Pl, Pr, a, Hfull, (phases & 2) ? ly.gH : gH, ctx->cdot, score,
+                                         mx, sinv, gPr, ctx->gPl, (phases & 2) ? ctx->rec : rec, ctx->part,
+                                         ctx->ga_partials, &n_part, galpha, ctx->st, phases));
+    if (phases & 1)
+      LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
+    return GATX_OK;
+  }
+  if (phases != 3 || !v.whole) return fail(ctx, GATX_ERR_UNSUPPORTED, "layer %d: only the streaming kernels run per block", l);
+  if (!ly.vec) {
+    LAUNCHED(launch_edge_backward_generic(gl, ly.H, ly.D, ly.Pl, Pr, a, Hfull, gH, score, mx, sinv, gPr, ctx->gPl, ctx->rec,
+                                          ctx->ga_partials, &n_part, galpha, ctx->st));
+    LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
+  } else {
+    LAUNCHED(launch_edge_backward_dst(gl, ly.H, ly.D, ly.Pl, Pr, a, Hfull, gH, score, mx, sinv, gPr, ctx->rec,
+                                      ctx->ga_partials, &n_part, galpha, ctx->st));
+    LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
+    LAUNCHED(launch_edge_backward_src(gl, ly.H, ly.D, a, gH, ctx->rec, ctx->gPl, ctx->st));
+  }
+  return GATX_OK;
+}
+
 int do_forward(gatx_ctx* ctx) {
   int rc = ensure_buffers(ctx);
   const unsigned char* mask = ctx->eval_mode ? ctx->eval_mask : ctx->train_mask;
   if (rc) return rc;
   if (!ctx->have_params) return fail(ctx, GATX_ERR_INVALID, "parameters not initialised");
-  const EdgeGraph g = edge_graph(ctx);
   const float* X = ctx->X0 + (int64_t)ctx->r0 * ctx->ld0;
   const float* X0all = ctx->X0;
   const bool drop = !ctx->eval_mode && ctx->p_drop > 0.f;
   if (drop) ++ctx->drop_step;
   if (!ctx->eval_mode) ctx->fwd_dropped = drop;
+  const bool p2p_any = ctx->world > 1 && ctx->peers_ready;
+  ctx->ev_used = 0;
+  if (p2p_any) {
+    // every rank has finished ALL its earlier work (the edge passes that read P_l and the gP_l scratch) before the
+    // first row of this forward is pushed into its buffers
+    stream_after(ctx, ctx->st_comm, ctx->st);
+    if ((rc = comm_barrier(ctx))) return rc;
+  }
+  {
+    PhaseTimer t(ctx, PH_GEMM_FWD);
+    for (int l = 0; l < ctx->L; ++l) {
+      Layer& ly = ctx->layers[l];
+      LAUNCHED(launch_pack_weights(ctx->params + ly.w_off, ly.F, ly.I, ly.Wcat, ly.ldk, ly.WcatT, ctx->st));
+    }
+  }
+  const RowView all = row_view(ctx, -1);
   for (int l = 0; l < ctx->L; ++l) {
     Layer& ly = ctx->layers[l];
     const bool replicated = l == 0 && ctx->world > 1;  // layer 0 with the input features on every rank
-    {
-      PhaseTimer t(ctx, PH_GEMM_FWD);
-      if (drop) {
-        // layer 0 keeps every rank's copy of ALL input rows dropped identically (the mask is a pure function of the
-        // global row); deeper layers drop their own rows of the previous layer's output
-        const int rows = l == 0 ? ctx->N : ctx->n_rows, row0 = l == 0 ? 0 : ctx->r0;
-        if (!ly.Xd) {
-          CK(dalloc(&ly.Xd, (size_t)rows * ly.ldx));
-          CK(cudaMemsetAsync(ly.Xd, 0, sizeof(float) * (size_t)rows * ly.ldx, ctx->st));  // zero padding columns
+    // with the peer-memory exchange, P_l / P_r of layers > 0 were produced and pushed block by block while the
+    // previous layer's edge pass was still running (below)
+    const bool piped_in = l > 0 && halo_p2p(ctx, ly.F);
+    if (!piped_in) {
+      {
+        PhaseTimer t(ctx, PH_GEMM_FWD);
+        if (drop) {
+          // layer 0 keeps every rank's copy of ALL input rows dropped identically (the mask is a pure function of the
+          // global row); deeper layers drop their own rows of the previous layer's output
+          const int rows = l == 0 ? ctx->N : ctx->n_rows, row0 = l == 0 ? 0 : ctx->r0;
+          if (!ly.Xd) {
+            CK(dalloc(&ly.Xd, (size_t)rows * ly.ldx));
+            CK(cudaMemsetAsync(ly.Xd, 0, sizeof(float) * (size_t)rows * ly.ldx, ctx->st));  // zero padding columns
+          }
+          LAUNCHED(launch_dropout(l == 0 ? ctx->X0 : X, ly.ldx, ly.Xd, ly.ldx, rows, ly.I, row0, ctx->p_drop,
+                                  ctx->drop_seed, l, ctx->drop_step, ctx->st));
+          X = l == 0 ? ly.Xd + (int64_t)ctx->r0 * ly.ldx : ly.Xd;
+          X0all = ly.Xd;
         }
-        LAUNCHED(launch_dropout(l == 0 ? ctx->X0 : X, ly.ldx, ly.Xd, ly.ldx, rows, ly.I, row0, ctx->p_drop,
-                                ctx->drop_seed, l, ctx->drop_step, ctx->st));
-        X = l == 0 ? ly.Xd + (int64_t)ctx->r0 * ly.ldx : ly.Xd;
-        X0all = ly.Xd;
+        // P_l = X W_l^T, P_r = X W_r^T : the only dense contraction of the forward (EB:303-316)
+        if (replicated) {
+          rc = gemm_tn_any(ctx, X0all, ly.ldx, ly.Wcat, ly.ldk, ly.Pl, ly.F, ctx->N, ly.F, ly.I);
+          if (!rc) rc = gemm_tn_any(ctx, X, ly.ldx, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, ly.Pr, ly.F, ctx->n_rows, ly.F, ly.I);
+        } else {
+          rc = gemm_project(ctx, X, ly.ldx, ly, ly.Pl + (int64_t)ctx->r0 * ly.F, ly.Pr, ctx->n_rows);
+        }
+        if (rc) return rc;
       }
-      LAUNCHED(launch_pack_weights(ctx->params + ly.w_off, ly.F, ly.I, ly.Wcat, ly.ldk, ly.WcatT, ctx->st));
-      // P_l = X W_l^T, P_r = X W_r^T : the only dense contraction of the forward (EB:303-316)
-      if (replicated) {
-        rc = gemm_tn_any(ctx, X0all, ly.ldx, ly.Wcat, ly.ldk, ly.Pl, ly.F, ctx->N, ly.F, ly.I);
-        if (!rc) rc = gemm_tn_any(ctx, X, ly.ldx, ly.Wcat + (int64_t)ly.F * ly.ldk, ly.ldk, ly.Pr, ly.F, ctx->n_rows, ly.F, ly.I);
-      } else {
-        rc = gemm_project(ctx, X, ly.ldx, ly);
+      if (!replicated) {
+        rc = comm_allgather_rows(ctx, ly.Pl, ly.F);
+        if (rc) return rc;
       }
-      if (rc) return rc;
     }
-    if (!replicated) {
-      rc = comm_allgather_rows(ctx, ly.Pl, ly.F, l);
-      if (rc) return rc;
-    }
-    {
+    const bool pipe_out = l + 1 < ctx->L && halo_p2p(ctx, ctx->layers[l + 1].F);
+    if (!pipe_out) {
       PhaseTimer t(ctx, PH_EDGE_FWD);
-      EdgeGraph gl = g;
-      gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
-      if (ctx->timing) {
-        for (auto& e : ly.kev)
-          if (!e) cudaEventCreate(&e);
-        gl.kernel_events = ly.kev;
-        ly.kev_fwd = true;
-      }
-      if (!ly.vec)
-        LAUNCHED(launch_edge_forward_generic(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
-                                             ly.score, ly.mx, ly.sinv, ctx->st));
-      else if (ctx->use_stream && edge_stream_supported(ly.H, ly.D))
-        LAUNCHED(launch_edge_forward_stream(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre,
-                                            ly.score, ly.mx, ly.sinv, ctx->part, ctx->st));
-      else
-        LAUNCHED(launch_edge_forward(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.hpre, ly.score,
-                                     ly.mx, ly.sinv, ctx->st));
+      if ((rc = fwd_edge(ctx, l, all))) return rc;
       if (ly.Hout != ly.Hfull) LAUNCHED(launch_head_mean(ly.Hfull, ctx->n_rows, ly.H, ly.D, ly.Hout, ctx->st));
+    } else {
+      // Pipeline over blocks of own destination rows: edge pass of layer l on block b, projection of layer l + 1 on
+      // the rows it just produced, then (exchange stream) the push of those projected rows into the peers that gather
+      // them -- which overlaps the edge pass of block b + 1.
+      Layer& nx = ctx->layers[l + 1];
+      const bool blk = blockable(ctx, l);
+      if (!blk) {
+        PhaseTimer t(ctx, PH_EDGE_FWD);
+        if ((rc = fwd_edge(ctx, l, all))) return rc;
+      }
+      if (drop && !nx.Xd) {
+        CK(dalloc(&nx.Xd, (size_t)ctx->n_rows * nx.ldx));
+        CK(cudaMemsetAsync(nx.Xd, 0, sizeof(float) * (size_t)ctx->n_rows * nx.ldx, ctx->st));
+      }
+      const int nblk = (int)ctx->blocks.size();
+      for (int b = 0; b < nblk; ++b) {
+        const RowView v = row_view(ctx, b);
+        if (v.nb <= 0) continue;
+        if (blk) {
+          PhaseTimer t(ctx, PH_EDGE_FWD);
+          if ((rc = fwd_edge(ctx, l, v))) return rc;
+        }
+        {
+          PhaseTimer t(ctx, PH_GEMM_FWD);
+          const float* Xb = ly.Hout + (int64_t)v.rb * nx.ldx;
+          if (drop) {
+            float* Xd = nx.Xd + (int64_t)v.rb * nx.ldx;
+            LAUNCHED(launch_dropout(Xb, nx.ldx, Xd, nx.ldx, v.nb, nx.I, ctx->r0 + v.rb, ctx->p_drop, ctx->drop_seed, l + 1,
+                                    ctx->drop_step, ctx->st));
+            Xb = Xd;
+          }
+          rc = gemm_project(ctx, Xb, nx.ldx, nx, nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, nx.Pr + (int64_t)v.rb * nx.F, v.nb);
+          if (rc) return rc;
+        }
+        stream_after(ctx, ctx->st_comm, ctx->st);
+        {
+          CommTimer ct(ctx, 0, (double)ctx->blocks[b].halo_rows * nx.F * 4.0);
+          LAUNCHED(launch_halo_push(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
+                                    ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm));
+        }
+      }
+      if ((rc = comm_barrier(ctx))) return rc;  // every rank's pushes have landed
+      compute_waits_comm(ctx);
     }
     X = ly.Hout;
   }
@@ -612,7 +821,6 @@ int do_forward(gatx_ctx* ctx) {
 int do_backward(gatx_ctx* ctx) {
   if (!ctx->have_bufs || !ctx->fwd_valid)
     return fail(ctx, GATX_ERR_INVALID, "gatx_forward must run before gatx_backward (gatx_evaluate does not count)");
-  const EdgeGraph g = edge_graph(ctx);
   int rc;
   {
     // gW_o += dz^T H_L  (EB:576-581)
@@ -622,39 +830,25 @@ int do_backward(gatx_ctx* ctx) {
                         ctx->n_rows);
     if (rc) return rc;
   }
+  const RowView all = row_view(ctx, -1);
+  std::vector<char> p1_done(ctx->L, 0);  // pass 1 of the layer already ran block by block inside the layer above
   for (int l = ctx->L - 1; l >= 0; --l) {
     Layer& ly = ctx->layers[l];
     const bool drop = ctx->fwd_dropped && ly.Xd;
     const float* Xall = drop ? ly.Xd : ctx->X0;  // layer 0: all input rows
     const float* X = l == 0 ? Xall + (int64_t)ctx->r0 * ctx->ld0 : (drop ? ly.Xd : ctx->layers[l - 1].Hout);
     const bool replicated = l == 0 && ctx->world > 1;
+    const bool exchanged = ctx->world > 1 && !replicated;
+    const bool piped = exchanged && halo_p2p(ctx, ly.F);
+    float* gPr = gpr_buf(ctx, l);
     {
       PhaseTimer t(ctx, PH_EDGE_BWD);
-      int n_part = 0;
-      EdgeGraph gl = g;
-      gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
-      if (ctx->timing) {
-        for (auto& e : ly.kev)
-          if (!e) cudaEventCreate(&e);
-        gl.kernel_events = ly.kev;
-        ly.kev_bwd = true;
-      }
-      if (!ly.vec) {
-        LAUNCHED(launch_edge_backward_generic(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
-                                              ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->gPl, ctx->rec, ctx->ga_partials,
-                                              &n_part, ly.galpha_dbg, ctx->st));
-        LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
-      } else if (ctx->use_stream && edge_stream_supported(ly.H, ly.D)) {
-        LAUNCHED(launch_edge_backward_stream(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
-                                             ctx->cdot, ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->gPl, ctx->rec,
-                                             ctx->part, ctx->ga_partials, &n_part, ly.galpha_dbg, ctx->st));
-        LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
-      } else {
-        LAUNCHED(launch_edge_backward_dst(gl, ly.H, ly.D, ly.Pl, ly.Pr, ctx->params + ly.a_off, ly.Hfull, ly.gH,
-                                          ly.score, ly.mx, ly.sinv, ctx->gPr, ctx->rec, ctx->ga_partials, &n_part,
-                                          ly.galpha_dbg, ctx->st));
-        LAUNCHED(launch_reduce_partials(ctx->ga_partials, n_part, ly.F, ctx->grads + ly.a_off, true, ctx->st));
-        LAUNCHED(launch_edge_backward_src(g, ly.H, ly.D, ctx->params + ly.a_off, ly.gH, ctx->rec, ctx->gPl, ctx->st));
+      const bool stream = ly.vec && ctx->use_stream && edge_stream_supported(ly.H, ly.D);
+      if (stream) {
+        if (!p1_done[l] && (rc = bwd_edge(ctx, l, all, 1))) return rc;
+        if ((rc = bwd_edge(ctx, l, all, 2))) return rc;
+      } else if ((rc = bwd_edge(ctx, l, all, 3))) {
+        return rc;
       }
       // gb = column sums of the pre-activation gradient (own rows; the all-reduce of the flat gradients adds the ranks)
       if (ly.b_off >= 0)
@@ -664,18 +858,14 @@ int do_backward(gatx_ctx* ctx) {
         else LAUNCHED(launch_unpack_rec_generic(ctx->rec, ctx->E, ly.H, ly.alpha_dbg, ly.ge_dbg, ctx->st));
         CK(cudaMemcpyAsync(ly.gPl_dbg, ctx->gPl, sizeof(float) * (size_t)ctx->N * ly.F, cudaMemcpyDeviceToDevice,
                            ctx->st));
-        CK(cudaMemcpyAsync(ly.gPr_dbg, ctx->gPr, sizeof(float) * (size_t)ctx->n_rows * ly.F,
-                           cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ly.gPr_dbg, gPr, sizeof(float) * (size_t)ctx->n_rows * ly.F, cudaMemcpyDeviceToDevice, ctx->st));
       }
     }
-    if (!replicated) {
-      rc = comm_reduce_rows(ctx, ctx->gPl, ly.F);
-      if (rc) return rc;
-    }
-    {
+    const float* gPl_own = ctx->gPl + (int64_t)ctx->r0 * ly.F;
+    float* gW = ctx->grads + ly.w_off;
+    if (!piped) {
+      if (exchanged && (rc = comm_reduce_rows(ctx, ctx->gPl, ly.F))) return rc;
       PhaseTimer t(ctx, PH_GEMM_BWD);
-      const float* gPl_own = ctx->gPl + (int64_t)ctx->r0 * ly.F;
-      float* gW = ctx->grads + ly.w_off;
       // gW_l = gP_l^T X, gW_r = gP_r^T X  (EB:771-782), W row stride 2I, W_r at column offset I.
       // Replicated layer 0: this rank's PARTIAL gP_l over all sources is contracted with the full X; the
       // all-reduce of the weight gradients completes the sum, so gP_l itself is never exchanged.
@@ -684,20 +874,67 @@ int do_backward(gatx_ctx* ctx) {
       else
         rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
-      rc = gemm_nt_reduce(ctx, ctx->gPr, ly.F, X, ly.ldx, gW + ly.I, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+      rc = gemm_nt_reduce(ctx, gPr, ly.F, X, ly.ldx, gW + ly.I, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
       if (l > 0) {
         // dL/dHout[l-1] = gP_l W_l + gP_r W_r  (EB:859-869); the LReLU derivative of EB:879-893 is
         // applied by the next edge backward when it loads this gradient.
         Layer& prev = ctx->layers[l - 1];
-        rc = gemm_input_grad(ctx, gPl_own, ctx->gPr, ly, prev.gH, prev.F);
+        rc = gemm_input_grad(ctx, gPl_own, gPr, ly, prev.gH, prev.F, ctx->n_rows);
         if (rc) return rc;
         // gradient w.r.t. the dropped input -> w.r.t. the previous layer's output: same mask, same scale
         if (drop)
           LAUNCHED(launch_dropout(prev.gH, prev.F, prev.gH, prev.F, ctx->n_rows, ly.I, ctx->r0, ctx->p_drop,
                                   ctx->drop_seed, l, ctx->drop_step, ctx->st));
       }
+      continue;
     }
+    // Peer-memory exchange, pipelined over blocks of own rows: (exchange stream) the owner pulls and sums the peers'
+    // partial gP_l rows of block b; (compute stream) input-gradient GEMM of block b, then prep + pass 1 of the layer
+    // BELOW on block b -- while the pull of block b + 1 is in flight.
+    stream_after(ctx, ctx->st_comm, ctx->st);
+    if ((rc = comm_barrier(ctx))) return rc;  // every rank's partial sums are complete
+    {
+      PhaseTimer t(ctx, PH_GEMM_BWD);  // needs nothing from the exchange: runs under the barrier and the first pull
+      rc = gemm_nt_reduce(ctx, gPr, ly.F, X, ly.ldx, gW + ly.I, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+      if (rc) return rc;
+    }
+    const bool fuse_p1 = l > 0 && blockable(ctx, l - 1);
+    const int nblk = (int)ctx->blocks.size();
+    for (int b = 0; b < nblk; ++b) {
+      const RowView v = row_view(ctx, b);
+      if (v.nb <= 0) continue;
+      {
+        CommTimer ct(ctx, 1, (double)ctx->blocks[b].halo_rows * ly.F * 4.0);
+        LAUNCHED(launch_halo_pull(ctx->gPl + (int64_t)(ctx->r0 + v.rb) * ly.F, ctx->r0 + v.rb, v.nb, ly.F,
+                                  ctx->ref_mask + v.rb, ctx->peer_gPl, ctx->rank, ctx->world, ctx->st_comm));
+      }
+      compute_waits_comm(ctx);
+      if (l > 0) {
+        Layer& prev = ctx->layers[l - 1];
+        {
+          PhaseTimer t(ctx, PH_GEMM_BWD);
+          float* gXb = prev.gH + (int64_t)v.rb * prev.F;
+          rc = gemm_input_grad(ctx, gPl_own + (int64_t)v.rb * ly.F, gPr + (int64_t)v.rb * ly.F, ly, gXb, prev.F, v.nb);
+          if (rc) return rc;
+          if (drop)
+            LAUNCHED(launch_dropout(gXb, prev.F, gXb, prev.F, v.nb, ly.I, ctx->r0 + v.rb, ctx->p_drop, ctx->drop_seed, l,
+                                    ctx->drop_step, ctx->st));
+        }
+        if (fuse_p1) {
+          PhaseTimer t(ctx, PH_EDGE_BWD);
+          if ((rc = bwd_edge(ctx, l - 1, v, 1))) return rc;
+        }
+      }
+    }
+    if (fuse_p1) p1_done[l - 1] = 1;
+    if ((rc = comm_barrier(ctx))) return rc;  // every owner has pulled: the peers may overwrite their gP_l scratch
+    {
+      PhaseTimer t(ctx, PH_GEMM_BWD);
+      rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+      if (rc) return rc;
+    }
+    compute_waits_comm(ctx);  // before the next pass 2 writes into the scratch the peers were reading
   }
   return GATX_OK;
 }
@@ -853,6 +1090,16 @@ int gatx_create(gatx_ctx** out, const gatx_config* cfg) {
     delete c;
     return GATX_ERR_CUDA;
   }
+  if (c->world > 1) {
+    // the exchange stream: highest priority, so that its (small) kernels get the first CTA slots the edge pass frees
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&c->st_comm, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaStreamDestroy(c->st);
+      delete c;
+      return GATX_ERR_CUDA;
+    }
+  }
   *out = c;
   return GATX_OK;
 }
@@ -861,6 +1108,7 @@ void gatx_destroy(gatx_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
+  if (ctx->st_comm) cudaStreamSynchronize(ctx->st_comm);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   if (ctx->epoch_exec) cudaGraphExecDestroy(ctx->epoch_exec);
   free_bufs(ctx);
@@ -877,6 +1125,12 @@ void gatx_destroy(gatx_ctx* ctx) {
     cudaEventDestroy(ctx->sw_a);
     cudaEventDestroy(ctx->sw_b);
   }
+  for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
+  for (auto& s : ctx->comm_spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  if (ctx->st_comm) cudaStreamDestroy(ctx->st_comm);
   cudaStreamDestroy(ctx->st);
   delete ctx;
 }
@@ -921,6 +1175,7 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   ctx->E = e1 - e0;
   int maxdeg = 0;
   std::vector<int> local_ptr(ctx->n_rows + 1), heavy;
+  std::vector<uint16_t> ref_own;  // ref_mask of the own rows (host copy, for the per-block halo counts)
   for (int i = 0; i < N; ++i) {
     if (row_ptr[i + 1] < row_ptr[i]) return fail(ctx, GATX_ERR_INVALID, "row_ptr not monotone at %d", i);
     const int d = row_ptr[i + 1] - row_ptr[i];
@@ -941,6 +1196,7 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
     int64_t halo = 0;
     for (int i = ctx->r0; i < ctx->r1; ++i) halo += __builtin_popcount((unsigned)(ref[i] & ~(1u << ctx->rank)));
     ctx->halo_rows = halo;
+    ref_own.assign(ref.begin() + ctx->r0, ref.begin() + ctx->r1);
     CK(dalloc(&ctx->ref_mask, (size_t)ctx->n_rows));
     if (ctx->n_rows)
       CK(cudaMemcpyAsync(ctx->ref_mask, ref.data() + ctx->r0, sizeof(uint16_t) * (size_t)ctx->n_rows,
@@ -982,6 +1238,58 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   CK(dalloc(&ctx->chunk_src, (size_t)ctx->n_chunks + 1));
   LAUNCHED(launch_chunk_rows(ctx->row_ptr, ctx->n_rows, ctx->E, ctx->chunk_T, ctx->n_chunks, ctx->chunk_row, ctx->st));
   LAUNCHED(launch_chunk_rows(ctx->csc_ptr, N, ctx->E, ctx->chunk_T, ctx->n_chunks, ctx->chunk_src, ctx->st));
+  if (ctx->world > 1) {
+    // blocks of own rows for the pipelined exchange (edge-balanced like the rank partition itself).  A block must still
+    // fill the GPU: at least 8 chunks per SM, unless GATX_HALO_BLOCKS forces a count (tests).
+    int K = 4;
+    bool forced = false;
+    if (const char* ev = getenv("GATX_HALO_BLOCKS")) {
+      const int k = atoi(ev);
+      if (k >= 1 && k <= 16) { K = k; forced = true; }
+    }
+    while (!forced && K > 1 && ctx->n_chunks / K < kNumSMs * 8) --K;
+    if (K > ctx->n_rows) K = ctx->n_rows > 0 ? ctx->n_rows : 1;
+    ctx->blocks.assign(K, gatx_ctx::RowBlock{});
+    std::vector<int> rb(K + 1, ctx->n_rows);
+    rb[0] = 0;
+    for (int k = 1, i = 0; k < K; ++k) {
+      const int64_t target = ctx->E * (int64_t)k / K;
+      while (i < ctx->n_rows && (int64_t)local_ptr[i] < target) ++i;
+      rb[k] = i;
+    }
+    std::vector<int> brp;
+    int64_t total_chunks = 0;
+    for (int k = 0; k < K; ++k) {
+      gatx_ctx::RowBlock& B = ctx->blocks[k];
+      B.r0 = rb[k];
+      B.n_rows = rb[k + 1] - rb[k];
+      B.e0 = local_ptr[rb[k]];
+      B.E = local_ptr[rb[k + 1]] - B.e0;
+      B.n_chunks = (int)((B.E + ctx->chunk_T - 1) / ctx->chunk_T);
+      total_chunks += B.n_chunks + 1;
+      for (int i = rb[k]; i <= rb[k + 1]; ++i) brp.push_back((int)(local_ptr[i] - B.e0));
+      for (int i = rb[k]; i < rb[k + 1] && !ref_own.empty(); ++i)
+        B.halo_rows += __builtin_popcount((unsigned)(ref_own[i] & ~(1u << ctx->rank)));
+    }
+    if (K > 1) {
+      CK(dalloc(&ctx->blk_row_ptr, brp.size()));
+      CK(dalloc(&ctx->blk_chunk_row, (size_t)total_chunks));
+      CK(cudaMemcpyAsync(ctx->blk_row_ptr, brp.data(), sizeof(int) * brp.size(), cudaMemcpyHostToDevice, ctx->st));
+      size_t po = 0, co = 0;
+      for (int k = 0; k < K; ++k) {
+        gatx_ctx::RowBlock& B = ctx->blocks[k];
+        B.row_ptr = ctx->blk_row_ptr + po;
+        B.chunk_row = ctx->blk_chunk_row + co;
+        po += (size_t)B.n_rows + 1;
+        co += (size_t)B.n_chunks + 1;
+        LAUNCHED(launch_chunk_rows(B.row_ptr, B.n_rows, B.E, ctx->chunk_T, B.n_chunks, B.chunk_row, ctx->st));
+      }
+      CK(cudaStreamSynchronize(ctx->st));  // `brp` goes out of scope
+    } else {
+      ctx->blocks[0].row_ptr = ctx->row_ptr;
+      ctx->blocks[0].chunk_row = ctx->chunk_row;
+    }
+  }
   // sources with a heavy out-degree (CTA-per-row in the source-major backward pass)
   std::vector<int> cptr((size_t)N + 1), heavy_s;
   CK(cudaMemcpyAsync(cptr.data(), ctx->csc_ptr, sizeof(int) * cptr.size(), cudaMemcpyDeviceToHost, ctx->st));
@@ -1226,6 +1534,7 @@ int gatx_train_epoch(gatx_ctx* ctx, int32_t t, float* avg_loss, float* accuracy)
   if (!ctx || t < 1) return fail(ctx, GATX_ERR_INVALID, "epoch index is 1-based");
   CK(cudaSetDevice(ctx->device));
   ctx->spans_used = 0;
+  ctx->comm_spans_used = 0;
   ctx->epoch_replayed = false;
   int rc;
   if (epoch_graph_wanted(ctx)) {
@@ -1310,6 +1619,7 @@ int gatx_sync(gatx_ctx* ctx) {
   if (!ctx) return GATX_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->st));
+  if (ctx->st_comm) CK(cudaStreamSynchronize(ctx->st_comm));
   return GATX_OK;
 }
 
@@ -1561,32 +1871,35 @@ int gatx_comm_init(gatx_ctx* ctx, const void* id128) {
 namespace {
 constexpr int kPeerMaxBufs = 24;
 struct PeerInfo {  // what one rank publishes; sizeof <= GATX_PEER_INFO_BYTES
-  int32_t magic, pid, device, n_bufs;  // buffers: P_l of layer 0..L-1, then the gP_l scratch
+  int32_t magic, pid, device, n_bufs;  // buffers: P_l of layer 0..L-1, the gP_l scratch, the barrier flags
   int64_t n_floats[kPeerMaxBufs];
   uint64_t raw[kPeerMaxBufs];
   cudaIpcMemHandle_t handle[kPeerMaxBufs];
 };
 static_assert(sizeof(PeerInfo) <= GATX_PEER_INFO_BYTES, "PeerInfo must fit the public blob");
-constexpr int32_t kPeerMagic = 0x47585031;  // "GXP1"
+constexpr int32_t kPeerMagic = 0x47585032;  // "GXP2"
 }  // namespace
 
 int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes) {
   if (!ctx || !out || bytes < GATX_PEER_INFO_BYTES) return fail(ctx, GATX_ERR_INVALID, "bad peer_export");
   if (ctx->world < 2 || ctx->world > kMaxPeers) return fail(ctx, GATX_ERR_INVALID, "peer exchange needs 2..%d ranks", kMaxPeers);
-  if (ctx->L + 1 > kPeerMaxBufs) return fail(ctx, GATX_ERR_UNSUPPORTED, "too many layers for the peer blob");
+  if (ctx->L + 2 > kPeerMaxBufs) return fail(ctx, GATX_ERR_UNSUPPORTED, "too many layers for the peer blob");
   CK(cudaSetDevice(ctx->device));
   int rc = ensure_buffers(ctx);
   if (rc) return rc;
+  CK(cudaMemsetAsync(ctx->halo_flags, 0, sizeof(uint32_t) * kMaxPeers, ctx->st));  // a new exchange starts at barrier 0
+  ctx->barrier_seq = 0;
+  CK(cudaStreamSynchronize(ctx->st));  // the flags are zero before any peer can see the handle
   PeerInfo info{};
   info.magic = kPeerMagic;
   info.pid = (int32_t)getpid();
   info.device = ctx->device;
-  info.n_bufs = ctx->L + 1;
+  info.n_bufs = ctx->L + 2;
   int64_t Fmax = 0;
   for (int l = 0; l < ctx->L; ++l) Fmax = ctx->layers[l].F > Fmax ? ctx->layers[l].F : Fmax;
-  for (int b = 0; b <= ctx->L; ++b) {
-    float* ptr = b < ctx->L ? ctx->layers[b].Pl : ctx->gPl;
-    info.n_floats[b] = (int64_t)ctx->N * (b < ctx->L ? ctx->layers[b].F : Fmax);
+  for (int b = 0; b <= ctx->L + 1; ++b) {
+    void* ptr = b < ctx->L ? (void*)ctx->layers[b].Pl : (b == ctx->L ? (void*)ctx->gPl : (void*)ctx->halo_flags);
+    info.n_floats[b] = b <= ctx->L ? (int64_t)ctx->N * (b < ctx->L ? ctx->layers[b].F : Fmax) : (int64_t)kMaxPeers;
     info.raw[b] = (uint64_t)(uintptr_t)ptr;
     CK(cudaIpcGetMemHandle(&info.handle[b], ptr));
   }
@@ -1604,12 +1917,14 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
   CK(cudaSetDevice(ctx->device));
   ctx->peer_Pl.assign(ctx->L, PeerPtrs{});
   ctx->peer_gPl = PeerPtrs{};
+  ctx->peer_flags = PeerFlags{};
+  ctx->peer_flags.p[ctx->rank] = ctx->halo_flags;
   int64_t Fmax = 0;
   for (int l = 0; l < ctx->L; ++l) Fmax = ctx->layers[l].F > Fmax ? ctx->layers[l].F : Fmax;
   for (int p = 0; p < ctx->world; ++p) {
     PeerInfo info;
     memcpy(&info, (const char*)all + (size_t)p * GATX_PEER_INFO_BYTES, sizeof info);
-    if (info.magic != kPeerMagic || info.n_bufs != ctx->L + 1)
+    if (info.magic != kPeerMagic || info.n_bufs != ctx->L + 2)
       return fail(ctx, GATX_ERR_INVALID, "peer blob of rank %d does not match this model", p);
     for (int b = 0; b <= ctx->L; ++b)
       if (info.n_floats[b] != (int64_t)ctx->N * (b < ctx->L ? ctx->layers[b].F : Fmax))
@@ -1626,7 +1941,7 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
         return fail(ctx, GATX_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
       cudaGetLastError();
     }
-    for (int b = 0; b <= ctx->L; ++b) {
+    for (int b = 0; b <= ctx->L + 1; ++b) {
       void* q = nullptr;
       if (same_process) {
         q = (void*)(uintptr_t)info.raw[b];
@@ -1635,12 +1950,9 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
         ctx->ipc_opened.push_back(q);
       }
       if (b < ctx->L) ctx->peer_Pl[b].p[p] = (float*)q;
-      else ctx->peer_gPl.p[p] = (float*)q;
+      else if (b == ctx->L) ctx->peer_gPl.p[p] = (float*)q;
+      else ctx->peer_flags.p[p] = (uint32_t*)q;
     }
-  }
-  if (!ctx->barrier_word) {
-    CK(dalloc(&ctx->barrier_word, 1));
-    CK(cudaMemsetAsync(ctx->barrier_word, 0, sizeof(float), ctx->st));
   }
   ctx->peers_ready = getenv("GATX_NO_P2P") == nullptr;
   return GATX_OK;
@@ -1650,9 +1962,27 @@ int gatx_peer_disable(gatx_ctx* ctx) {
   if (!ctx) return GATX_ERR_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
+  if (ctx->st_comm) cudaStreamSynchronize(ctx->st_comm);
   for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
   ctx->ipc_opened.clear();
   ctx->peers_ready = false;
+  return GATX_OK;
+}
+
+int gatx_halo_stats(gatx_ctx* ctx, double* out4) {
+  if (!ctx || !out4) return GATX_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->st));
+  if (ctx->st_comm) CK(cudaStreamSynchronize(ctx->st_comm));
+  out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+  for (size_t i = 0; i < ctx->comm_spans_used; ++i) {
+    float ms = 0.f;
+    const auto& s = ctx->comm_spans[i];
+    if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) continue;
+    out4[2 * s.dir] += s.bytes;
+    out4[2 * s.dir + 1] += ms;
+  }
+  cudaGetLastError();
   return GATX_OK;
 }
 

@@ -12,8 +12,12 @@
 //             ascending rank order -- a fixed order, so the result is reproducible run to run (NCCL's reduction tree
 //             gives no such promise across topologies).
 // Both kernels are one warp per row with 128-bit accesses; rows are 0.5-2 KB, NVLink sees full-line transfers.
-// Ordering between ranks is by stream-ordered barriers in gatx_api.cu (a 4-byte NCCL all-reduce before and after).
+// Ordering between ranks is by halo_barrier_kernel: flags in peer memory (st.release.sys / ld.acquire.sys), one
+// 32-thread CTA per barrier on the exchange stream -- no NCCL call, no host involvement.  The exchange runs on a stream
+// of its own, block of destination rows by block, so that it overlaps the edge passes (gatx_api.cu).
 #include "common.cuh"
+
+#include <cstdio>
 
 namespace gatx {
 
@@ -57,6 +61,7 @@ halo_push_kernel(const float* __restrict__ own_rows, int r0, int n_rows, int F, 
       }
     }
   }
+  __threadfence_system();  // the peer-memory stores are performed before the kernel (and the barrier behind it) completes
 }
 
 __global__ void __launch_bounds__(256)
@@ -92,6 +97,36 @@ halo_pull_kernel(float* __restrict__ own_rows, int r0, int n_rows, int F, const 
       }
     }
   }
+}
+
+__global__ void halo_barrier_kernel(PeerFlags flags, int me, int world, uint32_t seq) {
+  const int p = threadIdx.x;
+  if (p >= world || p == me) return;
+  __threadfence_system();
+  // arrive: slot `me` of peer p's array
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[p] + me), "r"(seq) : "memory");
+  // wait for peer p's arrival in slot p of my array (flags only grow: a peer may already be one barrier ahead)
+  const uint32_t* mine = flags.p[me] + p;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - seq) >= 0) break;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) {  // 20 s: a peer died or the ranks issued different exchange sequences
+      printf("gatx: halo barrier %u timed out on rank %d waiting for rank %d (flag %u)\n", seq, me, p, v);
+      __trap();
+    }
+    __nanosleep(64);
+  }
+  __threadfence_system();
+}
+
+int launch_halo_barrier(const PeerFlags& flags, int me, int world, uint32_t seq, cudaStream_t st) {
+  halo_barrier_kernel<<<1, 32, 0, st>>>(flags, me, world, seq);
+  return 1;
 }
 
 static int halo_blocks(int n_rows) {

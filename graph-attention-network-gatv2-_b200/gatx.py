@@ -26,7 +26,7 @@ EXPORTS = [
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
-    "gatx_device_count", "gatx_peer_disable", "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_bias", "gatx_set_bias_values",
+    "gatx_device_count", "gatx_peer_disable", "gatx_halo_stats", "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_bias", "gatx_set_bias_values",
 ]
 
 
@@ -342,6 +342,13 @@ class Engine:
         self.lib.gatx_halo_rows.restype = C.c_int64
         self.lib.gatx_halo_rows.argtypes = [C.c_void_p]
         return int(self.lib.gatx_halo_rows(self.ctx))
+
+    def halo_stats(self):
+        """NVLink bytes / busy milliseconds of the exchange kernels in the last epoch (timing enabled)."""
+        buf = (C.c_double * 4)()
+        self.lib.gatx_halo_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(self.lib.gatx_halo_stats(self.ctx, buf), "gatx_halo_stats")
+        return dict(push_bytes=buf[0], push_ms=buf[1], pull_bytes=buf[2], pull_ms=buf[3])
 
     def halo_active(self):
         self.lib.gatx_halo_active.argtypes = [C.c_void_p]

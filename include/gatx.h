@@ -191,7 +191,8 @@ int64_t gatx_tensor_size(gatx_ctx* ctx, int32_t which, int32_t layer); /* elemen
 int gatx_get_tensor(gatx_ctx* ctx, int32_t which, int32_t layer, void* dst, size_t bytes);
 /* Device milliseconds of the phases of the last gatx_train_epoch / forward / backward call:
  * out[0]=projection GEMMs, [1]=edge forward, [2]=classifier+loss, [3]=edge backward,
- * [4]=gradient GEMMs, [5]=optimizer, [6]=collectives, [7]=whole epoch.  Needs
+ * [4]=gradient GEMMs, [5]=optimizer, [6]=exchange (NCCL path: the collectives; peer-memory path: the time the compute
+ * stream WAITS for the exchange stream, i.e. the exposed part), [7]=whole epoch.  Needs
  * gatx_enable_timing(ctx, 1) (adds event records, no host syncs). */
 int gatx_enable_timing(gatx_ctx* ctx, int32_t on);
 int gatx_get_timing(gatx_ctx* ctx, float* out_ms, int32_t n);
@@ -246,6 +247,11 @@ int gatx_peer_disable(gatx_ctx* ctx);
  * would move (world - 1) * own rows.  Integer, identical to oracle/orc_halo_rows. */
 int64_t gatx_halo_rows(const gatx_ctx* ctx);
 int gatx_halo_active(const gatx_ctx* ctx); /* 1 when the peer-memory path is in use */
+/* NVLink traffic of the exchange kernels in the last epoch (timing enabled, peer-memory path): out4[0] = bytes this rank
+ * pushed into its peers' P_l buffers, [1] = milliseconds its push kernels were running, [2] = bytes it pulled from its
+ * peers' partial gP_l rows, [3] = milliseconds of the pull kernels.  The kernels run on the exchange stream underneath
+ * the edge passes, so these are busy times, not exposed times (phase 6 of gatx_get_timing is the exposed wait). */
+int gatx_halo_stats(gatx_ctx* ctx, double* out4);
 
 #ifdef __cplusplus
 }

@@ -46,20 +46,43 @@ def test_oracle_matches_reference_epoch1(path, orc):
     loss = m.loss()
     m.backward()
     L = len(heads)
+    # Reference defect D14 (found with the cora-shaped fixture): compute_output_gradients returns its out-of-range
+    # threads (EB:566) BEFORE the block-wide copy of W_o into shared memory (EB:585-588), so in the last block only
+    # the N % 128 surviving threads copy, and elements i >= N % 128 of W_o (i < C * D_L) stay uninitialised there.
+    # When 0 < N % 128 < C * D_L the gradients g_h of the last N % 128 nodes are garbage, and with them everything
+    # that sums over those nodes (ga, gW, and g_h of every node with an edge INTO them one layer down).  All of the
+    # reference's real datasets are hit (cora 20 < 56, pubmed 5 < 24, arxiv 127 < 2560, products 16 < 6016).
+    tail_nodes = N % 128
+    d14 = 0 < tail_nodes < m.C * outdims[-1]
+    bad = np.zeros(N, bool)
+    if d14:
+        bad[N - tail_nodes:] = True
     for l in range(L):
         assert rel_err(m.tensor(orc.T_SCORE, l).ravel(), g["ref_score_%d" % l]) < 2e-5, ("score", l)
         assert np.abs(m.tensor(orc.T_ALPHA, l).ravel() - g["ref_alpha_%d" % l]).max() < 2e-6, ("alpha", l)
         assert rel_err(m.tensor(orc.T_HPRE, l).ravel(), g["ref_hpre_%d" % l]) < 2e-5, ("hpre", l)
         assert rel_err(m.tensor(orc.T_HOUT, l).ravel(), g["ref_hout_%d" % l]) < 2e-5, ("hout", l)
-        assert rel_err(m.tensor(orc.T_GH, l).ravel(), g["ref_gh_%d" % l]) < 1e-4, ("g_h", l)
+    for l in range(L - 1, -1, -1):
+        mine, ref = m.tensor(orc.T_GH, l), g["ref_gh_%d" % l].reshape(N, -1)
+        assert rel_err(mine[~bad], ref[~bad]) < 1e-4, ("g_h", l)
+        if d14:
+            assert rel_err(mine[bad], ref[bad]) > 1e-2, "fixture no longer shows defect D14"
+            # one layer down, the garbage reaches every source of an edge into a bad node (gP_l) besides the node itself
+            rp, ci = g["row_ptr"], g["col_idx"]
+            srcs = np.concatenate([ci[rp[i]:rp[i + 1]] for i in np.flatnonzero(bad)])
+            bad = bad.copy()
+            bad[srcs] = True
     assert np.abs(m.tensor(orc.T_Y).ravel() - g["ref_y"]).max() < 2e-6
     la = orc.loss_acc(m.tensor(orc.T_Y), m.labels)
     assert np.abs(la["losses"] - g["ref_loss"]).max() < 2e-5
     assert np.array_equal(la["correct"], g["ref_correct"])  # predicted-label hits, bit-exact
     assert abs(loss["avg"] - g["loss_curve"][0, 0]) < 2e-6 + 1e-6  # printed with %f
+    assert rel_err(m.tensor(orc.T_GWO).ravel(), g["ref_gWo"]) < 1e-4  # computed before the defective copy (EB:576-581)
+    if d14:
+        assert "defect" in os.path.basename(path)
+        return  # ga and gW sum over the corrupted nodes
     ga = np.concatenate([m.tensor(orc.T_GA, l).ravel() for l in range(L)])
     assert rel_err(ga, g["ref_ga"]) < 1e-4
-    assert rel_err(m.tensor(orc.T_GWO).ravel(), g["ref_gWo"]) < 1e-4
     # gW layer by layer.  Reference defect D13: when 0 < E % 256 < 2*in_dim the threads of the last CTA
     # that returned early (EB:722) never zero their columns of sh_grad_w (EB:747-749); those columns of
     # the reference's gW are garbage and only the columns below E % 256 can be compared.

@@ -182,7 +182,7 @@ def test_products_full_size_properties(gatx, orc):
         srcs_hub = np.unique(np.concatenate([srcs, [hub_src]]))
         n1 = _check_layer_on_subgraph(eng, gatx, orc, 1, cfg, rp, ci, srcs_hub, extra)
         n2 = _check_layer_on_subgraph(eng, gatx, orc, 2, cfg, rp, ci, srcs_hub, extra)
-        assert n0 > 100000 and n1 > 1000000 and n2 == n1
+        assert n0 > 50000 and n1 > 1000000 and n2 == n1
         eng.close()
     assert losses[0] == losses[1]
     assert abs(losses[0][0] - np.log(cfg["C"])) < 0.5  # Xavier init: loss near log(47)
