@@ -75,6 +75,7 @@ struct EdgeGraph {
   // optional CUDA-event pairs around the three main streaming kernels of the layer being launched
   // (fwd, bwd pass 1, bwd pass 2); null = no timing
   cudaEvent_t* kernel_events;  // [6] = {fwd_a, fwd_b, dst_a, dst_b, src_a, src_b}
+  int reserve_ctas;            // CTA slots the streaming kernels leave to the exchange kernels running underneath (0 = none)
   Slopes slopes;               // LeakyReLU slopes of the layer being launched
   const float* bias;           // [F] added to the aggregate before the activation (extension); nullptr = none (reference)
 };
@@ -151,10 +152,12 @@ constexpr int kMaxPeers = 16;
 struct PeerPtrs {
   float* p[kMaxPeers];  // base of the peer's [N][F] buffer (this rank's own slot is unused)
 };
+// max_ctas > 0 caps the grid (the pipelined exchange runs underneath the edge passes in a fixed number of CTA slots)
 int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
-                     int me, cudaStream_t st);
+                     int me, cudaStream_t st, int max_ctas = 0);
 int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
-                     int world, cudaStream_t st);
+                     int world, cudaStream_t st, int max_ctas = 0);
+int halo_cta_slots();  // CTA slots of the exchange kernels (GATX_HALO_CTAS, default 48)
 // Device-side barrier across ranks through flags in peer memory: rank `me` stores `seq` (release, system scope) into
 // slot `me` of every peer's flag array, then waits (acquire) until every slot of its own array has reached `seq`.
 // Stream-ordered: everything this rank enqueued before it on `st` (and its peer-memory stores) is visible to a peer

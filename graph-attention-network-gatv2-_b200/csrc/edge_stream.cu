@@ -883,11 +883,15 @@ bool make_stream_shape(int H, int D, Shape* sh, int* nv) {
   return true;
 }
 
-int stream_grid(const void* kernel, size_t smem, int n_chunks) {
+// `reserve`: CTA slots left free for the exchange kernels that run underneath this launch (multi-GPU pipeline).  The
+// chunks are assigned statically (grid-stride), so every CTA of the grid must be resident at once: a CTA that had to
+// wait for a slot taken by another stream's kernel would run its whole share after the others finished.
+int stream_grid(const void* kernel, size_t smem, int n_chunks, int reserve) {
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSW * 32, smem);
   if (per_sm < 1) per_sm = 1;
-  int blocks = kNumSMs * per_sm;
+  int blocks = kNumSMs * per_sm - reserve;
+  if (blocks < kNumSMs) blocks = kNumSMs;
   const int need = (n_chunks + kSW - 1) / kSW;
   return blocks < need ? blocks : need;
 }
@@ -959,7 +963,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
     const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
     auto kern = edge_fwd_pair_kernel<R>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
+    const int blocks = stream_grid((const void*)kern, smem, g.n_chunks, eg.reserve_ctas);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
     // 512-byte rows: the cache-hint form of the bulk copy is slower than the plain one at this size (measured), no hints
     kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, Hout, hpre, score, mx, sinv, part);
@@ -976,7 +980,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
     const size_t smem = (size_t)kSW * R * NV * 128 * 4 + (size_t)kSW * R * 8;
     auto kern = edge_fwd_stream_kernel<NV, R, LPH>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int blocks = stream_grid((const void*)kern, smem, g.n_chunks);
+    const int blocks = stream_grid((const void*)kern, smem, g.n_chunks, eg.reserve_ctas);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
     kern<<<blocks, kSW * 32, smem, st>>>(g, colx, Pl, Pr, a, sh, Hout, hpre, score, mx, sinv, part);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[1], st);
@@ -1026,7 +1030,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
         auto kern = edge_bwd_dst_pair_kernel<R>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);
+        const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks, eg.reserve_ctas);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
         kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, gH, cdot, score, mx, sinv, gPr, rec, part,
                                              ga_partials, galpha_dbg);
@@ -1042,7 +1046,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         const size_t smem = (size_t)kSW * R * (F + 32) * 4 + (size_t)kSW * R * 8;
         auto kern = edge_bwd_src_pair_kernel<R>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks);
+        const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks, eg.reserve_ctas);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[4], st);
         kern<<<blocks, kSW * 32, smem, st>>>(gs, eg.csc_dst, eg.csc_eid, a, gH, rec, gPl, part);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[5], st);
@@ -1075,7 +1079,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
         auto kern = edge_bwd_dst_stream_kernel<NV, R, LPH>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks);
+        const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks, eg.reserve_ctas);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
         kern<<<blocks, kSW * 32, smem, st>>>(gd, colx, Pl, Pr, a, sh, gH, cdot, score, mx, sinv, gPr, rec, part,
                                              ga_partials, galpha_dbg, H);
@@ -1093,7 +1097,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         const size_t smem = (size_t)kSW * R * slot_floats * 4 + (size_t)kSW * R * 8;
         auto kern = edge_bwd_src_stream_kernel<NV, R>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks);
+        const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks, eg.reserve_ctas);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[4], st);
         kern<<<blocks, kSW * 32, smem, st>>>(gs, cdstx, eg.csc_eid, a, sh, gH, rec, gPl, part, slot_floats);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[5], st);

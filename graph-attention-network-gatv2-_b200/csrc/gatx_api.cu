@@ -410,6 +410,7 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   g.chunk_T = c->chunk_T; g.n_chunks = c->n_chunks; g.chunk_row = c->chunk_row; g.chunk_src = c->chunk_src;
   g.col_idx_hot = c->col_idx_hot; g.csc_dst_hot = c->csc_dst_hot; g.hot_wide_F = c->hot_wide_F;
   g.kernel_events = nullptr;
+  g.reserve_ctas = 0;
   g.slopes = c->slopes;
   g.bias = nullptr;
   return g;
@@ -581,6 +582,7 @@ RowView row_view(const gatx_ctx* ctx, int b) {
   v.g.n_chunks = B.n_chunks; v.g.chunk_row = B.chunk_row;
   v.g.col_idx_hot = ctx->col_idx_hot ? ctx->col_idx_hot + B.e0 : nullptr;
   v.g.heavy_rows = nullptr; v.g.n_heavy_rows = 0;
+  v.g.reserve_ctas = halo_cta_slots();  // the exchange of the neighbouring block runs underneath this launch
   return v;
 }
 // the streaming kernels take any view; the warp-per-row / generic kernels only the whole row range
@@ -771,7 +773,7 @@ int do_forward(gatx_ctx* ctx) {
         {
           CommTimer ct(ctx, 0, (double)ctx->blocks[b].halo_rows * nx.F * 4.0);
           LAUNCHED(launch_halo_push(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
-                                    ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm));
+                                    ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm, halo_cta_slots()));
         }
       }
       if ((rc = comm_barrier(ctx))) return rc;  // every rank's pushes have landed
@@ -907,7 +909,8 @@ int do_backward(gatx_ctx* ctx) {
       {
         CommTimer ct(ctx, 1, (double)ctx->blocks[b].halo_rows * ly.F * 4.0);
         LAUNCHED(launch_halo_pull(ctx->gPl + (int64_t)(ctx->r0 + v.rb) * ly.F, ctx->r0 + v.rb, v.nb, ly.F,
-                                  ctx->ref_mask + v.rb, ctx->peer_gPl, ctx->rank, ctx->world, ctx->st_comm));
+                                  ctx->ref_mask + v.rb, ctx->peer_gPl, ctx->rank, ctx->world, ctx->st_comm,
+                                  halo_cta_slots()));
       }
       compute_waits_comm(ctx);
       if (l > 0) {

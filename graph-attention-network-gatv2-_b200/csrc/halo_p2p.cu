@@ -18,6 +18,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace gatx {
 
@@ -30,7 +31,7 @@ __device__ __forceinline__ float4 ld_sys4(const float* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 halo_push_kernel(const float* __restrict__ own_rows, int r0, int n_rows, int F, const uint16_t* __restrict__ ref_mask,
                  PeerPtrs peers, int me) {
   const int lane = threadIdx.x & 31;
@@ -64,7 +65,10 @@ halo_push_kernel(const float* __restrict__ own_rows, int r0, int n_rows, int F, 
   __threadfence_system();  // the peer-memory stores are performed before the kernel (and the barrier behind it) completes
 }
 
-__global__ void __launch_bounds__(256)
+// One warp per own row.  The peers that hold a partial row are visited in ascending rank order (a fixed order: the sum
+// is reproducible), software-pipelined: the loads of the next contributing peer are in flight while the current one is
+// added, so a warp keeps two remote 2 KB reads outstanding instead of one (NVLink round trips are ~3 us).
+__global__ void __launch_bounds__(256, 4)
 halo_pull_kernel(float* __restrict__ own_rows, int r0, int n_rows, int F, const uint16_t* __restrict__ ref_mask,
                  PeerPtrs peers, int me, int world) {
   const int lane = threadIdx.x & 31;
@@ -75,20 +79,40 @@ halo_pull_kernel(float* __restrict__ own_rows, int r0, int n_rows, int F, const 
     float* mine = own_rows + (int64_t)row * F;
     const int64_t off = (int64_t)(r0 + row) * F;
     for (int k0 = 0; k0 < F; k0 += 512) {
-      float4 acc[4];
+      float4 acc[4], nxt[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int p = 0; p < world; ++p) {  // ascending rank order: deterministic sum
-        if (!((m >> p) & 1u)) continue;
+      uint32_t mm = m;
+      int p = __ffs(mm) - 1;
+      mm &= mm - 1;
+      {
         const float* src = p == me ? mine : peers.p[p] + off;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + 4 * (lane + 32 * j);
-          if (k < F) {
-            const float4 v = ld_sys4(src + k);  // peer memory: system-scope load, never a stale cached line
-            acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+          nxt[j] = k < F ? ld_sys4(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);  // peer memory: system-scope load
+        }
+      }
+      while (true) {
+        float4 cur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        const bool more = mm != 0;
+        if (more) {
+          p = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const float* src = p == me ? mine : peers.p[p] + off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 4 * (lane + 32 * j);
+            nxt[j] = k < F ? ld_sys4(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j].x += cur[j].x; acc[j].y += cur[j].y; acc[j].z += cur[j].z; acc[j].w += cur[j].w;
+        }
+        if (!more) break;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -129,23 +153,34 @@ int launch_halo_barrier(const PeerFlags& flags, int me, int world, uint32_t seq,
   return 1;
 }
 
-static int halo_blocks(int n_rows) {
+// Both kernels are CTAs of 256 threads with at most 64 registers per thread (launch bounds): 16 K registers and no
+// shared memory, i.e. one exchange CTA fits the slot of one streaming edge CTA (~20 K registers).  In the pipelined
+// epoch they run in halo_cta_slots() CTAs underneath an edge pass whose grid leaves exactly that many slots free.
+int halo_cta_slots() {
+  static const int n = [] {
+    const char* e = getenv("GATX_HALO_CTAS");
+    const int v = e ? atoi(e) : 48;
+    return v >= 4 && v <= kNumSMs * 2 ? v : 48;
+  }();
+  return n;
+}
+static int halo_blocks(int n_rows, int max_ctas) {
   int blocks = (n_rows + 7) / 8;
-  const int cap = kNumSMs * 8;
+  const int cap = max_ctas > 0 ? max_ctas : kNumSMs * 8;
   return blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
 }
 
 int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
-                     int me, cudaStream_t st) {
+                     int me, cudaStream_t st, int max_ctas) {
   if (n_rows <= 0) return 0;
-  halo_push_kernel<<<halo_blocks(n_rows), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me);
+  halo_push_kernel<<<halo_blocks(n_rows, max_ctas), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me);
   return 1;
 }
 
 int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
-                     int world, cudaStream_t st) {
+                     int world, cudaStream_t st, int max_ctas) {
   if (n_rows <= 0) return 0;
-  halo_pull_kernel<<<halo_blocks(n_rows), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me, world);
+  halo_pull_kernel<<<halo_blocks(n_rows, max_ctas), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me, world);
   return 1;
 }
 
