@@ -256,10 +256,9 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int src = __shfl_sync(0xffffffffu, idx_cur, s);
-      if (s < n && lane == 0) {
+      if (s < n) {
         const uint32_t slot = (it + s) % R;
-        mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
-        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(src) * F, kRowBytes, bar_s + slot * 8u, gp.of(src));
+        bulk_g2s_hint_elect(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(src) * F, kRowBytes, bar_s + slot * 8u, gp.of(src));
       }
     }
     float4 pr[NV], pr_n[NV];
@@ -301,15 +300,13 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       mbar_wait_s(bar_s + slot * 8u, ph);
       float4 v[NV];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + voff[j]);
+      for (int j = 0; j < NV; ++j) v[j] = lds4_s(ring_s + (uint32_t)(slot * F + voff[j]) * 4u);
       __syncwarp();  // every lane has read the slot before it is refilled
       {
         const int ni = i + R;
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
-        if (ni < n && lane == 0) {
-          mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
-          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
-        }
+        if (ni < n)
+          bulk_g2s_hint_elect(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
       }
       float2 pp = make_float2(0.f, 0.f);  // even / odd elements: two interleaved FFMA2 chains
 #pragma unroll
@@ -484,7 +481,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
   }
   __syncwarp();
   const GatherPolicy gp(g);
-  const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(bar);
+  const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(bar), rowbuf_s = smem_u32(rowbuf), rbar_s = smem_u32(rbar);
   float4 ga[NV];  // the attention vector a is only needed when a row segment is written: read it there (L1 hit)
 #pragma unroll
   for (int j = 0; j < NV; ++j) ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -511,19 +508,15 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int src = __shfl_sync(0xffffffffu, idx_cur, s);
-      if (s < n && lane == 0) {
+      if (s < n) {
         const uint32_t slot = (it + s) % R;
-        mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
-        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(src) * F, kRowBytes, bar_s + slot * 8u, gp.of(src));
+        bulk_g2s_hint_elect(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(src) * F, kRowBytes, bar_s + slot * 8u, gp.of(src));
       }
     }
     // row data (g_h row, P_r row) of r goes through the row buffer; once it sits in registers the buffer is free,
     // so row r + 1 is prefetched into the same buffer while row r is being processed
-    if (lane == 0) {
-      mbar_expect_tx(rbar, 2 * kRowBytes);
-      bulk_g2s_hint(rowbuf, gh + (int64_t)r * F, kRowBytes, rbar, gp.cold);
-      bulk_g2s_hint(rowbuf + F, Pr + (int64_t)r * F, kRowBytes, rbar, gp.cold);
-    }
+    bulk2_g2s_hint_elect(rowbuf_s, gh + (int64_t)r * F, kRowBytes, gp.cold, rowbuf_s + kRowBytes, Pr + (int64_t)r * F,
+                         kRowBytes, gp.cold, rbar_s);
     // score window: the scores of 32 consecutive edges are contiguous ([E][H]); the next window is
     // prefetched into registers while the current one is consumed from shared memory
     float scp[8];
@@ -557,11 +550,9 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     }
     __syncwarp();
     ++rk;
-    if (r + 1 < g.n_rows && lane == 0) {
-      mbar_expect_tx(rbar, 2 * kRowBytes);
-      bulk_g2s_hint(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
-      bulk_g2s_hint(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
-    }
+    if (r + 1 < g.n_rows)
+      bulk2_g2s_hint_elect(rowbuf_s, gh + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rowbuf_s + kRowBytes,
+                           Pr + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rbar_s);
     bool first_row = true;
     for (int i = 0; i < n; ++i) {
       const int e = e0 + i;
@@ -592,11 +583,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         __syncwarp();
         ++rk;
         if (r + 1 < g.n_rows) {
-          if (lane == 0) {
-            mbar_expect_tx(rbar, 2 * kRowBytes);
-            bulk_g2s_hint(rowbuf, gh + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
-            bulk_g2s_hint(rowbuf + F, Pr + (int64_t)(r + 1) * F, kRowBytes, rbar, gp.cold);
-          }
+          bulk2_g2s_hint_elect(rowbuf_s, gh + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rowbuf_s + kRowBytes,
+                               Pr + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rbar_s);
           load_scalars(qn, r + 1, H, hd, cdot, mx, sinv);
           next_end = __ldg(g.row_ptr + r + 2);
         }
@@ -621,15 +609,13 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       mbar_wait_s(bar_s + slot * 8u, ph);
       float4 v[NV];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = lds4(ring + slot * F + voff[j]);
+      for (int j = 0; j < NV; ++j) v[j] = lds4_s(ring_s + (uint32_t)(slot * F + voff[j]) * 4u);
       __syncwarp();
       {
         const int ni = i + R;
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
-        if (ni < n && lane == 0) {
-          mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes);
-          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
-        }
+        if (ni < n)
+          bulk_g2s_hint_elect(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
       }
       const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
       uint32_t* re = rec + (int64_t)e * RW;
@@ -779,11 +765,11 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int d = __shfl_sync(0xffffffffu, dst_cur, s), ee = __shfl_sync(0xffffffffu, eid_cur, s);
-      if (s < n && lane == 0) {
+      if (s < n) {
         const uint32_t slot = (it + s) % R;
-        mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes + kRecBytes);
-        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats) * 4u, gh + gp.id(d) * F, kRowBytes, bar_s + slot * 8u, gp.of(d));
-        bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats + F) * 4u, rec + (int64_t)ee * RW, kRecBytes, bar_s + slot * 8u, gp.cold);
+        bulk2_g2s_hint_elect(ring_s + (uint32_t)(slot * slot_floats) * 4u, gh + gp.id(d) * F, kRowBytes, gp.of(d),
+                             ring_s + (uint32_t)(slot * slot_floats + F) * 4u, rec + (int64_t)ee * RW, kRecBytes, gp.cold,
+                             bar_s + slot * 8u);
       }
     }
     float4 acc[NV];
@@ -816,17 +802,16 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
       }
       const uint32_t pos = it + i, slot = pos % R, ph = (pos / R) & 1;
       mbar_wait_s(bar_s + slot * 8u, ph);
-      const float* sl = ring + slot * slot_floats;
-      const uint32_t* rw = reinterpret_cast<const uint32_t*>(sl + F);
+      const uint32_t sl = ring_s + (uint32_t)(slot * slot_floats) * 4u, rw = sl + F * 4u;
       float4 gv[NV];
       uint4 kk[NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        gv[j] = lds4(sl + voff[j]);
-        kk[j] = *reinterpret_cast<const uint4*>(rw + 4 * j);
+        gv[j] = lds4_s(sl + (uint32_t)voff[j] * 4u);
+        kk[j] = lds4u_s(rw + 16u * j);
       }
-      const float al = __uint_as_float(rw[4 * NV + hd]);  // this lane's head
-      const float ge = __uint_as_float(rw[4 * NV + sh.H + hd]);
+      const float al = __uint_as_float(lds1u_s(rw + (uint32_t)(4 * NV + hd) * 4u));  // this lane's head
+      const float ge = __uint_as_float(lds1u_s(rw + (uint32_t)(4 * NV + sh.H + hd) * 4u));
       const float ges = ge * g.slopes.attn;
       const float2 al2 = splat2(al);
       __syncwarp();
@@ -835,11 +820,10 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
         const bool same = (ni >> 5) == (i >> 5);
         const int d = __shfl_sync(0xffffffffu, same ? dst_cur : dst_nxt, ni & 31);
         const int ee = __shfl_sync(0xffffffffu, same ? eid_cur : eid_nxt, ni & 31);
-        if (ni < n && lane == 0) {
-          mbar_expect_tx_s(bar_s + slot * 8u, kRowBytes + kRecBytes);
-          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats) * 4u, gh + gp.id(d) * F, kRowBytes, bar_s + slot * 8u, gp.of(d));
-          bulk_g2s_hint_s(ring_s + (uint32_t)(slot * slot_floats + F) * 4u, rec + (int64_t)ee * RW, kRecBytes, bar_s + slot * 8u, gp.cold);
-        }
+        if (ni < n)
+          bulk2_g2s_hint_elect(ring_s + (uint32_t)(slot * slot_floats) * 4u, gh + gp.id(d) * F, kRowBytes, gp.of(d),
+                               ring_s + (uint32_t)(slot * slot_floats + F) * 4u, rec + (int64_t)ee * RW, kRecBytes, gp.cold,
+                               bar_s + slot * 8u);
       }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {

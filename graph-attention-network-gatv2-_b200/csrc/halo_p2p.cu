@@ -149,6 +149,7 @@ __global__ void halo_barrier_kernel(PeerFlags flags, int me, int world, uint32_t
 }
 
 int launch_halo_barrier(const PeerFlags& flags, int me, int world, uint32_t seq, cudaStream_t st) {
+  prefer_max_shared(halo_barrier_kernel);
   halo_barrier_kernel<<<1, 32, 0, st>>>(flags, me, world, seq);
   return 1;
 }
@@ -164,6 +165,14 @@ int halo_cta_slots() {
   }();
   return n;
 }
+// The streaming edge kernels run with the SM's shared-memory carve-out at its maximum (64-70 KB per CTA, three CTAs
+// per SM).  A kernel that prefers the default carve-out cannot share an SM with them: the SM has to drain before its
+// L1 / shared split is changed, so an exchange CTA would keep the whole SM away from the edge pass for as long as it
+// runs (measured: the edge forward made no progress underneath the push).  Ask for the same carve-out.
+template <typename K>
+static void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 static int halo_blocks(int n_rows, int max_ctas) {
   int blocks = (n_rows + 7) / 8;
   const int cap = max_ctas > 0 ? max_ctas : kNumSMs * 8;
@@ -173,6 +182,7 @@ static int halo_blocks(int n_rows, int max_ctas) {
 int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
                      int me, cudaStream_t st, int max_ctas) {
   if (n_rows <= 0) return 0;
+  prefer_max_shared(halo_push_kernel);
   halo_push_kernel<<<halo_blocks(n_rows, max_ctas), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me);
   return 1;
 }
@@ -180,6 +190,7 @@ int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uin
 int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
                      int world, cudaStream_t st, int max_ctas) {
   if (n_rows <= 0) return 0;
+  prefer_max_shared(halo_pull_kernel);
   halo_pull_kernel<<<halo_blocks(n_rows, max_ctas), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me, world);
   return 1;
 }

@@ -82,6 +82,85 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// ---- single-lane issue through elect.sync --------------------------------------------------------------------------
+// `if (lane == 0) { expect_tx; cp.async.bulk }` makes ptxas emit a loop over the active lanes around UBLKCP (its operands
+// live in uniform registers, and the compiler cannot prove that one lane is active): ELECT + 4 R2UR + branch, ~20 issue
+// slots per copy.  With elect.sync the predicate is known to select exactly one lane, the shuffled gather index is moved
+// to the uniform datapath once and the address arithmetic runs there (UIMAD.WIDE): ~8 issue slots.  Call with all 32
+// lanes converged and warp-uniform operands; the condition around the call must be warp-uniform too.
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+      "}\n" ::"r"(dst),
+      "l"(src_gmem), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint_elect(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar,
+                                                    uint64_t policy) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+      "}\n" ::"r"(dst),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+// two copies completing on one barrier (a gathered row + its edge record, or the two row-buffer halves)
+__device__ __forceinline__ void bulk2_g2s_hint_elect(uint32_t dst0, const void* src0, uint32_t bytes0, uint64_t policy0,
+                                                     uint32_t dst1, const void* src1, uint32_t bytes1, uint64_t policy1,
+                                                     uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "add.u32 t, %2, %6;\n"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%8], t;\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%8], %3;\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%4], [%5], %6, [%8], %7;\n"
+      "}\n" ::"r"(dst0),
+      "l"(src0), "r"(bytes0), "l"(policy0), "r"(dst1), "l"(src1), "r"(bytes1), "l"(policy1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk2_g2s_elect(uint32_t dst0, const void* src0, uint32_t bytes0, uint32_t dst1,
+                                                const void* src1, uint32_t bytes1, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "add.u32 t, %2, %5;\n"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%6], t;\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%6];\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%4], %5, [%6];\n"
+      "}\n" ::"r"(dst0),
+      "l"(src0), "r"(bytes0), "r"(dst1), "l"(src1), "r"(bytes1), "r"(bar)
+      : "memory");
+}
+// 128-bit shared-memory load on a 32-bit shared address (no generic-to-shared conversion in the loop); volatile: the ring
+// slots are rewritten by the async proxy, the load must stay behind its mbarrier wait
+__device__ __forceinline__ float4 lds4_s(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds4u_s(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds1u_s(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
