@@ -22,6 +22,15 @@
 
 namespace gatx {
 
+// The streaming edge kernels run with the SM's shared-memory carve-out at its maximum (64-70 KB per CTA, three CTAs
+// per SM).  A kernel that prefers the default carve-out cannot share an SM with them: the SM has to drain before its
+// L1 / shared split is changed, so an exchange CTA would keep the whole SM away from the edge pass for as long as it
+// runs (measured: the edge forward made no progress underneath the push).  Ask for the same carve-out.
+template <typename K>
+static void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 __device__ __forceinline__ float4 ld_sys4(const float* p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -164,14 +173,6 @@ int halo_cta_slots() {
     return v >= 4 && v <= kNumSMs * 2 ? v : 48;
   }();
   return n;
-}
-// The streaming edge kernels run with the SM's shared-memory carve-out at its maximum (64-70 KB per CTA, three CTAs
-// per SM).  A kernel that prefers the default carve-out cannot share an SM with them: the SM has to drain before its
-// L1 / shared split is changed, so an exchange CTA would keep the whole SM away from the edge pass for as long as it
-// runs (measured: the edge forward made no progress underneath the push).  Ask for the same carve-out.
-template <typename K>
-static void prefer_max_shared(K kernel) {
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 static int halo_blocks(int n_rows, int max_ctas) {
   int blocks = (n_rows + 7) / 8;
