@@ -42,6 +42,10 @@ int launch_philox_uniform(float* out, int64_t n, float limit, uint64_t seed, uin
 // keep() is a pure function of (seed, layer, step, global row, column), see dropout_kernel
 int launch_dropout(const float* X, int64_t ldx, float* Y, int64_t ldy, int n_rows, int cols, int row0, float p,
                    uint64_t seed, int layer, int64_t step, cudaStream_t st);
+// out[e][h] = keep ? 1 / (1 - p) : 0 for local edges [0, E): (e, h) is kept iff word h % 4 of
+// Philox4x32-10(counter {edge0 + e, h / 4, 2^31 | layer, step}, key seed) >= floor(p * 2^32)  (edge0 + e: GLOBAL CSR position)
+int launch_attn_dropout_scale(float* out, int64_t E, int H, int64_t edge0, float p, uint64_t seed, int layer, int64_t step,
+                              cudaStream_t st);
 
 // gemm_simt.cu : C[m][n] (ldc) (+)= sum_k A(m,k) B(n,k), A(m,k) = A[m*sAm + k*sAk], same for B.
 int launch_gemm_simt(const float* A, int64_t sAm, int64_t sAk, const float* B, int64_t sBn, int64_t sBk,
@@ -78,6 +82,10 @@ struct EdgeGraph {
   int reserve_ctas;            // CTA slots the streaming kernels leave to the exchange kernels running underneath (0 = none)
   Slopes slopes;               // LeakyReLU slopes of the layer being launched
   const float* bias;           // [F] added to the aggregate before the activation (extension); nullptr = none (reference)
+  // attention-coefficient dropout (extension; nullptr = off, the reference): [E][H] keep / (1 - p) per (local edge, head).
+  // Forward: h = sum alpha * ascale * P_l (the softmax itself is not touched); pass 1: galpha carries ascale and the
+  // record keeps alpha * ascale for pass 2.
+  const float* ascale;
 };
 constexpr int kHeavyDeg = 1024;
 bool edge_shape_supported(int H, int D);

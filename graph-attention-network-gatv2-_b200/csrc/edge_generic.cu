@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kGW * 32)
 edge_fwd_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                         const float* __restrict__ Pl, const float* __restrict__ Pr, const float* __restrict__ a, int H,
                         int D, Slopes sl, const float* __restrict__ bias, float* __restrict__ Hout, float* __restrict__ hpre, float* __restrict__ score,
-                        float* __restrict__ mx, float* __restrict__ sinv) {
+                        float* __restrict__ mx, float* __restrict__ sinv, const float* __restrict__ ascale) {
   __shared__ float sc_s[kGW][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, F = H * D;
   const int row = blockIdx.x * kGW + warp;
@@ -72,7 +72,8 @@ edge_fwd_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const int* 
         const float mn = fmaxf(m[t], p);
         const float corr = __expf(m[t] - mn), w = __expf(p - mn);
         s[t] = s[t] * corr + w;
-        acc[t] = acc[t] * corr + w * v[t];
+        const float wd = ascale ? w * __ldg(ascale + (int64_t)e * H + hd[t]) : w;  // attention dropout: aggregate only
+        acc[t] = acc[t] * corr + wd * v[t];
         m[t] = mn;
       }
     }
@@ -103,7 +104,8 @@ edge_bwd_dst_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const i
                             float* __restrict__ gH,
                             const float* __restrict__ score, const float* __restrict__ mx,
                             const float* __restrict__ sinv, float* __restrict__ gPr, float* __restrict__ rec, int RW,
-                            float* __restrict__ ga_partials, float* __restrict__ galpha_dbg) {
+                            float* __restrict__ ga_partials, float* __restrict__ galpha_dbg,
+                            const float* __restrict__ ascale) {
   __shared__ float c_s[kGW][32], g_s[kGW][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, F = H * D;
   float av[T], ga[T];
@@ -144,11 +146,12 @@ edge_bwd_dst_generic_kernel(int n_rows, const int* __restrict__ row_ptr, const i
       head_sums<T>(gp, hd, H, g_s[warp], lane);
       float ge_l = 0.f;
       if (lane < H) {
-        const float galpha = g_s[warp][lane];
+        const float dsc = ascale ? __ldg(ascale + (int64_t)e * H + lane) : 1.f;  // attention dropout (1 when off)
+        const float galpha = g_s[warp][lane] * dsc;
         const float alpha = __expf(__ldg(score + (int64_t)e * H + lane) - __ldg(mx + (int64_t)row * H + lane)) *
                             __ldg(sinv + (int64_t)row * H + lane);  // EB:378-379
         ge_l = alpha * (galpha - c_s[warp][lane]);                   // EB:689-690 in closed form
-        rec[(int64_t)e * RW + lane] = alpha;
+        rec[(int64_t)e * RW + lane] = alpha * dsc;                   // pass 2 aggregates g_h with alpha * dsc
         rec[(int64_t)e * RW + H + lane] = ge_l;
         if (galpha_dbg) galpha_dbg[(int64_t)e * H + lane] = galpha;
       }
@@ -267,7 +270,7 @@ int launch_edge_forward_generic(const EdgeGraph& g, int H, int D, const float* P
   if (!edge_generic_supported(H, D) || tv < 0) return -1;
   if (g.n_rows <= 0) return 0;
   GENERIC_DISPATCH(tv, edge_fwd_generic_kernel<T><<<(g.n_rows + kGW - 1) / kGW, kGW * 32, 0, st>>>(
-                           g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, g.bias, Hout, hpre, score, mx, sinv));
+                           g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, g.bias, Hout, hpre, score, mx, sinv, g.ascale));
   return 1;
 }
 
@@ -286,7 +289,7 @@ int launch_edge_backward_generic(const EdgeGraph& g, int H, int D, const float* 
     edge_bwd_dst_generic_kernel<T><<<blocks, kGW * 32, 0, st>>>(g.n_rows, g.row_ptr, g.col_idx, Pl, Pr, a, H, D, g.slopes, g.bias,
                                                                 Hout, gH,
                                                                 score, mx, sinv, gPr, reinterpret_cast<float*>(rec), RW,
-                                                                ga_partials, galpha_dbg);
+                                                                ga_partials, galpha_dbg, g.ascale);
     edge_bwd_src_generic_kernel<T><<<(g.n_src + kGW - 1) / kGW, kGW * 32, 0, st>>>(
         g.n_src, g.csc_ptr, g.csc_dst, g.csc_eid, Pl, Pr, a, H, D, g.slopes, gH, reinterpret_cast<const float*>(rec), RW,
         gPl);

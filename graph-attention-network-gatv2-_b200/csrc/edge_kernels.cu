@@ -34,6 +34,7 @@ struct Shape {
   int H, D, F, lph, lg_lph;  // lph = D/4 chunks (lanes) per head
   Slopes sl;                 // LeakyReLU slopes (set by the launchers from EdgeGraph::slopes)
   const float* bias;         // [F] or nullptr (EdgeGraph::bias)
+  const float* ascale;       // [E][H] attention-dropout scale or nullptr (EdgeGraph::ascale)
 };
 
 __device__ __forceinline__ float head_reduce(float p, int lph) {
@@ -108,10 +109,12 @@ __device__ __forceinline__ void fwd_range(FwdState<NV>& st, int first, int end, 
           const float mn = fmaxf(st.m[j], p);
           const float corr = __expf(st.m[j] - mn), w = __expf(p - mn);
           st.s[j] = st.s[j] * corr + w;
-          st.acc[j].x = st.acc[j].x * corr + w * v[j].x;
-          st.acc[j].y = st.acc[j].y * corr + w * v[j].y;
-          st.acc[j].z = st.acc[j].z * corr + w * v[j].z;
-          st.acc[j].w = st.acc[j].w * corr + w * v[j].w;
+          // attention dropout scales the aggregated term only; the softmax denominator keeps every edge
+          const float wd = sh.ascale ? w * __ldg(sh.ascale + (int64_t)e * sh.H + ((li + j * LPR) >> sh.lg_lph)) : w;
+          st.acc[j].x = st.acc[j].x * corr + wd * v[j].x;
+          st.acc[j].y = st.acc[j].y * corr + wd * v[j].y;
+          st.acc[j].z = st.acc[j].z * corr + wd * v[j].z;
+          st.acc[j].w = st.acc[j].w * corr + wd * v[j].w;
           st.m[j] = mn;
         }
       }
@@ -303,9 +306,12 @@ __device__ __forceinline__ void bwd1_range(Bwd1Row<NV>& r, float4 (&ga)[NV], int
       uint32_t* re = rec + (int64_t)e * RW;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float galpha = head_reduce(dot4(r.gh[j], v[j]), sh.lph);
-        const float alpha = __expf(sc[j] - r.m[j]) * r.inv[j];  // EB:378-379
+        float galpha = head_reduce(dot4(r.gh[j], v[j]), sh.lph);
+        float alpha = __expf(sc[j] - r.m[j]) * r.inv[j];  // EB:378-379
+        const float dsc = (sh.ascale && ok) ? __ldg(sh.ascale + (int64_t)e * sh.H + ((li + j * LPR) >> sh.lg_lph)) : 1.f;
+        galpha *= dsc;                                          // h = sum alpha * dsc * P_l
         const float ge = ok ? alpha * (galpha - r.c[j]) : 0.f;  // EB:689-690 in closed form
+        alpha *= dsc;                                           // pass 2 aggregates g_h with alpha * dsc
         const float sx = v[j].x + r.pr[j].x, sy = v[j].y + r.pr[j].y, sz = v[j].z + r.pr[j].z,
                     sw = v[j].w + r.pr[j].w;
         // ga += ge * LReLU(s)  (EB:769)
@@ -667,6 +673,7 @@ int launch_edge_forward(const EdgeGraph& g, int H, int D, const float* Pl, const
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
   sh.sl = g.slopes;
   sh.bias = g.bias;
+  sh.ascale = g.ascale;
   if (g.n_rows <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
     edge_fwd_kernel<NV, LPR><<<(g.n_rows + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(
@@ -692,6 +699,7 @@ int launch_edge_backward_dst(const EdgeGraph& g, int H, int D, const float* Pl, 
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
   sh.sl = g.slopes;
   sh.bias = g.bias;
+  sh.ascale = g.ascale;
   *n_partials = 0;
   if (g.n_rows <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
@@ -727,6 +735,7 @@ int launch_edge_backward_src(const EdgeGraph& g, int H, int D, const float* a, c
   if (!make_shape(H, D, &sh, &nv, &lpr)) return -1;
   sh.sl = g.slopes;
   sh.bias = g.bias;
+  sh.ascale = g.ascale;
   if (g.n_src <= 0) return 0;
   GATX_DISPATCH(nv, lpr, {
     edge_bwd_src_kernel<NV, LPR><<<(g.n_src + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(

@@ -38,6 +38,7 @@ struct StreamGraph {
   uint32_t idx_mask;     // gather index = raw & idx_mask
   Slopes slopes;         // LeakyReLU slopes: attention score / layer activation
   const float* bias;     // [F] added to the aggregate before the activation, or nullptr
+  const float* ascale;   // [E][H] attention-dropout scale of the view's edges, or nullptr (EdgeGraph::ascale)
 };
 // L2 policies of the gathers: hot rows evict_last, everything streamed once evict_first (plain when hints are off)
 struct GatherPolicy {
@@ -323,7 +324,9 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       const float corr = up ? ex : 1.f, w = up ? 1.f : ex;
       const float mn = up ? p : st.m;
       st.s = st.s * corr + w;
-      const float2 corr2 = splat2(corr), w2 = splat2(w);
+      // attention dropout scales the aggregated term only; the softmax denominator keeps every edge
+      const float wd = g.ascale ? w * __ldg(g.ascale + (int64_t)e * sh.H + hd) : w;
+      const float2 corr2 = splat2(corr), w2 = splat2(wd);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {  // acc = acc * corr + (w * v), EB:415-422 without atomics (same rounding as the scalar form)
         const float2 a0 = fma2(lo2(st.acc[j]), corr2, mul2(w2, lo2(v[j])));
@@ -626,8 +629,11 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         gal2 = fma2_s(hi2(ghr[j]), hi2(v[j]), gal2);
       }
       float galpha = head_sum<LPH>(gal2.x + gal2.y, sh.lc);
-      const float alpha = __expf(sc[hd] - q.m) * q.inv;  // EB:378-379
+      float alpha = __expf(sc[hd] - q.m) * q.inv;        // EB:378-379
+      const float dsc = g.ascale ? __ldg(g.ascale + (int64_t)e * H + hd) : 1.f;  // attention dropout (1 when off)
+      galpha *= dsc;                                     // h = sum alpha * dsc * P_l
       const float ge = alpha * (galpha - q.c);           // EB:689-690 in closed form
+      alpha *= dsc;                                      // the record keeps alpha * dsc for pass 2
       const float ges = ge * g.slopes.attn;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
@@ -941,7 +947,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   if (eg.E == 0) return launches;
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
-  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias};
+  StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias, eg.ascale};
   if (use_pair(nv, sh)) {  // one head of 128 floats: two edges per loop iteration
     constexpr int R = 16;
     const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
@@ -993,8 +999,8 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
   const int* cdstx = hs.on ? eg.csc_dst_hot : eg.csc_dst;
-  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias};
-  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask, eg.slopes, eg.bias};
+  StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias, eg.ascale};
+  StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask, eg.slopes, eg.bias, eg.ascale};
   if (use_pair(nv, sh)) {
     constexpr int R = 16, F = kPF;
     if (do_p1 && eg.n_rows > 0) {

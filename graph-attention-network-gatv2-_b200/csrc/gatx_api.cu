@@ -79,6 +79,15 @@ struct gatx_ctx {
   uint64_t drop_seed = 0;
   int64_t drop_step = 0;     // training forwards since gatx_set_dropout
   bool fwd_dropped = false;  // the last training forward used dropout (the backward must use the same inputs / mask)
+  // attention-coefficient dropout (gatx_set_attn_dropout; the reference has none): the scale [E][H] of one layer is
+  // generated into a scratch buffer right before the kernels that read it (forward, then again in the backward)
+  float p_adrop = 0.f;
+  uint64_t adrop_seed = 0;
+  int64_t adrop_step = 0;
+  bool fwd_adropped = false;
+  float* ascale = nullptr;   // [E][Hmax]
+  int64_t ascale_key = -1;   // (step, layer) the buffer currently holds
+  int64_t edge0 = 0;         // global CSR position of this rank's first edge (the dropout draw is a function of it)
   // per-layer bias on the aggregate (gatx_set_bias): extra parameters [b_0 .. b_{L-1}] appended after W_o
   int use_bias = 0;
   int64_t bias_begin = 0, bias_end = 0;
@@ -274,6 +283,8 @@ void free_bufs(gatx_ctx* c) {
   }
   dfree(c->params); dfree(c->grads); dfree(c->adam_m); dfree(c->adam_v);
   dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials); dfree(c->colsum_partials);
+  dfree(c->ascale);
+  c->ascale_key = -1;
   dfree(c->rec); dfree(c->part); dfree(c->cdot); dfree(c->y); dfree(c->dz); dfree(c->z_dbg); dfree(c->WoT); dfree(c->pred);
   dfree(c->loss_partials); dfree(c->loss_sum); dfree(c->correct_partials); dfree(c->correct); dfree(c->red2);
   c->have_bufs = false;
@@ -413,6 +424,7 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
   g.reserve_ctas = 0;
   g.slopes = c->slopes;
   g.bias = nullptr;
+  g.ascale = nullptr;
   return g;
 }
 
@@ -592,12 +604,35 @@ bool blockable(const gatx_ctx* ctx, int l) {
 }
 float* gpr_buf(const gatx_ctx* ctx, int l) { return (ctx->gPr2 && ((ctx->L - 1 - l) & 1)) ? ctx->gPr2 : ctx->gPr; }
 
+// Attention-coefficient dropout: the scale of layer l for the current step, generated on the compute stream into the
+// scratch buffer (whole layer at once; a block view reads its slice).  nullptr when the option is off.
+int attn_scale(gatx_ctx* ctx, int l, bool active, const RowView& v, const float** out) {
+  *out = nullptr;
+  if (!active) return GATX_OK;
+  const Layer& ly = ctx->layers[l];
+  const int64_t key = ctx->adrop_step * 64 + l;
+  if (!ctx->ascale) {
+    int hmax = 1;
+    for (const Layer& q : ctx->layers) hmax = q.H > hmax ? q.H : hmax;
+    CK(dalloc(&ctx->ascale, (size_t)ctx->E * hmax));
+    ctx->ascale_key = -1;
+  }
+  if (ctx->ascale_key != key) {
+    LAUNCHED(launch_attn_dropout_scale(ctx->ascale, ctx->E, ly.H, ctx->edge0, ctx->p_adrop, ctx->adrop_seed, l,
+                                       ctx->adrop_step, ctx->st));
+    ctx->ascale_key = key;
+  }
+  *out = ctx->ascale + v.e0 * ly.H;
+  return GATX_OK;
+}
+
 // fused edge forward of layer l over a view (EB:279-459)
 int fwd_edge(gatx_ctx* ctx, int l, const RowView& v) {
   Layer& ly = ctx->layers[l];
   if (v.nb <= 0) return GATX_OK;
   EdgeGraph gl = v.g;
   gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
+  if (int rc = attn_scale(ctx, l, !ctx->eval_mode && ctx->p_adrop > 0.f, v, &gl.ascale)) return rc;
   if (ctx->timing && v.whole) {
     for (auto& e : ly.kev)
       if (!e) cudaEventCreate(&e);
@@ -626,6 +661,8 @@ int bwd_edge(gatx_ctx* ctx, int l, const RowView& v, int phases) {
   Layer& ly = ctx->layers[l];
   EdgeGraph gl = v.g;
   gl.bias = ly.b_off >= 0 ? ctx->params + ly.b_off : nullptr;
+  if (phases & 1)  // pass 1 re-generates the scale of the forward it differentiates (same step counter)
+    if (int rc = attn_scale(ctx, l, ctx->fwd_adropped, v, &gl.ascale)) return rc;
   if (ctx->timing && v.whole) {
     for (auto& e : ly.kev)
       if (!e) cudaEventCreate(&e);
@@ -678,6 +715,9 @@ int do_forward(gatx_ctx* ctx) {
   const bool drop = !ctx->eval_mode && ctx->p_drop > 0.f;
   if (drop) ++ctx->drop_step;
   if (!ctx->eval_mode) ctx->fwd_dropped = drop;
+  const bool adrop = !ctx->eval_mode && ctx->p_adrop > 0.f;
+  if (adrop) ++ctx->adrop_step;
+  if (!ctx->eval_mode) ctx->fwd_adropped = adrop;
   const bool p2p_any = ctx->world > 1 && ctx->peers_ready;
   ctx->ev_used = 0;
   if (p2p_any) {
@@ -994,7 +1034,7 @@ constexpr int64_t kGraphAutoMaxEdges = 8 << 20;  // beyond this the kernels are 
 
 bool epoch_graph_wanted(const gatx_ctx* ctx) {
   // dropout: the step counter is a kernel argument that changes every epoch
-  if (ctx->world != 1 || ctx->timing || ctx->graph_mode == 0 || ctx->p_drop > 0.f) return false;
+  if (ctx->world != 1 || ctx->timing || ctx->graph_mode == 0 || ctx->p_drop > 0.f || ctx->p_adrop > 0.f) return false;
   if (ctx->graph_mode == 1) return true;
   static const int env = [] {
     const char* e = getenv("GATX_CUDA_GRAPH");
@@ -1176,6 +1216,7 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   ctx->n_rows = ctx->r1 - ctx->r0;
   const int64_t e0 = row_ptr[ctx->r0], e1 = row_ptr[ctx->r1];
   ctx->E = e1 - e0;
+  ctx->edge0 = e0;
   int maxdeg = 0;
   std::vector<int> local_ptr(ctx->n_rows + 1), heavy;
   std::vector<uint16_t> ref_own;  // ref_mask of the own rows (host copy, for the per-block halo counts)
@@ -1607,6 +1648,16 @@ int gatx_set_dropout(gatx_ctx* ctx, float p, uint64_t seed) {
   ctx->p_drop = p;
   ctx->drop_seed = seed;
   ctx->drop_step = 0;
+  ctx->fwd_valid = false;
+  return GATX_OK;
+}
+
+int gatx_set_attn_dropout(gatx_ctx* ctx, float p, uint64_t seed) {
+  if (!ctx || !(p >= 0.f && p < 1.f)) return fail(ctx, GATX_ERR_INVALID, "dropout probability must lie in [0, 1)");
+  ctx->p_adrop = p;
+  ctx->adrop_seed = seed;
+  ctx->adrop_step = 0;
+  ctx->ascale_key = -1;
   ctx->fwd_valid = false;
   return GATX_OK;
 }

@@ -160,6 +160,38 @@ int launch_dropout(const float* X, int64_t ldx, float* Y, int64_t ldy, int n_row
   return 1;
 }
 
+__global__ void attn_dropout_scale_kernel(float* __restrict__ out, int64_t E, int H, int64_t edge0, uint32_t thresh,
+                                          float scale, uint64_t seed, uint32_t layer, uint32_t step) {
+  const int quads = (H + 3) / 4;
+  const int64_t total = E * quads;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i / quads;
+    const int q = (int)(i - e * quads);
+    uint32_t c[4] = {(uint32_t)(edge0 + e), (uint32_t)q, 0x80000000u | layer, step};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (4 * q + t < H) out[e * H + 4 * q + t] = c[t] >= thresh ? scale : 0.f;
+  }
+}
+int launch_attn_dropout_scale(float* out, int64_t E, int H, int64_t edge0, float p, uint64_t seed, int layer, int64_t step,
+                              cudaStream_t st) {
+  if (E <= 0 || H <= 0) return 0;
+  const int64_t total = E * ((H + 3) / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  attn_dropout_scale_kernel<<<(int)blocks, 256, 0, st>>>(out, E, H, edge0, thresh, 1.0f / (1.0f - p), seed, (uint32_t)layer,
+                                                        (uint32_t)step);
+  return 1;
+}
+
 __global__ void mark_hot_kernel(const int* __restrict__ idx, const int* __restrict__ ptr, int64_t E, int thr_wide,
                                 int thr_narrow, int* __restrict__ out) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {

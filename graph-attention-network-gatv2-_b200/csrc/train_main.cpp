@@ -299,7 +299,7 @@ struct Args {
   std::string optimizer = "sgd", dataset = "pubmed", data_root = "./data", load_w, dump_w;
   float lr = 0.0001f, beta1 = 0.9f, beta2 = 0.999f;
   // opt-in extensions; the defaults are the reference's fixed behaviour (slopes 0.01 / 0.01, no dropout)
-  float attn_slope = 0.01f, act_slope = 0.01f, dropout = 0.0f;
+  float attn_slope = 0.01f, act_slope = 0.01f, dropout = 0.0f, attn_dropout = 0.0f;
   unsigned long long seed = 0;
   bool seed_given = false;
   std::vector<int> heads, outdims;
@@ -383,6 +383,7 @@ int main(int argc, char** argv) {
     else if (arg == "--attn-slope" && i + 1 < argc) a.attn_slope = std::strtof(argv[++i], nullptr);
     else if (arg == "--act-slope" && i + 1 < argc) a.act_slope = std::strtof(argv[++i], nullptr);
     else if (arg == "--dropout" && i + 1 < argc) a.dropout = std::strtof(argv[++i], nullptr);
+    else if (arg == "--attn-dropout" && i + 1 < argc) a.attn_dropout = std::strtof(argv[++i], nullptr);
     else if (arg == "--bias") a.bias = true;
     else if (arg == "--check-replicas") a.check_replicas = true;
     // anything else is ignored, like the reference
@@ -670,6 +671,12 @@ int main(int argc, char** argv) {
     for (int r = 0; r < world; ++r)
       if (int rc = gatx_set_dropout(ctx[r], a.dropout, dseed)) return fail_ctx(ctx[r], "gatx_set_dropout", rc);
     std::cout << "Dropout: " << a.dropout << " on every layer's input (training forwards only)\n";
+  }
+  if (a.attn_dropout != 0.0f) {
+    const unsigned long long aseed = init_seed + 104729ull * (unsigned long long)first_epoch;
+    for (int r = 0; r < world; ++r)
+      if (int rc = gatx_set_attn_dropout(ctx[r], a.attn_dropout, aseed)) return fail_ctx(ctx[r], "gatx_set_attn_dropout", rc);
+    std::cout << "Attention dropout: " << a.attn_dropout << " on the attention coefficients (training forwards only)\n";
   }
   // evaluation forward on every rank; returns rank 0's (already all-reduced) scalars
   auto evaluate = [&](const unsigned char* m, float* lo, float* ac) -> int {

@@ -26,7 +26,7 @@ EXPORTS = [
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
     "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
-    "gatx_device_count", "gatx_peer_disable", "gatx_halo_stats", "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_bias", "gatx_set_bias_values",
+    "gatx_device_count", "gatx_peer_disable", "gatx_halo_stats", "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_attn_dropout", "gatx_set_bias", "gatx_set_bias_values",
 ]
 
 
@@ -274,6 +274,11 @@ class Engine:
         """Inverted dropout on every layer's input in training forwards (Philox, reproducible); p = 0 switches it off"""
         self.lib.gatx_set_dropout.argtypes = [C.c_void_p, C.c_float, C.c_uint64]
         self._ck(self.lib.gatx_set_dropout(self.ctx, p, seed), "gatx_set_dropout")
+
+    def set_attn_dropout(self, p, seed=0):
+        """Dropout on the attention coefficients in training forwards (Philox per (edge, head)); p = 0 switches it off"""
+        self.lib.gatx_set_attn_dropout.argtypes = [C.c_void_p, C.c_float, C.c_uint64]
+        self._ck(self.lib.gatx_set_attn_dropout(self.ctx, p, seed), "gatx_set_attn_dropout")
 
     def set_cuda_graph(self, mode):
         """-1 auto, 0 eager launches, 1 replay forward + backward of train_epoch as one CUDA graph"""

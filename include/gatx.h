@@ -150,6 +150,13 @@ int gatx_set_slopes(gatx_ctx* ctx, float attn_slope, float act_slope);
  * reproducible, identical on every rank of a partitioned run, re-generated (not stored) by the backward pass.
  * p = 0 switches it off.  0 <= p < 1. */
 int gatx_set_dropout(gatx_ctx* ctx, float p, uint64_t seed);
+/* Extension (the reference has no dropout): dropout with probability p on the ATTENTION COEFFICIENTS in
+ * training forwards: h_i = sum_j alpha_ij d_ij W_l x_j with d_ij = keep / (1 - p) per (edge, head); the softmax itself
+ * (EB:326-384) keeps every edge.  (edge e = GLOBAL CSR position, head h) of layer l in the k-th training forward since
+ * this call is kept iff word h % 4 of Philox4x32-10(counter {e, h / 4, 2^31 | l, k}, key seed) >= floor(p * 2^32):
+ * identical on every rank of a partitioned run, re-generated (not stored) by the backward pass.  Never applied in
+ * gatx_evaluate.  p = 0 switches it off.  0 <= p < 1. */
+int gatx_set_attn_dropout(gatx_ctx* ctx, float p, uint64_t seed);
 /* Extension (the reference has no bias): a learnable bias b_l [H*D] per layer added to the aggregate
  * before the activation, h_i = sum_j alpha_ij W_l x_j + b_l (rows without in-edges give LReLU(b_l)).  The biases are
  * appended to the flat parameter / state buffer after W_o ([.. | W_o | b_0 .. b_{L-1}]), start at zero in

@@ -536,3 +536,65 @@ def test_labels_outside_class_range_are_refused(gatx):
     assert np.isfinite(eng.train_epoch(1)[0])
     assert gatx.load().gatx_device_count() >= 1
     eng.close()
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("shape", EXT_SHAPES, ids=["narrow", "stream", "pair", "generic"])
+def test_attention_dropout_parity(gatx, orc, shape, mode):
+    """Opt-in extension: gatx_set_attn_dropout -- dropout on the attention COEFFICIENTS, h_i = sum_j alpha_ij
+    d_ij W_l x_j with d_ij = keep / (1 - p) drawn by Philox per (global edge, head) -- against the oracle's
+    orc_model_set_attn_dropout (itself pinned by PyTorch autograd, tests/test_oracle.py).  One shape per edge-kernel
+    family; two training epochs (new draws, updated weights), then an evaluation forward (no dropout) and the option
+    switched off again.  Not calling the setter is the reference model bit for bit (test_extension_flags)."""
+    N, E, I, C, heads, outdims, kind, hub = shape
+    p = make_problem(N, E, I, C, heads, outdims, kind, seed=N + 2, hub=hub)
+    ft, bt = FWD_TOL[mode], BWD_TOL[mode]
+    L = len(heads)
+    Eg = len(p["col_idx"])
+
+    def grads_close(a, b, what, t):  # see test_slopes_and_dropout_parity: L2 bound + outlier fraction (LeakyReLU' is a step)
+        a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+        scale = max(np.abs(b).max(), 1e-2)
+        assert np.linalg.norm(a - b) <= 3 * bt * t * max(np.linalg.norm(b), scale), what
+        assert np.mean(np.abs(a - b) > bt * t * scale) < 2e-3, what
+
+    eng = make_engine(gatx, p, gemm_mode=mode, keep_debug=True, optimizer="sgd", lr=1e-4)
+    ref = make_oracle(orc, p, optimizer="sgd", lr=1e-4)
+    eng.forward()
+    plain = eng.loss_acc()
+    eng.set_attn_dropout(0.4, 777)
+    ref.set_attn_dropout(0.4, 777)
+    for t in (1, 2):
+        eng.forward()
+        loss, _ = eng.loss_acc()
+        ref.forward()
+        rl = ref.loss()
+        for l in range(L):
+            H = heads[l]
+            # the stored attention coefficients stay the softmax; the aggregate uses the dropped ones
+            al = eng.tensor(gatx.T_ALPHA, l).reshape(Eg, H).T
+            assert np.abs(al - ref.tensor(orc.T_ALPHA, l)).max() < ft * 5 * t, ("alpha", l, t)
+            # one wrong keep bit moves an output element by O(alpha * P_l)
+            assert rel_err(eng.tensor(gatx.T_HOUT, l), ref.tensor(orc.T_HOUT, l).ravel()) < ft * 2 * t, ("Hout", l, t)
+        assert abs(loss - rl["avg"]) < max(ft * 5, 1e-5) * t * max(1.0, abs(rl["avg"]))
+        if t == 1:
+            assert abs(loss - plain[0]) > 1e-4  # the option does something
+        eng.backward()
+        ref.backward()
+        for l in range(L):
+            gh, gh_ref = eng.tensor(gatx.T_GH, l), ref.tensor(orc.T_GH, l).ravel()
+            assert np.linalg.norm(gh - gh_ref) < 3 * bt * t * max(np.linalg.norm(gh_ref), 1e-6), ("g_h", l, t)
+            grads_close(eng.tensor(gatx.T_GW, l), ref.tensor(orc.T_GW, l), ("gW", l, t), t)
+            grads_close(eng.tensor(gatx.T_GA, l), ref.tensor(orc.T_GA, l), ("ga", l, t), t)
+        grads_close(eng.tensor(gatx.T_GWO), ref.tensor(orc.T_GWO), ("gWo", t), t)
+        eng.step(t)
+        ref.step(t)
+    ev = eng.evaluate(None)
+    ref.forward(train=False)
+    assert abs(ev[0] - ref.loss()["avg"]) < max(ft * 10, 1e-4) * max(1.0, abs(ev[0]))
+    eng.set_attn_dropout(0.0)
+    eng.forward()
+    assert eng.loss_acc() == ev  # off again == an evaluation forward
+    with pytest.raises(gatx.GatxError):
+        eng.set_attn_dropout(1.0)
+    eng.close()
