@@ -1902,6 +1902,180 @@ int gatx_op_gemm(int32_t mode, int32_t form, const float* A, int64_t lda, const 
   return rc;
 }
 
+// ---- op-level entry points on host buffers: one kernel family at a time, for parity tests and ncu ------
+// The edge ops build a throw-away one-layer context around the caller's graph so that they run exactly the kernels
+// (family selection, chunking, fix-ups) the epoch runs for that (heads, outdim) shape.
+namespace {
+struct OpCtx {
+  gatx_ctx* c = nullptr;
+  ~OpCtx() { gatx_destroy(c); }
+};
+int op_make_ctx(OpCtx& o, int32_t N, int64_t E, const int32_t* row_ptr, const int32_t* col_idx, int32_t H, int32_t D) {
+  if (N <= 0 || E < 0 || !row_ptr || H <= 0 || D <= 0) return GATX_ERR_INVALID;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  gatx_config cfg{};
+  const int32_t heads[1] = {H}, outdims[1] = {D};
+  cfg.num_layers = 1; cfg.heads = heads; cfg.outdims = outdims; cfg.optimizer = GATX_OPT_SGD; cfg.lr = 0.f;
+  cfg.beta1 = 0.9f; cfg.beta2 = 0.999f; cfg.device = dev; cfg.gemm_mode = GATX_GEMM_FP32_SIMT; cfg.keep_debug = 1;
+  cfg.rank = 0; cfg.world = 1;
+  int rc = gatx_create(&o.c, &cfg);
+  if (rc) return rc;
+  if ((rc = gatx_set_graph_csr(o.c, N, E, row_ptr, col_idx))) return rc;
+  std::vector<float> x((size_t)N * 4, 0.f);
+  std::vector<int32_t> y((size_t)N, 0);
+  if ((rc = gatx_set_features(o.c, x.data(), 4))) return rc;
+  if ((rc = gatx_set_labels(o.c, y.data(), 1))) return rc;
+  return ensure_buffers(o.c);
+}
+int op_forward(gatx_ctx* ctx, const float* Pl, const float* Pr, const float* a) {
+  Layer& ly = ctx->layers[0];
+  const size_t nf = sizeof(float) * (size_t)ctx->N * ly.F;
+  CK(cudaMemcpyAsync(ly.Pl, Pl, nf, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ly.Pr, Pr, nf, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->params + ly.a_off, a, sizeof(float) * ly.F, cudaMemcpyHostToDevice, ctx->st));
+  return fwd_edge(ctx, 0, row_view(ctx, -1));
+}
+}  // namespace
+
+int gatx_op_edge_fwd(int32_t N, int64_t E, const int32_t* row_ptr, const int32_t* col_idx, int32_t H, int32_t D,
+                     const float* Pl, const float* Pr, const float* a, float* score, float* alpha, float* hpre,
+                     float* Hout) {
+  if (!Pl || !Pr || !a) return GATX_ERR_INVALID;
+  OpCtx o;
+  int rc = op_make_ctx(o, N, E, row_ptr, col_idx, H, D);
+  if (rc) return rc;
+  gatx_ctx* ctx = o.c;
+  if ((rc = op_forward(ctx, Pl, Pr, a))) return rc;
+  Layer& ly = ctx->layers[0];
+  const size_t nf = sizeof(float) * (size_t)N * ly.F, ne = sizeof(float) * (size_t)E * H;
+  if (score && E) CK(cudaMemcpyAsync(score, ly.score, ne, cudaMemcpyDeviceToHost, ctx->st));
+  if (alpha && E) {
+    LAUNCHED(launch_alpha_from_score(ly.score, ctx->coo_dst, ly.mx, ly.sinv, E, H, ly.alpha_dbg, ctx->st));
+    CK(cudaMemcpyAsync(alpha, ly.alpha_dbg, ne, cudaMemcpyDeviceToHost, ctx->st));
+  }
+  if (hpre) CK(cudaMemcpyAsync(hpre, ly.hpre, nf, cudaMemcpyDeviceToHost, ctx->st));
+  if (Hout) CK(cudaMemcpyAsync(Hout, ly.Hfull, nf, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaGetLastError());
+  return GATX_OK;
+}
+
+int gatx_op_edge_bwd(int32_t N, int64_t E, const int32_t* row_ptr, const int32_t* col_idx, int32_t H, int32_t D,
+                     const float* Pl, const float* Pr, const float* a, const float* gHout, float* g_pre, float* gPl,
+                     float* gPr, float* ga, float* ge) {
+  if (!Pl || !Pr || !a || !gHout) return GATX_ERR_INVALID;
+  OpCtx o;
+  int rc = op_make_ctx(o, N, E, row_ptr, col_idx, H, D);
+  if (rc) return rc;
+  gatx_ctx* ctx = o.c;
+  if ((rc = op_forward(ctx, Pl, Pr, a))) return rc;
+  Layer& ly = ctx->layers[0];
+  const size_t nf = sizeof(float) * (size_t)N * ly.F, ne = sizeof(float) * (size_t)E * H;
+  CK(cudaMemcpyAsync(ly.gH, gHout, nf, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemsetAsync(ctx->grads + ly.a_off, 0, sizeof(float) * ly.F, ctx->st));
+  const RowView all = row_view(ctx, -1);
+  const bool stream = ly.vec && ctx->use_stream && edge_stream_supported(ly.H, ly.D);
+  if (stream) {
+    if ((rc = bwd_edge(ctx, 0, all, 1))) return rc;
+    if ((rc = bwd_edge(ctx, 0, all, 2))) return rc;
+  } else if ((rc = bwd_edge(ctx, 0, all, 3))) {
+    return rc;
+  }
+  if (g_pre) CK(cudaMemcpyAsync(g_pre, ly.gH, nf, cudaMemcpyDeviceToHost, ctx->st));
+  if (gPl) CK(cudaMemcpyAsync(gPl, ctx->gPl, nf, cudaMemcpyDeviceToHost, ctx->st));
+  if (gPr) CK(cudaMemcpyAsync(gPr, ctx->gPr, nf, cudaMemcpyDeviceToHost, ctx->st));
+  if (ga) CK(cudaMemcpyAsync(ga, ctx->grads + ly.a_off, sizeof(float) * ly.F, cudaMemcpyDeviceToHost, ctx->st));
+  if (ge && E) {
+    if (ly.vec) LAUNCHED(launch_unpack_rec(ctx->rec, E, ly.H, ly.D, ly.alpha_dbg, ly.ge_dbg, ctx->st));
+    else LAUNCHED(launch_unpack_rec_generic(ctx->rec, E, ly.H, ly.alpha_dbg, ly.ge_dbg, ctx->st));
+    CK(cudaMemcpyAsync(ge, ly.ge_dbg, ne, cudaMemcpyDeviceToHost, ctx->st));
+  }
+  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaGetLastError());
+  return GATX_OK;
+}
+
+int gatx_op_softmax_ce(int32_t N, int32_t C, const float* z, const int32_t* labels, const uint8_t* mask, float* y,
+                       float* dz, int32_t* pred, double* loss_sum, int64_t* correct) {
+  if (N <= 0 || C <= 0 || !z || !labels) return GATX_ERR_INVALID;
+  for (int i = 0; i < N; ++i)
+    if (labels[i] < 0 || labels[i] >= C) return GATX_ERR_INVALID;
+  const int ldc = (C + 3) / 4 * 4;
+  float *dzin = nullptr, *dy = nullptr, *ddz = nullptr;
+  int *dl = nullptr, *dp = nullptr, *cp = nullptr;
+  unsigned char* dm = nullptr;
+  double *lp = nullptr, *ls = nullptr;
+  long long* cc = nullptr;
+  cudaStream_t st = nullptr;
+  int rc = GATX_OK, n_part = 0;
+  const size_t nz = sizeof(float) * (size_t)N * ldc;
+  if (cudaMalloc(&dzin, nz) != cudaSuccess || cudaMalloc(&dy, nz) != cudaSuccess || cudaMalloc(&ddz, nz) != cudaSuccess ||
+      cudaMalloc(&dl, sizeof(int) * N) != cudaSuccess || cudaMalloc(&dp, sizeof(int) * N) != cudaSuccess ||
+      cudaMalloc(&cp, sizeof(int) * kHeadBlocks) != cudaSuccess || cudaMalloc(&lp, sizeof(double) * kHeadBlocks) != cudaSuccess ||
+      cudaMalloc(&ls, sizeof(double)) != cudaSuccess || cudaMalloc(&cc, sizeof(long long)) != cudaSuccess ||
+      (mask && cudaMalloc(&dm, N) != cudaSuccess) || cudaStreamCreate(&st) != cudaSuccess)
+    rc = GATX_ERR_CUDA;
+  if (!rc) {
+    cudaMemsetAsync(dzin, 0, nz, st);
+    cudaMemcpy2DAsync(dzin, sizeof(float) * ldc, z, sizeof(float) * C, sizeof(float) * C, N, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dl, labels, sizeof(int) * N, cudaMemcpyHostToDevice, st);
+    if (mask) cudaMemcpyAsync(dm, mask, N, cudaMemcpyHostToDevice, st);
+    int n1 = launch_softmax_ce(dzin, dl, N, C, ldc, dy, ddz, dp, lp, cp, &n_part, dm, st);
+    int n2 = n1 < 0 ? -1 : launch_loss_finalize(lp, cp, n_part, ls, cc, st);
+    if (n1 < 0 || n2 < 0) rc = GATX_ERR_UNSUPPORTED;
+    if (!rc) {
+      if (y) cudaMemcpy2DAsync(y, sizeof(float) * C, dy, sizeof(float) * ldc, sizeof(float) * C, N, cudaMemcpyDeviceToHost, st);
+      if (dz) cudaMemcpy2DAsync(dz, sizeof(float) * C, ddz, sizeof(float) * ldc, sizeof(float) * C, N, cudaMemcpyDeviceToHost, st);
+      if (pred) cudaMemcpyAsync(pred, dp, sizeof(int) * N, cudaMemcpyDeviceToHost, st);
+      long long ch = 0;
+      if (loss_sum) cudaMemcpyAsync(loss_sum, ls, sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(&ch, cc, sizeof(long long), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = GATX_ERR_CUDA;
+      if (correct) *correct = (int64_t)ch;
+    }
+  }
+  cudaFree(dzin); cudaFree(dy); cudaFree(ddz); cudaFree(dl); cudaFree(dp); cudaFree(cp); cudaFree(lp); cudaFree(ls);
+  cudaFree(cc); cudaFree(dm);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
+int gatx_op_optimizer(int64_t n, const int64_t* group_end3, int32_t optimizer, int32_t clip, float lr, float beta1,
+                      float beta2, int32_t t, float* params, float* grads, float* adam_m, float* adam_v) {
+  if (n <= 0 || !group_end3 || !params || !grads || t < 1) return GATX_ERR_INVALID;
+  if (optimizer == GATX_OPT_ADAM && (!adam_m || !adam_v)) return GATX_ERR_INVALID;
+  if (!(0 <= group_end3[0] && group_end3[0] <= group_end3[1] && group_end3[1] <= group_end3[2] && group_end3[2] == n))
+    return GATX_ERR_INVALID;
+  float *dp = nullptr, *dg = nullptr, *dm = nullptr, *dv = nullptr, *np_ = nullptr;
+  cudaStream_t st = nullptr;
+  int rc = GATX_OK;
+  const size_t nb = sizeof(float) * (size_t)n;
+  if (cudaMalloc(&dp, nb) != cudaSuccess || cudaMalloc(&dg, nb) != cudaSuccess || cudaMalloc(&dm, nb) != cudaSuccess ||
+      cudaMalloc(&dv, nb) != cudaSuccess || cudaMalloc(&np_, sizeof(float) * 6 * kOptimBlocks) != cudaSuccess ||
+      cudaStreamCreate(&st) != cudaSuccess)
+    rc = GATX_ERR_CUDA;
+  if (!rc) {
+    cudaMemcpyAsync(dp, params, nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dg, grads, nb, cudaMemcpyHostToDevice, st);
+    if (adam_m) cudaMemcpyAsync(dm, adam_m, nb, cudaMemcpyHostToDevice, st); else cudaMemsetAsync(dm, 0, nb, st);
+    if (adam_v) cudaMemcpyAsync(dv, adam_v, nb, cudaMemcpyHostToDevice, st); else cudaMemsetAsync(dv, 0, nb, st);
+    OptimGroups grp{};
+    grp.begin[0] = 0; grp.end[0] = group_end3[0];
+    grp.begin[1] = group_end3[0]; grp.end[1] = group_end3[1];
+    grp.begin[2] = group_end3[1]; grp.end[2] = group_end3[2];
+    if (launch_optimizer(dp, dg, dm, dv, n, grp, clip != 0, optimizer, lr, beta1, beta2, t, np_, st) < 0) rc = GATX_ERR_UNSUPPORTED;
+    cudaMemcpyAsync(params, dp, nb, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(grads, dg, nb, cudaMemcpyDeviceToHost, st);  // zeroed by the update (EB:1631-1633)
+    if (adam_m) cudaMemcpyAsync(adam_m, dm, nb, cudaMemcpyDeviceToHost, st);
+    if (adam_v) cudaMemcpyAsync(adam_v, dv, nb, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = rc ? rc : GATX_ERR_CUDA;
+  }
+  cudaFree(dp); cudaFree(dg); cudaFree(dm); cudaFree(dv); cudaFree(np_);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
 int gatx_comm_unique_id(void* out128) {
   if (!out128 || !g_nccl.load()) return GATX_ERR_NCCL;
   ncclUniqueId id;

@@ -24,7 +24,7 @@ EXPORTS = [
     "gatx_set_features", "gatx_set_labels", "gatx_graph_info", "gatx_partition_rows", "gatx_init_params",
     "gatx_set_params", "gatx_set_wo", "gatx_forward", "gatx_loss_acc", "gatx_backward", "gatx_step",
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
-    "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm",
+    "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm", "gatx_op_edge_fwd", "gatx_op_edge_bwd", "gatx_op_softmax_ce", "gatx_op_optimizer",
     "gatx_comm_unique_id", "gatx_comm_init", "gatx_peer_export", "gatx_peer_import", "gatx_halo_rows", "gatx_halo_active",
     "gatx_device_count", "gatx_peer_disable", "gatx_halo_stats", "gatx_set_cuda_graph", "gatx_cuda_graph_active", "gatx_set_slopes", "gatx_set_dropout", "gatx_set_attn_dropout", "gatx_set_bias", "gatx_set_bias_values",
 ]
@@ -111,6 +111,77 @@ def op_gemm(A, B, form=0, mode=GEMM_TF32_TC):
     if rc:
         raise GatxError("gatx_op_gemm failed: %d" % rc)
     return Cm
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def op_edge_fwd(row_ptr, col_idx, H, D, Pl, Pr, a):
+    """Fused edge forward of one layer on host arrays -> dict(score [E][H], alpha [E][H], hpre, Hout [N][H*D])."""
+    rp, ci = np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(col_idx, np.int32)
+    N, E, F = len(rp) - 1, len(ci), H * D
+    Pl, Pr, a = _f32(Pl), _f32(Pr), _f32(a)
+    out = dict(score=np.zeros((E, H), np.float32), alpha=np.zeros((E, H), np.float32), hpre=np.zeros((N, F), np.float32),
+               Hout=np.zeros((N, F), np.float32))
+    lib = load()
+    lib.gatx_op_edge_fwd.argtypes = [C.c_int32, C.c_int64] + [C.c_void_p] * 2 + [C.c_int32] * 2 + [C.c_void_p] * 7
+    rc = lib.gatx_op_edge_fwd(N, E, rp.ctypes.data, ci.ctypes.data, H, D, Pl.ctypes.data, Pr.ctypes.data, a.ctypes.data,
+                              out["score"].ctypes.data, out["alpha"].ctypes.data, out["hpre"].ctypes.data,
+                              out["Hout"].ctypes.data)
+    if rc:
+        raise GatxError("gatx_op_edge_fwd failed: %d" % rc)
+    return out
+
+
+def op_edge_bwd(row_ptr, col_idx, H, D, Pl, Pr, a, gHout):
+    """Fused edge backward of one layer on host arrays -> dict(g_pre, gPl, gPr [N][H*D], ga [H*D], ge [E][H])."""
+    rp, ci = np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(col_idx, np.int32)
+    N, E, F = len(rp) - 1, len(ci), H * D
+    Pl, Pr, a, gHout = _f32(Pl), _f32(Pr), _f32(a), _f32(gHout)
+    out = dict(g_pre=np.zeros((N, F), np.float32), gPl=np.zeros((N, F), np.float32), gPr=np.zeros((N, F), np.float32),
+               ga=np.zeros(F, np.float32), ge=np.zeros((E, H), np.float32))
+    lib = load()
+    lib.gatx_op_edge_bwd.argtypes = [C.c_int32, C.c_int64] + [C.c_void_p] * 2 + [C.c_int32] * 2 + [C.c_void_p] * 9
+    rc = lib.gatx_op_edge_bwd(N, E, rp.ctypes.data, ci.ctypes.data, H, D, Pl.ctypes.data, Pr.ctypes.data, a.ctypes.data,
+                              gHout.ctypes.data, out["g_pre"].ctypes.data, out["gPl"].ctypes.data, out["gPr"].ctypes.data,
+                              out["ga"].ctypes.data, out["ge"].ctypes.data)
+    if rc:
+        raise GatxError("gatx_op_edge_bwd failed: %d" % rc)
+    return out
+
+
+def op_softmax_ce(z, labels, mask=None):
+    """Softmax + CE + argmax + dz on logits [N][C] -> dict(y, dz, pred, loss_sum, correct)."""
+    z, labels = _f32(z), np.ascontiguousarray(labels, np.int32)
+    N, Cc = z.shape
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    y, dz, pred = np.zeros_like(z), np.zeros_like(z), np.zeros(N, np.int32)
+    ls, cc = C.c_double(), C.c_int64()
+    lib = load()
+    lib.gatx_op_softmax_ce.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 8
+    rc = lib.gatx_op_softmax_ce(N, Cc, z.ctypes.data, labels.ctypes.data, None if m is None else m.ctypes.data,
+                                y.ctypes.data, dz.ctypes.data, pred.ctypes.data, C.addressof(ls), C.addressof(cc))
+    if rc:
+        raise GatxError("gatx_op_softmax_ce failed: %d" % rc)
+    return dict(y=y, dz=dz, pred=pred, loss_sum=ls.value, correct=cc.value)
+
+
+def op_optimizer(params, grads, group_ends, optimizer="adam", clip=False, lr=1e-3, beta1=0.9, beta2=0.999, t=1, m=None, v=None):
+    """One clip + Adam / SGD step on flat host vectors (returned updated: params, grads (zeroed), m, v)."""
+    p, g = _f32(params).copy(), _f32(grads).copy()
+    n = len(p)
+    adam = optimizer == "adam"
+    mm = (np.zeros(n, np.float32) if m is None else _f32(m).copy()) if adam else None
+    vv = (np.zeros(n, np.float32) if v is None else _f32(v).copy()) if adam else None
+    ge = (C.c_int64 * 3)(*[int(x) for x in group_ends])
+    lib = load()
+    lib.gatx_op_optimizer.argtypes = [C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32] + [C.c_void_p] * 4
+    rc = lib.gatx_op_optimizer(n, ge, 1 if adam else 0, int(clip), lr, beta1, beta2, t, p.ctypes.data, g.ctypes.data,
+                               None if mm is None else mm.ctypes.data, None if vv is None else vv.ctypes.data)
+    if rc:
+        raise GatxError("gatx_op_optimizer failed: %d" % rc)
+    return p, g, mm, vv
 
 
 def comm_unique_id():

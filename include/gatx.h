@@ -228,6 +228,29 @@ int gatx_set_state(gatx_ctx* ctx, const float* src, size_t bytes);
 int gatx_op_gemm(int32_t mode, int32_t form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                  int64_t ldc, int32_t M, int32_t N, int64_t K);
 
+/* Fused edge forward of ONE layer on host buffers (EB:279-459: gatv2_edge_score_kernel, compute_max_sum_attn_score,
+ * compute_attn_coeff, aggregate_kernel, postActivationLayerOutput) through the kernel family the epoch would pick for
+ * (heads, outdim).  Pl, Pr [N][H*D] are the projected source / destination features, a [H*D]; any output may be NULL.
+ * score, alpha [E][H] edge-major; hpre, Hout [N][H*D] (heads concatenated: hidden-layer semantics, EB:450-457). */
+int gatx_op_edge_fwd(int32_t num_nodes, int64_t num_edges, const int32_t* row_ptr, const int32_t* col_idx, int32_t heads,
+                     int32_t outdim, const float* Pl, const float* Pr, const float* a, float* score, float* alpha,
+                     float* hpre, float* Hout);
+/* Fused edge backward of ONE layer (EB:612-798 per-edge parts + EB:879-893): runs the forward above, then prep + pass 1 +
+ * pass 2 with gHout [N][H*D] = dL/dHout.  Outputs (any may be NULL): g_pre [N][F] = gHout * LReLU'(h), gPl / gPr [N][F]
+ * gradients w.r.t. the projected features, ga [F], ge [E][H] gradient w.r.t. the attention logits. */
+int gatx_op_edge_bwd(int32_t num_nodes, int64_t num_edges, const int32_t* row_ptr, const int32_t* col_idx, int32_t heads,
+                     int32_t outdim, const float* Pl, const float* Pr, const float* a, const float* gHout, float* g_pre,
+                     float* gPl, float* gPr, float* ga, float* ge);
+/* Softmax + cross-entropy + first-max argmax + dz = y - onehot on logits z [N][C] (EB:132-141, 514-550, 566-572); mask
+ * (uint8 [N], NULL = all nodes) as in gatx_set_train_mask.  loss_sum = sum of -log(max(p, 1e-12)) over counted nodes. */
+int gatx_op_softmax_ce(int32_t num_nodes, int32_t num_classes, const float* z, const int32_t* labels, const uint8_t* mask,
+                       float* y, float* dz, int32_t* pred, double* loss_sum, int64_t* correct);
+/* One optimizer step on a flat parameter vector (EB:250-278 clip per group at 5.0, EB:896-923 Adam / SGD, EB:1631-1633
+ * gradient reset): group_end3 = end offsets of the three clip groups {all W}, {all a}, {W_o} (group_end3[2] = n); t is the
+ * 1-based epoch.  params / grads / adam_m / adam_v are updated in place (adam_* may be NULL for SGD). */
+int gatx_op_optimizer(int64_t n, const int64_t* group_end3, int32_t optimizer, int32_t clip, float lr, float beta1,
+                      float beta2, int32_t t, float* params, float* grads, float* adam_m, float* adam_v);
+
 /* ---- multi-GPU (one context per rank, NCCL over NVLink) --------------------------------- */
 /* 128-byte NCCL unique id made on rank 0, distributed by the caller (torchrun store, MPI, file) */
 int gatx_comm_unique_id(void* out128);
