@@ -163,8 +163,18 @@ struct PeerPtrs {
 // max_ctas > 0 caps the grid (the pipelined exchange runs underneath the edge passes in a fixed number of CTA slots)
 int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
                      int me, cudaStream_t st, int max_ctas = 0);
-int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
-                     int world, cudaStream_t st, int max_ctas = 0);
+// backward exchange: scatter of partial rows into the owners' staging buffers, then the owner's local ordered sum
+struct ScatterPlan {
+  int n_seg;                    // one segment per other rank
+  int cum[kMaxPeers + 1];       // prefix sums of the segments' row counts
+  int row0[kMaxPeers];          // first global row of the segment (a row block of its owner)
+  int owner_row0[kMaxPeers];    // first global row the owner owns
+  float* dst[kMaxPeers];        // owner's staging slot of THIS rank: [owner's n_rows][F]
+};
+int launch_halo_scatter(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan, cudaStream_t st,
+                        int max_ctas);
+int launch_halo_sum(float* own_rows, int row_off, int n_rows, int n_rows_total, int F, const uint16_t* ref_mask,
+                    const float* stage, int me, int world, cudaStream_t st);
 int halo_cta_slots();  // CTA slots of the exchange kernels (GATX_HALO_CTAS, default 48)
 // Device-side barrier across ranks through flags in peer memory: rank `me` stores `seq` (release, system scope) into
 // slot `me` of every peer's flag array, then waits (acquire) until every slot of its own array has reached `seq`.

@@ -159,7 +159,12 @@ struct gatx_ctx {
   int64_t halo_rows = 0;         // sum over own rows of the number of OTHER ranks referencing them
   bool peers_ready = false;
   std::vector<PeerPtrs> peer_Pl;  // per layer
-  PeerPtrs peer_gPl{};
+  // backward exchange: every rank scatters its partial gP_l rows into slot `sender` of the owner's staging buffer
+  float* stage = nullptr;          // [world][n_rows][Fmax]
+  PeerPtrs peer_stage{};
+  unsigned char* my_ref = nullptr; // [N] 1 = one of this rank's edges gathers the source (its partial row is non-zero)
+  std::vector<int> all_blk;        // [world][K + 1] global row bounds of every rank's blocks
+  std::vector<int64_t> scatter_rows;  // [K] rows this rank sends for block b (all owners)
   std::vector<void*> ipc_opened;
   // exchange stream + flag barriers in peer memory (halo_p2p.cu)
   cudaStream_t st_comm = nullptr;
@@ -257,8 +262,10 @@ void free_graph(gatx_ctx* c) {
   dfree(c->row_ptr); dfree(c->col_idx); dfree(c->coo_src); dfree(c->coo_dst); dfree(c->in_deg);
   dfree(c->csc_ptr); dfree(c->csc_dst); dfree(c->csc_eid); dfree(c->heavy_rows); dfree(c->heavy_srcs);
   dfree(c->chunk_row); dfree(c->chunk_src); dfree(c->ref_mask); dfree(c->col_idx_hot); dfree(c->csc_dst_hot);
-  dfree(c->blk_row_ptr); dfree(c->blk_chunk_row);
+  dfree(c->blk_row_ptr); dfree(c->blk_chunk_row); dfree(c->my_ref);
   c->blocks.clear();
+  c->all_blk.clear();
+  c->scatter_rows.clear();
   c->have_graph = false;
   ++c->gen;
 }
@@ -269,6 +276,7 @@ void free_bufs(gatx_ctx* c) {
   c->peers_ready = false;
   dfree(c->halo_flags);
   dfree(c->gPr2);
+  dfree(c->stage);
   for (auto& l : c->layers) {
     dfree(l.Wcat); dfree(l.WcatT); dfree(l.Pl); dfree(l.Pr); dfree(l.Xd);
     if (l.Hout != l.Hfull) dfree(l.Hout);
@@ -375,6 +383,7 @@ int ensure_buffers(gatx_ctx* ctx) {
   CK(dalloc(&ctx->gPr, (size_t)nr * Fmax));
   if (ctx->blocks.size() > 1) CK(dalloc(&ctx->gPr2, (size_t)nr * Fmax));
   if (ctx->world > 1) {
+    CK(dalloc(&ctx->stage, (size_t)ctx->world * nr * Fmax));
     CK(dalloc(&ctx->halo_flags, (size_t)kMaxPeers));
     CK(cudaMemsetAsync(ctx->halo_flags, 0, sizeof(uint32_t) * kMaxPeers, ctx->st));
     ctx->barrier_seq = 0;
@@ -931,13 +940,14 @@ int do_backward(gatx_ctx* ctx) {
       }
       continue;
     }
-    // Peer-memory exchange, pipelined over blocks of own rows: (exchange stream) the owner pulls and sums the peers'
-    // partial gP_l rows of block b; (compute stream) input-gradient GEMM of block b, then prep + pass 1 of the layer
-    // BELOW on block b -- while the pull of block b + 1 is in flight.
+    // Peer-memory exchange, pipelined over blocks of own rows.  Exchange stream: every rank scatters its partial gP_l
+    // rows of block b (of every owner) into the owners' staging buffers, then a flag barrier.  Compute stream: the owner
+    // adds its own and the staged partials of block b in rank order (local memory), input-gradient GEMM of block b, then
+    // prep + pass 1 of the layer BELOW on block b -- while the scatter of block b + 1 is in flight.
     stream_after(ctx, ctx->st_comm, ctx->st);
-    if ((rc = comm_barrier(ctx))) return rc;  // every rank's partial sums are complete
+    if ((rc = comm_barrier(ctx))) return rc;  // every owner is done with the staging contents of the previous exchange
     {
-      PhaseTimer t(ctx, PH_GEMM_BWD);  // needs nothing from the exchange: runs under the barrier and the first pull
+      PhaseTimer t(ctx, PH_GEMM_BWD);  // needs nothing from the exchange: runs under the first scatter
       rc = gemm_nt_reduce(ctx, gPr, ly.F, X, ly.ldx, gW + ly.I, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
     }
@@ -945,14 +955,29 @@ int do_backward(gatx_ctx* ctx) {
     const int nblk = (int)ctx->blocks.size();
     for (int b = 0; b < nblk; ++b) {
       const RowView v = row_view(ctx, b);
+      {
+        ScatterPlan plan{};
+        for (int p = 0; p < ctx->world; ++p) {
+          if (p == ctx->rank) continue;
+          const int* ab = ctx->all_blk.data() + (size_t)p * (nblk + 1);
+          const int sg = plan.n_seg++;
+          plan.row0[sg] = ab[b];
+          plan.owner_row0[sg] = ctx->bounds[p];
+          plan.cum[sg + 1] = plan.cum[sg] + (ab[b + 1] - ab[b]);
+          // the owner's staging slot of this rank, viewed with this layer's row pitch
+          plan.dst[sg] = ctx->peer_stage.p[p] + (int64_t)ctx->rank * (ctx->bounds[p + 1] - ctx->bounds[p]) * ly.F;
+        }
+        CommTimer ct(ctx, 1, (double)ctx->scatter_rows[b] * ly.F * 4.0);
+        LAUNCHED(launch_halo_scatter(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->st_comm, halo_cta_slots()));
+      }
+      if ((rc = comm_barrier(ctx))) return rc;  // block b of every rank's partial rows has landed at its owner
+      compute_waits_comm(ctx);
       if (v.nb <= 0) continue;
       {
-        CommTimer ct(ctx, 1, (double)ctx->blocks[b].halo_rows * ly.F * 4.0);
-        LAUNCHED(launch_halo_pull(ctx->gPl + (int64_t)(ctx->r0 + v.rb) * ly.F, ctx->r0 + v.rb, v.nb, ly.F,
-                                  ctx->ref_mask + v.rb, ctx->peer_gPl, ctx->rank, ctx->world, ctx->st_comm,
-                                  halo_cta_slots()));
+        PhaseTimer t(ctx, PH_COMM);  // the owner's ordered sum (local memory) belongs to the exchange
+        LAUNCHED(launch_halo_sum(ctx->gPl + (int64_t)(ctx->r0 + v.rb) * ly.F, v.rb, v.nb, ctx->n_rows, ly.F,
+                                 ctx->ref_mask + v.rb, ctx->stage, ctx->rank, ctx->world, ctx->st));
       }
-      compute_waits_comm(ctx);
       if (l > 0) {
         Layer& prev = ctx->layers[l - 1];
         {
@@ -971,13 +996,11 @@ int do_backward(gatx_ctx* ctx) {
       }
     }
     if (fuse_p1) p1_done[l - 1] = 1;
-    if ((rc = comm_barrier(ctx))) return rc;  // every owner has pulled: the peers may overwrite their gP_l scratch
     {
       PhaseTimer t(ctx, PH_GEMM_BWD);
       rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
     }
-    compute_waits_comm(ctx);  // before the next pass 2 writes into the scratch the peers were reading
   }
   return GATX_OK;
 }
@@ -1220,6 +1243,7 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   int maxdeg = 0;
   std::vector<int> local_ptr(ctx->n_rows + 1), heavy;
   std::vector<uint16_t> ref_own;  // ref_mask of the own rows (host copy, for the per-block halo counts)
+  std::vector<unsigned char> my_ref_host;  // [N] this rank's edges gather the source
   for (int i = 0; i < N; ++i) {
     if (row_ptr[i + 1] < row_ptr[i]) return fail(ctx, GATX_ERR_INVALID, "row_ptr not monotone at %d", i);
     const int d = row_ptr[i + 1] - row_ptr[i];
@@ -1241,6 +1265,8 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
     for (int i = ctx->r0; i < ctx->r1; ++i) halo += __builtin_popcount((unsigned)(ref[i] & ~(1u << ctx->rank)));
     ctx->halo_rows = halo;
     ref_own.assign(ref.begin() + ctx->r0, ref.begin() + ctx->r1);
+    my_ref_host.resize((size_t)N);
+    for (int i = 0; i < N; ++i) my_ref_host[i] = (unsigned char)((ref[i] >> ctx->rank) & 1u);
     CK(dalloc(&ctx->ref_mask, (size_t)ctx->n_rows));
     if (ctx->n_rows)
       CK(cudaMemcpyAsync(ctx->ref_mask, ref.data() + ctx->r0, sizeof(uint16_t) * (size_t)ctx->n_rows,
@@ -1283,37 +1309,67 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
   LAUNCHED(launch_chunk_rows(ctx->row_ptr, ctx->n_rows, ctx->E, ctx->chunk_T, ctx->n_chunks, ctx->chunk_row, ctx->st));
   LAUNCHED(launch_chunk_rows(ctx->csc_ptr, N, ctx->E, ctx->chunk_T, ctx->n_chunks, ctx->chunk_src, ctx->st));
   if (ctx->world > 1) {
-    // blocks of own rows for the pipelined exchange (edge-balanced like the rank partition itself).  A block must still
-    // fill the GPU: at least 8 chunks per SM, unless GATX_HALO_BLOCKS forces a count (tests).
+    // Blocks of own rows for the pipelined exchange (edge-balanced like the rank partition itself).  A block must still
+    // fill the GPU: at least 8 chunks per SM on EVERY rank (the block count is part of the exchange protocol, so it is
+    // derived from the global row_ptr), unless GATX_HALO_BLOCKS forces a count (tests).
     int K = 4;
     bool forced = false;
     if (const char* ev = getenv("GATX_HALO_BLOCKS")) {
       const int k = atoi(ev);
       if (k >= 1 && k <= 16) { K = k; forced = true; }
     }
-    while (!forced && K > 1 && ctx->n_chunks / K < kNumSMs * 8) --K;
-    if (K > ctx->n_rows) K = ctx->n_rows > 0 ? ctx->n_rows : 1;
-    ctx->blocks.assign(K, gatx_ctx::RowBlock{});
-    std::vector<int> rb(K + 1, ctx->n_rows);
-    rb[0] = 0;
-    for (int k = 1, i = 0; k < K; ++k) {
-      const int64_t target = ctx->E * (int64_t)k / K;
-      while (i < ctx->n_rows && (int64_t)local_ptr[i] < target) ++i;
-      rb[k] = i;
+    int64_t min_chunks = INT64_MAX;
+    int min_rows = N;
+    for (int p = 0; p < ctx->world; ++p) {
+      const int64_t ep = (int64_t)row_ptr[ctx->bounds[p + 1]] - row_ptr[ctx->bounds[p]];
+      min_chunks = std::min<int64_t>(min_chunks, (ep + ctx->chunk_T - 1) / ctx->chunk_T);
+      min_rows = std::min(min_rows, ctx->bounds[p + 1] - ctx->bounds[p]);
     }
+    while (!forced && K > 1 && min_chunks / K < kNumSMs * 8) --K;
+    if (K > min_rows) K = min_rows > 0 ? min_rows : 1;
+    // every rank's blocks (global rows): rank p's block k starts at the first own row whose edge offset >= k E_p / K
+    ctx->all_blk.assign((size_t)ctx->world * (K + 1), 0);
+    for (int p = 0; p < ctx->world; ++p) {
+      const int b0 = ctx->bounds[p], b1 = ctx->bounds[p + 1];
+      const int64_t base = row_ptr[b0], ep = (int64_t)row_ptr[b1] - base;
+      int* ab = ctx->all_blk.data() + (size_t)p * (K + 1);
+      ab[0] = b0;
+      ab[K] = b1;
+      for (int k = 1, i = b0; k < K; ++k) {
+        const int64_t target = ep * (int64_t)k / K;
+        while (i < b1 && (int64_t)row_ptr[i] - base < target) ++i;
+        ab[k] = i;
+      }
+    }
+    ctx->blocks.assign(K, gatx_ctx::RowBlock{});
+    const int* rbg = ctx->all_blk.data() + (size_t)ctx->rank * (K + 1);
     std::vector<int> brp;
     int64_t total_chunks = 0;
     for (int k = 0; k < K; ++k) {
       gatx_ctx::RowBlock& B = ctx->blocks[k];
-      B.r0 = rb[k];
-      B.n_rows = rb[k + 1] - rb[k];
-      B.e0 = local_ptr[rb[k]];
-      B.E = local_ptr[rb[k + 1]] - B.e0;
+      const int lo = rbg[k] - ctx->r0, hi = rbg[k + 1] - ctx->r0;
+      B.r0 = lo;
+      B.n_rows = hi - lo;
+      B.e0 = local_ptr[lo];
+      B.E = local_ptr[hi] - B.e0;
       B.n_chunks = (int)((B.E + ctx->chunk_T - 1) / ctx->chunk_T);
       total_chunks += B.n_chunks + 1;
-      for (int i = rb[k]; i <= rb[k + 1]; ++i) brp.push_back((int)(local_ptr[i] - B.e0));
-      for (int i = rb[k]; i < rb[k + 1] && !ref_own.empty(); ++i)
+      for (int i = lo; i <= hi; ++i) brp.push_back((int)(local_ptr[i] - B.e0));
+      for (int i = lo; i < hi && !ref_own.empty(); ++i)
         B.halo_rows += __builtin_popcount((unsigned)(ref_own[i] & ~(1u << ctx->rank)));
+    }
+    if (!my_ref_host.empty()) {
+      // rows this rank sends in the backward exchange of block k: referenced sources inside block k of every other owner
+      ctx->scatter_rows.assign(K, 0);
+      for (int p = 0; p < ctx->world; ++p) {
+        if (p == ctx->rank) continue;
+        const int* ab = ctx->all_blk.data() + (size_t)p * (K + 1);
+        for (int k = 0; k < K; ++k)
+          for (int i = ab[k]; i < ab[k + 1]; ++i) ctx->scatter_rows[k] += my_ref_host[i];
+      }
+      CK(dalloc(&ctx->my_ref, (size_t)N));
+      CK(cudaMemcpyAsync(ctx->my_ref, my_ref_host.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->st));
+      CK(cudaStreamSynchronize(ctx->st));
     }
     if (K > 1) {
       CK(dalloc(&ctx->blk_row_ptr, brp.size()));
@@ -2112,6 +2168,7 @@ int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes) {
   if (!ctx || !out || bytes < GATX_PEER_INFO_BYTES) return fail(ctx, GATX_ERR_INVALID, "bad peer_export");
   if (ctx->world < 2 || ctx->world > kMaxPeers) return fail(ctx, GATX_ERR_INVALID, "peer exchange needs 2..%d ranks", kMaxPeers);
   if (ctx->L + 2 > kPeerMaxBufs) return fail(ctx, GATX_ERR_UNSUPPORTED, "too many layers for the peer blob");
+  if (!ctx->my_ref) return fail(ctx, GATX_ERR_INVALID, "the graph was set for a single rank");
   CK(cudaSetDevice(ctx->device));
   int rc = ensure_buffers(ctx);
   if (rc) return rc;
@@ -2126,8 +2183,10 @@ int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes) {
   int64_t Fmax = 0;
   for (int l = 0; l < ctx->L; ++l) Fmax = ctx->layers[l].F > Fmax ? ctx->layers[l].F : Fmax;
   for (int b = 0; b <= ctx->L + 1; ++b) {
-    void* ptr = b < ctx->L ? (void*)ctx->layers[b].Pl : (b == ctx->L ? (void*)ctx->gPl : (void*)ctx->halo_flags);
-    info.n_floats[b] = b <= ctx->L ? (int64_t)ctx->N * (b < ctx->L ? ctx->layers[b].F : Fmax) : (int64_t)kMaxPeers;
+    // buffers: P_l of layer 0..L-1, the staging buffer of the backward exchange, the barrier flags
+    void* ptr = b < ctx->L ? (void*)ctx->layers[b].Pl : (b == ctx->L ? (void*)ctx->stage : (void*)ctx->halo_flags);
+    info.n_floats[b] = b < ctx->L ? (int64_t)ctx->N * ctx->layers[b].F
+                                  : (b == ctx->L ? (int64_t)ctx->world * ctx->n_rows * Fmax : (int64_t)kMaxPeers);
     info.raw[b] = (uint64_t)(uintptr_t)ptr;
     CK(cudaIpcGetMemHandle(&info.handle[b], ptr));
   }
@@ -2144,7 +2203,7 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
   if (!ctx->comm) return fail(ctx, GATX_ERR_INVALID, "gatx_comm_init must come first (barriers)");
   CK(cudaSetDevice(ctx->device));
   ctx->peer_Pl.assign(ctx->L, PeerPtrs{});
-  ctx->peer_gPl = PeerPtrs{};
+  ctx->peer_stage = PeerPtrs{};
   ctx->peer_flags = PeerFlags{};
   ctx->peer_flags.p[ctx->rank] = ctx->halo_flags;
   int64_t Fmax = 0;
@@ -2155,7 +2214,8 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
     if (info.magic != kPeerMagic || info.n_bufs != ctx->L + 2)
       return fail(ctx, GATX_ERR_INVALID, "peer blob of rank %d does not match this model", p);
     for (int b = 0; b <= ctx->L; ++b)
-      if (info.n_floats[b] != (int64_t)ctx->N * (b < ctx->L ? ctx->layers[b].F : Fmax))
+      if (info.n_floats[b] != (b < ctx->L ? (int64_t)ctx->N * ctx->layers[b].F
+                                          : (int64_t)ctx->world * (ctx->bounds[p + 1] - ctx->bounds[p]) * Fmax))
         return fail(ctx, GATX_ERR_INVALID, "peer blob of rank %d: buffer %d has another size", p, b);
     if (p == ctx->rank) continue;
     const bool same_process = info.pid == (int32_t)getpid();
@@ -2178,7 +2238,7 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
         ctx->ipc_opened.push_back(q);
       }
       if (b < ctx->L) ctx->peer_Pl[b].p[p] = (float*)q;
-      else if (b == ctx->L) ctx->peer_gPl.p[p] = (float*)q;
+      else if (b == ctx->L) ctx->peer_stage.p[p] = (float*)q;
       else ctx->peer_flags.p[p] = (uint32_t*)q;
     }
   }

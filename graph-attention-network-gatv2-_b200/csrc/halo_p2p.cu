@@ -7,8 +7,10 @@
 //             that never gather the row do not receive it.  On the products-shaped R-MAT graph a rank references
 //             93 / 82 / 67 % of all sources at 2 / 4 / 8 ranks, so the halo moves 0.86 / 0.76 / 0.63 of the bytes an
 //             all-gather moves.
-//   backward: every rank holds partial sums gP_l[src] over ITS edges for all sources it references.  halo_pull_kernel
-//             makes the owner of a row read the partial rows of exactly those peers (same mask) and add them in
+//   backward: every rank holds partial sums gP_l[src] over ITS edges for all sources it references.  halo_scatter_kernel
+//             stores the rows owned by other ranks into the owners' staging buffers (posted NVLink stores: remote
+//             LOADS would need ~2 MB in flight per GPU to cover the NVLink round trip, i.e. a third of the SMs);
+//             halo_sum_kernel then adds, on the owner and from local memory, its own partial and the staged ones in
 //             ascending rank order -- a fixed order, so the result is reproducible run to run (NCCL's reduction tree
 //             gives no such promise across topologies).
 // Both kernels are one warp per row with 128-bit accesses; rows are 0.5-2 KB, NVLink sees full-line transfers.
@@ -74,54 +76,65 @@ halo_push_kernel(const float* __restrict__ own_rows, int r0, int n_rows, int F, 
   __threadfence_system();  // the peer-memory stores are performed before the kernel (and the barrier behind it) completes
 }
 
-// One warp per own row.  The peers that hold a partial row are visited in ascending rank order (a fixed order: the sum
-// is reproducible), software-pipelined: the loads of the next contributing peer are in flight while the current one is
-// added, so a warp keeps two remote 2 KB reads outstanding instead of one (NVLink round trips are ~3 us).
+// Backward exchange, sender side: this rank holds partial sums gP_l[src] over ITS edges for every source it references.
+// For the sources owned by other ranks it stores the partial row into slot `me` of the owner's staging buffer
+// (stage[sender][local row][F]) -- posted NVLink stores only, no remote loads, so a few hundred warps keep the link
+// busy.  One launch covers one row block of every owner (the plan lists the global row range of that block per owner).
 __global__ void __launch_bounds__(256, 4)
-halo_pull_kernel(float* __restrict__ own_rows, int r0, int n_rows, int F, const uint16_t* __restrict__ ref_mask,
-                 PeerPtrs peers, int me, int world) {
+halo_scatter_kernel(const float* __restrict__ partial, int F, const unsigned char* __restrict__ my_ref, ScatterPlan plan) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int total = plan.cum[plan.n_seg];
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < total; t += warps) {
+    int sgm = 0;
+    while (t >= plan.cum[sgm + 1]) ++sgm;
+    const int row = plan.row0[sgm] + (t - plan.cum[sgm]);  // global source row, owned by the segment's rank
+    if (!my_ref[row]) continue;                            // none of this rank's edges gathers it: nothing to send
+    const float* src = partial + (int64_t)row * F;
+    float* dst = plan.dst[sgm] + (int64_t)(row - plan.owner_row0[sgm]) * F;
+    for (int k0 = 0; k0 < F; k0 += 512) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + 4 * (lane + 32 * j);
+        if (k < F) v[j] = ldg4(src + k);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + 4 * (lane + 32 * j);
+        if (k < F) st4(dst + k, v[j]);
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+// Backward exchange, owner side (local memory only): own row = own partial + the staged partials of the ranks whose
+// mask bit is set, added in ascending rank order -- a fixed order, so the sum is reproducible run to run.
+__global__ void __launch_bounds__(256)
+halo_sum_kernel(float* __restrict__ own_rows, int row_off, int n_rows, int n_rows_total, int F,
+                const uint16_t* __restrict__ ref_mask, const float* __restrict__ stage, int me, int world) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
     const uint32_t m = ref_mask[row];
     if ((m & ~(1u << me)) == 0) continue;  // only this rank (or nobody) touches the row: already complete
     float* mine = own_rows + (int64_t)row * F;
-    const int64_t off = (int64_t)(r0 + row) * F;
     for (int k0 = 0; k0 < F; k0 += 512) {
-      float4 acc[4], nxt[4];
+      float4 acc[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint32_t mm = m;
-      int p = __ffs(mm) - 1;
-      mm &= mm - 1;
-      {
-        const float* src = p == me ? mine : peers.p[p] + off;
+      for (int p = 0; p < world; ++p) {
+        if (!((m >> p) & 1u)) continue;
+        const float* src = p == me ? mine : stage + ((int64_t)p * n_rows_total + row_off + row) * F;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + 4 * (lane + 32 * j);
-          nxt[j] = k < F ? ld_sys4(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);  // peer memory: system-scope load
-        }
-      }
-      while (true) {
-        float4 cur[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-        const bool more = mm != 0;
-        if (more) {
-          p = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const float* src = p == me ? mine : peers.p[p] + off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = k0 + 4 * (lane + 32 * j);
-            nxt[j] = k < F ? ld_sys4(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < F) {
+            const float4 v = ld_sys4(src + k);  // written by a peer over NVLink: never a stale cached line
+            acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
           }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[j].x += cur[j].x; acc[j].y += cur[j].y; acc[j].z += cur[j].z; acc[j].w += cur[j].w;
-        }
-        if (!more) break;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -188,11 +201,20 @@ int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uin
   return 1;
 }
 
-int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
-                     int world, cudaStream_t st, int max_ctas) {
+int launch_halo_scatter(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan, cudaStream_t st,
+                        int max_ctas) {
+  const int total = plan.cum[plan.n_seg];
+  if (total <= 0) return 0;
+  prefer_max_shared(halo_scatter_kernel);
+  halo_scatter_kernel<<<halo_blocks(total, max_ctas), 256, 0, st>>>(partial, F, my_ref, plan);
+  return 1;
+}
+
+int launch_halo_sum(float* own_rows, int row_off, int n_rows, int n_rows_total, int F, const uint16_t* ref_mask,
+                    const float* stage, int me, int world, cudaStream_t st) {
   if (n_rows <= 0) return 0;
-  prefer_max_shared(halo_pull_kernel);
-  halo_pull_kernel<<<halo_blocks(n_rows, max_ctas), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me, world);
+  halo_sum_kernel<<<halo_blocks(n_rows, 0), 256, 0, st>>>(own_rows, row_off, n_rows, n_rows_total, F, ref_mask, stage, me,
+                                                          world);
   return 1;
 }
 
