@@ -42,33 +42,49 @@ __device__ __forceinline__ float4 ld_sys4(const float* p) {
   return v;
 }
 
+// Two rows per warp and trip: the loads of both rows (4 KB) are in flight before the first store is issued, which
+// halves the number of warps needed to keep the link busy (the kernel runs in a fixed, small number of CTA slots).
 __global__ void __launch_bounds__(256, 4)
 halo_push_kernel(const float* __restrict__ own_rows, int r0, int n_rows, int F, const uint16_t* __restrict__ ref_mask,
                  PeerPtrs peers, int me) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t not_me = ~(1u << me);
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
-    uint32_t m = ref_mask[row] & not_me;
-    if (!m) continue;
-    const float* src = own_rows + (int64_t)row * F;
-    const int64_t off = (int64_t)(r0 + row) * F;
-    for (int k0 = 0; k0 < F; k0 += 512) {  // up to 4 float4 per lane in flight
-      float4 v[4];
+  for (int rowA = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; rowA < n_rows; rowA += 2 * warps) {
+    const int rowB = rowA + warps;
+    const uint32_t mA = ref_mask[rowA] & not_me, mB = rowB < n_rows ? (ref_mask[rowB] & not_me) : 0u;
+    if (!(mA | mB)) continue;
+    const float* srcA = own_rows + (int64_t)rowA * F;
+    const float* srcB = own_rows + (int64_t)rowB * F;
+    const int64_t offA = (int64_t)(r0 + rowA) * F, offB = (int64_t)(r0 + rowB) * F;
+    for (int k0 = 0; k0 < F; k0 += 512) {  // up to 8 float4 per lane in flight
+      float4 va[4], vb[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + 4 * (lane + 32 * j);
-        if (k < F) v[j] = ldg4(src + k);
+        if (k < F && mA) va[j] = ldg4(srcA + k);
+        if (k < F && mB) vb[j] = ldg4(srcB + k);
       }
-      uint32_t mm = m;
+      uint32_t mm = mA;
       while (mm) {
         const int p = __ffs(mm) - 1;
         mm &= mm - 1;
-        float* dst = peers.p[p] + off;
+        float* dst = peers.p[p] + offA;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + 4 * (lane + 32 * j);
-          if (k < F) st4(dst + k, v[j]);
+          if (k < F) st4(dst + k, va[j]);
+        }
+      }
+      mm = mB;
+      while (mm) {
+        const int p = __ffs(mm) - 1;
+        mm &= mm - 1;
+        float* dst = peers.p[p] + offB;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + 4 * (lane + 32 * j);
+          if (k < F) st4(dst + k, vb[j]);
         }
       }
     }
@@ -85,25 +101,37 @@ halo_scatter_kernel(const float* __restrict__ partial, int F, const unsigned cha
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int total = plan.cum[plan.n_seg];
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < total; t += warps) {
-    int sgm = 0;
-    while (t >= plan.cum[sgm + 1]) ++sgm;
-    const int row = plan.row0[sgm] + (t - plan.cum[sgm]);  // global source row, owned by the segment's rank
-    if (!my_ref[row]) continue;                            // none of this rank's edges gathers it: nothing to send
-    const float* src = partial + (int64_t)row * F;
-    float* dst = plan.dst[sgm] + (int64_t)(row - plan.owner_row0[sgm]) * F;
-    for (int k0 = 0; k0 < F; k0 += 512) {
-      float4 v[4];
+  for (int tA = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tA < total; tA += 2 * warps) {
+    const float *src[2] = {nullptr, nullptr};
+    float* dst[2] = {nullptr, nullptr};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = k0 + 4 * (lane + 32 * j);
-        if (k < F) v[j] = ldg4(src + k);
-      }
+    for (int u = 0; u < 2; ++u) {
+      const int t = tA + u * warps;
+      if (t >= total) continue;
+      int sgm = 0;
+      while (t >= plan.cum[sgm + 1]) ++sgm;
+      const int row = plan.row0[sgm] + (t - plan.cum[sgm]);  // global source row, owned by the segment's rank
+      if (!my_ref[row]) continue;                            // none of this rank's edges gathers it: nothing to send
+      src[u] = partial + (int64_t)row * F;
+      dst[u] = plan.dst[sgm] + (int64_t)(row - plan.owner_row0[sgm]) * F;
+    }
+    if (!src[0] && !src[1]) continue;
+    for (int k0 = 0; k0 < F; k0 += 512) {  // both rows' loads (up to 4 KB per warp) in flight before the stores
+      float4 v[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = k0 + 4 * (lane + 32 * j);
-        if (k < F) st4(dst + k, v[j]);
-      }
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + 4 * (lane + 32 * j);
+          if (k < F && src[u]) v[u][j] = ldg4(src[u] + k);
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + 4 * (lane + 32 * j);
+          if (k < F && src[u]) st4(dst[u] + k, v[u][j]);
+        }
     }
   }
   __threadfence_system();

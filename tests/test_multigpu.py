@@ -111,9 +111,9 @@ def test_two_ranks_match_one(world, p2p, monkeypatch):
     eng.evaluate(None)  # the workers' predictions come from an evaluation forward after the last update
     for o in outs:
         for (l, a), (rl, ra) in zip(o["losses"], ref_losses):
-            assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 2e-3
+            assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 5e-3
         for (l, a), (rl, ra) in zip(o["masked"] + [o["masked_eval"]], ref_masked + [ref_masked_eval]):
-            assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 2e-3
+            assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 5e-3
         for l in range(3):
             assert rel_err(o["W"][l], eng.tensor(gatx.T_W, l)) < 2e-3
         assert rel_err(o["Wo"], eng.tensor(gatx.T_WO)) < 2e-3
