@@ -51,6 +51,10 @@ int launch_attn_dropout_scale(float* out, int64_t E, int H, int64_t edge0, float
 int launch_gemm_simt(const float* A, int64_t sAm, int64_t sAk, const float* B, int64_t sBn, int64_t sBk,
                      float* C, int64_t ldc, int M, int N, int64_t K, bool accumulate, float* splitk_ws,
                      size_t splitk_ws_bytes, cudaStream_t st);
+// 3xTF32 operand split: hi = x with the low 13 mantissa bits cleared (exactly what kind::tf32 reads), lo = x - hi (exact
+// in fp32).  Writes hi to out_hi[r][c] and lo to out_lo[r][c] for r < rows, c < cols; columns [cols, cols_pad) are zeroed.
+int launch_split_tf32(const float* X, int64_t ldx, int64_t rows, int cols, int cols_pad, float* out_hi, int64_t ld_hi,
+                      float* out_lo, int64_t ld_lo, cudaStream_t st);
 // packs EB-layout W [F][2I] into Wcat [2F][ldk] (rows 0..F-1 = W_l, F..2F-1 = W_r, zero padded)
 // and WcatT [I][2F]
 int launch_pack_weights(const float* W, int F, int I, float* Wcat, int ldk, float* WcatT, cudaStream_t st);

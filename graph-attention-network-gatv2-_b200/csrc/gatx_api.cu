@@ -141,6 +141,8 @@ struct gatx_ctx {
   std::vector<Layer> layers;
   // scratch
   float *gPl = nullptr, *gPr = nullptr, *ga_partials = nullptr, *splitk_ws = nullptr, *norm_partials = nullptr;
+  float* x3_ws = nullptr;  // operand splits of the 3xTF32 GEMM mode (grown on demand)
+  size_t x3_floats = 0;
   float* gPr2 = nullptr;  // second gP_r scratch: the pipelined backward writes layer l - 1's while layer l's is still read
   uint32_t* rec = nullptr;
   float *part = nullptr, *cdot = nullptr;
@@ -290,6 +292,8 @@ void free_bufs(gatx_ctx* c) {
     l.kev_fwd = l.kev_bwd = false;
   }
   dfree(c->params); dfree(c->grads); dfree(c->adam_m); dfree(c->adam_v);
+  dfree(c->x3_ws);
+  c->x3_floats = 0;
   dfree(c->gPl); dfree(c->gPr); dfree(c->ga_partials); dfree(c->splitk_ws); dfree(c->norm_partials); dfree(c->colsum_partials);
   dfree(c->ascale);
   c->ascale_key = -1;
@@ -438,8 +442,67 @@ EdgeGraph edge_graph(const gatx_ctx* c) {
 }
 
 // P_l | P_r = X [W_l ; W_r]^T in one pass over X (Wcat is [2F][ldk], rows 0..F-1 = W_l) for `rows` rows of X.
+// ---- 3xTF32: fp32-grade contractions on the tensor cores ------------------------------------------------------------
+// x = hi + lo with hi = the TF32 part of x (what kind::tf32 reads: the low 13 mantissa bits dropped) and lo = x - hi
+// (exact).  A B^T ~= A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T, all three accumulated in fp32 in the same TMEM tile by the
+// existing kernels: the first two as ONE product over the concatenated contraction index ([A_hi | A_lo] . [B_hi | B_hi]),
+// the third as the kernel's second operand pair.  The dropped lo * lo term is ~2^-22 of the product.
+constexpr int kX3Fallback = 1000;
+int x3_reserve(gatx_ctx* ctx, size_t floats, float** out) {
+  if (ctx->x3_floats < floats) {
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(dalloc(&ctx->x3_ws, floats));
+    ctx->x3_floats = floats;
+  }
+  *out = ctx->x3_ws;
+  return GATX_OK;
+}
+// C0 | C1 (split at n_split) (+)= A[M][K] B[N][K]^T
+int gemm3x_tn(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, int K, float* C0, float* C1,
+              int n_split, int64_t ldc, int M, int N, bool accumulate) {
+  const int Kp = (K + 3) / 4 * 4;
+  float* ws;
+  int rc = x3_reserve(ctx, (size_t)M * 2 * Kp + (size_t)N * 3 * Kp, &ws);
+  if (rc) return rc;
+  float* A2 = ws;                              // [M][2 Kp] = [A_hi | A_lo]
+  float* B2 = A2 + (size_t)M * 2 * Kp;         // [N][2 Kp] = [B_hi | B_hi]
+  float* Blo = B2 + (size_t)N * 2 * Kp;        // [N][Kp]
+  LAUNCHED(launch_split_tf32(A, lda, M, K, Kp, A2, 2 * Kp, A2 + Kp, 2 * Kp, ctx->st));
+  LAUNCHED(launch_split_tf32(B, ldb, N, K, Kp, B2, 2 * Kp, Blo, Kp, ctx->st));
+  CK(cudaMemcpy2DAsync(B2 + Kp, sizeof(float) * 2 * Kp, B2, sizeof(float) * 2 * Kp, sizeof(float) * Kp, N,
+                       cudaMemcpyDeviceToDevice, ctx->st));
+  int n = launch_gemm_tc_tn2(A2, 2 * Kp, B2, 2 * Kp, 2 * Kp, A2, 2 * Kp, Blo, Kp, Kp, C0, C1, n_split, ldc, M, N,
+                             accumulate, ctx->st);
+  if (n < 0) return kX3Fallback;  // a shape the tensor-core kernel does not take: the caller runs the fp32 CUDA-core GEMM
+  ctx->launches += n;
+  return GATX_OK;
+}
+// C[M][N] += A[K][M]^T B[K][N] (contraction over nodes)
+int gemm3x_atb(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+               int64_t K) {
+  const int Mp = (M + 3) / 4 * 4, Np = (N + 3) / 4 * 4;
+  float* ws;
+  int rc = x3_reserve(ctx, (size_t)K * 2 * (Mp + Np), &ws);
+  if (rc) return rc;
+  float *Ahi = ws, *Alo = Ahi + (size_t)K * Mp, *Bhi = Alo + (size_t)K * Mp, *Blo = Bhi + (size_t)K * Np;
+  LAUNCHED(launch_split_tf32(A, lda, K, M, Mp, Ahi, Mp, Alo, Mp, ctx->st));
+  LAUNCHED(launch_split_tf32(B, ldb, K, N, Np, Bhi, Np, Blo, Np, ctx->st));
+  const float* as[3] = {Alo, Ahi, Ahi};  // the small terms first
+  const float* bs[3] = {Bhi, Blo, Bhi};
+  for (int i = 0; i < 3; ++i) {
+    int n = launch_gemm_tc_atb(as[i], Mp, bs[i], Np, C, ldc, M, N, K, ctx->splitk_ws, ctx->splitk_ws_bytes, ctx->st);
+    if (n < 0) return i == 0 ? kX3Fallback : fail(ctx, GATX_ERR_UNSUPPORTED, "3xTF32: A^T B GEMM rejected M=%d N=%d", M, N);
+    ctx->launches += n;
+  }
+  return GATX_OK;
+}
+
 int gemm_project(gatx_ctx* ctx, const float* X, int ldx, const Layer& ly, float* Pl_rows, float* Pr_rows, int rows) {
   if (rows <= 0) return GATX_OK;
+  if (ctx->gemm_mode == GATX_GEMM_3XTF32_TC) {
+    const int rc = gemm3x_tn(ctx, X, ldx, ly.Wcat, ly.ldk, ly.I, Pl_rows, Pr_rows, ly.F, ly.F, rows, 2 * ly.F, false);
+    if (rc != kX3Fallback) return rc;
+  }
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
     int n = launch_gemm_tc_tn2(X, ldx, ly.Wcat, ly.ldk, ly.I, nullptr, 0, nullptr, 0, 0, Pl_rows, Pr_rows, ly.F, ly.F,
                                rows, 2 * ly.F, false, ctx->st);
@@ -456,6 +519,10 @@ int gemm_project(gatx_ctx* ctx, const float* X, int ldx, const Layer& ly, float*
 // C[M][N] = A[M][K] B[N][K]^T with the configured arithmetic
 int gemm_tn_any(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
                 int N, int K) {
+  if (ctx->gemm_mode == GATX_GEMM_3XTF32_TC) {
+    const int rc = gemm3x_tn(ctx, A, lda, B, ldb, K, C, C, N, ldc, M, N, false);
+    if (rc != kX3Fallback) return rc;
+  }
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
     int n = launch_gemm_tc_tn(A, lda, B, ldb, C, ldc, M, N, K, false, ctx->st);
     if (n >= 0) {
@@ -470,6 +537,11 @@ int gemm_tn_any(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int6
 int gemm_input_grad(gatx_ctx* ctx, const float* gPl_rows, const float* gPr_rows, const Layer& ly, float* gX, int ldg,
                     int rows) {
   if (rows <= 0) return GATX_OK;
+  if (ctx->gemm_mode == GATX_GEMM_3XTF32_TC) {
+    int rc = gemm3x_tn(ctx, gPl_rows, ly.F, ly.WcatT, 2 * ly.F, ly.F, gX, gX, ly.I, ldg, rows, ly.I, false);
+    if (rc == GATX_OK) return gemm3x_tn(ctx, gPr_rows, ly.F, ly.WcatT + ly.F, 2 * ly.F, ly.F, gX, gX, ly.I, ldg, rows, ly.I, true);
+    if (rc != kX3Fallback) return rc;
+  }
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
     int n = launch_gemm_tc_tn2(gPl_rows, ly.F, ly.WcatT, 2 * ly.F, ly.F, gPr_rows, ly.F, ly.WcatT + ly.F, 2 * ly.F, ly.F,
                                gX, gX, ly.I, ldg, rows, ly.I, false, ctx->st);
@@ -487,6 +559,10 @@ int gemm_input_grad(gatx_ctx* ctx, const float* gPl_rows, const float* gPr_rows,
 // C[M][N] (ldc) += A^T B with A [K][>=M] (lda), B [K][>=N] (ldb): contraction over the node dimension.
 int gemm_nt_reduce(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                    int M, int N, int64_t K) {
+  if (ctx->gemm_mode == GATX_GEMM_3XTF32_TC) {
+    const int rc = gemm3x_atb(ctx, A, lda, B, ldb, C, ldc, M, N, K);
+    if (rc != kX3Fallback) return rc;
+  }
   if (ctx->gemm_mode == GATX_GEMM_TF32_TC) {
     int n = launch_gemm_tc_atb(A, lda, B, ldb, C, ldc, M, N, K, ctx->splitk_ws, ctx->splitk_ws_bytes, ctx->st);
     if (n >= 0) {

@@ -139,4 +139,31 @@ int launch_pack_weights(const float* W, int F, int I, float* Wcat, int ldk, floa
   return 1;
 }
 
+
+__global__ void split_tf32_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int cols, int cols_pad,
+                                  float* __restrict__ hi, int64_t ld_hi, float* __restrict__ lo, int64_t ld_lo) {
+  const int64_t total = rows * cols_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols_pad;
+    const int c = (int)(i - r * cols_pad);
+    float h = 0.f, l = 0.f;
+    if (c < cols) {
+      const float x = X[r * ldx + c];
+      h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+      l = x - h;
+    }
+    hi[r * ld_hi + c] = h;
+    lo[r * ld_lo + c] = l;
+  }
+}
+int launch_split_tf32(const float* X, int64_t ldx, int64_t rows, int cols, int cols_pad, float* out_hi, int64_t ld_hi,
+                      float* out_lo, int64_t ld_lo, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return 0;
+  const int64_t total = rows * cols_pad;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  split_tf32_kernel<<<(int)blocks, 256, 0, st>>>(X, ldx, rows, cols, cols_pad, out_hi, ld_hi, out_lo, ld_lo);
+  return 1;
+}
+
 }  // namespace gatx

@@ -7,7 +7,7 @@
 //            --data-root, env DATA_ROOT; unknown flags are ignored like the reference (EB:942-1077)
 //   stdout : configuration block (EB:1024-1040), dataset lines (EB:1076-1111), per epoch
 //            "\nEpoch %d\n", "\nAvg Loss: %f, Accuracy: %.2f%%\n", " total time: <ms> ms" (EB:1372, 547, 1641)
-// Additions that do not change the defaults: --seed S, --gemm tf32|fp32, --gpus N (destination-row partition,
+// Additions that do not change the defaults: --seed S, --gemm tf32|fp32|3xtf32, --gpus N (destination-row partition,
 // one host thread + one context per GPU), --load-weights DIR / --dump-weights DIR (W.bin a.bin Wo.bin, raw fp32
 // in the reference's layouts), --save-checkpoint FILE / --resume FILE (parameters + Adam moments + epoch counter),
 // --quiet-epochs k (print only every k-th epoch), --no-cache (do not read/write the binary dataset cache
@@ -370,7 +370,7 @@ int main(int argc, char** argv) {
     else if (arg == "--data-root" && i + 1 < argc) a.data_root = argv[++i];
     else if (arg == "--seed" && i + 1 < argc) { a.seed = std::strtoull(argv[++i], nullptr, 10); a.seed_given = true; }
     else if (arg == "--gpus" && i + 1 < argc) a.gpus = std::max(1, std::atoi(argv[++i]));
-    else if (arg == "--gemm" && i + 1 < argc) a.gemm = std::string(argv[++i]) == "fp32" ? GATX_GEMM_FP32_SIMT : GATX_GEMM_TF32_TC;
+    else if (arg == "--gemm" && i + 1 < argc) { const std::string m = argv[++i]; a.gemm = m == "fp32" ? GATX_GEMM_FP32_SIMT : (m == "3xtf32" ? GATX_GEMM_3XTF32_TC : GATX_GEMM_TF32_TC); }
     else if (arg == "--load-weights" && i + 1 < argc) a.load_w = argv[++i];
     else if (arg == "--dump-weights" && i + 1 < argc) a.dump_w = argv[++i];
     else if (arg == "--quiet-epochs" && i + 1 < argc) a.every = std::max(1, std::atoi(argv[++i]));

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("GATX_LIB") or os.path.join(HERE, "libgatx.so")
 (T_W, T_A, T_WO, T_GW, T_GA, T_GWO, T_PL, T_PR, T_SCORE, T_ALPHA, T_HPRE, T_HOUT, T_Y, T_GH, T_Z, T_PRED,
  T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID, T_GPL, T_GPR, T_GALPHA, T_GE, T_B, T_GB) = range(28)
 _INT_TENSORS = {T_PRED, T_COO_SRC, T_COO_DST, T_IN_DEGREE, T_CSC_PTR, T_CSC_DST, T_CSC_EID}
-GEMM_TF32_TC, GEMM_FP32_SIMT = 0, 1
+GEMM_TF32_TC, GEMM_FP32_SIMT, GEMM_3XTF32_TC = 0, 1, 2
 PEER_INFO_BYTES = 2048
 PHASES = ("gemm_fwd", "edge_fwd", "head", "edge_bwd", "gemm_bwd", "optimizer", "comm", "epoch")
 

@@ -45,7 +45,11 @@ enum { GATX_OPT_SGD = 0, GATX_OPT_ADAM = 1 };
 /* Projection / gradient GEMM arithmetic. */
 enum {
   GATX_GEMM_TF32_TC = 0, /* tcgen05 tensor cores, TF32 inputs, fp32 accumulate (default) */
-  GATX_GEMM_FP32_SIMT = 1 /* fp32 FMA on CUDA cores (tight-tolerance parity runs) */
+  GATX_GEMM_FP32_SIMT = 1, /* fp32 FMA on CUDA cores (tight-tolerance parity runs) */
+  /* fp32-grade results ON the tensor cores: every operand is split into hi (its TF32 part) + lo (the exact remainder)
+   * and hi*hi + lo*hi + hi*lo is accumulated into the same TMEM tile (the lo*lo term, 2^-22 relative, is dropped).
+   * Same tolerances and bit-exact predicted labels as GATX_GEMM_FP32_SIMT at a fraction of its time. */
+  GATX_GEMM_3XTF32_TC = 2
 };
 
 /* Replaces the CLI-derived locals of EB:934-1040 (L, head[], out_dim[], optimizer, lr, betas,
