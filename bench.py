@@ -308,8 +308,11 @@ def run_gatx(args):
             blobs = [None] * world
             dist.all_gather_object(blobs, eng.peer_export())
             eng.peer_import(blobs)
-        halo = {"exchange": "nvlink peer-memory push/pull kernels on an exchange stream, pipelined over row blocks, "
-                            "flag barriers in peer memory" if eng.halo_active() else "nccl broadcast/reduce",
+        mode_sm = os.environ.get("GATX_HALO_MODE") == "sm"
+        halo = {"exchange": ("NVLink peer memory, pipelined over row blocks under the edge passes, flag barriers in peer "
+                             "memory; transport: " + ("SM push / scatter kernels (halo rows only)" if mode_sm else
+                                                      "copy engines (peer-to-peer DMA of row blocks, no SM)"))
+                if eng.halo_active() else "nccl broadcast/reduce",
                 "rows_pushed_per_layer_rank0": push_rows,
                 "allgather_rows_rank0": (world - 1) * (info["row_end"] - info["row_begin"])}
     t = 0
@@ -426,13 +429,13 @@ def run_gatx(args):
     if halo is not None and halo_stats is not None and halo_stats["push_ms"] > 0:
         # rank 0's exchange kernels in the last timed epoch: bytes over NVLink / time the kernels were running (they
         # run underneath the edge passes; the EXPOSED part is phase_ms_per_epoch.comm)
-        halo["nvlink_push_gbs_rank0"] = halo_stats["push_bytes"] / 1e9 / (halo_stats["push_ms"] * 1e-3)
-        halo["nvlink_pull_gbs_rank0"] = (halo_stats["pull_bytes"] / 1e9 / (halo_stats["pull_ms"] * 1e-3)
-                                         if halo_stats["pull_ms"] > 0 else None)
-        halo["push_gb_per_epoch_rank0"] = halo_stats["push_bytes"] / 1e9
-        halo["pull_gb_per_epoch_rank0"] = halo_stats["pull_bytes"] / 1e9
-        halo["push_busy_ms_rank0"] = halo_stats["push_ms"]
-        halo["pull_busy_ms_rank0"] = halo_stats["pull_ms"]
+        halo["nvlink_fwd_gbs_rank0"] = halo_stats["push_bytes"] / 1e9 / (halo_stats["push_ms"] * 1e-3)
+        halo["nvlink_bwd_gbs_rank0"] = (halo_stats["pull_bytes"] / 1e9 / (halo_stats["pull_ms"] * 1e-3)
+                                        if halo_stats["pull_ms"] > 0 else None)
+        halo["fwd_gb_per_epoch_rank0"] = halo_stats["push_bytes"] / 1e9
+        halo["bwd_gb_per_epoch_rank0"] = halo_stats["pull_bytes"] / 1e9
+        halo["fwd_busy_ms_rank0"] = halo_stats["push_ms"]
+        halo["bwd_busy_ms_rank0"] = halo_stats["pull_ms"]
     if rank == 0:
         line = {
             "metric": "train_edges_per_s", "value": E / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,

@@ -170,12 +170,20 @@ struct gatx_ctx {
   std::vector<void*> ipc_opened;
   // exchange stream + flag barriers in peer memory (halo_p2p.cu)
   cudaStream_t st_comm = nullptr;
+  // Default transport of the exchange: the copy engines.  Block by block, the own rows of P_l (forward) and this rank's
+  // partial gP_l rows (backward) are contiguous ranges, so they travel as peer-to-peer cudaMemcpyAsync on kCeStreams DMA
+  // streams and use NO SM: kernels that drive NVLink from the SMs need a third of the SMs' warps in flight to cover the
+  // link's round trip, which costs the concurrently running edge pass as much as it hides (measured on 8 GPUs).
+  // GATX_HALO_MODE=sm selects the SM kernels (halo-only push / scatter, fewer bytes) instead.
+  static constexpr int kCeStreams = 4;
+  cudaStream_t st_ce[kCeStreams] = {nullptr, nullptr, nullptr, nullptr};
+  bool halo_ce = true;
   uint32_t* halo_flags = nullptr;  // [kMaxPeers] slot p: the last barrier rank p has reached
   PeerFlags peer_flags{};
   uint32_t barrier_seq = 0;
   std::vector<cudaEvent_t> ev_pool;  // cross-stream ordering events, reused every epoch
   size_t ev_used = 0;
-  struct CommSpan { int dir; double bytes; cudaEvent_t a, b; };  // dir 0 = push, 1 = pull (timing enabled)
+  struct CommSpan { int dir; double bytes; cudaEvent_t a, b; int lane = 0; };  // dir 0 = forward, 1 = backward; lane = DMA stream
   std::vector<CommSpan> comm_spans;
   size_t comm_spans_used = 0;
   // timing
@@ -606,6 +614,43 @@ int comm_barrier(gatx_ctx* ctx) {
   LAUNCHED(launch_halo_barrier(ctx->peer_flags, ctx->rank, ctx->world, ctx->barrier_seq, ctx->st_comm));
   return GATX_OK;
 }
+// DMA transport: `rows` rows of pitch F from `src` to `dst_of(p)` on every peer, round-robin over the DMA streams, each of
+// which first waits for everything enqueued on `after` so far.  The copies use no SM.
+template <typename DstOf>
+int ce_copy_to_peers(gatx_ctx* ctx, cudaStream_t after, const float* src, size_t bytes, DstOf dst_of, int dir) {
+  if (!bytes) return GATX_OK;
+  cudaEvent_t go = next_event(ctx);
+  CK(cudaEventRecord(go, after));
+  for (int k = 0; k < gatx_ctx::kCeStreams; ++k) CK(cudaStreamWaitEvent(ctx->st_ce[k], go, 0));
+  int i = 0;
+  for (int p = 0; p < ctx->world; ++p) {
+    if (p == ctx->rank) continue;
+    const int lane = (i++ + ctx->rank) % gatx_ctx::kCeStreams;
+    cudaStream_t s = ctx->st_ce[lane];
+    size_t span = (size_t)-1;
+    if (ctx->timing) {
+      if (ctx->comm_spans_used == ctx->comm_spans.size()) {
+        gatx_ctx::CommSpan sp{dir, 0.0, nullptr, nullptr};
+        cudaEventCreate(&sp.a);
+        cudaEventCreate(&sp.b);
+        ctx->comm_spans.push_back(sp);
+      }
+      span = ctx->comm_spans_used++;
+      ctx->comm_spans[span].dir = dir;
+      ctx->comm_spans[span].bytes = (double)bytes;
+      ctx->comm_spans[span].lane = lane;
+      cudaEventRecord(ctx->comm_spans[span].a, s);
+    }
+    CK(cudaMemcpyAsync(dst_of(p), src, bytes, cudaMemcpyDeviceToDevice, s));
+    if (span != (size_t)-1) cudaEventRecord(ctx->comm_spans[span].b, s);
+  }
+  return GATX_OK;
+}
+// the exchange stream continues only after every DMA stream has drained
+void comm_waits_ce(gatx_ctx* ctx) {
+  for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_comm, ctx->st_ce[k]);
+}
+
 // timing of the exchange kernels themselves (on st_comm): bytes over NVLink and busy time per direction
 struct CommTimer {
   gatx_ctx* c;
@@ -621,6 +666,7 @@ struct CommTimer {
     idx = c->comm_spans_used++;
     c->comm_spans[idx].dir = dir;
     c->comm_spans[idx].bytes = bytes;
+    c->comm_spans[idx].lane = 0;
     cudaEventRecord(c->comm_spans[idx].a, c->st_comm);
   }
   ~CommTimer() {
@@ -679,7 +725,8 @@ RowView row_view(const gatx_ctx* ctx, int b) {
   v.g.n_chunks = B.n_chunks; v.g.chunk_row = B.chunk_row;
   v.g.col_idx_hot = ctx->col_idx_hot ? ctx->col_idx_hot + B.e0 : nullptr;
   v.g.heavy_rows = nullptr; v.g.n_heavy_rows = 0;
-  v.g.reserve_ctas = halo_cta_slots();  // the exchange of the neighbouring block runs underneath this launch
+  // SM transport: the exchange kernels of the neighbouring block run underneath this launch in their own CTA slots
+  v.g.reserve_ctas = ctx->halo_ce ? 0 : halo_cta_slots();
   return v;
 }
 // the streaming kernels take any view; the warp-per-row / generic kernels only the whole row range
@@ -810,6 +857,8 @@ int do_forward(gatx_ctx* ctx) {
     // first row of this forward is pushed into its buffers
     stream_after(ctx, ctx->st_comm, ctx->st);
     if ((rc = comm_barrier(ctx))) return rc;
+    if (ctx->halo_ce)
+      for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_ce[k], ctx->st_comm);
   }
   {
     PhaseTimer t(ctx, PH_GEMM_FWD);
@@ -894,13 +943,20 @@ int do_forward(gatx_ctx* ctx) {
           rc = gemm_project(ctx, Xb, nx.ldx, nx, nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, nx.Pr + (int64_t)v.rb * nx.F, v.nb);
           if (rc) return rc;
         }
-        stream_after(ctx, ctx->st_comm, ctx->st);
-        {
+        if (ctx->halo_ce) {
+          const int64_t off = (int64_t)(ctx->r0 + v.rb) * nx.F;
+          const PeerPtrs& pp = ctx->peer_Pl[l + 1];
+          rc = ce_copy_to_peers(ctx, ctx->st, nx.Pl + off, sizeof(float) * (size_t)v.nb * nx.F,
+                                [&](int p) { return pp.p[p] + off; }, 0);
+          if (rc) return rc;
+        } else {
+          stream_after(ctx, ctx->st_comm, ctx->st);
           CommTimer ct(ctx, 0, (double)ctx->blocks[b].halo_rows * nx.F * 4.0);
           LAUNCHED(launch_halo_push(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
                                     ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm, halo_cta_slots()));
         }
       }
+      if (ctx->halo_ce) comm_waits_ce(ctx);
       if ((rc = comm_barrier(ctx))) return rc;  // every rank's pushes have landed
       compute_waits_comm(ctx);
     }
@@ -1031,7 +1087,39 @@ int do_backward(gatx_ctx* ctx) {
     const int nblk = (int)ctx->blocks.size();
     for (int b = 0; b < nblk; ++b) {
       const RowView v = row_view(ctx, b);
-      {
+      if (ctx->halo_ce) {
+        // this rank's partial rows of block b of every owner: one contiguous DMA copy per owner into its staging slot
+        int i = 0;
+        if (b == 0)  // behind the barrier that opened this exchange; later blocks follow in stream order
+          for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_ce[k], ctx->st_comm);
+        for (int p = 0; p < ctx->world; ++p) {
+          if (p == ctx->rank) continue;
+          const int* ab = ctx->all_blk.data() + (size_t)p * (nblk + 1);
+          const size_t bytes = sizeof(float) * (size_t)(ab[b + 1] - ab[b]) * ly.F;
+          const int lane = (i++ + ctx->rank) % gatx_ctx::kCeStreams;
+          cudaStream_t s = ctx->st_ce[lane];
+          if (!bytes) continue;
+          float* dst = ctx->peer_stage.p[p] +
+                       ((int64_t)ctx->rank * (ctx->bounds[p + 1] - ctx->bounds[p]) + (ab[b] - ctx->bounds[p])) * ly.F;
+          size_t span = (size_t)-1;
+          if (ctx->timing) {
+            if (ctx->comm_spans_used == ctx->comm_spans.size()) {
+              gatx_ctx::CommSpan sp{1, 0.0, nullptr, nullptr};
+              cudaEventCreate(&sp.a);
+              cudaEventCreate(&sp.b);
+              ctx->comm_spans.push_back(sp);
+            }
+            span = ctx->comm_spans_used++;
+            ctx->comm_spans[span].dir = 1;
+            ctx->comm_spans[span].bytes = (double)bytes;
+            ctx->comm_spans[span].lane = lane;
+            cudaEventRecord(ctx->comm_spans[span].a, s);
+          }
+          CK(cudaMemcpyAsync(dst, ctx->gPl + (int64_t)ab[b] * ly.F, bytes, cudaMemcpyDeviceToDevice, s));
+          if (span != (size_t)-1) cudaEventRecord(ctx->comm_spans[span].b, s);
+        }
+        comm_waits_ce(ctx);
+      } else {
         ScatterPlan plan{};
         for (int p = 0; p < ctx->world; ++p) {
           if (p == ctx->rank) continue;
@@ -1241,6 +1329,13 @@ int gatx_create(gatx_ctx** out, const gatx_config* cfg) {
       delete c;
       return GATX_ERR_CUDA;
     }
+    for (auto& s : c->st_ce)
+      if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) {
+        delete c;
+        return GATX_ERR_CUDA;
+      }
+    const char* hm = getenv("GATX_HALO_MODE");
+    c->halo_ce = !(hm && std::string(hm) == "sm");
   }
   *out = c;
   return GATX_OK;
@@ -1273,6 +1368,8 @@ void gatx_destroy(gatx_ctx* ctx) {
     cudaEventDestroy(s.b);
   }
   if (ctx->st_comm) cudaStreamDestroy(ctx->st_comm);
+  for (auto& s : ctx->st_ce)
+    if (s) cudaStreamDestroy(s);
   cudaStreamDestroy(ctx->st);
   delete ctx;
 }
@@ -2339,13 +2436,17 @@ int gatx_halo_stats(gatx_ctx* ctx, double* out4) {
   CK(cudaStreamSynchronize(ctx->st));
   if (ctx->st_comm) CK(cudaStreamSynchronize(ctx->st_comm));
   out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+  double lane_ms[2][gatx_ctx::kCeStreams] = {};
   for (size_t i = 0; i < ctx->comm_spans_used; ++i) {
     float ms = 0.f;
     const auto& s = ctx->comm_spans[i];
     if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) continue;
     out4[2 * s.dir] += s.bytes;
-    out4[2 * s.dir + 1] += ms;
+    lane_ms[s.dir][s.lane % gatx_ctx::kCeStreams] += ms;
   }
+  // the DMA streams run side by side: the busy time of a direction is that of its busiest stream
+  for (int d = 0; d < 2; ++d)
+    for (int k = 0; k < gatx_ctx::kCeStreams; ++k) out4[2 * d + 1] = std::max(out4[2 * d + 1], lane_ms[d][k]);
   cudaGetLastError();
   return GATX_OK;
 }

@@ -281,10 +281,11 @@ int gatx_peer_disable(gatx_ctx* ctx);
  * would move (world - 1) * own rows.  Integer, identical to oracle/orc_halo_rows. */
 int64_t gatx_halo_rows(const gatx_ctx* ctx);
 int gatx_halo_active(const gatx_ctx* ctx); /* 1 when the peer-memory path is in use */
-/* NVLink traffic of the exchange kernels in the last epoch (timing enabled, peer-memory path): out4[0] = bytes this rank
- * pushed into its peers' P_l buffers, [1] = milliseconds its push kernels were running, [2] = bytes it pulled from its
- * peers' partial gP_l rows, [3] = milliseconds of the pull kernels.  The kernels run on the exchange stream underneath
- * the edge passes, so these are busy times, not exposed times (phase 6 of gatx_get_timing is the exposed wait). */
+/* NVLink traffic of the exchange in the last epoch (timing enabled, peer-memory path): out4[0] = bytes this rank sent in
+ * the forward exchange (projected rows into its peers' P_l buffers), [1] = milliseconds its busiest DMA stream (or its
+ * push kernels, GATX_HALO_MODE=sm) spent on them, [2] / [3] = the same for the backward exchange (partial gP_l rows into
+ * the owners' staging buffers).  The transfers run underneath the edge passes, so these are busy times, not exposed
+ * times (phase 6 of gatx_get_timing is the exposed wait). */
 int gatx_halo_stats(gatx_ctx* ctx, double* out4);
 
 #ifdef __cplusplus
