@@ -74,15 +74,18 @@ def _worker(rank, world, idfile, q, mode, p2p):
     eng.close()
 
 
-@pytest.mark.parametrize("p2p", [3, 1, 0], ids=["nvlink-peer-halo-3-blocks", "nvlink-peer-halo-1-block", "nccl"])
+@pytest.mark.parametrize("p2p,transport", [(3, "ce"), (3, "sm"), (1, "ce"), (0, "nccl")],
+                         ids=["peer-memory-3-blocks-dma", "peer-memory-3-blocks-sm-kernels", "peer-memory-1-block-dma", "nccl"])
 @pytest.mark.parametrize("world", [2])
-def test_two_ranks_match_one(world, p2p, monkeypatch):
-    """p2p = number of row blocks of the pipelined peer-memory exchange (0: NCCL collectives).  With 3 blocks the
-    3 000-node problem exercises the block views of the streaming kernels (rebased row_ptr, per-block chunk tables,
-    rows cut by block-local chunk boundaries), the exchange stream, the flag barriers and the double-buffered gP_r."""
+def test_two_ranks_match_one(world, p2p, transport, monkeypatch):
+    """p2p = number of row blocks of the pipelined peer-memory exchange (0: NCCL collectives); transport = copy engines
+    (default) or the SM push / scatter kernels.  With 3 blocks the 3 000-node problem exercises the block views of the
+    streaming kernels (rebased row_ptr, per-block chunk tables, rows cut by block-local chunk boundaries), the exchange
+    streams, the flag barriers, the staging buffers of the backward exchange and the double-buffered gP_r."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     monkeypatch.setenv("GATX_HALO_BLOCKS", str(max(p2p, 1)))  # inherited by the spawned ranks
+    monkeypatch.setenv("GATX_HALO_MODE", transport)
     sys.path.insert(0, os.path.join(HERE, "..", "graph-attention-network-gatv2-_b200"))
     import gatx
     from helpers import make_engine, rel_err
