@@ -175,8 +175,8 @@ struct gatx_ctx {
   // streams and use NO SM: kernels that drive NVLink from the SMs need a third of the SMs' warps in flight to cover the
   // link's round trip, which costs the concurrently running edge pass as much as it hides (measured on 8 GPUs).
   // GATX_HALO_MODE=sm selects the SM kernels (halo-only push / scatter, fewer bytes) instead.
-  static constexpr int kCeStreams = 4;
-  cudaStream_t st_ce[kCeStreams] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kCeStreams = 8;
+  cudaStream_t st_ce[kCeStreams] = {};
   bool halo_ce = true;
   uint32_t* halo_flags = nullptr;  // [kMaxPeers] slot p: the last barrier rank p has reached
   PeerFlags peer_flags{};
@@ -614,18 +614,17 @@ int comm_barrier(gatx_ctx* ctx) {
   LAUNCHED(launch_halo_barrier(ctx->peer_flags, ctx->rank, ctx->world, ctx->barrier_seq, ctx->st_comm));
   return GATX_OK;
 }
-// DMA transport: `rows` rows of pitch F from `src` to `dst_of(p)` on every peer, round-robin over the DMA streams, each of
-// which first waits for everything enqueued on `after` so far.  The copies use no SM.
-template <typename DstOf>
-int ce_copy_to_peers(gatx_ctx* ctx, cudaStream_t after, const float* src, size_t bytes, DstOf dst_of, int dir) {
-  if (!bytes) return GATX_OK;
-  cudaEvent_t go = next_event(ctx);
-  CK(cudaEventRecord(go, after));
-  for (int k = 0; k < gatx_ctx::kCeStreams; ++k) CK(cudaStreamWaitEvent(ctx->st_ce[k], go, 0));
-  int i = 0;
-  for (int p = 0; p < ctx->world; ++p) {
-    if (p == ctx->rank) continue;
-    const int lane = (i++ + ctx->rank) % gatx_ctx::kCeStreams;
+// DMA transport.  One peer copy = `rows` rows of pitch F; a single copy engine moves ~430 GB/s over NVLink 5 (measured),
+// so a copy is cut into row ranges issued on different DMA streams when there are fewer peers than streams.  No SM is used.
+int ce_copy_rows(gatx_ctx* ctx, float* dst, const float* src, int64_t rows, int F, int dir, int* rr) {
+  if (rows <= 0) return GATX_OK;
+  int pieces = gatx_ctx::kCeStreams / (ctx->world - 1);
+  if (pieces < 1) pieces = 1;
+  if ((int64_t)pieces > rows) pieces = (int)rows;
+  for (int q = 0; q < pieces; ++q) {
+    const int64_t a = rows * q / pieces, b = rows * (q + 1) / pieces;
+    const size_t bytes = sizeof(float) * (size_t)(b - a) * F;
+    const int lane = ((*rr)++ + ctx->rank) % gatx_ctx::kCeStreams;
     cudaStream_t s = ctx->st_ce[lane];
     size_t span = (size_t)-1;
     if (ctx->timing) {
@@ -641,7 +640,7 @@ int ce_copy_to_peers(gatx_ctx* ctx, cudaStream_t after, const float* src, size_t
       ctx->comm_spans[span].lane = lane;
       cudaEventRecord(ctx->comm_spans[span].a, s);
     }
-    CK(cudaMemcpyAsync(dst_of(p), src, bytes, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(dst + a * F, src + a * F, bytes, cudaMemcpyDeviceToDevice, s));
     if (span != (size_t)-1) cudaEventRecord(ctx->comm_spans[span].b, s);
   }
   return GATX_OK;
@@ -945,10 +944,11 @@ int do_forward(gatx_ctx* ctx) {
         }
         if (ctx->halo_ce) {
           const int64_t off = (int64_t)(ctx->r0 + v.rb) * nx.F;
-          const PeerPtrs& pp = ctx->peer_Pl[l + 1];
-          rc = ce_copy_to_peers(ctx, ctx->st, nx.Pl + off, sizeof(float) * (size_t)v.nb * nx.F,
-                                [&](int p) { return pp.p[p] + off; }, 0);
-          if (rc) return rc;
+          for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_ce[k], ctx->st);  // the block's GEMM is done
+          int rr = 0;
+          for (int p = 0; p < ctx->world; ++p)
+            if (p != ctx->rank && (rc = ce_copy_rows(ctx, ctx->peer_Pl[l + 1].p[p] + off, nx.Pl + off, v.nb, nx.F, 0, &rr)))
+              return rc;
         } else {
           stream_after(ctx, ctx->st_comm, ctx->st);
           CommTimer ct(ctx, 0, (double)ctx->blocks[b].halo_rows * nx.F * 4.0);
@@ -1089,34 +1089,15 @@ int do_backward(gatx_ctx* ctx) {
       const RowView v = row_view(ctx, b);
       if (ctx->halo_ce) {
         // this rank's partial rows of block b of every owner: one contiguous DMA copy per owner into its staging slot
-        int i = 0;
         if (b == 0)  // behind the barrier that opened this exchange; later blocks follow in stream order
           for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_ce[k], ctx->st_comm);
+        int rr = 0;
         for (int p = 0; p < ctx->world; ++p) {
           if (p == ctx->rank) continue;
           const int* ab = ctx->all_blk.data() + (size_t)p * (nblk + 1);
-          const size_t bytes = sizeof(float) * (size_t)(ab[b + 1] - ab[b]) * ly.F;
-          const int lane = (i++ + ctx->rank) % gatx_ctx::kCeStreams;
-          cudaStream_t s = ctx->st_ce[lane];
-          if (!bytes) continue;
           float* dst = ctx->peer_stage.p[p] +
                        ((int64_t)ctx->rank * (ctx->bounds[p + 1] - ctx->bounds[p]) + (ab[b] - ctx->bounds[p])) * ly.F;
-          size_t span = (size_t)-1;
-          if (ctx->timing) {
-            if (ctx->comm_spans_used == ctx->comm_spans.size()) {
-              gatx_ctx::CommSpan sp{1, 0.0, nullptr, nullptr};
-              cudaEventCreate(&sp.a);
-              cudaEventCreate(&sp.b);
-              ctx->comm_spans.push_back(sp);
-            }
-            span = ctx->comm_spans_used++;
-            ctx->comm_spans[span].dir = 1;
-            ctx->comm_spans[span].bytes = (double)bytes;
-            ctx->comm_spans[span].lane = lane;
-            cudaEventRecord(ctx->comm_spans[span].a, s);
-          }
-          CK(cudaMemcpyAsync(dst, ctx->gPl + (int64_t)ab[b] * ly.F, bytes, cudaMemcpyDeviceToDevice, s));
-          if (span != (size_t)-1) cudaEventRecord(ctx->comm_spans[span].b, s);
+          if ((rc = ce_copy_rows(ctx, dst, ctx->gPl + (int64_t)ab[b] * ly.F, ab[b + 1] - ab[b], ly.F, 1, &rr))) return rc;
         }
         comm_waits_ce(ctx);
       } else {

@@ -117,9 +117,16 @@ def test_two_ranks_match_one(world, p2p, transport, monkeypatch):
             assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 5e-3
         for (l, a), (rl, ra) in zip(o["masked"] + [o["masked_eval"]], ref_masked + [ref_masked_eval]):
             assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 5e-3
+        # Adam's update lr * m / (sqrt(v) + eps) is a sign function for |g| ~ eps: an element whose gradient is ~0 moves by up
+        # to +-lr per epoch depending on the summation order (one rank vs partial sums per rank), so the parameters are
+        # compared by the fraction of elements that differ (the loss curves above are the tight check)
+        def close(a, b):
+            a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+            scale = np.abs(b).max()
+            return np.mean(np.abs(a - b) > 2e-3 * scale) < 2e-3 and np.abs(a - b).max() < 6 * 0.01 * 1.01
         for l in range(3):
-            assert rel_err(o["W"][l], eng.tensor(gatx.T_W, l)) < 2e-3
-        assert rel_err(o["Wo"], eng.tensor(gatx.T_WO)) < 2e-3
+            assert close(o["W"][l], eng.tensor(gatx.T_W, l)), l
+        assert close(o["Wo"], eng.tensor(gatx.T_WO))
     assert outs[0]["rows"][1] == outs[1]["rows"][0] and outs[1]["rows"][1] == 3000
     pred = np.concatenate([o["pred"] for o in outs])
     assert (pred != eng.tensor(gatx.T_PRED)).mean() < 0.01
