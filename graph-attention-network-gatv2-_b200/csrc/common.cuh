@@ -173,10 +173,17 @@ struct ScatterPlan {
   int cum[kMaxPeers + 1];       // prefix sums of the segments' row counts
   int row0[kMaxPeers];          // first global row of the segment (a row block of its owner)
   int owner_row0[kMaxPeers];    // first global row the owner owns
+  int owner[kMaxPeers];         // rank that owns the segment's rows
   float* dst[kMaxPeers];        // owner's staging slot of THIS rank: [owner's n_rows][F]
 };
 int launch_halo_scatter(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan, cudaStream_t st,
                         int max_ctas);
+// bulk-copy (TMA) transport of the same two steps: one elected lane per warp moves whole rows global -> shared -> peer
+bool halo_bulk_supported(int F);
+int launch_halo_push_bulk(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
+                          int me, cudaStream_t st, int max_ctas);
+int launch_halo_scatter_bulk(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan,
+                             const PeerPtrs& stage_base, int me, cudaStream_t st, int max_ctas);
 int launch_halo_sum(float* own_rows, int row_off, int n_rows, int n_rows_total, int F, const uint16_t* ref_mask,
                     const float* stage, int me, int world, cudaStream_t st);
 int halo_cta_slots();  // CTA slots of the exchange kernels (GATX_HALO_CTAS, default 48)

@@ -177,7 +177,8 @@ struct gatx_ctx {
   // GATX_HALO_MODE=sm selects the SM kernels (halo-only push / scatter, fewer bytes) instead.
   static constexpr int kCeStreams = 8;
   cudaStream_t st_ce[kCeStreams] = {};
-  bool halo_ce = true;
+  bool halo_ce = false;   // GATX_HALO_MODE=ce
+  bool halo_bulk = true;  // default: bulk-copy (TMA) kernels; GATX_HALO_MODE=sm selects the ld / st kernels
   uint32_t* halo_flags = nullptr;  // [kMaxPeers] slot p: the last barrier rank p has reached
   PeerFlags peer_flags{};
   uint32_t barrier_seq = 0;
@@ -952,8 +953,13 @@ int do_forward(gatx_ctx* ctx) {
         } else {
           stream_after(ctx, ctx->st_comm, ctx->st);
           CommTimer ct(ctx, 0, (double)ctx->blocks[b].halo_rows * nx.F * 4.0);
-          LAUNCHED(launch_halo_push(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
-                                    ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm, halo_cta_slots()));
+          if (ctx->halo_bulk && halo_bulk_supported(nx.F))
+            LAUNCHED(launch_halo_push_bulk(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
+                                           ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm,
+                                           halo_cta_slots()));
+          else
+            LAUNCHED(launch_halo_push(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
+                                      ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm, halo_cta_slots()));
         }
       }
       if (ctx->halo_ce) comm_waits_ce(ctx);
@@ -1107,13 +1113,18 @@ int do_backward(gatx_ctx* ctx) {
           const int* ab = ctx->all_blk.data() + (size_t)p * (nblk + 1);
           const int sg = plan.n_seg++;
           plan.row0[sg] = ab[b];
+          plan.owner[sg] = p;
           plan.owner_row0[sg] = ctx->bounds[p];
           plan.cum[sg + 1] = plan.cum[sg] + (ab[b + 1] - ab[b]);
           // the owner's staging slot of this rank, viewed with this layer's row pitch
           plan.dst[sg] = ctx->peer_stage.p[p] + (int64_t)ctx->rank * (ctx->bounds[p + 1] - ctx->bounds[p]) * ly.F;
         }
         CommTimer ct(ctx, 1, (double)ctx->scatter_rows[b] * ly.F * 4.0);
-        LAUNCHED(launch_halo_scatter(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->st_comm, halo_cta_slots()));
+        if (ctx->halo_bulk && halo_bulk_supported(ly.F))
+          LAUNCHED(launch_halo_scatter_bulk(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->peer_stage, ctx->rank, ctx->st_comm,
+                                            halo_cta_slots()));
+        else
+          LAUNCHED(launch_halo_scatter(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->st_comm, halo_cta_slots()));
       }
       if ((rc = comm_barrier(ctx))) return rc;  // block b of every rank's partial rows has landed at its owner
       compute_waits_comm(ctx);
@@ -1316,7 +1327,8 @@ int gatx_create(gatx_ctx** out, const gatx_config* cfg) {
         return GATX_ERR_CUDA;
       }
     const char* hm = getenv("GATX_HALO_MODE");
-    c->halo_ce = !(hm && std::string(hm) == "sm");
+    c->halo_ce = hm && std::string(hm) == "ce";
+    c->halo_bulk = !hm || std::string(hm) == "bulk";
   }
   *out = c;
   return GATX_OK;

@@ -18,6 +18,7 @@
 // 32-thread CTA per barrier on the exchange stream -- no NCCL call, no host involvement.  The exchange runs on a stream
 // of its own, block of destination rows by block, so that it overlaps the edge passes (gatx_api.cu).
 #include "common.cuh"
+#include "ptx.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -90,6 +91,123 @@ halo_push_kernel(const float* __restrict__ own_rows, int r0, int n_rows, int F, 
     }
   }
   __threadfence_system();  // the peer-memory stores are performed before the kernel (and the barrier behind it) completes
+}
+
+// ---- bulk-copy (TMA) transport ------------------------------------------------------------------------------------------
+// Driving NVLink with ld / st from the SMs needs hundreds of warps to keep enough bytes in flight, and those warps take
+// CTA slots and issue bandwidth from the edge pass that runs at the same time.  Here one elected lane per warp moves whole
+// rows with bulk async copies: global -> shared ring (cp.async.bulk, mbarrier completion), then shared -> the peers'
+// global memory (cp.async.bulk.global.shared::cta, bulk groups).  A warp keeps LA rows of loads and LA rows of stores in
+// flight from a ring of 2 LA slots without holding a byte in registers, so 32 CTAs of 4 warps saturate the link.
+// job.mode 0: forward push of own rows to the peers of ref_mask; 1: backward scatter of partial rows to their owner.
+struct BulkJob {
+  int mode, F, me, n_items;
+  const float* src;             // mode 0: first own row of the block; mode 1: partial gP_l, global rows
+  int64_t push_off;             // mode 0: (global row of the block's first row) * F
+  const uint16_t* ref_mask;     // mode 0: [n_items]
+  const unsigned char* my_ref;  // mode 1: [N]
+  PeerPtrs base;                // mode 0: peers' P_l; mode 1: owners' staging buffers
+  ScatterPlan plan;             // mode 1 (dst[] = owner's slot of this rank, relative to owner_row0)
+};
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_all() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+constexpr int kBulkWarps = 4;
+// shared memory: ring [warps][2 LA][row] | mbarriers [warps][2 LA] u64 | offsets [warps][2 LA] i64 | masks [warps][2 LA] u32
+template <int LA>
+__global__ void __launch_bounds__(kBulkWarps * 32)
+halo_bulk_kernel(BulkJob job) {
+  constexpr int NS = 2 * LA;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)job.F * 4u;
+  const uint32_t ring_s = smem_u32(smem_raw) + (uint32_t)warp * NS * row_bytes;
+  uint8_t* tail = smem_raw + (size_t)kBulkWarps * NS * row_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail) + warp * NS;
+  int64_t* meta_off = reinterpret_cast<int64_t*>(tail + (size_t)kBulkWarps * NS * 8) + warp * NS;
+  uint32_t* meta_mask = reinterpret_cast<uint32_t*>(tail + (size_t)kBulkWarps * NS * 16) + warp * NS;
+  if (lane == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const uint32_t bar_s = smem_u32(bar);
+  const int total_warps = gridDim.x * kBulkWarps;
+  uint32_t issued = 0, consumed = 0;  // warp-uniform; lane 0 alone issues the asynchronous operations (bulk groups are
+                                      // per-thread state)
+
+  auto consume = [&]() {  // stores of the oldest loaded row
+    if (lane == 0) {
+      const uint32_t slot = consumed % NS, ph = (consumed / NS) & 1;
+      mbar_wait_s(bar_s + slot * 8u, ph);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      uint32_t m = meta_mask[slot];
+      const int64_t off = meta_off[slot];
+      while (m) {
+        const int p = __ffs(m) - 1;
+        m &= m - 1;
+        bulk_s2g(job.base.p[p] + off, ring_s + slot * row_bytes, row_bytes);
+      }
+      bulk_commit_all();
+    }
+    ++consumed;
+  };
+  auto step = [&](const float* src, uint32_t mask, int64_t off) {  // warp-uniform arguments
+    if (issued - consumed >= (uint32_t)LA) consume();
+    if (lane == 0) {
+      bulk_wait_read_all<LA>();  // the stores that last read this slot (issued 2 LA rows ago) have drained it
+      const uint32_t slot = issued % NS;
+      meta_mask[slot] = mask;
+      meta_off[slot] = off;
+      mbar_expect_tx_s(bar_s + slot * 8u, row_bytes);
+      bulk_g2s_s(ring_s + slot * row_bytes, src, row_bytes, bar_s + slot * 8u);
+    }
+    ++issued;
+  };
+
+  for (int base = (blockIdx.x * kBulkWarps + warp) * 32; base < job.n_items; base += total_warps * 32) {
+    const int t = base + lane;
+    uint32_t mask = 0;
+    int64_t off = 0;
+    const float* src = nullptr;
+    if (t < job.n_items) {
+      if (job.mode == 0) {
+        mask = job.ref_mask[t] & ~(1u << job.me);
+        off = job.push_off + (int64_t)t * job.F;
+        src = job.src + (int64_t)t * job.F;
+      } else {
+        int sgm = 0;
+        while (t >= job.plan.cum[sgm + 1]) ++sgm;
+        const int row = job.plan.row0[sgm] + (t - job.plan.cum[sgm]);
+        if (job.my_ref[row]) {
+          // plan.dst[sgm] - base.p[owner] is constant per segment; keep the offset relative to the owner's base
+          const int owner = job.plan.owner[sgm];
+          mask = 1u << owner;
+          off = (job.plan.dst[sgm] - job.base.p[owner]) + (int64_t)(row - job.plan.owner_row0[sgm]) * job.F;
+          src = job.src + (int64_t)row * job.F;
+        }
+      }
+    }
+    uint32_t bal = __ballot_sync(0xffffffffu, mask != 0);
+    while (bal) {
+      const int l = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const uint32_t m_u = __shfl_sync(0xffffffffu, mask, l);
+      const int64_t off_u = __shfl_sync(0xffffffffu, off, l);
+      const uint64_t src_u = __shfl_sync(0xffffffffu, (uint64_t)(uintptr_t)src, l);
+      step(reinterpret_cast<const float*>((uintptr_t)src_u), m_u, off_u);
+    }
+  }
+  while (consumed < issued) consume();
+  if (lane == 0) bulk_wait_all();  // every store has been performed, not only read out of shared memory
+  __syncwarp();
+  __threadfence_system();
 }
 
 // Backward exchange, sender side: this rank holds partial sums gP_l[src] over ITS edges for every source it references.
@@ -227,6 +345,45 @@ int launch_halo_push(const float* own_rows, int r0, int n_rows, int F, const uin
   prefer_max_shared(halo_push_kernel);
   halo_push_kernel<<<halo_blocks(n_rows, max_ctas), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me);
   return 1;
+}
+
+static int launch_bulk(const BulkJob& job, cudaStream_t st, int max_ctas) {
+  if (job.n_items <= 0) return 0;
+  const size_t ring = (size_t)16384;  // bytes of ring per warp
+  int la = (int)(ring / ((size_t)job.F * 4) / 2);
+  la = la >= 16 ? 16 : (la >= 8 ? 8 : (la >= 4 ? 4 : 2));
+  const size_t smem = (size_t)kBulkWarps * 2 * la * job.F * 4 + (size_t)kBulkWarps * 2 * la * (8 + 4 + 8) + 64;
+  int blocks = (job.n_items + kBulkWarps * 32 - 1) / (kBulkWarps * 32);
+  const int cap = max_ctas > 0 ? max_ctas : kNumSMs;
+  if (blocks > cap) blocks = cap;
+#define BULK_LAUNCH(LA)                                                                                          \
+  do {                                                                                                           \
+    cudaFuncSetAttribute(halo_bulk_kernel<LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    prefer_max_shared(halo_bulk_kernel<LA>);                                                                     \
+    halo_bulk_kernel<LA><<<blocks, kBulkWarps * 32, smem, st>>>(job);                                            \
+  } while (0)
+  if (la == 16) BULK_LAUNCH(16);
+  else if (la == 8) BULK_LAUNCH(8);
+  else if (la == 4) BULK_LAUNCH(4);
+  else BULK_LAUNCH(2);
+#undef BULK_LAUNCH
+  return 1;
+}
+bool halo_bulk_supported(int F) { return F % 4 == 0 && (size_t)F * 4 * 2 * 2 * kBulkWarps <= 200 * 1024; }
+
+int launch_halo_push_bulk(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
+                          int me, cudaStream_t st, int max_ctas) {
+  BulkJob job{};
+  job.mode = 0; job.F = F; job.me = me; job.n_items = n_rows; job.src = own_rows; job.push_off = (int64_t)r0 * F;
+  job.ref_mask = ref_mask; job.base = peers;
+  return launch_bulk(job, st, max_ctas);
+}
+int launch_halo_scatter_bulk(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan,
+                             const PeerPtrs& stage_base, int me, cudaStream_t st, int max_ctas) {
+  BulkJob job{};
+  job.mode = 1; job.F = F; job.me = me; job.n_items = plan.cum[plan.n_seg]; job.src = partial; job.my_ref = my_ref;
+  job.base = stage_base; job.plan = plan;
+  return launch_bulk(job, st, max_ctas);
 }
 
 int launch_halo_scatter(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan, cudaStream_t st,
