@@ -56,7 +56,9 @@ def _worker(rank, world, idfile, q, mode, p2p):
     if p2p:
         eng.peer_import(_exchange(os.path.dirname(idfile), "peer", rank, world, eng.peer_export()))
         assert eng.halo_active()
-    losses = [eng.train_epoch(t) for t in range(1, 5)]
+    losses = [eng.train_epoch(1)]
+    W1 = [eng.tensor(gatx.T_W, l) for l in range(3)] + [eng.tensor(gatx.T_WO)]  # parameters after ONE update
+    losses += [eng.train_epoch(t) for t in range(2, 5)]
     ev = eng.evaluate(None)  # two evaluation forwards back to back: the exchange must not race with itself
     ev2 = eng.evaluate(None)
     assert ev == ev2
@@ -68,7 +70,7 @@ def _worker(rank, world, idfile, q, mode, p2p):
     eng.set_train_mask(None)
     eng.evaluate(None)
     info = eng.graph_info()
-    out = dict(rank=rank, losses=losses, halo_rows=eng.halo_rows(), masked=masked, masked_eval=masked_eval, W=[eng.tensor(gatx.T_W, l) for l in range(3)], Wo=eng.tensor(gatx.T_WO),
+    out = dict(rank=rank, losses=losses, halo_rows=eng.halo_rows(), masked=masked, masked_eval=masked_eval, W1=W1,
                rows=(info["row_begin"], info["row_end"]), pred=eng.tensor(gatx.T_PRED))
     q.put(out)
     eng.close()
@@ -105,7 +107,9 @@ def test_two_ranks_match_one(world, p2p, transport, monkeypatch):
     import orc
     assert [o["halo_rows"] for o in outs] == orc.halo_rows(p["row_ptr"], p["col_idx"], world).tolist()  # bit-exact
     eng = make_engine(gatx, p, optimizer="adam", lr=0.01, clip=True, gemm_mode=mode)
-    ref_losses = [eng.train_epoch(t) for t in range(1, 5)]
+    ref_losses = [eng.train_epoch(1)]
+    ref_W1 = [eng.tensor(gatx.T_W, l) for l in range(3)] + [eng.tensor(gatx.T_WO)]
+    ref_losses += [eng.train_epoch(t) for t in range(2, 5)]
     eng.evaluate(None)
     mask = (np.arange(len(p["labels"])) % 3 == 0).astype(np.uint8)
     eng.set_train_mask(mask)
@@ -118,16 +122,14 @@ def test_two_ranks_match_one(world, p2p, transport, monkeypatch):
             assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 5e-3
         for (l, a), (rl, ra) in zip(o["masked"] + [o["masked_eval"]], ref_masked + [ref_masked_eval]):
             assert abs(l - rl) < 2e-4 * max(1.0, rl) and abs(a - ra) < 5e-3
-        # Adam's update lr * m / (sqrt(v) + eps) is a sign function for |g| ~ eps: an element whose gradient is ~0 moves by up
-        # to +-lr per epoch depending on the summation order (one rank vs partial sums per rank), so the parameters are
-        # compared by the fraction of elements that differ (the loss curves above are the tight check)
-        def close(a, b):
+        # Parameters are compared after ONE update.  Adam's first step is lr * g / (|g| + eps): a sign function, so an
+        # element whose gradient is at rounding level (|g| ~ eps) moves by anything in [-lr, lr] depending on the summation
+        # order (one rank vs partial sums per rank), and from there the runs drift apart chaotically -- measured with
+        # tools/multi_gpu_weight_drift.py: max |dW| 2e-4 after 1 epoch, 2e-3 after 2, 2e-2 after 4, IDENTICAL for the NCCL,
+        # ld / st, bulk-copy and DMA transports and every block count.  The loss curves above are the multi-epoch check.
+        for a, b in zip(o["W1"], ref_W1):
             a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-            scale = np.abs(b).max()
-            return np.mean(np.abs(a - b) > 2e-3 * scale) < 2e-3 and np.abs(a - b).max() < 6 * 0.01 * 1.01
-        for l in range(3):
-            assert close(o["W"][l], eng.tensor(gatx.T_W, l)), l
-        assert close(o["Wo"], eng.tensor(gatx.T_WO))
+            assert np.mean(np.abs(a - b) > 1e-5) < 2e-3 and np.abs(a - b).max() <= 2 * 0.01 * 1.001
     assert outs[0]["rows"][1] == outs[1]["rows"][0] and outs[1]["rows"][1] == 3000
     pred = np.concatenate([o["pred"] for o in outs])
     assert (pred != eng.tensor(gatx.T_PRED)).mean() < 0.01
