@@ -308,13 +308,12 @@ def run_gatx(args):
             blobs = [None] * world
             dist.all_gather_object(blobs, eng.peer_export())
             eng.peer_import(blobs)
-        tmode = os.environ.get("GATX_HALO_MODE", "bulk")
+        tmode = os.environ.get("GATX_HALO_MODE", "pull")
         halo = {"exchange": ("NVLink peer memory, pipelined over row blocks under the edge passes, flag barriers in peer "
                              "memory; transport: " +
-                             {"sm": "ld / st push + scatter kernels (halo rows only)",
-                              "ce": "copy engines (peer-to-peer DMA of whole row blocks)"}.get(
-                                 tmode, "bulk-copy (TMA) push + scatter kernels: global -> shared ring -> peer global, halo "
-                                        "rows only"))
+                             ("bulk-copy (TMA) push + scatter kernels (global -> shared ring -> peer global), staging + local "
+                              "ordered sum" if tmode == "bulk" else "ld / st kernels: owner pushes P_l rows (forward), owner "
+                              "pulls and sums partial gP_l rows in rank order (backward); halo rows only"))
                 if eng.halo_active() else "nccl broadcast/reduce",
                 "rows_pushed_per_layer_rank0": push_rows,
                 "allgather_rows_rank0": (world - 1) * (info["row_end"] - info["row_begin"])}

@@ -176,9 +176,7 @@ struct ScatterPlan {
   int owner[kMaxPeers];         // rank that owns the segment's rows
   float* dst[kMaxPeers];        // owner's staging slot of THIS rank: [owner's n_rows][F]
 };
-int launch_halo_scatter(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan, cudaStream_t st,
-                        int max_ctas);
-// bulk-copy (TMA) transport of the same two steps: one elected lane per warp moves whole rows global -> shared -> peer
+// bulk-copy (TMA) transport (GATX_HALO_MODE=bulk): one lane per warp moves whole rows global -> shared ring -> peer global
 bool halo_bulk_supported(int F);
 int launch_halo_push_bulk(const float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers,
                           int me, cudaStream_t st, int max_ctas);
@@ -186,7 +184,9 @@ int launch_halo_scatter_bulk(const float* partial, int F, const unsigned char* m
                              const PeerPtrs& stage_base, int me, cudaStream_t st, int max_ctas);
 int launch_halo_sum(float* own_rows, int row_off, int n_rows, int n_rows_total, int F, const uint16_t* ref_mask,
                     const float* stage, int me, int world, cudaStream_t st);
-int halo_cta_slots();  // CTA slots of the exchange kernels (GATX_HALO_CTAS, default 48)
+int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
+                     int world, cudaStream_t st, int max_ctas = 0);
+int halo_cta_slots();  // CTA slots of the exchange kernels (GATX_HALO_CTAS, default 148)
 // Device-side barrier across ranks through flags in peer memory: rank `me` stores `seq` (release, system scope) into
 // slot `me` of every peer's flag array, then waits (acquire) until every slot of its own array has reached `seq`.
 // Stream-ordered: everything this rank enqueued before it on `st` (and its peer-memory stores) is visible to a peer

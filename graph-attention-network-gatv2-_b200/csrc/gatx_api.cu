@@ -170,15 +170,11 @@ struct gatx_ctx {
   std::vector<void*> ipc_opened;
   // exchange stream + flag barriers in peer memory (halo_p2p.cu)
   cudaStream_t st_comm = nullptr;
-  // Default transport of the exchange: the copy engines.  Block by block, the own rows of P_l (forward) and this rank's
-  // partial gP_l rows (backward) are contiguous ranges, so they travel as peer-to-peer cudaMemcpyAsync on kCeStreams DMA
-  // streams and use NO SM: kernels that drive NVLink from the SMs need a third of the SMs' warps in flight to cover the
-  // link's round trip, which costs the concurrently running edge pass as much as it hides (measured on 8 GPUs).
-  // GATX_HALO_MODE=sm selects the SM kernels (halo-only push / scatter, fewer bytes) instead.
-  static constexpr int kCeStreams = 8;
-  cudaStream_t st_ce[kCeStreams] = {};
-  bool halo_ce = false;   // GATX_HALO_MODE=ce
-  bool halo_bulk = true;  // default: bulk-copy (TMA) kernels; GATX_HALO_MODE=sm selects the ld / st kernels
+  // Transport of the exchange.  Default: ld / st kernels -- forward the owner pushes its rows into the peers that gather
+  // them, backward the owner pulls and sums the peers' partial rows.  GATX_HALO_MODE=bulk: bulk-copy (TMA) kernels in both
+  // directions (forward push, backward scatter into the owners' staging buffers + a local ordered sum).
+  bool halo_bulk = false;
+  PeerPtrs peer_gPl{};
   uint32_t* halo_flags = nullptr;  // [kMaxPeers] slot p: the last barrier rank p has reached
   PeerFlags peer_flags{};
   uint32_t barrier_seq = 0;
@@ -615,42 +611,6 @@ int comm_barrier(gatx_ctx* ctx) {
   LAUNCHED(launch_halo_barrier(ctx->peer_flags, ctx->rank, ctx->world, ctx->barrier_seq, ctx->st_comm));
   return GATX_OK;
 }
-// DMA transport.  One peer copy = `rows` rows of pitch F; a single copy engine moves ~430 GB/s over NVLink 5 (measured),
-// so a copy is cut into row ranges issued on different DMA streams when there are fewer peers than streams.  No SM is used.
-int ce_copy_rows(gatx_ctx* ctx, float* dst, const float* src, int64_t rows, int F, int dir, int* rr) {
-  if (rows <= 0) return GATX_OK;
-  int pieces = gatx_ctx::kCeStreams / (ctx->world - 1);
-  if (pieces < 1) pieces = 1;
-  if ((int64_t)pieces > rows) pieces = (int)rows;
-  for (int q = 0; q < pieces; ++q) {
-    const int64_t a = rows * q / pieces, b = rows * (q + 1) / pieces;
-    const size_t bytes = sizeof(float) * (size_t)(b - a) * F;
-    const int lane = ((*rr)++ + ctx->rank) % gatx_ctx::kCeStreams;
-    cudaStream_t s = ctx->st_ce[lane];
-    size_t span = (size_t)-1;
-    if (ctx->timing) {
-      if (ctx->comm_spans_used == ctx->comm_spans.size()) {
-        gatx_ctx::CommSpan sp{dir, 0.0, nullptr, nullptr};
-        cudaEventCreate(&sp.a);
-        cudaEventCreate(&sp.b);
-        ctx->comm_spans.push_back(sp);
-      }
-      span = ctx->comm_spans_used++;
-      ctx->comm_spans[span].dir = dir;
-      ctx->comm_spans[span].bytes = (double)bytes;
-      ctx->comm_spans[span].lane = lane;
-      cudaEventRecord(ctx->comm_spans[span].a, s);
-    }
-    CK(cudaMemcpyAsync(dst + a * F, src + a * F, bytes, cudaMemcpyDeviceToDevice, s));
-    if (span != (size_t)-1) cudaEventRecord(ctx->comm_spans[span].b, s);
-  }
-  return GATX_OK;
-}
-// the exchange stream continues only after every DMA stream has drained
-void comm_waits_ce(gatx_ctx* ctx) {
-  for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_comm, ctx->st_ce[k]);
-}
-
 // timing of the exchange kernels themselves (on st_comm): bytes over NVLink and busy time per direction
 struct CommTimer {
   gatx_ctx* c;
@@ -726,7 +686,7 @@ RowView row_view(const gatx_ctx* ctx, int b) {
   v.g.col_idx_hot = ctx->col_idx_hot ? ctx->col_idx_hot + B.e0 : nullptr;
   v.g.heavy_rows = nullptr; v.g.n_heavy_rows = 0;
   // SM transport: the exchange kernels of the neighbouring block run underneath this launch in their own CTA slots
-  v.g.reserve_ctas = ctx->halo_ce ? 0 : halo_cta_slots();
+  v.g.reserve_ctas = halo_cta_slots();
   return v;
 }
 // the streaming kernels take any view; the warp-per-row / generic kernels only the whole row range
@@ -857,8 +817,6 @@ int do_forward(gatx_ctx* ctx) {
     // first row of this forward is pushed into its buffers
     stream_after(ctx, ctx->st_comm, ctx->st);
     if ((rc = comm_barrier(ctx))) return rc;
-    if (ctx->halo_ce)
-      for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_ce[k], ctx->st_comm);
   }
   {
     PhaseTimer t(ctx, PH_GEMM_FWD);
@@ -943,14 +901,7 @@ int do_forward(gatx_ctx* ctx) {
           rc = gemm_project(ctx, Xb, nx.ldx, nx, nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, nx.Pr + (int64_t)v.rb * nx.F, v.nb);
           if (rc) return rc;
         }
-        if (ctx->halo_ce) {
-          const int64_t off = (int64_t)(ctx->r0 + v.rb) * nx.F;
-          for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_ce[k], ctx->st);  // the block's GEMM is done
-          int rr = 0;
-          for (int p = 0; p < ctx->world; ++p)
-            if (p != ctx->rank && (rc = ce_copy_rows(ctx, ctx->peer_Pl[l + 1].p[p] + off, nx.Pl + off, v.nb, nx.F, 0, &rr)))
-              return rc;
-        } else {
+        {
           stream_after(ctx, ctx->st_comm, ctx->st);
           CommTimer ct(ctx, 0, (double)ctx->blocks[b].halo_rows * nx.F * 4.0);
           if (ctx->halo_bulk && halo_bulk_supported(nx.F))
@@ -962,7 +913,6 @@ int do_forward(gatx_ctx* ctx) {
                                       ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm, halo_cta_slots()));
         }
       }
-      if (ctx->halo_ce) comm_waits_ce(ctx);
       if ((rc = comm_barrier(ctx))) return rc;  // every rank's pushes have landed
       compute_waits_comm(ctx);
     }
@@ -1078,6 +1028,57 @@ int do_backward(gatx_ctx* ctx) {
       }
       continue;
     }
+    if (!(ctx->halo_bulk && halo_bulk_supported(ly.F))) {
+      // Peer-memory exchange, pipelined over blocks of own rows: (exchange stream) the owner pulls and sums the peers'
+      // partial gP_l rows of block b; (compute stream) input-gradient GEMM of block b, then prep + pass 1 of the layer
+      // BELOW on block b -- while the pull of block b + 1 is in flight.
+      stream_after(ctx, ctx->st_comm, ctx->st);
+      if ((rc = comm_barrier(ctx))) return rc;  // every rank's partial sums are complete
+      {
+        PhaseTimer t(ctx, PH_GEMM_BWD);  // needs nothing from the exchange: runs under the barrier and the first pull
+        rc = gemm_nt_reduce(ctx, gPr, ly.F, X, ly.ldx, gW + ly.I, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+        if (rc) return rc;
+      }
+      const bool fuse_p1 = l > 0 && blockable(ctx, l - 1);
+      const int nblk = (int)ctx->blocks.size();
+      for (int b = 0; b < nblk; ++b) {
+        const RowView v = row_view(ctx, b);
+        if (v.nb <= 0) continue;
+        {
+          CommTimer ct(ctx, 1, (double)ctx->blocks[b].halo_rows * ly.F * 4.0);
+          LAUNCHED(launch_halo_pull(ctx->gPl + (int64_t)(ctx->r0 + v.rb) * ly.F, ctx->r0 + v.rb, v.nb, ly.F,
+                                    ctx->ref_mask + v.rb, ctx->peer_gPl, ctx->rank, ctx->world, ctx->st_comm,
+                                    halo_cta_slots()));
+        }
+        compute_waits_comm(ctx);
+        if (l > 0) {
+          Layer& prev = ctx->layers[l - 1];
+          {
+            PhaseTimer t(ctx, PH_GEMM_BWD);
+            float* gXb = prev.gH + (int64_t)v.rb * prev.F;
+            rc = gemm_input_grad(ctx, gPl_own + (int64_t)v.rb * ly.F, gPr + (int64_t)v.rb * ly.F, ly, gXb, prev.F, v.nb);
+            if (rc) return rc;
+            if (drop)
+              LAUNCHED(launch_dropout(gXb, prev.F, gXb, prev.F, v.nb, ly.I, ctx->r0 + v.rb, ctx->p_drop, ctx->drop_seed, l,
+                                      ctx->drop_step, ctx->st));
+          }
+          if (fuse_p1) {
+            PhaseTimer t(ctx, PH_EDGE_BWD);
+            if ((rc = bwd_edge(ctx, l - 1, v, 1))) return rc;
+          }
+        }
+      }
+      if (fuse_p1) p1_done[l - 1] = 1;
+      if ((rc = comm_barrier(ctx))) return rc;  // every owner has pulled: the peers may overwrite their gP_l scratch
+      {
+        PhaseTimer t(ctx, PH_GEMM_BWD);
+        rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
+        if (rc) return rc;
+      }
+      compute_waits_comm(ctx);  // before the next pass 2 writes into the scratch the peers were reading
+
+      continue;
+    }
     // Peer-memory exchange, pipelined over blocks of own rows.  Exchange stream: every rank scatters its partial gP_l
     // rows of block b (of every owner) into the owners' staging buffers, then a flag barrier.  Compute stream: the owner
     // adds its own and the staged partials of block b in rank order (local memory), input-gradient GEMM of block b, then
@@ -1093,20 +1094,7 @@ int do_backward(gatx_ctx* ctx) {
     const int nblk = (int)ctx->blocks.size();
     for (int b = 0; b < nblk; ++b) {
       const RowView v = row_view(ctx, b);
-      if (ctx->halo_ce) {
-        // this rank's partial rows of block b of every owner: one contiguous DMA copy per owner into its staging slot
-        if (b == 0)  // behind the barrier that opened this exchange; later blocks follow in stream order
-          for (int k = 0; k < gatx_ctx::kCeStreams; ++k) stream_after(ctx, ctx->st_ce[k], ctx->st_comm);
-        int rr = 0;
-        for (int p = 0; p < ctx->world; ++p) {
-          if (p == ctx->rank) continue;
-          const int* ab = ctx->all_blk.data() + (size_t)p * (nblk + 1);
-          float* dst = ctx->peer_stage.p[p] +
-                       ((int64_t)ctx->rank * (ctx->bounds[p + 1] - ctx->bounds[p]) + (ab[b] - ctx->bounds[p])) * ly.F;
-          if ((rc = ce_copy_rows(ctx, dst, ctx->gPl + (int64_t)ab[b] * ly.F, ab[b + 1] - ab[b], ly.F, 1, &rr))) return rc;
-        }
-        comm_waits_ce(ctx);
-      } else {
+      {
         ScatterPlan plan{};
         for (int p = 0; p < ctx->world; ++p) {
           if (p == ctx->rank) continue;
@@ -1120,11 +1108,8 @@ int do_backward(gatx_ctx* ctx) {
           plan.dst[sg] = ctx->peer_stage.p[p] + (int64_t)ctx->rank * (ctx->bounds[p + 1] - ctx->bounds[p]) * ly.F;
         }
         CommTimer ct(ctx, 1, (double)ctx->scatter_rows[b] * ly.F * 4.0);
-        if (ctx->halo_bulk && halo_bulk_supported(ly.F))
-          LAUNCHED(launch_halo_scatter_bulk(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->peer_stage, ctx->rank, ctx->st_comm,
-                                            halo_cta_slots()));
-        else
-          LAUNCHED(launch_halo_scatter(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->st_comm, halo_cta_slots()));
+        LAUNCHED(launch_halo_scatter_bulk(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->peer_stage, ctx->rank, ctx->st_comm,
+                                          halo_cta_slots()));
       }
       if ((rc = comm_barrier(ctx))) return rc;  // block b of every rank's partial rows has landed at its owner
       compute_waits_comm(ctx);
@@ -1157,7 +1142,7 @@ int do_backward(gatx_ctx* ctx) {
       rc = gemm_nt_reduce(ctx, gPl_own, ly.F, X, ly.ldx, gW, 2 * ly.I, ly.F, ly.I, ctx->n_rows);
       if (rc) return rc;
     }
-  }
+    }
   return GATX_OK;
 }
 
@@ -1321,14 +1306,8 @@ int gatx_create(gatx_ctx** out, const gatx_config* cfg) {
       delete c;
       return GATX_ERR_CUDA;
     }
-    for (auto& s : c->st_ce)
-      if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) {
-        delete c;
-        return GATX_ERR_CUDA;
-      }
     const char* hm = getenv("GATX_HALO_MODE");
-    c->halo_ce = hm && std::string(hm) == "ce";
-    c->halo_bulk = !hm || std::string(hm) == "bulk";
+    c->halo_bulk = hm && std::string(hm) == "bulk";
   }
   *out = c;
   return GATX_OK;
@@ -1361,8 +1340,6 @@ void gatx_destroy(gatx_ctx* ctx) {
     cudaEventDestroy(s.b);
   }
   if (ctx->st_comm) cudaStreamDestroy(ctx->st_comm);
-  for (auto& s : ctx->st_ce)
-    if (s) cudaStreamDestroy(s);
   cudaStreamDestroy(ctx->st);
   delete ctx;
 }
@@ -2327,13 +2304,13 @@ struct PeerInfo {  // what one rank publishes; sizeof <= GATX_PEER_INFO_BYTES
   cudaIpcMemHandle_t handle[kPeerMaxBufs];
 };
 static_assert(sizeof(PeerInfo) <= GATX_PEER_INFO_BYTES, "PeerInfo must fit the public blob");
-constexpr int32_t kPeerMagic = 0x47585032;  // "GXP2"
+constexpr int32_t kPeerMagic = 0x47585033;  // "GXP3"
 }  // namespace
 
 int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes) {
   if (!ctx || !out || bytes < GATX_PEER_INFO_BYTES) return fail(ctx, GATX_ERR_INVALID, "bad peer_export");
   if (ctx->world < 2 || ctx->world > kMaxPeers) return fail(ctx, GATX_ERR_INVALID, "peer exchange needs 2..%d ranks", kMaxPeers);
-  if (ctx->L + 2 > kPeerMaxBufs) return fail(ctx, GATX_ERR_UNSUPPORTED, "too many layers for the peer blob");
+  if (ctx->L + 3 > kPeerMaxBufs) return fail(ctx, GATX_ERR_UNSUPPORTED, "too many layers for the peer blob");
   if (!ctx->my_ref) return fail(ctx, GATX_ERR_INVALID, "the graph was set for a single rank");
   CK(cudaSetDevice(ctx->device));
   int rc = ensure_buffers(ctx);
@@ -2345,14 +2322,16 @@ int gatx_peer_export(gatx_ctx* ctx, void* out, size_t bytes) {
   info.magic = kPeerMagic;
   info.pid = (int32_t)getpid();
   info.device = ctx->device;
-  info.n_bufs = ctx->L + 2;
+  info.n_bufs = ctx->L + 3;
   int64_t Fmax = 0;
   for (int l = 0; l < ctx->L; ++l) Fmax = ctx->layers[l].F > Fmax ? ctx->layers[l].F : Fmax;
-  for (int b = 0; b <= ctx->L + 1; ++b) {
-    // buffers: P_l of layer 0..L-1, the staging buffer of the backward exchange, the barrier flags
-    void* ptr = b < ctx->L ? (void*)ctx->layers[b].Pl : (b == ctx->L ? (void*)ctx->stage : (void*)ctx->halo_flags);
+  for (int b = 0; b <= ctx->L + 2; ++b) {
+    // buffers: P_l of layer 0..L-1, the staging buffer of the backward exchange, the barrier flags, the gP_l scratch
+    void* ptr = b < ctx->L ? (void*)ctx->layers[b].Pl
+                           : (b == ctx->L ? (void*)ctx->stage : (b == ctx->L + 1 ? (void*)ctx->halo_flags : (void*)ctx->gPl));
     info.n_floats[b] = b < ctx->L ? (int64_t)ctx->N * ctx->layers[b].F
-                                  : (b == ctx->L ? (int64_t)ctx->world * ctx->n_rows * Fmax : (int64_t)kMaxPeers);
+                                  : (b == ctx->L ? (int64_t)ctx->world * ctx->n_rows * Fmax
+                                                 : (b == ctx->L + 1 ? (int64_t)kMaxPeers : (int64_t)ctx->N * Fmax));
     info.raw[b] = (uint64_t)(uintptr_t)ptr;
     CK(cudaIpcGetMemHandle(&info.handle[b], ptr));
   }
@@ -2370,6 +2349,7 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
   CK(cudaSetDevice(ctx->device));
   ctx->peer_Pl.assign(ctx->L, PeerPtrs{});
   ctx->peer_stage = PeerPtrs{};
+  ctx->peer_gPl = PeerPtrs{};
   ctx->peer_flags = PeerFlags{};
   ctx->peer_flags.p[ctx->rank] = ctx->halo_flags;
   int64_t Fmax = 0;
@@ -2377,7 +2357,7 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
   for (int p = 0; p < ctx->world; ++p) {
     PeerInfo info;
     memcpy(&info, (const char*)all + (size_t)p * GATX_PEER_INFO_BYTES, sizeof info);
-    if (info.magic != kPeerMagic || info.n_bufs != ctx->L + 2)
+    if (info.magic != kPeerMagic || info.n_bufs != ctx->L + 3)
       return fail(ctx, GATX_ERR_INVALID, "peer blob of rank %d does not match this model", p);
     for (int b = 0; b <= ctx->L; ++b)
       if (info.n_floats[b] != (b < ctx->L ? (int64_t)ctx->N * ctx->layers[b].F
@@ -2395,7 +2375,7 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
         return fail(ctx, GATX_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
       cudaGetLastError();
     }
-    for (int b = 0; b <= ctx->L + 1; ++b) {
+    for (int b = 0; b <= ctx->L + 2; ++b) {
       void* q = nullptr;
       if (same_process) {
         q = (void*)(uintptr_t)info.raw[b];
@@ -2405,7 +2385,8 @@ int gatx_peer_import(gatx_ctx* ctx, const void* all, size_t bytes) {
       }
       if (b < ctx->L) ctx->peer_Pl[b].p[p] = (float*)q;
       else if (b == ctx->L) ctx->peer_stage.p[p] = (float*)q;
-      else ctx->peer_flags.p[p] = (uint32_t*)q;
+      else if (b == ctx->L + 1) ctx->peer_flags.p[p] = (uint32_t*)q;
+      else ctx->peer_gPl.p[p] = (float*)q;
     }
   }
   ctx->peers_ready = getenv("GATX_NO_P2P") == nullptr;
@@ -2429,17 +2410,15 @@ int gatx_halo_stats(gatx_ctx* ctx, double* out4) {
   CK(cudaStreamSynchronize(ctx->st));
   if (ctx->st_comm) CK(cudaStreamSynchronize(ctx->st_comm));
   out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
-  double lane_ms[2][gatx_ctx::kCeStreams] = {};
+  double lane_ms[2][1] = {};
   for (size_t i = 0; i < ctx->comm_spans_used; ++i) {
     float ms = 0.f;
     const auto& s = ctx->comm_spans[i];
     if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) continue;
     out4[2 * s.dir] += s.bytes;
-    lane_ms[s.dir][s.lane % gatx_ctx::kCeStreams] += ms;
+    lane_ms[s.dir][0] += ms;
   }
-  // the DMA streams run side by side: the busy time of a direction is that of its busiest stream
-  for (int d = 0; d < 2; ++d)
-    for (int k = 0; k < gatx_ctx::kCeStreams; ++k) out4[2 * d + 1] = std::max(out4[2 * d + 1], lane_ms[d][k]);
+  for (int d = 0; d < 2; ++d) out4[2 * d + 1] = lane_ms[d][0];
   cudaGetLastError();
   return GATX_OK;
 }

@@ -7,12 +7,12 @@
 //             that never gather the row do not receive it.  On the products-shaped R-MAT graph a rank references
 //             93 / 82 / 67 % of all sources at 2 / 4 / 8 ranks, so the halo moves 0.86 / 0.76 / 0.63 of the bytes an
 //             all-gather moves.
-//   backward: every rank holds partial sums gP_l[src] over ITS edges for all sources it references.  halo_scatter_kernel
-//             stores the rows owned by other ranks into the owners' staging buffers (posted NVLink stores: remote
-//             LOADS would need ~2 MB in flight per GPU to cover the NVLink round trip, i.e. a third of the SMs);
-//             halo_sum_kernel then adds, on the owner and from local memory, its own partial and the staged ones in
-//             ascending rank order -- a fixed order, so the result is reproducible run to run (NCCL's reduction tree
-//             gives no such promise across topologies).
+//   backward: every rank holds partial sums gP_l[src] over ITS edges for all sources it references.  Default
+//             (halo_pull_kernel): the owner of a row reads the partial rows of exactly the peers whose mask bit is set
+//             and adds them in ascending rank order -- a fixed order, so the result is reproducible run to run (NCCL's
+//             reduction tree gives no such promise across topologies).  Alternative (GATX_HALO_MODE=bulk): the senders
+//             scatter their partial rows into the owners' staging buffers with bulk copies (posted stores only) and
+//             halo_sum_kernel adds them on the owner, from local memory, in the same rank order.
 // Both kernels are one warp per row with 128-bit accesses; rows are 0.5-2 KB, NVLink sees full-line transfers.
 // Ordering between ranks is by halo_barrier_kernel: flags in peer memory (st.release.sys / ld.acquire.sys), one
 // 32-thread CTA per barrier on the exchange stream -- no NCCL call, no host involvement.  The exchange runs on a stream
@@ -210,49 +210,62 @@ halo_bulk_kernel(BulkJob job) {
   __threadfence_system();
 }
 
-// Backward exchange, sender side: this rank holds partial sums gP_l[src] over ITS edges for every source it references.
-// For the sources owned by other ranks it stores the partial row into slot `me` of the owner's staging buffer
-// (stage[sender][local row][F]) -- posted NVLink stores only, no remote loads, so a few hundred warps keep the link
-// busy.  One launch covers one row block of every owner (the plan lists the global row range of that block per owner).
+// One warp per own row.  The peers that hold a partial row are visited in ascending rank order (a fixed order: the sum
+// is reproducible), software-pipelined: the loads of the next contributing peer are in flight while the current one is
+// added, so a warp keeps two remote 2 KB reads outstanding instead of one (NVLink round trips are ~3 us).
 __global__ void __launch_bounds__(256, 4)
-halo_scatter_kernel(const float* __restrict__ partial, int F, const unsigned char* __restrict__ my_ref, ScatterPlan plan) {
+halo_pull_kernel(float* __restrict__ own_rows, int r0, int n_rows, int F, const uint16_t* __restrict__ ref_mask,
+                 PeerPtrs peers, int me, int world) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int total = plan.cum[plan.n_seg];
-  for (int tA = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tA < total; tA += 2 * warps) {
-    const float *src[2] = {nullptr, nullptr};
-    float* dst[2] = {nullptr, nullptr};
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+    const uint32_t m = ref_mask[row];
+    if ((m & ~(1u << me)) == 0) continue;  // only this rank (or nobody) touches the row: already complete
+    float* mine = own_rows + (int64_t)row * F;
+    const int64_t off = (int64_t)(r0 + row) * F;
+    for (int k0 = 0; k0 < F; k0 += 512) {
+      float4 acc[4], nxt[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = tA + u * warps;
-      if (t >= total) continue;
-      int sgm = 0;
-      while (t >= plan.cum[sgm + 1]) ++sgm;
-      const int row = plan.row0[sgm] + (t - plan.cum[sgm]);  // global source row, owned by the segment's rank
-      if (!my_ref[row]) continue;                            // none of this rank's edges gathers it: nothing to send
-      src[u] = partial + (int64_t)row * F;
-      dst[u] = plan.dst[sgm] + (int64_t)(row - plan.owner_row0[sgm]) * F;
-    }
-    if (!src[0] && !src[1]) continue;
-    for (int k0 = 0; k0 < F; k0 += 512) {  // both rows' loads (up to 4 KB per warp) in flight before the stores
-      float4 v[2][4];
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t mm = m;
+      int p = __ffs(mm) - 1;
+      mm &= mm - 1;
+      {
+        const float* src = p == me ? mine : peers.p[p] + off;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + 4 * (lane + 32 * j);
-          if (k < F && src[u]) v[u][j] = ldg4(src[u] + k);
+          nxt[j] = k < F ? ld_sys4(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);  // peer memory: system-scope load
         }
+      }
+      while (true) {
+        float4 cur[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        const bool more = mm != 0;
+        if (more) {
+          p = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const float* src = p == me ? mine : peers.p[p] + off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 4 * (lane + 32 * j);
+            nxt[j] = k < F ? ld_sys4(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int k = k0 + 4 * (lane + 32 * j);
-          if (k < F && src[u]) st4(dst[u] + k, v[u][j]);
+          acc[j].x += cur[j].x; acc[j].y += cur[j].y; acc[j].z += cur[j].z; acc[j].w += cur[j].w;
         }
+        if (!more) break;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + 4 * (lane + 32 * j);
+        if (k < F) st4(mine + k, acc[j]);
+      }
     }
   }
-  __threadfence_system();
 }
 
 // Backward exchange, owner side (local memory only): own row = own partial + the staged partials of the ranks whose
@@ -328,8 +341,8 @@ int launch_halo_barrier(const PeerFlags& flags, int me, int world, uint32_t seq,
 int halo_cta_slots() {
   static const int n = [] {
     const char* e = getenv("GATX_HALO_CTAS");
-    const int v = e ? atoi(e) : 48;
-    return v >= 4 && v <= kNumSMs * 2 ? v : 48;
+    const int v = e ? atoi(e) : kNumSMs;
+    return v >= 4 && v <= kNumSMs * 2 ? v : kNumSMs;
   }();
   return n;
 }
@@ -386,12 +399,11 @@ int launch_halo_scatter_bulk(const float* partial, int F, const unsigned char* m
   return launch_bulk(job, st, max_ctas);
 }
 
-int launch_halo_scatter(const float* partial, int F, const unsigned char* my_ref, const ScatterPlan& plan, cudaStream_t st,
-                        int max_ctas) {
-  const int total = plan.cum[plan.n_seg];
-  if (total <= 0) return 0;
-  prefer_max_shared(halo_scatter_kernel);
-  halo_scatter_kernel<<<halo_blocks(total, max_ctas), 256, 0, st>>>(partial, F, my_ref, plan);
+int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
+                     int world, cudaStream_t st, int max_ctas) {
+  if (n_rows <= 0) return 0;
+  prefer_max_shared(halo_pull_kernel);
+  halo_pull_kernel<<<halo_blocks(n_rows, max_ctas), 256, 0, st>>>(own_rows, r0, n_rows, F, ref_mask, peers, me, world);
   return 1;
 }
 

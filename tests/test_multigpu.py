@@ -76,13 +76,13 @@ def _worker(rank, world, idfile, q, mode, p2p):
     eng.close()
 
 
-@pytest.mark.parametrize("p2p,transport", [(3, "bulk"), (3, "sm"), (3, "ce"), (1, "bulk"), (0, "nccl")],
-                         ids=["peer-memory-3-blocks-bulk-copy", "peer-memory-3-blocks-ld-st", "peer-memory-3-blocks-dma",
-                              "peer-memory-1-block-bulk-copy", "nccl"])
+@pytest.mark.parametrize("p2p,transport", [(3, "pull"), (3, "bulk"), (1, "pull"), (0, "nccl")],
+                         ids=["peer-memory-3-blocks-push-pull", "peer-memory-3-blocks-bulk-copy", "peer-memory-1-block-push-pull",
+                              "nccl"])
 @pytest.mark.parametrize("world", [2])
 def test_two_ranks_match_one(world, p2p, transport, monkeypatch):
-    """p2p = number of row blocks of the pipelined peer-memory exchange (0: NCCL collectives); transport = bulk-copy (TMA)
-    kernels (default), ld / st kernels, or the copy engines.  With 3 blocks the 3 000-node problem exercises the block views of the
+    """p2p = number of row blocks of the pipelined peer-memory exchange (0: NCCL collectives); transport = ld / st push + pull
+    kernels (default) or the bulk-copy (TMA) push + scatter kernels with staging buffers and a local ordered sum.  With 3 blocks the 3 000-node problem exercises the block views of the
     streaming kernels (rebased row_ptr, per-block chunk tables, rows cut by block-local chunk boundaries), the exchange
     streams, the flag barriers, the staging buffers of the backward exchange and the double-buffered gP_r."""
     if torch.cuda.device_count() < world:
