@@ -1361,6 +1361,26 @@ int gatx_partition_rows(int32_t num_nodes, const int32_t* row_ptr, int32_t world
   return GATX_OK;
 }
 
+int gatx_row_blocks(int32_t num_nodes, const int32_t* row_ptr, int32_t world, int32_t num_blocks, int32_t* out) {
+  if (num_nodes < 0 || !row_ptr || world < 1 || num_blocks < 1 || !out) return GATX_ERR_INVALID;
+  std::vector<int32_t> bounds((size_t)world + 1);
+  gatx_partition_rows(num_nodes, row_ptr, world, bounds.data());
+  const int K = num_blocks;
+  for (int p = 0; p < world; ++p) {
+    const int b0 = bounds[p], b1 = bounds[p + 1];
+    const int64_t base = row_ptr[b0], ep = (int64_t)row_ptr[b1] - base;
+    int32_t* ab = out + (size_t)p * (K + 1);
+    ab[0] = b0;
+    ab[K] = b1;
+    for (int k = 1, i = b0; k < K; ++k) {  // first own row whose edge offset reaches k E_p / K
+      const int64_t target = ep * (int64_t)k / K;
+      while (i < b1 && (int64_t)row_ptr[i] - base < target) ++i;
+      ab[k] = i;
+    }
+  }
+  return GATX_OK;
+}
+
 int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_ptr, const int32_t* col_idx) {
   if (!ctx || N <= 0 || E < 0 || !row_ptr || (E > 0 && !col_idx)) return fail(ctx, GATX_ERR_INVALID, "bad graph");
   if (row_ptr[0] != 0 || (int64_t)row_ptr[N] != E) return fail(ctx, GATX_ERR_INVALID, "row_ptr[N] != num_edges");
@@ -1472,18 +1492,7 @@ int gatx_set_graph_csr(gatx_ctx* ctx, int32_t N, int64_t E, const int32_t* row_p
     if (K > min_rows) K = min_rows > 0 ? min_rows : 1;
     // every rank's blocks (global rows): rank p's block k starts at the first own row whose edge offset >= k E_p / K
     ctx->all_blk.assign((size_t)ctx->world * (K + 1), 0);
-    for (int p = 0; p < ctx->world; ++p) {
-      const int b0 = ctx->bounds[p], b1 = ctx->bounds[p + 1];
-      const int64_t base = row_ptr[b0], ep = (int64_t)row_ptr[b1] - base;
-      int* ab = ctx->all_blk.data() + (size_t)p * (K + 1);
-      ab[0] = b0;
-      ab[K] = b1;
-      for (int k = 1, i = b0; k < K; ++k) {
-        const int64_t target = ep * (int64_t)k / K;
-        while (i < b1 && (int64_t)row_ptr[i] - base < target) ++i;
-        ab[k] = i;
-      }
-    }
+    gatx_row_blocks(N, row_ptr, ctx->world, K, ctx->all_blk.data());
     ctx->blocks.assign(K, gatx_ctx::RowBlock{});
     const int* rbg = ctx->all_blk.data() + (size_t)ctx->rank * (K + 1);
     std::vector<int> brp;

@@ -21,7 +21,7 @@ PHASES = ("gemm_fwd", "edge_fwd", "head", "edge_bwd", "gemm_bwd", "optimizer", "
 
 EXPORTS = [
     "gatx_create", "gatx_destroy", "gatx_last_error", "gatx_version", "gatx_set_graph_csr",
-    "gatx_set_features", "gatx_set_labels", "gatx_graph_info", "gatx_partition_rows", "gatx_init_params",
+    "gatx_set_features", "gatx_set_labels", "gatx_graph_info", "gatx_partition_rows", "gatx_row_blocks", "gatx_init_params",
     "gatx_set_params", "gatx_set_wo", "gatx_forward", "gatx_loss_acc", "gatx_backward", "gatx_step",
     "gatx_train_epoch", "gatx_sync", "gatx_tensor_size", "gatx_get_tensor", "gatx_enable_timing",
     "gatx_get_timing", "gatx_get_edge_kernel_ms", "gatx_timer_start", "gatx_timer_stop", "gatx_launch_count", "gatx_edge_bytes", "gatx_state_size", "gatx_get_state", "gatx_set_state", "gatx_set_train_mask", "gatx_evaluate", "gatx_op_gemm", "gatx_op_edge_fwd", "gatx_op_edge_bwd", "gatx_op_softmax_ce", "gatx_op_optimizer",
@@ -94,6 +94,18 @@ def partition_rows(row_ptr, world):
     if rc:
         raise GatxError("gatx_partition_rows failed: %d" % rc)
     return b
+
+
+def row_blocks(row_ptr, world, num_blocks):
+    """[world][num_blocks + 1] global row bounds of every rank's exchange blocks."""
+    row_ptr = np.ascontiguousarray(row_ptr, np.int32)
+    out = np.empty((world, num_blocks + 1), np.int32)
+    lib = load()
+    lib.gatx_row_blocks.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    rc = lib.gatx_row_blocks(len(row_ptr) - 1, row_ptr.ctypes.data, world, num_blocks, out.ctypes.data)
+    if rc:
+        raise GatxError("gatx_row_blocks failed: %d" % rc)
+    return out
 
 
 def op_gemm(A, B, form=0, mode=GEMM_TF32_TC):

@@ -136,6 +136,12 @@ int gatx_graph_info(gatx_ctx* ctx, int32_t* max_degree, int32_t* num_classes,
 int gatx_partition_rows(int32_t num_nodes, const int32_t* row_ptr, int32_t world,
                         int32_t* bounds);
 
+/* Blocks of the pipelined exchange (host-side helper, new work: the reference is single-GPU): every rank's own rows
+ * [bounds[p], bounds[p+1]) cut into num_blocks edge-balanced blocks, out[p][k] = first GLOBAL row of block k of rank p,
+ * out[p][num_blocks] = bounds[p+1].  The block table is part of the exchange protocol (every rank derives the same one
+ * from the global row_ptr).  out holds world * (num_blocks + 1) entries. */
+int gatx_row_blocks(int32_t num_nodes, const int32_t* row_ptr, int32_t world, int32_t num_blocks, int32_t* out);
+
 /* ---- parameters ------------------------------------------------------------------------- */
 /* Replaces setup_states_kernel + xavier_init_kernel_curand (EB:181-248, launch EB:1300-1323):
  * same distributions (limits EB:208, EB:236), counter-based and reproducible from `seed`. */

@@ -307,3 +307,19 @@ def attn_dropout_scale(H, E, p, seed, layer, step):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def row_blocks(row_ptr, R, K):
+    """Blocks of the pipelined multi-GPU exchange (new work; bit-exact target for gatx_row_blocks): rank p's own rows cut
+    into K edge-balanced blocks, out[p][k] = first own row whose edge offset (relative to the rank's first edge) reaches
+    floor(k E_p / K).  Independent numpy formulation (searchsorted on the rebased row_ptr)."""
+    b = partition_rows(row_ptr, R).astype(np.int64)
+    rp = np.asarray(row_ptr, np.int64)
+    out = np.empty((R, K + 1), np.int32)
+    for p in range(R):
+        base, ep = rp[b[p]], rp[b[p + 1]] - rp[b[p]]
+        targets = ep * np.arange(K + 1, dtype=np.int64) // K
+        rel = rp[b[p]:b[p + 1] + 1] - base
+        out[p] = b[p] + np.searchsorted(rel[:-1] if len(rel) > 1 else rel, targets, side="left")
+        out[p][0], out[p][K] = b[p], b[p + 1]
+    return out

@@ -48,6 +48,25 @@ def test_partition_rows_bit_exact(lib, orc, R):
     assert np.array_equal(gatx.partition_rows(row_ptr, R), orc.partition_rows(row_ptr, R))
 
 
+@pytest.mark.parametrize("R", [1, 2, 3, 8])
+@pytest.mark.parametrize("K", [1, 3, 4])
+def test_row_blocks_bit_exact(lib, orc, R, K):
+    """Block table of the pipelined multi-GPU exchange: every rank derives the same table from the global row_ptr, so it
+    must be bit-exact (against an independent numpy formulation), cover every own row exactly once and balance EDGES."""
+    import gatx
+    for N, E, kind in ((3000, 40000, "rmat"), (97, 97, "uniform"), (500, 9000, "uniform")):
+        row_ptr, _ = datasets.make_graph(N, E, kind, 11)
+        blk = gatx.row_blocks(row_ptr, R, K)
+        assert np.array_equal(blk, orc.row_blocks(row_ptr, R, K))
+        bounds = orc.partition_rows(row_ptr, R)
+        assert np.array_equal(blk[:, 0], bounds[:-1]) and np.array_equal(blk[:, -1], bounds[1:])
+        assert (np.diff(blk, axis=1) >= 0).all()
+        if kind == "uniform" and N == 500:  # a flat degree distribution: blocks within two rows' worth of the ideal
+            edges = np.diff(np.asarray(row_ptr, np.int64)[blk], axis=1)
+            ideal = edges.sum(1, keepdims=True) / K
+            assert (np.abs(edges - ideal) <= 2 * np.diff(row_ptr).max() + 1).all()
+
+
 def test_sass_is_sm100a_only(lib):
     import subprocess
     import gatx
