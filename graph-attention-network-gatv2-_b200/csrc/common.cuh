@@ -127,7 +127,8 @@ int launch_edge_forward_stream(const EdgeGraph& g, int H, int D, const float* Pl
                                float* Hout, float* hpre, float* score, float* mx, float* sinv, float* part,
                                cudaStream_t st);
 // phases bit 0: prep (g_h in place + cdot) + pass 1 (gPr, rec, ga partials) over g's destination rows;
-// bit 1: pass 2 (gPl) over g's sources.  The multi-GPU epoch runs pass 1 per block of destination rows (a block is
+// bit 1: pass 2 (gPl) over g's sources; bit 2 (with bit 0): skip the prep, g_h already holds the pre-activation gradient
+// and cdot the segment sums (written by the input-gradient GEMM's fused epilogue, gemm_tc.cuh GemmFuse).  The multi-GPU epoch runs pass 1 per block of destination rows (a block is
 // an EdgeGraph of its own: rebased row_ptr, its own chunks, pointers offset to the block) and pass 2 once.
 int launch_edge_backward_stream(const EdgeGraph& g, int H, int D, const float* Pl, const float* Pr, const float* a,
                                 const float* Hout, float* gH, float* cdot, const float* score, const float* mx,
@@ -186,7 +187,7 @@ int launch_halo_sum(float* own_rows, int row_off, int n_rows, int n_rows_total, 
                     const float* stage, int me, int world, cudaStream_t st);
 int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
                      int world, cudaStream_t st, int max_ctas = 0);
-int halo_cta_slots();  // CTA slots of the exchange kernels (GATX_HALO_CTAS, default 148)
+int halo_cta_slots(int world);  // CTA slots of the exchange kernels (GATX_HALO_CTAS; default 20 per peer, at most 148)
 // Device-side barrier across ranks through flags in peer memory: rank `me` stores `seq` (release, system scope) into
 // slot `me` of every peer's flag array, then waits (acquire) until every slot of its own array has reached `seq`.
 // Stream-ordered: everything this rank enqueued before it on `st` (and its peer-memory stores) is visible to a peer

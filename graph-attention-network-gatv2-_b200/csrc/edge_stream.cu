@@ -993,6 +993,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   sh.slopes = eg.slopes;
   sh.bias = eg.bias;
   const bool do_p1 = (phases & 1) != 0, do_p2 = (phases & 2) != 0;
+  const bool prepared = (phases & 4) != 0;  // the input-gradient GEMM's epilogue already wrote g_pre and cdot
   if (do_p1) *n_partials = 0;
   if (eg.n_rows <= 0 && !do_p2) return 0;
   if (eg.n_rows <= 0 && eg.n_src <= 0) return 0;
@@ -1006,9 +1007,12 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
     if (do_p1 && eg.n_rows > 0) {
       int blocks = (eg.n_rows + 7) / 8;
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-      edge_bwd_prep_kernel<1><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+      if (!prepared) {
+        edge_bwd_prep_kernel<1><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+        ++launches;
+      }
       fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);
-      launches += 2;
+      ++launches;
     }
     if (do_p2) {
       fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);
@@ -1054,9 +1058,12 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
     if (do_p1 && eg.n_rows > 0) {
       int blocks = (eg.n_rows + 7) / 8;
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-      edge_bwd_prep_kernel<NV><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+      if (!prepared) {
+        edge_bwd_prep_kernel<NV><<<blocks, 256, 0, st>>>(eg.n_rows, sh, Hout, gH, cdot);
+        ++launches;
+      }
       fill_empty_rows_kernel<<<(eg.n_rows + 255) / 256, 256, 0, st>>>(eg.row_ptr, eg.n_rows, F, gPr);  // 8 warps x 32 rows
-      launches += 2;
+      ++launches;
     }
     if (do_p2) {
       fill_empty_rows_kernel<<<(eg.n_src + 255) / 256, 256, 0, st>>>(eg.csc_ptr, eg.n_src, F, gPl);

@@ -65,6 +65,7 @@ struct Layer {
   float *galpha_dbg = nullptr, *gPl_dbg = nullptr, *gPr_dbg = nullptr, *alpha_dbg = nullptr, *ge_dbg = nullptr;
   cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool kev_fwd = false, kev_bwd = false;  // recorded since timing was enabled
+  bool gh_prepared = false;  // the input-gradient GEMM above already wrote g_pre into gH and the segment sums into cdot
 };
 
 }  // namespace
@@ -539,9 +540,21 @@ int gemm_tn_any(gatx_ctx* ctx, const float* A, int64_t lda, const float* B, int6
   return GATX_OK;
 }
 // gX[n][i] = sum_r gP_l[n][r] W_l[r][i] + gP_r[n][r] W_r[r][i]   (WcatT is [I][2F]) for `rows` rows
+// `fuse` (optional): epilogue that turns the tile into the pre-activation gradient of the layer below and its segment sums
+// (see GemmFuse); *fused tells the caller whether it ran (tensor-core path with 256-column tiles only).
 int gemm_input_grad(gatx_ctx* ctx, const float* gPl_rows, const float* gPr_rows, const Layer& ly, float* gX, int ldg,
-                    int rows) {
+                    int rows, const GemmFuse* fuse = nullptr, bool* fused = nullptr) {
+  if (fused) *fused = false;
   if (rows <= 0) return GATX_OK;
+  if (ctx->gemm_mode == GATX_GEMM_TF32_TC && fuse && fuse->Hout) {
+    int n = launch_gemm_tc_tn2(gPl_rows, ly.F, ly.WcatT, 2 * ly.F, ly.F, gPr_rows, ly.F, ly.WcatT + ly.F, 2 * ly.F, ly.F,
+                               gX, gX, ly.I, ldg, rows, ly.I, false, ctx->st, fuse);
+    if (n >= 0) {
+      ctx->launches += n;
+      if (fused) *fused = true;
+      return GATX_OK;
+    }
+  }
   if (ctx->gemm_mode == GATX_GEMM_3XTF32_TC) {
     int rc = gemm3x_tn(ctx, gPl_rows, ly.F, ly.WcatT, 2 * ly.F, ly.F, gX, gX, ly.I, ldg, rows, ly.I, false);
     if (rc == GATX_OK) return gemm3x_tn(ctx, gPr_rows, ly.F, ly.WcatT + ly.F, 2 * ly.F, ly.F, gX, gX, ly.I, ldg, rows, ly.I, true);
@@ -686,7 +699,7 @@ RowView row_view(const gatx_ctx* ctx, int b) {
   v.g.col_idx_hot = ctx->col_idx_hot ? ctx->col_idx_hot + B.e0 : nullptr;
   v.g.heavy_rows = nullptr; v.g.n_heavy_rows = 0;
   // SM transport: the exchange kernels of the neighbouring block run underneath this launch in their own CTA slots
-  v.g.reserve_ctas = halo_cta_slots();
+  v.g.reserve_ctas = halo_cta_slots(ctx->world);
   return v;
 }
 // the streaming kernels take any view; the warp-per-row / generic kernels only the whole row range
@@ -775,6 +788,7 @@ int bwd_edge(gatx_ctx* ctx, int l, const RowView& v, int phases) {
   if (ly.vec && ctx->use_stream && edge_stream_supported(ly.H, ly.D)) {
     if ((phases & 1) && v.nb <= 0) phases &= ~1;
     if (!phases) return GATX_OK;
+    if ((phases & 1) && ly.gh_prepared) phases |= 4;
     // pass 2 walks the transposed graph of ALL local edges and reads g_h / rec by local row / edge id: whole range only
     LAUNCHED(launch_edge_backward_stream(gl, ly.H, ly.D, ly.Pl, Pr, a, Hfull, (phases & 2) ? ly.gH : gH, ctx->cdot, score,
                                          mx, sinv, gPr, ctx->gPl, (phases & 2) ? ctx->rec : rec, ctx->part,
@@ -907,10 +921,10 @@ int do_forward(gatx_ctx* ctx) {
           if (ctx->halo_bulk && halo_bulk_supported(nx.F))
             LAUNCHED(launch_halo_push_bulk(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
                                            ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm,
-                                           halo_cta_slots()));
+                                           halo_cta_slots(ctx->world)));
           else
             LAUNCHED(launch_halo_push(nx.Pl + (int64_t)(ctx->r0 + v.rb) * nx.F, ctx->r0 + v.rb, v.nb, nx.F,
-                                      ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm, halo_cta_slots()));
+                                      ctx->ref_mask + v.rb, ctx->peer_Pl[l + 1], ctx->rank, ctx->st_comm, halo_cta_slots(ctx->world)));
         }
       }
       if ((rc = comm_barrier(ctx))) return rc;  // every rank's pushes have landed
@@ -957,6 +971,26 @@ int do_forward(gatx_ctx* ctx) {
   return GATX_OK;
 }
 
+// Epilogue arguments that make the input-gradient GEMM of layer l write the pre-activation gradient of layer l - 1 (rows
+// [rb, rb + nb) of the own rows) and its segment sums; off (Hout == nullptr) when the layer below does not run the streaming
+// kernels (their prep is the only one that can be skipped), with dropout (the mask is applied between GEMM and prep), or
+// when GATX_NO_FUSE_PREP is set (A/B).
+GemmFuse prep_fuse(const gatx_ctx* ctx, int l, int rb, bool drop) {
+  GemmFuse f{};
+  static const bool off = getenv("GATX_NO_FUSE_PREP") != nullptr;
+  if (off || l <= 0 || drop) return f;
+  const Layer& prev = ctx->layers[l - 1];
+  if (!(prev.vec && ctx->use_stream && edge_stream_supported(prev.H, prev.D))) return f;
+  f.Hout = prev.Hfull + (int64_t)rb * prev.F;
+  f.ld = prev.F;
+  f.cdot = ctx->cdot;  // rows of the view the following pass 1 is launched on
+  f.bias = prev.b_off >= 0 ? ctx->params + prev.b_off : nullptr;
+  f.act_slope = ctx->slopes.act;
+  f.head_dim = prev.D;
+  f.heads = prev.H;
+  return f;
+}
+
 int do_backward(gatx_ctx* ctx) {
   if (!ctx->have_bufs || !ctx->fwd_valid)
     return fail(ctx, GATX_ERR_INVALID, "gatx_forward must run before gatx_backward (gatx_evaluate does not count)");
@@ -970,6 +1004,7 @@ int do_backward(gatx_ctx* ctx) {
     if (rc) return rc;
   }
   const RowView all = row_view(ctx, -1);
+  for (Layer& q : ctx->layers) q.gh_prepared = false;
   std::vector<char> p1_done(ctx->L, 0);  // pass 1 of the layer already ran block by block inside the layer above
   for (int l = ctx->L - 1; l >= 0; --l) {
     Layer& ly = ctx->layers[l];
@@ -1019,7 +1054,8 @@ int do_backward(gatx_ctx* ctx) {
         // dL/dHout[l-1] = gP_l W_l + gP_r W_r  (EB:859-869); the LReLU derivative of EB:879-893 is
         // applied by the next edge backward when it loads this gradient.
         Layer& prev = ctx->layers[l - 1];
-        rc = gemm_input_grad(ctx, gPl_own, gPr, ly, prev.gH, prev.F, ctx->n_rows);
+        const GemmFuse fz = prep_fuse(ctx, l, 0, drop);
+        rc = gemm_input_grad(ctx, gPl_own, gPr, ly, prev.gH, prev.F, ctx->n_rows, &fz, &prev.gh_prepared);
         if (rc) return rc;
         // gradient w.r.t. the dropped input -> w.r.t. the previous layer's output: same mask, same scale
         if (drop)
@@ -1048,7 +1084,7 @@ int do_backward(gatx_ctx* ctx) {
           CommTimer ct(ctx, 1, (double)ctx->blocks[b].halo_rows * ly.F * 4.0);
           LAUNCHED(launch_halo_pull(ctx->gPl + (int64_t)(ctx->r0 + v.rb) * ly.F, ctx->r0 + v.rb, v.nb, ly.F,
                                     ctx->ref_mask + v.rb, ctx->peer_gPl, ctx->rank, ctx->world, ctx->st_comm,
-                                    halo_cta_slots()));
+                                    halo_cta_slots(ctx->world)));
         }
         compute_waits_comm(ctx);
         if (l > 0) {
@@ -1056,7 +1092,9 @@ int do_backward(gatx_ctx* ctx) {
           {
             PhaseTimer t(ctx, PH_GEMM_BWD);
             float* gXb = prev.gH + (int64_t)v.rb * prev.F;
-            rc = gemm_input_grad(ctx, gPl_own + (int64_t)v.rb * ly.F, gPr + (int64_t)v.rb * ly.F, ly, gXb, prev.F, v.nb);
+            const GemmFuse fz = prep_fuse(ctx, l, v.rb, drop);  // every block of a layer takes the same path
+            rc = gemm_input_grad(ctx, gPl_own + (int64_t)v.rb * ly.F, gPr + (int64_t)v.rb * ly.F, ly, gXb, prev.F, v.nb, &fz,
+                                 &prev.gh_prepared);
             if (rc) return rc;
             if (drop)
               LAUNCHED(launch_dropout(gXb, prev.F, gXb, prev.F, v.nb, ly.I, ctx->r0 + v.rb, ctx->p_drop, ctx->drop_seed, l,
@@ -1109,7 +1147,7 @@ int do_backward(gatx_ctx* ctx) {
         }
         CommTimer ct(ctx, 1, (double)ctx->scatter_rows[b] * ly.F * 4.0);
         LAUNCHED(launch_halo_scatter_bulk(ctx->gPl, ly.F, ctx->my_ref, plan, ctx->peer_stage, ctx->rank, ctx->st_comm,
-                                          halo_cta_slots()));
+                                          halo_cta_slots(ctx->world)));
       }
       if ((rc = comm_barrier(ctx))) return rc;  // block b of every rank's partial rows has landed at its owner
       compute_waits_comm(ctx);
@@ -1124,7 +1162,9 @@ int do_backward(gatx_ctx* ctx) {
         {
           PhaseTimer t(ctx, PH_GEMM_BWD);
           float* gXb = prev.gH + (int64_t)v.rb * prev.F;
-          rc = gemm_input_grad(ctx, gPl_own + (int64_t)v.rb * ly.F, gPr + (int64_t)v.rb * ly.F, ly, gXb, prev.F, v.nb);
+          const GemmFuse fz = prep_fuse(ctx, l, v.rb, drop);  // every block of a layer takes the same path
+          rc = gemm_input_grad(ctx, gPl_own + (int64_t)v.rb * ly.F, gPr + (int64_t)v.rb * ly.F, ly, gXb, prev.F, v.nb, &fz,
+                               &prev.gh_prepared);
           if (rc) return rc;
           if (drop)
             LAUNCHED(launch_dropout(gXb, prev.F, gXb, prev.F, v.nb, ly.I, ctx->r0 + v.rb, ctx->p_drop, ctx->drop_seed, l,

@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(TnPersist::kThreadsP)
 gemm_tf32_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                                const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
-                               int K0, int K1, int n_split, int M, int N, int tiles_n, int num_tiles) {
+                               int K0, int K1, int n_split, int M, int N, int tiles_n, int num_tiles, GemmFuse fuse) {
   using S = TnPersist;
   constexpr int BN = S::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -460,11 +460,40 @@ gemm_tf32_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const _
       const int row0 = m0 + q * 32;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
+      float hdot = 0.f;  // fused epilogue: running g . Hout (- g_pre . bias) of the head the chunks belong to
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         if (n0 + c0 >= N) break;
         uint32_t v[32];
+        float4 ho[8];
+        const int frow = row0 + lane, fcol = n0 + c0;
+        const bool fz = fuse.Hout != nullptr && frow < M;
+        if (fz) {  // this lane's row of the layer output: 128 contiguous bytes, in flight while the accumulator is read
+          const float4* hp = reinterpret_cast<const float4*>(fuse.Hout + (int64_t)frow * fuse.ld + fcol);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ho[c] = __ldg(hp + c);
+        }
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, v);
+        if (fuse.Hout != nullptr) {
+          if (fz) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float h4[4] = {ho[c].x, ho[c].y, ho[c].z, ho[c].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float g = __uint_as_float(v[4 * c + t]);
+                const float gp = g * (h4[t] > 0.f ? 1.f : fuse.act_slope);  // EB:879-893: LReLU'(h) has the sign of LReLU(h)
+                hdot = fmaf(g, h4[t], hdot);
+                if (fuse.bias) hdot = fmaf(-gp, __ldg(fuse.bias + fcol + 4 * c + t), hdot);
+                v[4 * c + t] = __float_as_uint(gp);
+              }
+            }
+          }
+          if ((fcol + 32) % fuse.head_dim == 0) {  // the head ends with this chunk (head_dim % 32 == 0)
+            if (fz) fuse.cdot[(int64_t)frow * fuse.heads + fcol / fuse.head_dim] = hdot;
+            hdot = 0.f;
+          }
+        }
         if (lane == 0) bulk_wait_read<0>();  // the previous store of this warp has read the box
         __syncwarp();
         const uint32_t rowaddr = box + (uint32_t)lane * 128u;
@@ -737,11 +766,16 @@ int launch_atb(const CUtensorMap& a, const CUtensorMap& b, int64_t K, float* C, 
 
 int launch_gemm_tc_tn2(const float* A0, int64_t lda0, const float* B0, int64_t ldb0, int K0, const float* A1,
                        int64_t lda1, const float* B1, int64_t ldb1, int K1, float* C0, float* C1, int n_split,
-                       int64_t ldc, int M, int N, bool accumulate, cudaStream_t st) {
+                       int64_t ldc, int M, int N, bool accumulate, cudaStream_t st, const GemmFuse* fuse) {
   if (M <= 0 || N <= 0 || K0 <= 0) return -1;
   if (n_split <= 0 || n_split > N) n_split = N;
   const int bn = pick_bn(N, n_split);
   if (bn < 0) return -1;
+  const bool want_fuse = fuse && fuse->Hout;
+  // the fused epilogue lives in the persistent 256-column kernel: whole heads per 128-column half, one output matrix
+  if (want_fuse && (bn != 256 || accumulate || n_split != N || fuse->head_dim < 32 || fuse->head_dim % 32 || 128 % fuse->head_dim ||
+                    N % fuse->head_dim || fuse->ld % 4 || (reinterpret_cast<uintptr_t>(fuse->Hout) & 15)))
+    return -1;
   CUtensorMap a0, b0, a1, b1;
   if (!make_map(&a0, A0, M, K0, lda0, BK, BM) || !make_map(&b0, B0, N, K0, ldb0, BK, bn)) return -1;
   if (K1 > 0) {
@@ -773,9 +807,10 @@ int launch_gemm_tc_tn2(const float* A0, int64_t lda0, const float* B0, int64_t l
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
     gemm_tf32_tn_persistent_kernel<<<grid, TnPersist::kThreadsP, TnPersist::kBytes, st>>>(a0, b0, a1, b1, c0, c1, K0, K1, n_split, M, N,
-                                                                              tiles_n, num_tiles);
+                                                                              tiles_n, num_tiles, want_fuse ? *fuse : GemmFuse{});
     return 1;
   }
+  if (want_fuse) return -1;
   switch (bn) {
     case 256: return launch_tn<256>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);
     case 128: return launch_tn<128>(a0, b0, a1, b1, c0, c1, tma_store, K0, K1, C0, C1, n_split, ldc, M, N, accumulate, st);

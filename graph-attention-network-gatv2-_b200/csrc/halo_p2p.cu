@@ -338,13 +338,19 @@ int launch_halo_barrier(const PeerFlags& flags, int me, int world, uint32_t seq,
 // Both kernels are CTAs of 256 threads with at most 64 registers per thread (launch bounds): 16 K registers and no
 // shared memory, i.e. one exchange CTA fits the slot of one streaming edge CTA (~20 K registers).  In the pipelined
 // epoch they run in halo_cta_slots() CTAs underneath an edge pass whose grid leaves exactly that many slots free.
-int halo_cta_slots() {
-  static const int n = [] {
+// How many slots: the exchange must move its bytes in the time of the edge pass it hides under, and an ld / st kernel
+// moves ~5 GB/s per CTA over NVLink.  The bytes per rank stay ~constant with the rank count while the edge pass shrinks
+// as 1 / world, so the slots grow with it: 20 per peer (measured on the products shape: 2 GPUs need < 24 slots -- with 148
+// reserved the edge passes lose a third of their CTAs for nothing, 114 ms instead of 102 -- 8 GPUs want all 148).
+int halo_cta_slots(int world) {
+  static const int forced = [] {
     const char* e = getenv("GATX_HALO_CTAS");
-    const int v = e ? atoi(e) : kNumSMs;
-    return v >= 4 && v <= kNumSMs * 2 ? v : kNumSMs;
+    const int v = e ? atoi(e) : 0;
+    return v >= 4 && v <= kNumSMs * 2 ? v : 0;
   }();
-  return n;
+  if (forced) return forced;
+  const int n = 20 * (world > 1 ? world - 1 : 1);
+  return n < kNumSMs ? n : kNumSMs;
 }
 static int halo_blocks(int n_rows, int max_ctas) {
   int blocks = (n_rows + 7) / 8;
