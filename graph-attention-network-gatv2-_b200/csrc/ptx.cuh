@@ -161,6 +161,17 @@ __device__ __forceinline__ uint32_t lds1u_s(uint32_t addr) {
   return v;
 }
 
+// ---- cp.async (LDGSTS): 16 bytes per lane global -> shared, completion by per-thread groups ---------------------------
+// A warp-wide cp.async moves one 512-byte row with ONE instruction and no uniform-register traffic (a bulk copy of the
+// same row costs ~20 issue slots: elect, four R2UR, expect_tx, UBLKCP); the consumer waits with cp.async.wait_group
+// instead of polling an mbarrier.  .cg: cached in L2 only (the gathered rows are used once per warp).
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
