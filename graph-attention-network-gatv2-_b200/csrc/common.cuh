@@ -187,7 +187,7 @@ int launch_halo_sum(float* own_rows, int row_off, int n_rows, int n_rows_total, 
                     const float* stage, int me, int world, cudaStream_t st);
 int launch_halo_pull(float* own_rows, int r0, int n_rows, int F, const uint16_t* ref_mask, const PeerPtrs& peers, int me,
                      int world, cudaStream_t st, int max_ctas = 0);
-int halo_cta_slots(int world);  // CTA slots of the exchange kernels (GATX_HALO_CTAS; default 20 per peer, at most 148)
+int halo_cta_slots(int world);  // CTA slots of the exchange kernels (GATX_HALO_CTAS); 0 = no cap, no reservation (default)
 // Device-side barrier across ranks through flags in peer memory: rank `me` stores `seq` (release, system scope) into
 // slot `me` of every peer's flag array, then waits (acquire) until every slot of its own array has reached `seq`.
 // Stream-ordered: everything this rank enqueued before it on `st` (and its peer-memory stores) is visible to a peer

@@ -338,19 +338,18 @@ int launch_halo_barrier(const PeerFlags& flags, int me, int world, uint32_t seq,
 // Both kernels are CTAs of 256 threads with at most 64 registers per thread (launch bounds): 16 K registers and no
 // shared memory, i.e. one exchange CTA fits the slot of one streaming edge CTA (~20 K registers).  In the pipelined
 // epoch they run in halo_cta_slots() CTAs underneath an edge pass whose grid leaves exactly that many slots free.
-// How many slots: the exchange must move its bytes in the time of the edge pass it hides under, and an ld / st kernel
-// moves ~5 GB/s per CTA over NVLink.  The bytes per rank stay ~constant with the rank count while the edge pass shrinks
-// as 1 / world, so the slots grow with it: 20 per peer (measured on the products shape: 2 GPUs need < 24 slots -- with 148
-// reserved the edge passes lose a third of their CTAs for nothing, 114 ms instead of 102 -- 8 GPUs want all 148).
-int halo_cta_slots(int world) {
+// GATX_HALO_CTAS=S runs the exchange kernels in S CTA slots and makes the streaming edge kernels leave exactly S slots free
+// (their chunks are assigned statically, so every CTA of their grid must be resident).  Measured on the products shape
+// (profiles/r2_multi_gpu_transports.md): few slots starve the exchange (S = 24: pull at 98 GB/s), many starve the edge pass
+// (S = 148 on 2 GPUs: 114 ms instead of 102), and no S beats the default -- no cap and no reservation: the exchange kernels
+// take whatever the edge pass leaves and the edge pass absorbs the imbalance.
+int halo_cta_slots(int /*world*/) {
   static const int forced = [] {
     const char* e = getenv("GATX_HALO_CTAS");
     const int v = e ? atoi(e) : 0;
     return v >= 4 && v <= kNumSMs * 2 ? v : 0;
   }();
-  if (forced) return forced;
-  const int n = 20 * (world > 1 ? world - 1 : 1);
-  return n < kNumSMs ? n : kNumSMs;
+  return forced;
 }
 static int halo_blocks(int n_rows, int max_ctas) {
   int blocks = (n_rows + 7) / 8;
