@@ -214,7 +214,9 @@ __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, co
 }
 
 // ------------------------------------------------------------------------------------ forward
-template <int NV, int R, int LPH>
+// ADROP: attention-coefficient dropout compiled in (a template parameter, not a run-time test of g.ascale: the predicated-off
+// address arithmetic and load of the scale cost ~7 issue slots per edge in kernels that are bound by instruction issue)
+template <int NV, int R, int LPH, bool ADROP>
 __global__ void __launch_bounds__(kSW * 32)
 edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const float* __restrict__ Pl,
                        const float* __restrict__ Pr, const float* __restrict__ a, Shape sh, float* __restrict__ Hout,
@@ -325,7 +327,8 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       const float mn = up ? p : st.m;
       st.s = st.s * corr + w;
       // attention dropout scales the aggregated term only; the softmax denominator keeps every edge
-      const float wd = g.ascale ? w * __ldg(g.ascale + (int64_t)e * sh.H + hd) : w;
+      float wd = w;
+      if constexpr (ADROP) wd = w * __ldg(g.ascale + (int64_t)e * sh.H + hd);
       const float2 corr2 = splat2(corr), w2 = splat2(wd);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {  // acc = acc * corr + (w * v), EB:415-422 without atomics (same rounding as the scalar form)
@@ -458,7 +461,7 @@ __device__ __forceinline__ void load_scalars(RowScalars& q, int row, int H, int 
 }
 
 // smem per warp: ring [R][F] | rowbuf [2F] (g_h row, P_r row) | score window [2][32*H] | barriers [R + 1]
-template <int NV, int R, int LPH>
+template <int NV, int R, int LPH, bool ADROP>
 __global__ void __launch_bounds__(kSW * 32)
 edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const float* __restrict__ Pl,
                            const float* __restrict__ Pr, const float* __restrict__ a, Shape sh,
@@ -630,7 +633,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       }
       float galpha = head_sum<LPH>(gal2.x + gal2.y, sh.lc);
       float alpha = __expf(sc[hd] - q.m) * q.inv;        // EB:378-379
-      const float dsc = g.ascale ? __ldg(g.ascale + (int64_t)e * H + hd) : 1.f;  // attention dropout (1 when off)
+      float dsc = 1.f;  // attention dropout (1 when off)
+      if constexpr (ADROP) dsc = __ldg(g.ascale + (int64_t)e * H + hd);
       galpha *= dsc;                                     // h = sum alpha * dsc * P_l
       const float ge = alpha * (galpha - q.c);           // EB:689-690 in closed form
       alpha *= dsc;                                      // the record keeps alpha * dsc for pass 2
@@ -951,7 +955,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   if (use_pair(nv, sh)) {  // one head of 128 floats: two edges per loop iteration
     constexpr int R = 16;
     const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
-    auto kern = edge_fwd_pair_kernel<R>;
+    auto kern = eg.ascale ? edge_fwd_pair_kernel<R, true> : edge_fwd_pair_kernel<R, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int blocks = stream_grid((const void*)kern, smem, g.n_chunks, eg.reserve_ctas);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
@@ -968,7 +972,7 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   STREAM_DISPATCH(nv, sh.lc, {
     constexpr int R = ring_depth<NV>();
     const size_t smem = (size_t)kSW * R * NV * 128 * 4 + (size_t)kSW * R * 8;
-    auto kern = edge_fwd_stream_kernel<NV, R, LPH>;
+    auto kern = eg.ascale ? edge_fwd_stream_kernel<NV, R, LPH, true> : edge_fwd_stream_kernel<NV, R, LPH, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int blocks = stream_grid((const void*)kern, smem, g.n_chunks, eg.reserve_ctas);
     if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
@@ -1022,7 +1026,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
       if (do_p1) {
         const size_t per_warp = (size_t)(R * F + 2 * F + 64) * 4;
         const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
-        auto kern = edge_bwd_dst_pair_kernel<R>;
+        auto kern = eg.ascale ? edge_bwd_dst_pair_kernel<R, true> : edge_bwd_dst_pair_kernel<R, false>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks, eg.reserve_ctas);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
@@ -1074,7 +1078,7 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
         constexpr int R = NV == 4 ? 4 : 8;
         const size_t per_warp = (size_t)(R * F + 2 * F + 2 * 32 * H) * 4;
         const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
-        auto kern = edge_bwd_dst_stream_kernel<NV, R, LPH>;
+        auto kern = eg.ascale ? edge_bwd_dst_stream_kernel<NV, R, LPH, true> : edge_bwd_dst_stream_kernel<NV, R, LPH, false>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks, eg.reserve_ctas);
         if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
