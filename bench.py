@@ -408,7 +408,7 @@ def run_gatx(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     agg = (fb + bb) / 1e9 / (edge_ms * 1e-3) if edge_ms > 0 else 0.0
     traffic = None
-    tj = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    tj = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
     if kernels:
         dom = max(kernels, key=lambda k: k["ms"])
         if os.path.exists(tj) and world == 1:
