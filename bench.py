@@ -393,8 +393,8 @@ def run_gatx(args):
         p1 = 4.0 * (Nl + 1) + El * (4.0 + 4.0 * F) + 8.0 * H * El + 12.0 * Nl * F
         p2 = b - p1
         ms3 = kernel_ms[l]
-        # one head of 128 floats runs the two-edges-per-trip kernels of edge_stream_pair.inc (ncu names *_pair_kernel)
-        fam = "pair" if (H == 1 and D == 128 and not os.environ.get("GATX_NO_PAIR")) else "stream"
+        # one head of 128 / 64 floats runs the two-edges-per-trip kernels of edge_stream_pair.inc (ncu names *_pair_kernel)
+        fam = "pair" if (H == 1 and (D == 64 or (D == 128 and not os.environ.get("GATX_NO_PAIR")))) else "stream"
         for name, key, by in (("edge_fwd_%s_kernel" % fam, "fwd", f), ("edge_bwd_dst_%s_kernel" % fam, "bwd_dst", p1),
                               ("edge_bwd_src_%s_kernel" % fam, "bwd_src", p2)):
             if ms3[key] > 0:

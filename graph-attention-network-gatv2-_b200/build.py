@@ -25,7 +25,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build_" + VARIANT if VARIANT else "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "gatx.h"))
     jobs = []
     for src in SOURCES:

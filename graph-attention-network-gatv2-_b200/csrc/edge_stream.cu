@@ -197,10 +197,11 @@ __device__ __forceinline__ void fwd_finalize(const FwdState<NV>& st, int row, co
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     float4 h = make_float4(st.acc[j].x * inv, st.acc[j].y * inv, st.acc[j].z * inv, st.acc[j].w * inv);
-    if (sh.bias) {
+    if (sh.bias && (NV > 1 || lc_off<NV>(lane, j) < sh.F)) {
       const float4 b = ldg4(sh.bias + lc_off<NV>(lane, j));
       h = make_float4(h.x + b.x, h.y + b.y, h.z + b.z, h.w + b.w);
     }
+    if (NV == 1 && lc_off<NV>(lane, j) >= sh.F) continue;  // 64-float rows (pair kernels): lanes 16-31 hold nothing
     const int64_t off = (int64_t)row * sh.F + lc_off<NV>(lane, j);
     if (hpre) st4(hpre + off, h);
     const float sc = sh.slopes.act;
@@ -430,18 +431,19 @@ edge_bwd_prep_kernel(int n_rows, Shape sh, const float* __restrict__ Hout, float
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * 8) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int64_t off = (int64_t)row * sh.F + 4 * (lane + 32 * j);
-      const float4 g = *reinterpret_cast<const float4*>(gH + off);
+      const bool in_row = NV > 1 || 4 * lane < sh.F;  // 64-float rows: lanes 16-31 only take part in the shuffles
+      const int64_t off = (int64_t)row * sh.F + (in_row ? 4 * (lane + 32 * j) : 0);
+      const float4 g = in_row ? *reinterpret_cast<const float4*>(gH + off) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 ho = ldg4(Hout + off);
       const float sc = sh.slopes.act;
       const float4 gp = make_float4(g.x * lrelu_grad(ho.x, sc), g.y * lrelu_grad(ho.y, sc), g.z * lrelu_grad(ho.z, sc),
                                     g.w * lrelu_grad(ho.w, sc));
       // sum_seg alpha*galpha = g_pre . (h - bias) = gH . Hout - g_pre . bias  (LReLU'(h) h = LReLU(h))
       float cd = dot4(g, ho);
-      if (sh.bias) cd -= dot4(gp, ldg4(sh.bias + 4 * (lane + 32 * j)));
+      if (sh.bias && in_row) cd -= dot4(gp, ldg4(sh.bias + 4 * (lane + 32 * j)));
       const float c = head_reduce(cd, sh.lph);
-      st4(gH + off, gp);
-      if (head_lane) cdot[(int64_t)row * sh.H + ((lane + 32 * j) >> sh.lg_lph)] = c;
+      if (in_row) st4(gH + off, gp);
+      if (head_lane && in_row) cdot[(int64_t)row * sh.H + ((lane + 32 * j) >> sh.lg_lph)] = c;
     }
   }
 }
@@ -698,10 +700,10 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
 }
 
 // sums the pieces of a row that straddles chunk boundaries (pass 1: gP_r, pass 2: gP_l)
-template <int NV>
+template <int NV, int F = NV * 128>
 __global__ void __launch_bounds__(kSW * 32)
 edge_sum_fixup_kernel(StreamGraph g, const float* __restrict__ part, float* __restrict__ out) {
-  constexpr int F = NV * 128;
+  static_assert(F == NV * 128 || (NV == 1 && F == 64), "row width");
   const int c = blockIdx.x * kSW + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= g.n_chunks - 1) return;
   const int b = (c + 1) * g.T;
@@ -709,6 +711,7 @@ edge_sum_fixup_kernel(StreamGraph g, const float* __restrict__ part, float* __re
   const int rs = __ldg(g.row_ptr + rr);
   if (rs >= b || rs < c * g.T) return;
   const int c_last = (__ldg(g.row_ptr + rr + 1) - 1) / g.T;
+  if (4 * lane >= F) return;
   float4 acc[NV];
   {
     const float* p = part + ((int64_t)c * 2 + (rs == c * g.T ? 0 : 1)) * F;
@@ -863,8 +866,9 @@ bool make_stream_shape(int H, int D, Shape* sh, int* nv) {
   const int lph = D / 4;
   if (lph & (lph - 1)) return false;
   const int F = H * D;
-  if (F % 128) return false;
-  const int NV = F / 128;
+  const bool narrow = H == 1 && D == 64;  // one head of 64 floats: the PF = 64 pair kernels, half a warp per row
+  if (F % 128 && !narrow) return false;
+  const int NV = narrow ? 1 : F / 128;
   if (NV != 1 && NV != 2 && NV != 4) return false;
   int lg = 0;
   while ((1 << lg) < lph) ++lg;
@@ -905,8 +909,14 @@ HotSel hot_select(const EdgeGraph& eg, int F) {
 
 bool use_pair(int nv, const Shape& sh) {
   static const bool off = getenv("GATX_NO_PAIR") != nullptr;
+  if (sh.F == 64) return true;  // no other kernel family in this file handles 64-float rows
   return !off && nv == 1 && sh.H == 1 && sh.lph == 32;
 }
+#define PAIR_DISPATCH_PF(F_, ...)                        \
+  do {                                                   \
+    if ((F_) == 64) { constexpr int PF = 64; __VA_ARGS__; } \
+    else { constexpr int PF = 128; __VA_ARGS__; }        \
+  } while (0)
 
 #define STREAM_DISPATCH_NV(nv, ...)                          \
   do {                                                       \
@@ -933,7 +943,7 @@ int64_t edge_stream_part_floats(int H, int D, int n_chunks) {
   Shape sh;
   int nv;
   if (!make_stream_shape(H, D, &sh, &nv)) return 0;
-  return (int64_t)n_chunks * 2 * (sh.F + 2 * nv * 32);
+  return (int64_t)n_chunks * 2 * (nv * 128 + 2 * nv * 32);  // fwd_part_floats<NV>(), the largest user
 }
 
 int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* Pl, const float* Pr, const float* a,
@@ -952,16 +962,18 @@ int launch_edge_forward_stream(const EdgeGraph& eg, int H, int D, const float* P
   const HotSel hs = hot_select(eg, sh.F);
   const int* colx = hs.on ? eg.col_idx_hot : eg.col_idx;
   StreamGraph g{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias, eg.ascale};
-  if (use_pair(nv, sh)) {  // one head of 128 floats: two edges per loop iteration
-    constexpr int R = 16;
-    const size_t smem = (size_t)kSW * R * kPF * 4 + (size_t)kSW * R * 8;
-    auto kern = eg.ascale ? edge_fwd_pair_kernel<R, true> : edge_fwd_pair_kernel<R, false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int blocks = stream_grid((const void*)kern, smem, g.n_chunks, eg.reserve_ctas);
-    if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
-    // 512-byte rows: the cache-hint form of the bulk copy is slower than the plain one at this size (measured), no hints
-    kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, Hout, hpre, score, mx, sinv, part);
-    if (eg.kernel_events) cudaEventRecord(eg.kernel_events[1], st);
+  if (use_pair(nv, sh)) {  // one head of 128 / 64 floats: two edges per loop iteration
+    PAIR_DISPATCH_PF(sh.F, {
+      constexpr int R = 16;
+      const size_t smem = (size_t)kSW * R * PF * 4 + (size_t)kSW * R * 8;
+      auto kern = eg.ascale ? edge_fwd_pair_kernel<R, true, PF> : edge_fwd_pair_kernel<R, false, PF>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      const int blocks = stream_grid((const void*)kern, smem, g.n_chunks, eg.reserve_ctas);
+      if (eg.kernel_events) cudaEventRecord(eg.kernel_events[0], st);
+      // 512-byte rows: the cache-hint form of the bulk copy is slower than the plain one at this size (measured), no hints
+      kern<<<blocks, kSW * 32, smem, st>>>(g, eg.col_idx, Pl, Pr, a, Hout, hpre, score, mx, sinv, part);
+      if (eg.kernel_events) cudaEventRecord(eg.kernel_events[1], st);
+    });
     ++launches;
     if (g.n_chunks > 1) {
       edge_fwd_fixup_kernel<1><<<(g.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(g, sh, part, Hout, hpre, mx, sinv);
@@ -1007,7 +1019,8 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
   StreamGraph gd{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_rows, eg.row_ptr, eg.chunk_row, hs.bit, hs.mask, eg.slopes, eg.bias, eg.ascale};
   StreamGraph gs{(int)eg.E, eg.chunk_T, eg.n_chunks, eg.n_src, eg.csc_ptr, eg.chunk_src, hs.bit, hs.mask, eg.slopes, eg.bias, eg.ascale};
   if (use_pair(nv, sh)) {
-    constexpr int R = 16, F = kPF;
+    constexpr int R = 16;
+    const int F = sh.F;
     if (do_p1 && eg.n_rows > 0) {
       int blocks = (eg.n_rows + 7) / 8;
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
@@ -1024,35 +1037,39 @@ int launch_edge_backward_stream(const EdgeGraph& eg, int H, int D, const float* 
     }
     if (eg.E > 0) {
       if (do_p1) {
-        const size_t per_warp = (size_t)(R * F + 2 * F + 64) * 4;
-        const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
-        auto kern = eg.ascale ? edge_bwd_dst_pair_kernel<R, true> : edge_bwd_dst_pair_kernel<R, false>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks, eg.reserve_ctas);
-        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
-        kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, gH, cdot, score, mx, sinv, gPr, rec, part,
-                                             ga_partials, galpha_dbg);
-        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[3], st);
-        *n_partials = blocks;
-        ++launches;
-        if (gd.n_chunks > 1) {
-          edge_sum_fixup_kernel<1><<<(gd.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gd, part, gPr);
+        PAIR_DISPATCH_PF(F, {
+          const size_t per_warp = (size_t)(R * PF + 2 * PF + 64) * 4;
+          const size_t smem = kSW * per_warp + (size_t)kSW * (R + 1) * 8;
+          auto kern = eg.ascale ? edge_bwd_dst_pair_kernel<R, true, PF> : edge_bwd_dst_pair_kernel<R, false, PF>;
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          const int blocks = stream_grid((const void*)kern, smem, gd.n_chunks, eg.reserve_ctas);
+          if (eg.kernel_events) cudaEventRecord(eg.kernel_events[2], st);
+          kern<<<blocks, kSW * 32, smem, st>>>(gd, eg.col_idx, Pl, Pr, a, gH, cdot, score, mx, sinv, gPr, rec, part,
+                                               ga_partials, galpha_dbg);
+          if (eg.kernel_events) cudaEventRecord(eg.kernel_events[3], st);
+          *n_partials = blocks;
           ++launches;
-        }
+          if (gd.n_chunks > 1) {
+            edge_sum_fixup_kernel<1, PF><<<(gd.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gd, part, gPr);
+            ++launches;
+          }
+        });
       }
       if (do_p2) {
-        const size_t smem = (size_t)kSW * R * (F + 32) * 4 + (size_t)kSW * R * 8;
-        auto kern = edge_bwd_src_pair_kernel<R>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks, eg.reserve_ctas);
-        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[4], st);
-        kern<<<blocks, kSW * 32, smem, st>>>(gs, eg.csc_dst, eg.csc_eid, a, gH, rec, gPl, part);
-        if (eg.kernel_events) cudaEventRecord(eg.kernel_events[5], st);
-        ++launches;
-        if (gs.n_chunks > 1) {
-          edge_sum_fixup_kernel<1><<<(gs.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gs, part, gPl);
+        PAIR_DISPATCH_PF(F, {
+          const size_t smem = (size_t)kSW * R * (PF + 32) * 4 + (size_t)kSW * R * 8;
+          auto kern = edge_bwd_src_pair_kernel<R, PF>;
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          const int blocks = stream_grid((const void*)kern, smem, gs.n_chunks, eg.reserve_ctas);
+          if (eg.kernel_events) cudaEventRecord(eg.kernel_events[4], st);
+          kern<<<blocks, kSW * 32, smem, st>>>(gs, eg.csc_dst, eg.csc_eid, a, gH, rec, gPl, part);
+          if (eg.kernel_events) cudaEventRecord(eg.kernel_events[5], st);
           ++launches;
-        }
+          if (gs.n_chunks > 1) {
+            edge_sum_fixup_kernel<1, PF><<<(gs.n_chunks - 1 + kSW - 1) / kSW, kSW * 32, 0, st>>>(gs, part, gPl);
+            ++launches;
+          }
+        });
       }
     }
     return launches;

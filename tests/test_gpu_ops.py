@@ -24,11 +24,11 @@ def gatx():
     return g
 
 
-# (heads, outdim): warp-per-row, streaming 512-float rows, pair (1 x 128), generic scalar
-FAMILIES = [(8, 8), (4, 128), (1, 128), (3, 5)]
+# (heads, outdim): warp-per-row, streaming 512-float rows, pair (1 x 128), generic scalar, pair with 64-float rows
+FAMILIES = [(8, 8), (4, 128), (1, 128), (3, 5), (1, 64)]
 
 
-@pytest.mark.parametrize("H,D", FAMILIES, ids=["narrow", "stream", "pair", "generic"])
+@pytest.mark.parametrize("H,D", FAMILIES, ids=["narrow", "stream", "pair", "generic", "pair64"])
 def test_op_edge_forward_and_backward(gatx, orc, H, D):
     N, E = 1500, 14000
     rp, ci = datasets.make_graph(N, E, "rmat", 31)

@@ -34,6 +34,7 @@ SHAPES = [
     (1200, 20000, 16, 4, (2, 4, 1), (64, 128, 128), "rmat", 700),  # streaming kernels, 128/512-float rows
     (300, 2500, 11, 5, (3, 2, 1), (5, 12, 7), "rmat", None),    # generic scalar kernels: odd head dims
     (200, 1500, 9, 3, (5, 1), (6, 200), "uniform", 150),        # generic kernels: D = 200 (> 128), F = 30
+    (2500, 9000, 12, 3, (4, 1), (64, 64), "uniform", 1500),     # 64-float pair kernels (arxiv's last layer) with hub rows
 ]
 
 
@@ -107,12 +108,13 @@ def test_forward_backward_parity(gatx, orc, shape, mode):
     eng.close()
 
 
+@pytest.mark.parametrize("last", [128, 64])
 @pytest.mark.parametrize("chunk", ["32", "64", "1000"])
-def test_streaming_chunk_sizes(gatx, orc, chunk, monkeypatch):
+def test_streaming_chunk_sizes(gatx, orc, chunk, last, monkeypatch):
     """Edge-balanced streaming kernels with tiny / odd chunk sizes: rows straddle many chunk boundaries,
     some chunks lie entirely inside one hub row, the last chunk is short."""
     monkeypatch.setenv("GATX_CHUNK", chunk)
-    p = make_problem(900, 7000, 10, 4, (4, 2, 1), (32, 128, 128), "rmat", seed=21, hub=600)
+    p = make_problem(900, 7000, 10, 4, (4, 2, 1), (32, 128, last), "rmat", seed=21, hub=600)
     eng = make_engine(gatx, p, gemm_mode=1, keep_debug=True)
     ref = make_oracle(orc, p)
     eng.forward(); eng.backward()
@@ -120,7 +122,13 @@ def test_streaming_chunk_sizes(gatx, orc, chunk, monkeypatch):
     for l in range(3):
         assert rel_err(eng.tensor(gatx.T_HOUT, l), ref.tensor(orc.T_HOUT, l).ravel()) < 4e-5, ("Hout", l)
         assert rel_err(eng.tensor(gatx.T_GH, l), ref.tensor(orc.T_GH, l).ravel()) < 2e-4, ("g_h", l)
-        assert rel_err(eng.tensor(gatx.T_GW, l), ref.tensor(orc.T_GW, l).ravel()) < 2e-4, ("gW", l)
+        # gW: L2 bound, and 1e-3 on the maximum.  One pre-activation s = P_l[src] + P_r[dst] of layer 1 lies within
+        # rounding distance of 0 on this graph: LeakyReLU' takes the other branch in fp32 than in the oracle's fp64 sum,
+        # which moves ONE gP element by ge * a_k * (1 - slope) (g_e itself agrees to 3e-7, tools/debug_pair64.py small);
+        # how far that shows in gW depends on the g_h arriving from the layer above (3.2e-4 with a 64-float last layer)
+        gW, gW_ref = eng.tensor(gatx.T_GW, l), ref.tensor(orc.T_GW, l).ravel()
+        assert np.linalg.norm(gW - gW_ref) < 2e-4 * np.linalg.norm(gW_ref), ("gW L2", l)
+        assert rel_err(gW, gW_ref) < 1e-3, ("gW", l)
         assert rel_err(eng.tensor(gatx.T_GA, l), ref.tensor(orc.T_GA, l).ravel(), floor=1e-2) < 2e-4, ("ga", l)
     eng.close()
 
@@ -375,11 +383,11 @@ def test_cuda_graph_replay_is_bit_identical(gatx, mode):
 
 
 # one shape per edge-kernel family: narrow rows, streaming (128 / 512-float rows) + pair (single head x 128), generic
-EXT_SHAPES = [SHAPES[0], SHAPES[7], SHAPES[6], SHAPES[8]]
+EXT_SHAPES = [SHAPES[0], SHAPES[7], SHAPES[6], SHAPES[8], SHAPES[10]]
 
 
 @pytest.mark.parametrize("mode", [1, 0])
-@pytest.mark.parametrize("shape", EXT_SHAPES, ids=["narrow", "stream", "pair", "generic"])
+@pytest.mark.parametrize("shape", EXT_SHAPES, ids=["narrow", "stream", "pair", "generic", "pair64"])
 def test_slopes_and_dropout_parity(gatx, orc, shape, mode):
     """Opt-in extensions: gatx_set_slopes (attention / activation LeakyReLU slopes) and gatx_set_dropout
     (Philox input dropout) against the oracle's same-named variants: two training epochs, so the second uses new
@@ -458,7 +466,7 @@ def test_dropout_reproducible_and_graph_free(gatx):
 
 
 @pytest.mark.parametrize("mode", [1, 0])
-@pytest.mark.parametrize("shape", EXT_SHAPES + [SHAPES[4]], ids=["narrow", "stream", "pair", "generic", "two-head-last"])
+@pytest.mark.parametrize("shape", EXT_SHAPES + [SHAPES[4]], ids=["narrow", "stream", "pair", "generic", "pair64", "two-head-last"])
 def test_bias_parity(gatx, orc, shape, mode):
     """Opt-in per-layer bias (gatx_set_bias): forward values, gb and the updated biases against the oracle over two
     clipped epochs, on a graph where some rows have no in-edge (their aggregate is the bias alone)."""
@@ -542,7 +550,7 @@ def test_labels_outside_class_range_are_refused(gatx):
 
 
 @pytest.mark.parametrize("mode", [1, 0])
-@pytest.mark.parametrize("shape", EXT_SHAPES, ids=["narrow", "stream", "pair", "generic"])
+@pytest.mark.parametrize("shape", EXT_SHAPES, ids=["narrow", "stream", "pair", "generic", "pair64"])
 def test_attention_dropout_parity(gatx, orc, shape, mode):
     """Opt-in extension: gatx_set_attn_dropout -- dropout on the attention COEFFICIENTS, h_i = sum_j alpha_ij
     d_ij W_l x_j with d_ij = keep / (1 - p) drawn by Philox per (global edge, head) -- against the oracle's
