@@ -159,11 +159,14 @@ def test_products_full_size_properties(gatx, orc):
         del Pl, alpha
         # --- backward properties ---
         eng.backward()
-        ge = eng.tensor(gatx.T_GE, 0).reshape(E, H).astype(np.float64)
-        seg0 = np.add.reduceat(ge, rp[:-1].astype(np.int64), axis=0)
-        segabs = np.add.reduceat(np.abs(ge), rp[:-1].astype(np.int64), axis=0)
-        assert np.abs(seg0).max() < 1e-4 * max(segabs.max(), 1e-30)
-        del ge
+        # softmax backward: g_e sums to zero over every in-edge segment -- checked on EVERY edge of every layer (layer 2
+        # runs the pair kernels; a stale row or ring slot in pass 1 breaks this for the row it hits)
+        for l in range(3):
+            ge = eng.tensor(gatx.T_GE, l).reshape(E, cfg["heads"][l]).astype(np.float64)
+            seg0 = np.add.reduceat(ge, rp[:-1].astype(np.int64), axis=0)
+            segabs = np.add.reduceat(np.abs(ge), rp[:-1].astype(np.int64), axis=0)
+            assert np.abs(seg0).max() < 1e-4 * max(segabs.max(), 1e-30), l
+            del ge, seg0, segabs
         for l in (2, 0):
             Hl = cfg["heads"][l]
             F = Hl * cfg["outdims"][l]
