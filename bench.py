@@ -289,7 +289,18 @@ def run_gatx(args):
     if world > 1:
         ids = [gatx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        eng.comm_init(ids[0])
+        # NCCL prints its version banner with printf when the box sets NCCL_DEBUG=VERSION (NCCL_DEBUG_FILE does not move
+        # it): file descriptor 1 points at stderr while the communicator is created, stdout keeps to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            eng.comm_init(ids[0])
+        finally:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)  # the banner sits in C stdio's buffer when stdout is a pipe
+            os.dup2(saved, 1)
+            os.close(saved)
     # pinned host copies of the per-epoch inputs for the end-to-end leg
     Xp = torch.empty((N, cfg["I"]), dtype=torch.float32, pin_memory=True)
     Xp.numpy()[:] = ds["X"]
