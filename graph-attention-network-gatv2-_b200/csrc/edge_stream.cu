@@ -523,6 +523,8 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     }
     // row data (g_h row, P_r row) of r goes through the row buffer; once it sits in registers the buffer is free,
     // so row r + 1 is prefetched into the same buffer while row r is being processed
+    // generic loads have read the row buffer (previous chunk / row): order them before the async-proxy overwrite
+    fence_proxy_async_smem();
     bulk2_g2s_hint_elect(rowbuf_s, gh + (int64_t)r * F, kRowBytes, gp.cold, rowbuf_s + kRowBytes, Pr + (int64_t)r * F,
                          kRowBytes, gp.cold, rbar_s);
     // score window: the scores of 32 consecutive edges are contiguous ([E][H]); the next window is
@@ -558,9 +560,11 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
     }
     __syncwarp();
     ++rk;
-    if (r + 1 < g.n_rows)
+    if (r + 1 < g.n_rows) {
+      fence_proxy_async_smem();
       bulk2_g2s_hint_elect(rowbuf_s, gh + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rowbuf_s + kRowBytes,
                            Pr + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rbar_s);
+    }
     bool first_row = true;
     for (int i = 0; i < n; ++i) {
       const int e = e0 + i;
@@ -591,6 +595,7 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
         __syncwarp();
         ++rk;
         if (r + 1 < g.n_rows) {
+          fence_proxy_async_smem();
           bulk2_g2s_hint_elect(rowbuf_s, gh + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rowbuf_s + kRowBytes,
                                Pr + (int64_t)(r + 1) * F, kRowBytes, gp.cold, rbar_s);
           load_scalars(qn, r + 1, H, hd, cdot, mx, sinv);

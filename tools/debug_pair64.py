@@ -28,14 +28,16 @@ else:  # "arxiv" / "race"
     p = dict(row_ptr=ds["row_ptr"], col_idx=ds["col_idx"], X=ds["X"], labels=ds["labels"], Ws=Ws, As=As, Wo=Wo,
              heads=cfg["heads"], outdims=cfg["outdims"], C=cfg["C"])
 eng = make_engine(gatx, p, gemm_mode=1, keep_debug=True)
-if which == "race":  # the same backward several times against one oracle pass: a race shows as a changing set of wrong edges
-    ref = make_oracle(orc, p)
-    ref.forward(); ref.backward()
+if which in ("race", "race0"):  # the same backward several times: a race shows as a changing set of wrong edges
     l = len(p["heads"]) - 1
     H = p["heads"][l]
     E = len(p["col_idx"])
-    ge_ref, al_ref = ref.tensor(orc.T_GE, l) if hasattr(orc, "T_GE") else None, ref.tensor(orc.T_ALPHA, l)
-    ga_ref = ref.tensor(orc.T_GA, l).ravel()
+    if which == "race":  # with one oracle pass beside it
+        ref = make_oracle(orc, p)
+        ref.forward(); ref.backward()
+        ga_ref = ref.tensor(orc.T_GA, l).ravel()
+    else:
+        ga_ref = np.zeros(p["heads"][l] * p["outdims"][l], np.float32)
     prev = None
     for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 6):
         eng.forward(); eng.backward()
