@@ -22,6 +22,14 @@ namespace gatx {
 namespace {
 
 constexpr int kSW = 4;  // warps per CTA
+// -DGATX_RING_FENCE: fence.proxy.async before every per-edge refill of a bulk-copy ring slot (the slot was read by generic
+// loads one instruction earlier; see the row buffer of pass 1).  Off by default: never observed to matter (all-edge checks at
+// products size), costs an instruction per edge -- to be measured.
+#ifdef GATX_RING_FENCE
+#define RING_REFILL_FENCE() fence_proxy_async_smem()
+#else
+#define RING_REFILL_FENCE()
+#endif
 
 struct Shape {
   int H, D, F, lph, lg_lph;  // lph = D / 4: lanes per head in the node-wise kernels' layout (lane + 32 j)
@@ -309,8 +317,10 @@ edge_fwd_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const flo
       {
         const int ni = i + R;
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
-        if (ni < n)
+        if (ni < n) {
+          RING_REFILL_FENCE();
           bulk_g2s_hint_elect(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
+        }
       }
       float2 pp = make_float2(0.f, 0.f);  // even / odd elements: two interleaved FFMA2 chains
 #pragma unroll
@@ -627,8 +637,10 @@ edge_bwd_dst_stream_kernel(StreamGraph g, const int* __restrict__ col_idx, const
       {
         const int ni = i + R;
         const int srcn = __shfl_sync(0xffffffffu, ((ni >> 5) == (i >> 5)) ? idx_cur : idx_nxt, ni & 31);
-        if (ni < n)
+        if (ni < n) {
+          RING_REFILL_FENCE();
           bulk_g2s_hint_elect(ring_s + (uint32_t)(slot * F) * 4u, Pl + gp.id(srcn) * F, kRowBytes, bar_s + slot * 8u, gp.of(srcn));
+        }
       }
       const float* sc = scwin + ((i >> 5) & 1) * 32 * H + (i & 31) * H;
       uint32_t* re = rec + (int64_t)e * RW;
@@ -838,10 +850,12 @@ edge_bwd_src_stream_kernel(StreamGraph g, const int* __restrict__ csc_dst, const
         const bool same = (ni >> 5) == (i >> 5);
         const int d = __shfl_sync(0xffffffffu, same ? dst_cur : dst_nxt, ni & 31);
         const int ee = __shfl_sync(0xffffffffu, same ? eid_cur : eid_nxt, ni & 31);
-        if (ni < n)
+        if (ni < n) {
+          RING_REFILL_FENCE();
           bulk2_g2s_hint_elect(ring_s + (uint32_t)(slot * slot_floats) * 4u, gh + gp.id(d) * F, kRowBytes, gp.of(d),
                                ring_s + (uint32_t)(slot * slot_floats + F) * 4u, rec + (int64_t)ee * RW, kRecBytes, gp.cold,
                                bar_s + slot * 8u);
+        }
       }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
